@@ -1,0 +1,493 @@
+// align.cu — K4/K5 and the Levenberg-Marquardt driver.
+//
+// K4  linearize        = NanoGICP::update_correspondences + NanoGICP::linearize fused
+//                        (reference include/nano_gicp/impl/nano_gicp_impl.hpp:173-211, :213-270):
+//                        per source point  q = float(T) * p  ->  bounded 1-NN on the target grid  ->
+//                        M = (C_B + R C_A R^T)^-1  ->  J^T M J / J^T M e / e^T M e, reduced with warp
+//                        shuffles and per-block partials into one packed {H(21), b(6), err} per call.
+// K5  compute_error    = NanoGICP::compute_error (:272-296) with correspondences and M frozen.
+// LM  align_fused      = LsqRegistration::computeTransformation / step_lm / step_gn / is_converged
+//                        (include/nano_gicp/impl/lsq_registration_impl.hpp:89-208) as ONE persistent
+//                        cooperative kernel: K4 and K5 phases separated by a grid barrier, the 6x6
+//                        pivoted LDL^T solve and the accept/reject logic done redundantly by every
+//                        block from the same fixed-order sum of partials (bit-deterministic, no host
+//                        round trip until the final transform is read back).
+//
+// Per source point K4 touches p_A 16 B + C_A 48 B + p_B 16 B + C_B 48 B + corr 4 B = 132 B of
+// compulsory traffic (+48 B M +16 B p_B stored for K5, which then reads 16+48+16+4 = 84 B).
+#include "internal.h"
+#include "grid_search.cuh"
+#include "gicp_math.cuh"
+
+namespace ngicp {
+
+constexpr int AL_THREADS = 128;
+constexpr int AL_WARPS = AL_THREADS / 32;
+
+struct XformF { float m[12]; };   // rows: m[r*4+c], c=3 is translation; float cast of the double state
+struct AlignArgs {
+  const float4* src_pts; const double* src_cov; int ns;
+  GridView tgt; const double* tgt_cov;
+  double* mahal; int* corr; float* sqd; float4* tgt_pt;
+  double* partials;  // [2][max_blocks][NRED]
+  int max_blocks;
+  int batch;         // source points handled per warp batch (1..32)
+};
+
+__device__ __forceinline__ void make_xforms(const Iso3& x, XformF& f) {
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+#pragma unroll
+    for (int c = 0; c < 3; c++) f.m[r * 4 + c] = (float)x.R[r * 3 + c];
+    f.m[r * 4 + 3] = (float)x.t[r];
+  }
+}
+
+// Eigen's Isometry3f * Vector4f: per row a balanced-tree sum of four float products, never fused
+__device__ __forceinline__ float xform_row(const float* m, float x, float y, float z) {
+  return __fadd_rn(__fadd_rn(__fmul_rn(m[0], x), __fmul_rn(m[1], y)), __fadd_rn(__fmul_rn(m[2], z), __fmul_rn(m[3], 1.0f)));
+}
+
+// one warp: correspondences + Mahalanobis + H/b/err contributions of `cnt` source points starting at i0
+__device__ __forceinline__ void linearize_batch(const AlignArgs& a, const GridParams& gp, const XformF& Tf, const Iso3& Td,
+                                                float cap_d2, double thr2, int i0, int cnt, double* acc) {
+  const int lane = threadIdx.x & 31;
+  float my_d = FLT_MAX;
+  int my_p = -1;
+  for (int t = 0; t < cnt; ++t) {
+    const float4 p = __ldg(a.src_pts + i0 + t);
+    const float qx = xform_row(Tf.m + 0, p.x, p.y, p.z), qy = xform_row(Tf.m + 4, p.x, p.y, p.z), qz = xform_row(Tf.m + 8, p.x, p.y, p.z);
+    WarpBest1 rs;
+    rs.init();
+    if (isfinite(qx) && isfinite(qy) && isfinite(qz)) grid_search_warp(a.tgt, gp, qx, qy, qz, cap_d2, rs);
+    rs.finalize();
+    if (lane == t) { my_d = rs.d; my_p = rs.p; }
+  }
+  if (lane < cnt) {
+    const int i = i0 + lane;
+    int corr = -1;
+    if (my_p >= 0 && (double)my_d < thr2) {
+      const float4 p = __ldg(a.src_pts + i);
+      const float4 tp = __ldg(a.tgt.sorted + my_p);
+      corr = __float_as_int(tp.w);
+      double CA[6], CB[6], RCR[6], M[6];
+      const double* ca = a.src_cov + (size_t)i * 6;
+      const double* cb = a.tgt_cov + (size_t)corr * 6;
+#pragma unroll
+      for (int j = 0; j < 6; j++) { CA[j] = __ldg(ca + j); CB[j] = __ldg(cb + j); }
+      sym3_rcr(CB, Td.R, CA, RCR);
+      sym3_inverse(RCR, M);
+      const double px = (double)p.x, py = (double)p.y, pz = (double)p.z;
+      double tA[3], e[3];
+      tA[0] = Td.R[0] * px + Td.R[1] * py + Td.R[2] * pz + Td.t[0];
+      tA[1] = Td.R[3] * px + Td.R[4] * py + Td.R[5] * pz + Td.t[1];
+      tA[2] = Td.R[6] * px + Td.R[7] * py + Td.R[8] * pz + Td.t[2];
+      e[0] = (double)tp.x - tA[0]; e[1] = (double)tp.y - tA[1]; e[2] = (double)tp.z - tA[2];
+      gicp_accumulate(tA, e, M, acc);
+      double* md = a.mahal + (size_t)i * 6;
+#pragma unroll
+      for (int j = 0; j < 6; j++) md[j] = M[j];
+      a.tgt_pt[i] = tp;
+    }
+    a.corr[i] = corr;
+    a.sqd[i] = my_d;
+  }
+}
+
+__device__ __forceinline__ double error_point(const AlignArgs& a, const Iso3& Td, int i) {
+  if (a.corr[i] < 0) return 0.0;
+  const float4 p = __ldg(a.src_pts + i);
+  const float4 tp = a.tgt_pt[i];
+  const double* md = a.mahal + (size_t)i * 6;
+  const double px = (double)p.x, py = (double)p.y, pz = (double)p.z;
+  const double e0 = (double)tp.x - (Td.R[0] * px + Td.R[1] * py + Td.R[2] * pz + Td.t[0]);
+  const double e1 = (double)tp.y - (Td.R[3] * px + Td.R[4] * py + Td.R[5] * pz + Td.t[1]);
+  const double e2 = (double)tp.z - (Td.R[6] * px + Td.R[7] * py + Td.R[8] * pz + Td.t[2]);
+  const double m0 = md[0] * e0 + md[1] * e1 + md[2] * e2;
+  const double m1 = md[1] * e0 + md[3] * e1 + md[4] * e2;
+  const double m2 = md[2] * e0 + md[4] * e1 + md[5] * e2;
+  return e0 * m0 + e1 * m1 + e2 * m2;
+}
+
+// block-level fixed-order reduction of NV values per thread -> out[0..NV) (written by threads < NV)
+template <int NV>
+__device__ __forceinline__ void block_reduce_store(double* acc, double (*s_red)[NRED], double* out) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+  for (int j = 0; j < NV; j++) acc[j] = warp_sum(acc[j]);
+  if (lane == 0) {
+#pragma unroll
+    for (int j = 0; j < NV; j++) s_red[w][j] = acc[j];
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s = 0.0;
+#pragma unroll
+    for (int ww = 0; ww < AL_WARPS; ww++) s += s_red[ww][threadIdx.x];
+    out[threadIdx.x] = s;
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------
+// stepped mode: one launch per phase
+// ------------------------------------------------------------------------------------------
+struct IsoArg { Iso3 x; };
+
+__global__ void __launch_bounds__(AL_THREADS) linearize_kernel(AlignArgs a, IsoArg T, float cap_d2, double thr2) {
+  __shared__ double s_red[AL_WARPS][NRED];
+  const GridParams gp = load_grid(a.tgt.desc);
+  XformF Tf;
+  make_xforms(T.x, Tf);
+  double acc[NRED];
+#pragma unroll
+  for (int j = 0; j < NRED; j++) acc[j] = 0.0;
+  const int nbatches = (a.ns + a.batch - 1) / a.batch;
+  const int gw = blockIdx.x * AL_WARPS + (threadIdx.x >> 5);
+  for (int bch = gw; bch < nbatches; bch += gridDim.x * AL_WARPS) {
+    const int i0 = bch * a.batch;
+    linearize_batch(a, gp, Tf, T.x, cap_d2, thr2, i0, min(a.batch, a.ns - i0), acc);
+  }
+  block_reduce_store<NRED>(acc, s_red, a.partials + (size_t)blockIdx.x * NRED);
+}
+
+__global__ void __launch_bounds__(AL_THREADS) compute_error_kernel(AlignArgs a, IsoArg T) {
+  __shared__ double s_red[AL_WARPS][NRED];
+  double acc[1] = {0.0};
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.ns; i += gridDim.x * blockDim.x) acc[0] += error_point(a, T.x, i);
+  block_reduce_store<1>(acc, s_red, a.partials + (size_t)blockIdx.x * NRED);
+}
+
+__global__ void reduce_partials_kernel(const double* __restrict__ partials, int nblocks, int nv, double* __restrict__ out) {
+  const int t = threadIdx.x;
+  if (t < nv) {
+    double s = 0.0;
+    for (int b = 0; b < nblocks; b++) s += partials[(size_t)b * NRED + t];
+    out[t] = s;
+  }
+}
+
+static inline float cap_from(double max_corr_dist) {
+  const double c2 = max_corr_dist * max_corr_dist;
+  return c2 >= (double)FLT_MAX ? FLT_MAX : (float)c2 * 1.000001f + 1e-30f;
+}
+
+static AlignArgs make_args(const AlignBuffers& ab, int blocks_hint) {
+  AlignArgs a;
+  a.src_pts = ab.src_pts; a.src_cov = ab.src_cov; a.ns = ab.ns;
+  a.tgt = ab.tgt; a.tgt_cov = ab.tgt_cov;
+  a.mahal = ab.mahal; a.corr = ab.corr; a.sqd = ab.sqd; a.tgt_pt = ab.tgt_pt;
+  a.partials = ab.partials; a.max_blocks = ab.max_blocks;
+  // points per warp batch: spread the searches over all resident warps
+  const int warps = blocks_hint * AL_WARPS;
+  int b = (ab.ns + warps - 1) / warps;
+  a.batch = b < 1 ? 1 : (b > 32 ? 32 : b);
+  return a;
+}
+
+static int stepped_blocks(const AlignBuffers& ab) {
+  int blocks = (ab.ns + AL_THREADS - 1) / AL_THREADS;
+  if (blocks < 1) blocks = 1;
+  if (blocks > ab.max_blocks) blocks = ab.max_blocks;
+  return blocks;
+}
+
+cudaError_t launch_linearize(const AlignBuffers& ab, const double* T16, double max_corr_dist, cudaStream_t st) {
+  const int blocks = stepped_blocks(ab);
+  AlignArgs a = make_args(ab, blocks);
+  IsoArg T;
+  iso_from_colmajor16(T16, T.x);
+  linearize_kernel<<<blocks, AL_THREADS, 0, st>>>(a, T, cap_from(max_corr_dist), max_corr_dist * max_corr_dist);
+  reduce_partials_kernel<<<1, 32, 0, st>>>(a.partials, blocks, NRED, ab.reduced);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_compute_error(const AlignBuffers& ab, const double* T16, cudaStream_t st) {
+  const int blocks = stepped_blocks(ab);
+  AlignArgs a = make_args(ab, blocks);
+  IsoArg T;
+  iso_from_colmajor16(T16, T.x);
+  compute_error_kernel<<<blocks, AL_THREADS, 0, st>>>(a, T);
+  reduce_partials_kernel<<<1, 32, 0, st>>>(a.partials, blocks, 1, ab.reduced);
+  return cudaGetLastError();
+}
+
+__global__ void export_mahal_kernel(const double* __restrict__ mahal, const int* __restrict__ corr, int n, double* __restrict__ out16) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    double* o = out16 + (size_t)i * 16;
+    for (int j = 0; j < 16; j++) o[j] = 0.0;
+    if (corr[i] >= 0) {
+      const double* m = mahal + (size_t)i * 6;
+      o[0] = m[0]; o[1] = m[1]; o[2] = m[2];
+      o[4] = m[1]; o[5] = m[3]; o[6] = m[4];
+      o[8] = m[2]; o[9] = m[4]; o[10] = m[5];
+    }
+  }
+}
+cudaError_t launch_export_mahal(const AlignBuffers& ab, double* out16, cudaStream_t st) {
+  if (ab.ns <= 0) return cudaSuccess;
+  export_mahal_kernel<<<(ab.ns + 255) / 256, 256, 0, st>>>(ab.mahal, ab.corr, ab.ns, out16);
+  return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------
+// fused mode: the whole optimisation in one persistent cooperative kernel
+// ------------------------------------------------------------------------------------------
+struct LmParams {
+  int max_iterations, lm_max_iterations, optimizer;
+  double rot_eps, trans_eps, lm_init_lambda_factor, thr2;
+  float cap_d2;
+};
+struct Guess16 { float g[16]; };
+
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
+// Grid-wide reduction of per-block partials, all blocks co-resident (cooperative launch).
+// Every block stores its partial, then arrives on a monotonic counter; the LAST block to arrive sums
+// all partials in a fixed order (so the result does not depend on which block that is), publishes the
+// totals and releases a phase flag the other blocks wait on.  One barrier latency per phase, O(blocks)
+// traffic, bit-deterministic.
+struct GridSync {
+  unsigned* arrive;   // bar[0]
+  unsigned* flag;     // bar[1]
+  double* totals;     // [2][NRED] in global memory
+  unsigned phase;     // phases completed so far
+};
+
+template <int NV>
+__device__ __forceinline__ void grid_reduce(double* acc, double (*s_red)[NRED], double* s_tot, double* partials, GridSync& gs) {
+  __shared__ int s_last;
+  block_reduce_store<NV>(acc, s_red, partials + (size_t)blockIdx.x * NRED);
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned prev = atomicAdd(gs.arrive, 1u);
+    s_last = (prev == (gs.phase + 1u) * gridDim.x - 1u) ? 1 : 0;
+  }
+  __syncthreads();
+  double* tot = gs.totals + (size_t)(gs.phase & 1u) * NRED;
+  if (s_last) {
+    __threadfence();
+    const int v = threadIdx.x & 31, seg = threadIdx.x >> 5;
+    if (v < NV) {
+      double s = 0.0;
+      for (unsigned bk = seg; bk < gridDim.x; bk += AL_WARPS) s += __ldcg(partials + (size_t)bk * NRED + v);
+      s_red[seg][v] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+      double s = 0.0;
+#pragma unroll
+      for (int sg = 0; sg < AL_WARPS; sg++) s += s_red[sg][threadIdx.x];
+      __stcg(tot + threadIdx.x, s);
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(gs.flag), "r"(gs.phase + 1u) : "memory");
+    }
+  }
+  if (threadIdx.x == 0) {
+    while (ld_acquire_u32(gs.flag) < gs.phase + 1u) { }
+    __threadfence();
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) s_tot[threadIdx.x] = __ldcg(tot + threadIdx.x);
+  gs.phase++;
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(AL_THREADS) align_fused_kernel(AlignArgs a, LmParams prm, Guess16 guess, ngicp_result* __restrict__ res, unsigned* bar, double* totals) {
+  __shared__ double s_red[AL_WARPS][NRED];
+  __shared__ double s_tot[NRED];
+  __shared__ Iso3 s_x;        // transform used by the next phase
+  __shared__ int s_decision;
+  const GridParams gp = load_grid(a.tgt.desc);
+  const int nbatches = (a.ns + a.batch - 1) / a.batch;
+  const int gw = blockIdx.x * AL_WARPS + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  GridSync gs;
+  gs.arrive = bar; gs.flag = bar + 1; gs.totals = totals; gs.phase = 0;
+
+  // scalar LM state, kept by thread 0 of every block (identical everywhere)
+  Iso3 x0, xi, delta;
+  double H36[36], b6[6], d6[6];
+  double lambda = -1.0, y0 = 0.0, nu = 2.0;
+  double final_H[36];
+  int nr_iterations = 0, n_lin = 0, n_err = 0, lm_failed = 0;
+  bool converged = false;
+  if (threadIdx.x == 0) {
+    double g16[16];
+    for (int i = 0; i < 16; i++) g16[i] = (double)guess.g[i];
+    iso_from_colmajor16(g16, x0);
+    iso_identity(delta);
+    for (int i = 0; i < 36; i++) final_H[i] = (i % 7 == 0) ? 1.0 : 0.0;
+    for (int i = 0; i < 6; i++) d6[i] = 0.0;
+    s_x = x0;
+  }
+  __syncthreads();
+
+  for (int it = 0; it < prm.max_iterations; ++it) {
+    // ---------------- linearize at s_x ----------------
+    {
+      const Iso3 T = s_x;
+      XformF Tf;
+      make_xforms(T, Tf);
+      double acc[NRED];
+#pragma unroll
+      for (int j = 0; j < NRED; j++) acc[j] = 0.0;
+      for (int bch = gw; bch < nbatches; bch += gridDim.x * AL_WARPS) {
+        const int i0 = bch * a.batch;
+        linearize_batch(a, gp, Tf, T, prm.cap_d2, prm.thr2, i0, min(a.batch, a.ns - i0), acc);
+      }
+      grid_reduce<NRED>(acc, s_red, s_tot, a.partials, gs);
+    }
+    int outcome = 0;  // 1: step returned true, 0: LM failed
+    if (threadIdx.x == 0) {
+      nr_iterations = it;
+      n_lin++;
+      unpack_H(s_tot, H36);
+      for (int i = 0; i < 6; i++) b6[i] = s_tot[21 + i];
+      y0 = s_tot[27];
+    }
+    if (prm.optimizer == NGICP_OPT_GAUSS_NEWTON) {
+      if (threadIdx.x == 0) {
+        double nb[6];
+        for (int i = 0; i < 6; i++) nb[i] = -b6[i];
+        ldlt6_solve(H36, nb, d6);
+        delta_from_step(d6, delta);
+        iso_mul(delta, x0, xi);
+        x0 = xi;
+        for (int i = 0; i < 36; i++) final_H[i] = H36[i];
+        converged = lm_is_converged(delta, prm.rot_eps, prm.trans_eps);
+        s_x = x0;
+        s_decision = converged ? 2 : 1;
+      }
+      __syncthreads();
+      outcome = 1;
+    } else {
+      if (threadIdx.x == 0) {
+        if (lambda < 0.0) {
+          double mx = 0.0;
+          for (int i = 0; i < 6; i++) mx = fmax(mx, fabs(H36[i * 7]));
+          lambda = prm.lm_init_lambda_factor * mx;
+        }
+        nu = 2.0;
+      }
+      for (int j = 0; j < prm.lm_max_iterations; ++j) {
+        if (threadIdx.x == 0) {
+          double A[36], nb[6];
+          for (int i = 0; i < 36; i++) A[i] = H36[i];
+          for (int i = 0; i < 6; i++) { A[i * 7] += lambda; nb[i] = -b6[i]; }
+          ldlt6_solve(A, nb, d6);
+          delta_from_step(d6, delta);
+          iso_mul(delta, x0, xi);
+          s_x = xi;
+        }
+        __syncthreads();
+        // ---------------- compute_error at xi ----------------
+        {
+          const Iso3 T = s_x;
+          double acc[1] = {0.0};
+          for (int bch = gw; bch < nbatches; bch += gridDim.x * AL_WARPS) {
+            const int i0 = bch * a.batch;
+            if (lane < min(a.batch, a.ns - i0)) acc[0] += error_point(a, T, i0 + lane);
+          }
+          grid_reduce<1>(acc, s_red, s_tot, a.partials, gs);
+        }
+        if (threadIdx.x == 0) {
+          n_err++;
+          const double yi = s_tot[0];
+          double denom = 0.0;
+          for (int i = 0; i < 6; i++) denom += d6[i] * (lambda * d6[i] - b6[i]);
+          const double rho = (y0 - yi) / denom;
+          int dec;
+          if (rho < 0) {
+            if (lm_is_converged(delta, prm.rot_eps, prm.trans_eps)) dec = 3;  // return true without moving x0
+            else { lambda = nu * lambda; nu = 2 * nu; dec = 0; }
+          } else {
+            x0 = xi;
+            // std::max(1/3, v) returns 1/3 unless 1/3 < v (same NaN behaviour)
+            const double v = 1.0 - pow(2.0 * rho - 1.0, 3.0);
+            lambda = lambda * ((1.0 / 3.0 < v) ? v : 1.0 / 3.0);
+            for (int i = 0; i < 36; i++) final_H[i] = H36[i];
+            dec = 1;
+          }
+          s_decision = dec;
+        }
+        __syncthreads();
+        const int dec = s_decision;
+        __syncthreads();
+        if (dec != 0) { outcome = 1; break; }
+      }
+      if (threadIdx.x == 0) {
+        if (outcome == 0) lm_failed = 1;
+        else converged = lm_is_converged(delta, prm.rot_eps, prm.trans_eps);
+        s_x = x0;
+        s_decision = (outcome == 0) ? 0 : (converged ? 2 : 1);
+      }
+      __syncthreads();
+    }
+    const int dec = s_decision;
+    __syncthreads();
+    if (dec == 0 || dec == 2) break;
+  }
+
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    double T16[16];
+    iso_to_colmajor16(x0, T16);
+    for (int i = 0; i < 16; i++) { res->final_x[i] = T16[i]; res->final_transformation[i] = (float)T16[i]; }
+    for (int i = 0; i < 36; i++) res->final_hessian[i] = final_H[i];
+    res->lm_lambda = lambda;
+    res->last_error = y0;
+    res->nr_iterations = nr_iterations;
+    res->converged = converged ? 1 : 0;
+    res->n_linearize = n_lin;
+    res->n_compute_error = n_err;
+    res->lm_failed = lm_failed;
+    res->reserved = 0;
+  }
+}
+
+int align_fused_max_blocks(int device) {
+  static int cached[64] = {0};
+  if (device >= 0 && device < 64 && cached[device]) return cached[device];
+  int per_sm = 0, sms = 0;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, align_fused_kernel, AL_THREADS, 0);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  int v = per_sm * sms;
+  if (v < 1) v = 1;
+  if (device >= 0 && device < 64) cached[device] = v;
+  return v;
+}
+
+cudaError_t launch_align_fused(const AlignBuffers& ab, const ngicp_params& p, const float* guess16, ngicp_result* res_dev,
+                               unsigned* barrier, int device, cudaStream_t st) {
+  int blocks = (ab.ns + 2 * AL_WARPS - 1) / (2 * AL_WARPS);   // aim at >= 2 searches per warp
+  const int lim = align_fused_max_blocks(device);
+  if (blocks > lim) blocks = lim;
+  if (blocks > ab.max_blocks) blocks = ab.max_blocks;
+  if (blocks < 1) blocks = 1;
+  AlignArgs a = make_args(ab, blocks);
+  LmParams prm;
+  prm.max_iterations = p.max_iterations;
+  prm.lm_max_iterations = p.lm_max_iterations;
+  prm.optimizer = p.optimizer;
+  prm.rot_eps = p.rotation_epsilon;
+  prm.trans_eps = p.transformation_epsilon;
+  prm.lm_init_lambda_factor = p.lm_init_lambda_factor;
+  prm.thr2 = p.max_correspondence_distance * p.max_correspondence_distance;
+  prm.cap_d2 = cap_from(p.max_correspondence_distance);
+  Guess16 g;
+  for (int i = 0; i < 16; i++) g.g[i] = guess16 ? guess16[i] : ((i % 5 == 0) ? 1.0f : 0.0f);
+  cudaError_t e = cudaMemsetAsync(barrier, 0, sizeof(unsigned) * 4, st);
+  if (e != cudaSuccess) return e;
+  double* totals = ab.reduced;  // [2][NRED]
+  void* args[] = {(void*)&a, (void*)&prm, (void*)&g, (void*)&res_dev, (void*)&barrier, (void*)&totals};
+  return cudaLaunchCooperativeKernel((const void*)align_fused_kernel, dim3(blocks), dim3(AL_THREADS), args, 0, st);
+}
+
+}  // namespace ngicp

@@ -1,0 +1,622 @@
+// api.cu — the C ABI of libnanogicp_b200.so (include/nanogicp_c.h) and the host side of a handle:
+// device-resident clouds / covariances with O(1) sharing and swapping, the stepped LM driver, and
+// the import/export of Eigen::Matrix4d covariance records.
+#include <cstdio>
+#include <cstring>
+#include <cmath>
+#include <new>
+
+#include "internal.h"
+#include "gicp_math.cuh"
+
+using namespace ngicp;
+
+struct ngicp_handle {
+  int device = 0;
+  StreamPtr stream;
+  ngicp_params prm;
+  std::string err;
+  CloudPtr src, tgt;
+  CovsPtr src_cov, tgt_cov;
+  Scratch sc;
+  ngicp_result* res_pinned = nullptr;   // pinned host mirror of the fused kernel's result
+  double* red_pinned = nullptr;         // pinned host mirror of reduced[]
+  cudaEvent_t ev[6][2] = {};            // one begin/end pair per timed phase
+  bool ev_used[6] = {false, false, false, false, false, false};
+  ngicp_timings tm;
+  bool lin_valid = false;               // correspondences_/mahalanobis_ valid for compute_error
+  int align_max_blocks = 2048;
+};
+
+namespace {
+
+int fail(ngicp_t* h, int code, const char* what, cudaError_t e = cudaSuccess) {
+  if (h) {
+    char buf[512];
+    if (e != cudaSuccess) snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+    else snprintf(buf, sizeof buf, "%s", what);
+    h->err = buf;
+  }
+  return code;
+}
+
+#define NG_CUDA(h, call)                                              \
+  do {                                                                \
+    cudaError_t _e = (call);                                          \
+    if (_e != cudaSuccess) return fail(h, NGICP_E_CUDA, #call, _e);   \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) { cudaGetDevice(&prev); if (prev != dev) cudaSetDevice(dev); else prev = -1; }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+
+enum Phase { PH_SET_SRC = 0, PH_SET_TGT, PH_COV_SRC, PH_COV_TGT, PH_ALIGN, PH_VOXEL, PH_COUNT };
+inline void ph_begin(ngicp_t* h, int ph) { cudaEventRecord(h->ev[ph][0], h->stream->s); }
+inline void ph_end(ngicp_t* h, int ph) { cudaEventRecord(h->ev[ph][1], h->stream->s); h->ev_used[ph] = true; }
+
+__global__ void mat4_to_sym6_kernel(const double* __restrict__ m, int n, double* __restrict__ c) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double* s = m + (size_t)i * 16;
+    double* d = c + (size_t)i * 6;
+    // column-major 4x4: (r,c) at [c*4+r]; upper triangle of the 3x3 block
+    d[0] = s[0]; d[1] = s[4]; d[2] = s[8]; d[3] = s[5]; d[4] = s[9]; d[5] = s[10];
+  }
+}
+__global__ void sym6_to_mat4_kernel(const double* __restrict__ c, int n, double* __restrict__ m) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const double* s = c + (size_t)i * 6;
+    double* d = m + (size_t)i * 16;
+    d[0] = s[0]; d[1] = s[1]; d[2] = s[2]; d[3] = 0.0;
+    d[4] = s[1]; d[5] = s[3]; d[6] = s[4]; d[7] = 0.0;
+    d[8] = s[2]; d[9] = s[4]; d[10] = s[5]; d[11] = 0.0;
+    d[12] = 0.0; d[13] = 0.0; d[14] = 0.0; d[15] = 0.0;
+  }
+}
+struct Mat16f { float m[16]; };
+__global__ void transform_points_kernel(const float4* __restrict__ pts, int n, Mat16f T, float4* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = pts[i];
+    float r[3];
+#pragma unroll
+    for (int k = 0; k < 3; k++)
+      r[k] = __fadd_rn(__fadd_rn(__fmul_rn(T.m[0 * 4 + k], p.x), __fmul_rn(T.m[1 * 4 + k], p.y)), __fadd_rn(__fmul_rn(T.m[2 * 4 + k], p.z), T.m[3 * 4 + k]));
+    out[i] = make_float4(r[0], r[1], r[2], 1.0f);
+  }
+}
+__global__ void vox_passthrough_kernel(const float4* __restrict__ pts, int n, float* __restrict__ out) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = pts[i];
+    float4* o = reinterpret_cast<float4*>(out + (size_t)i * 8);
+    o[0] = make_float4(p.x, p.y, p.z, 1.0f);
+    o[1] = make_float4(p.w, 0.f, 0.f, 0.f);
+  }
+}
+
+inline int blocks_for(int n) { int g = (n + 255) / 256; return g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g); }
+
+int set_cloud(ngicp_t* h, int which, const void* pts, size_t n, size_t stride, bool index) {
+  if (!h) return NGICP_E_INVALID;
+  if ((!pts && n) || stride < 12 || (stride & 3) || n > 0x7fffff00u) return fail(h, NGICP_E_INVALID, "bad cloud arguments");
+  DeviceGuard g(h->device);
+  CloudPtr c(new (std::nothrow) DevCloud());
+  if (!c) return fail(h, NGICP_E_INVALID, "out of host memory");
+  const int ph = which == NGICP_SOURCE ? PH_SET_SRC : PH_SET_TGT;
+  ph_begin(h, ph);
+  NG_CUDA(h, upload_cloud(*c, pts, n, stride, h->sc, h->stream));
+  if (index) NG_CUDA(h, build_index(*c, h->prm.grid_cell_size, h->prm.grid_table_cells, h->sc, h->stream));
+  ph_end(h, ph);
+  if (which == NGICP_SOURCE) { h->src = c; if (index) h->src_cov.reset(); }
+  else { h->tgt = c; h->tgt_cov.reset(); }
+  h->lin_valid = false;
+  return NGICP_OK;
+}
+
+int ensure_index(ngicp_t* h, CloudPtr& c) {
+  if (c->indexed) return NGICP_OK;
+  NG_CUDA(h, build_index(*c, h->prm.grid_cell_size, h->prm.grid_table_cells, h->sc, h->stream));
+  return NGICP_OK;
+}
+
+int calc_covs(ngicp_t* h, int which) {
+  if (!h) return NGICP_E_INVALID;
+  DeviceGuard g(h->device);
+  CloudPtr& c = which == NGICP_SOURCE ? h->src : h->tgt;
+  if (!c) return fail(h, NGICP_E_STATE, "calculate covariances: cloud not set");
+  const int k = h->prm.k_correspondences;
+  if (k < 1 || k > KNN_MAX_K) return fail(h, NGICP_E_UNSUPPORTED, "k_correspondences must be in [1,32]");
+  if (c->n < k) return fail(h, NGICP_E_TOO_FEW_POINTS, "cloud has fewer points than k_correspondences");
+  int rc = ensure_index(h, c);  // calculate_covariances re-targets the kd-tree when needed (nano_gicp_impl.hpp:304-306)
+  if (rc) return rc;
+  CovsPtr cv(new (std::nothrow) DevCovs());
+  if (!cv) return fail(h, NGICP_E_INVALID, "out of host memory");
+  cv->n = c->n;
+  NG_CUDA(h, cv->c.alloc(sizeof(double) * 6 * (size_t)c->n, h->stream));
+  const int ph = which == NGICP_SOURCE ? PH_COV_SRC : PH_COV_TGT;
+  ph_begin(h, ph);
+  NG_CUDA(h, launch_covariances(*c, k, h->prm.regularization_method, cv->c.as<double>(), h->stream->s));
+  ph_end(h, ph);
+  (which == NGICP_SOURCE ? h->src_cov : h->tgt_cov) = cv;
+  h->lin_valid = false;
+  return NGICP_OK;
+}
+
+int set_covs(ngicp_t* h, int which, const double* covs, size_t n) {
+  if (!h || (!covs && n)) return NGICP_E_INVALID;
+  DeviceGuard g(h->device);
+  CovsPtr cv(new (std::nothrow) DevCovs());
+  cv->n = (int)n;
+  NG_CUDA(h, cv->c.alloc(sizeof(double) * 6 * (n ? n : 1), h->stream));
+  if (n) {
+    NG_CUDA(h, h->sc.cov_stage.reserve(sizeof(double) * 16 * n, h->stream));
+    NG_CUDA(h, cudaMemcpyAsync(h->sc.cov_stage.p, covs, sizeof(double) * 16 * n, cudaMemcpyDefault, h->stream->s));
+    mat4_to_sym6_kernel<<<blocks_for((int)n), 256, 0, h->stream->s>>>(h->sc.cov_stage.as<double>(), (int)n, cv->c.as<double>());
+    NG_CUDA(h, cudaGetLastError());
+  }
+  (which == NGICP_SOURCE ? h->src_cov : h->tgt_cov) = cv;
+  h->lin_valid = false;
+  return NGICP_OK;
+}
+
+int get_covs(ngicp_t* h, int which, double* out, size_t n) {
+  if (!h || !out) return NGICP_E_INVALID;
+  DeviceGuard g(h->device);
+  CovsPtr& cv = which == NGICP_SOURCE ? h->src_cov : h->tgt_cov;
+  if (!cv || (size_t)cv->n != n) return fail(h, NGICP_E_COV_SIZE, "get covariances: size mismatch");
+  if (n == 0) return NGICP_OK;
+  NG_CUDA(h, h->sc.cov_stage.reserve(sizeof(double) * 16 * n, h->stream));
+  sym6_to_mat4_kernel<<<blocks_for((int)n), 256, 0, h->stream->s>>>(cv->c.as<double>(), (int)n, h->sc.cov_stage.as<double>());
+  NG_CUDA(h, cudaGetLastError());
+  NG_CUDA(h, cudaMemcpyAsync(out, h->sc.cov_stage.p, sizeof(double) * 16 * n, cudaMemcpyDefault, h->stream->s));
+  NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
+  return NGICP_OK;
+}
+
+// everything align/linearize need; also performs the lazy covariance computation of
+// NanoGICP::computeTransformation (nano_gicp_impl.hpp:163-168) when `lazy` is set
+int prepare_align(ngicp_t* h, bool lazy, AlignBuffers& ab) {
+  if (!h->src || !h->tgt) return fail(h, NGICP_E_STATE, "align: source/target not set");
+  if (h->src->n == 0 || h->tgt->n == 0) return fail(h, NGICP_E_STATE, "align: empty cloud");
+  if (!h->tgt->indexed) return fail(h, NGICP_E_STATE, "align: target has no search index");
+  if (!h->src_cov || h->src_cov->n != h->src->n) {
+    if (!lazy) return fail(h, NGICP_E_COV_SIZE, "source covariances missing");
+    int rc = calc_covs(h, NGICP_SOURCE);
+    if (rc) return rc;
+  }
+  if (!h->tgt_cov || h->tgt_cov->n != h->tgt->n) {
+    if (!lazy) return fail(h, NGICP_E_COV_SIZE, "target covariances missing");
+    int rc = calc_covs(h, NGICP_TARGET);
+    if (rc) return rc;
+  }
+  const size_t ns = (size_t)h->src->n;
+  Scratch& sc = h->sc;
+  NG_CUDA(h, sc.mahal.reserve(sizeof(double) * 6 * ns, h->stream));
+  NG_CUDA(h, sc.corr.reserve(sizeof(int) * ns, h->stream));
+  NG_CUDA(h, sc.sqd.reserve(sizeof(float) * ns, h->stream));
+  NG_CUDA(h, sc.tgt_pt.reserve(sizeof(float4) * ns, h->stream));
+  NG_CUDA(h, sc.partials.reserve(sizeof(double) * NRED * (size_t)h->align_max_blocks, h->stream));
+  NG_CUDA(h, sc.reduced.reserve(sizeof(double) * 64, h->stream));
+  NG_CUDA(h, sc.lm_state.reserve(sizeof(ngicp_result), h->stream));
+  NG_CUDA(h, sc.barrier.reserve(64, h->stream));
+  ab.src_pts = h->src->pts.as<float4>(); ab.src_cov = h->src_cov->c.as<double>(); ab.ns = h->src->n;
+  ab.tgt = h->tgt->view(); ab.tgt_cov = h->tgt_cov->c.as<double>(); ab.nt = h->tgt->n;
+  ab.mahal = sc.mahal.as<double>(); ab.corr = sc.corr.as<int>(); ab.sqd = sc.sqd.as<float>(); ab.tgt_pt = sc.tgt_pt.as<float4>();
+  ab.partials = sc.partials.as<double>(); ab.reduced = sc.reduced.as<double>(); ab.max_blocks = h->align_max_blocks;
+  return NGICP_OK;
+}
+
+int fetch_reduced(ngicp_t* h, int count) {
+  NG_CUDA(h, cudaMemcpyAsync(h->red_pinned, h->sc.reduced.p, sizeof(double) * count, cudaMemcpyDeviceToHost, h->stream->s));
+  NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
+  return NGICP_OK;
+}
+
+// host-stepped LM: identical decisions to the fused kernel, one launch per phase
+int align_stepped(ngicp_t* h, const AlignBuffers& ab, const float* guess16, ngicp_result* out) {
+  const ngicp_params& p = h->prm;
+  Iso3 x0, xi, delta;
+  double g16[16];
+  for (int i = 0; i < 16; i++) g16[i] = guess16 ? (double)guess16[i] : ((i % 5 == 0) ? 1.0 : 0.0);
+  iso_from_colmajor16(g16, x0);
+  iso_identity(delta);
+  double H36[36], b6[6], d6[6] = {0, 0, 0, 0, 0, 0}, final_H[36];
+  for (int i = 0; i < 36; i++) final_H[i] = (i % 7 == 0) ? 1.0 : 0.0;
+  double lambda = -1.0, y0 = 0.0;
+  int nr_iterations = 0, n_lin = 0, n_err = 0, lm_failed = 0;
+  bool converged = false;
+  double T16[16];
+  for (int it = 0; it < p.max_iterations && !converged; ++it) {
+    nr_iterations = it;
+    iso_to_colmajor16(x0, T16);
+    NG_CUDA(h, launch_linearize(ab, T16, p.max_correspondence_distance, h->stream->s));
+    int rc = fetch_reduced(h, NRED);
+    if (rc) return rc;
+    n_lin++;
+    unpack_H(h->red_pinned, H36);
+    for (int i = 0; i < 6; i++) b6[i] = h->red_pinned[21 + i];
+    y0 = h->red_pinned[27];
+    bool ok = false;
+    if (p.optimizer == NGICP_OPT_GAUSS_NEWTON) {
+      double nb[6];
+      for (int i = 0; i < 6; i++) nb[i] = -b6[i];
+      ldlt6_solve(H36, nb, d6);
+      delta_from_step(d6, delta);
+      iso_mul(delta, x0, xi);
+      x0 = xi;
+      memcpy(final_H, H36, sizeof final_H);
+      ok = true;
+    } else {
+      if (lambda < 0.0) {
+        double mx = 0.0;
+        for (int i = 0; i < 6; i++) mx = fmax(mx, fabs(H36[i * 7]));
+        lambda = p.lm_init_lambda_factor * mx;
+      }
+      double nu = 2.0;
+      for (int j = 0; j < p.lm_max_iterations; ++j) {
+        double A[36], nb[6];
+        memcpy(A, H36, sizeof A);
+        for (int i = 0; i < 6; i++) { A[i * 7] += lambda; nb[i] = -b6[i]; }
+        ldlt6_solve(A, nb, d6);
+        delta_from_step(d6, delta);
+        iso_mul(delta, x0, xi);
+        iso_to_colmajor16(xi, T16);
+        NG_CUDA(h, launch_compute_error(ab, T16, h->stream->s));
+        rc = fetch_reduced(h, 1);
+        if (rc) return rc;
+        n_err++;
+        const double yi = h->red_pinned[0];
+        double denom = 0.0;
+        for (int i = 0; i < 6; i++) denom += d6[i] * (lambda * d6[i] - b6[i]);
+        const double rho = (y0 - yi) / denom;
+        if (rho < 0) {
+          if (lm_is_converged(delta, p.rotation_epsilon, p.transformation_epsilon)) { ok = true; break; }
+          lambda = nu * lambda;
+          nu = 2 * nu;
+          continue;
+        }
+        x0 = xi;
+        const double v = 1.0 - pow(2.0 * rho - 1.0, 3.0);
+        lambda = lambda * ((1.0 / 3.0 < v) ? v : 1.0 / 3.0);
+        memcpy(final_H, H36, sizeof final_H);
+        ok = true;
+        break;
+      }
+    }
+    if (!ok) { lm_failed = 1; break; }
+    converged = lm_is_converged(delta, p.rotation_epsilon, p.transformation_epsilon);
+  }
+  iso_to_colmajor16(x0, T16);
+  for (int i = 0; i < 16; i++) { out->final_x[i] = T16[i]; out->final_transformation[i] = (float)T16[i]; }
+  memcpy(out->final_hessian, final_H, sizeof final_H);
+  out->lm_lambda = lambda;
+  out->last_error = y0;
+  out->nr_iterations = nr_iterations;
+  out->converged = converged ? 1 : 0;
+  out->n_linearize = n_lin;
+  out->n_compute_error = n_err;
+  out->lm_failed = lm_failed;
+  out->reserved = 0;
+  return NGICP_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* ngicp_version(void) { return "nanogicp-b200 0.1 sm_100a"; }
+
+void ngicp_params_default(ngicp_params* p) {
+  if (!p) return;
+  p->k_correspondences = 20;
+  p->max_correspondence_distance = (double)FLT_MAX;
+  p->max_iterations = 64;
+  p->transformation_epsilon = 5e-4;
+  p->rotation_epsilon = 2e-3;
+  p->optimizer = NGICP_OPT_LEVENBERG_MARQUARDT;
+  p->lm_max_iterations = 10;
+  p->lm_init_lambda_factor = 1e-9;
+  p->regularization_method = NGICP_REG_PLANE;
+  p->grid_cell_size = 0.f;
+  p->grid_table_cells = 1 << 23;
+  p->align_mode = NGICP_ALIGN_FUSED;
+}
+
+int ngicp_create(int device, ngicp_t** out) {
+  if (!out) return NGICP_E_INVALID;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) return NGICP_E_CUDA;  // no CPU fallback, by design
+  if (device < 0 || device >= count) return NGICP_E_INVALID;
+  DeviceGuard g(device);
+  ngicp_handle* h = new (std::nothrow) ngicp_handle();
+  if (!h) return NGICP_E_INVALID;
+  h->device = device;
+  ngicp_params_default(&h->prm);
+  memset(&h->tm, 0, sizeof h->tm);
+  h->stream.reset(new StreamRef());
+  if (cudaStreamCreateWithFlags(&h->stream->s, cudaStreamNonBlocking) != cudaSuccess) { delete h; return NGICP_E_CUDA; }
+  h->stream->owned = true;
+  // keep freed blocks in the stream-ordered pool instead of returning them to the driver
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t thr = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
+  }
+  bool ok = cudaMallocHost(&h->res_pinned, sizeof(ngicp_result)) == cudaSuccess &&
+            cudaMallocHost(&h->red_pinned, sizeof(double) * 64) == cudaSuccess;
+  for (int i = 0; ok && i < PH_COUNT; i++)
+    ok = cudaEventCreate(&h->ev[i][0]) == cudaSuccess && cudaEventCreate(&h->ev[i][1]) == cudaSuccess;
+  if (!ok) {
+    ngicp_destroy(h);
+    return NGICP_E_CUDA;
+  }
+  *out = h;
+  return NGICP_OK;
+}
+
+void ngicp_destroy(ngicp_t* h) {
+  if (!h) return;
+  DeviceGuard g(h->device);
+  if (h->stream && h->stream->s) cudaStreamSynchronize(h->stream->s);
+  h->src.reset(); h->tgt.reset(); h->src_cov.reset(); h->tgt_cov.reset();
+  if (h->res_pinned) cudaFreeHost(h->res_pinned);
+  if (h->red_pinned) cudaFreeHost(h->red_pinned);
+  for (int i = 0; i < PH_COUNT; i++)
+    for (int j = 0; j < 2; j++)
+      if (h->ev[i][j]) cudaEventDestroy(h->ev[i][j]);
+  delete h;
+}
+
+const char* ngicp_last_error(const ngicp_t* h) { return h ? h->err.c_str() : "null handle"; }
+
+int ngicp_set_stream(ngicp_t* h, void* cuda_stream) {
+  if (!h) return NGICP_E_INVALID;
+  DeviceGuard g(h->device);
+  cudaStreamSynchronize(h->stream->s);
+  StreamPtr s(new StreamRef());
+  if (cuda_stream) { s->s = (cudaStream_t)cuda_stream; s->owned = false; }
+  else {
+    if (cudaStreamCreateWithFlags(&s->s, cudaStreamNonBlocking) != cudaSuccess) return fail(h, NGICP_E_CUDA, "cudaStreamCreate");
+    s->owned = true;
+  }
+  h->stream = s;
+  return NGICP_OK;
+}
+void* ngicp_get_stream(const ngicp_t* h) { return h ? (void*)h->stream->s : nullptr; }
+
+int ngicp_sync(ngicp_t* h) {
+  if (!h) return NGICP_E_INVALID;
+  DeviceGuard g(h->device);
+  NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
+  return NGICP_OK;
+}
+
+int ngicp_get_timings(ngicp_t* h, ngicp_timings* out) {
+  if (!h || !out) return NGICP_E_INVALID;
+  DeviceGuard g(h->device);
+  NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
+  float* slots[PH_COUNT] = {&h->tm.set_source_ms, &h->tm.set_target_ms, &h->tm.source_covs_ms, &h->tm.target_covs_ms, &h->tm.align_ms, &h->tm.voxel_ms};
+  for (int i = 0; i < PH_COUNT; i++)
+    if (h->ev_used[i]) cudaEventElapsedTime(slots[i], h->ev[i][0], h->ev[i][1]);
+  *out = h->tm;
+  return NGICP_OK;
+}
+
+int ngicp_set_params(ngicp_t* h, const ngicp_params* p) {
+  if (!h || !p) return NGICP_E_INVALID;
+  if (p->k_correspondences < 1 || p->k_correspondences > KNN_MAX_K) return fail(h, NGICP_E_UNSUPPORTED, "k_correspondences must be in [1,32]");
+  if (p->regularization_method < 0 || p->regularization_method > 4) return fail(h, NGICP_E_INVALID, "unknown regularization method");  // the reference abort()s here (nano_gicp_impl.hpp:336-338)
+  if (p->grid_table_cells < 64) return fail(h, NGICP_E_INVALID, "grid_table_cells too small");
+  h->prm = *p;
+  return NGICP_OK;
+}
+int ngicp_get_params(const ngicp_t* h, ngicp_params* p) {
+  if (!h || !p) return NGICP_E_INVALID;
+  *p = h->prm;
+  return NGICP_OK;
+}
+
+int ngicp_set_source(ngicp_t* h, const void* pts, size_t n, size_t stride) { return set_cloud(h, NGICP_SOURCE, pts, n, stride, true); }
+int ngicp_set_target(ngicp_t* h, const void* pts, size_t n, size_t stride) { return set_cloud(h, NGICP_TARGET, pts, n, stride, true); }
+int ngicp_register_source(ngicp_t* h, const void* pts, size_t n, size_t stride) { return set_cloud(h, NGICP_SOURCE, pts, n, stride, false); }
+
+int ngicp_share_source(ngicp_t* dst, const ngicp_t* src) {
+  if (!dst || !src) return NGICP_E_INVALID;
+  if (dst->device != src->device) return fail(dst, NGICP_E_INVALID, "handles live on different devices");
+  if (!src->src) return fail(dst, NGICP_E_STATE, "share: source not set");
+  cudaStreamSynchronize(src->stream->s);  // the index must be complete before another stream reads it
+  dst->src = src->src;
+  dst->lin_valid = false;
+  return NGICP_OK;
+}
+int ngicp_share_source_covs(ngicp_t* dst, const ngicp_t* src) {
+  if (!dst || !src) return NGICP_E_INVALID;
+  if (dst->device != src->device) return fail(dst, NGICP_E_INVALID, "handles live on different devices");
+  cudaStreamSynchronize(src->stream->s);
+  dst->src_cov = src->src_cov;
+  dst->lin_valid = false;
+  return NGICP_OK;
+}
+
+int ngicp_swap(ngicp_t* h) {
+  if (!h) return NGICP_E_INVALID;
+  h->src.swap(h->tgt);
+  h->src_cov.swap(h->tgt_cov);
+  h->lin_valid = false;
+  return NGICP_OK;
+}
+int ngicp_clear_source(ngicp_t* h) { if (!h) return NGICP_E_INVALID; h->src.reset(); h->src_cov.reset(); h->lin_valid = false; return NGICP_OK; }
+int ngicp_clear_target(ngicp_t* h) { if (!h) return NGICP_E_INVALID; h->tgt.reset(); h->tgt_cov.reset(); h->lin_valid = false; return NGICP_OK; }
+size_t ngicp_cloud_size(const ngicp_t* h, int which) {
+  if (!h) return 0;
+  const CloudPtr& c = which == NGICP_SOURCE ? h->src : h->tgt;
+  return c ? (size_t)c->n : 0;
+}
+
+int ngicp_calc_source_covs(ngicp_t* h) { return calc_covs(h, NGICP_SOURCE); }
+int ngicp_calc_target_covs(ngicp_t* h) { return calc_covs(h, NGICP_TARGET); }
+int ngicp_set_source_covs(ngicp_t* h, const double* covs, size_t n) { return set_covs(h, NGICP_SOURCE, covs, n); }
+int ngicp_set_target_covs(ngicp_t* h, const double* covs, size_t n) { return set_covs(h, NGICP_TARGET, covs, n); }
+int ngicp_clear_covs(ngicp_t* h, int which) {
+  if (!h) return NGICP_E_INVALID;
+  (which == NGICP_SOURCE ? h->src_cov : h->tgt_cov).reset();
+  h->lin_valid = false;
+  return NGICP_OK;
+}
+size_t ngicp_covs_size(const ngicp_t* h, int which) {
+  if (!h) return 0;
+  const CovsPtr& c = which == NGICP_SOURCE ? h->src_cov : h->tgt_cov;
+  return c ? (size_t)c->n : 0;
+}
+int ngicp_get_source_covs(ngicp_t* h, double* out, size_t n) { return get_covs(h, NGICP_SOURCE, out, n); }
+int ngicp_get_target_covs(ngicp_t* h, double* out, size_t n) { return get_covs(h, NGICP_TARGET, out, n); }
+
+int ngicp_align(ngicp_t* h, const float* guess16, ngicp_result* out) {
+  if (!h || !out) return NGICP_E_INVALID;
+  DeviceGuard g(h->device);
+  AlignBuffers ab;
+  int rc = prepare_align(h, true, ab);
+  if (rc) return rc;
+  ph_begin(h, PH_ALIGN);
+  if (h->prm.align_mode == NGICP_ALIGN_STEPPED) {
+    rc = align_stepped(h, ab, guess16, out);
+    if (rc) return rc;
+  } else {
+    ngicp_result* res_dev = h->sc.lm_state.as<ngicp_result>();
+    NG_CUDA(h, launch_align_fused(ab, h->prm, guess16, res_dev, h->sc.barrier.as<unsigned>(), h->device, h->stream->s));
+    NG_CUDA(h, cudaMemcpyAsync(h->res_pinned, res_dev, sizeof(ngicp_result), cudaMemcpyDeviceToHost, h->stream->s));
+    NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
+    *out = *h->res_pinned;
+  }
+  ph_end(h, PH_ALIGN);
+  h->lin_valid = true;
+  if (out->lm_failed) fprintf(stderr, "lm not converged!!\n");  // lsq_registration_impl.hpp:106
+  return NGICP_OK;
+}
+
+int ngicp_transform_source(ngicp_t* h, const float* T16, float* out_xyz1, size_t n) {
+  if (!h || !T16 || !out_xyz1) return NGICP_E_INVALID;
+  if (!h->src || (size_t)h->src->n != n) return fail(h, NGICP_E_STATE, "transform: source size mismatch");
+  if (n == 0) return NGICP_OK;
+  DeviceGuard g(h->device);
+  NG_CUDA(h, h->sc.queries.reserve(sizeof(float4) * n, h->stream));
+  Mat16f T;
+  memcpy(T.m, T16, sizeof T.m);
+  transform_points_kernel<<<blocks_for((int)n), 256, 0, h->stream->s>>>(h->src->pts.as<float4>(), (int)n, T, h->sc.queries.as<float4>());
+  NG_CUDA(h, cudaGetLastError());
+  NG_CUDA(h, cudaMemcpyAsync(out_xyz1, h->sc.queries.p, sizeof(float4) * n, cudaMemcpyDefault, h->stream->s));
+  NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
+  return NGICP_OK;
+}
+
+int ngicp_voxel_filter(ngicp_t* h, const void* in, size_t n, size_t stride, float leaf, void* out, size_t cap, size_t* m) {
+  if (!h || !m || (!in && n) || stride < 12 || (stride & 3) || !(leaf > 0.f) || n > 0x7fffff00u) return h ? fail(h, NGICP_E_INVALID, "bad voxel filter arguments") : NGICP_E_INVALID;
+  DeviceGuard g(h->device);
+  *m = 0;
+  ph_begin(h, PH_VOXEL);
+  size_t mm = 0;
+  int overflow = 0;
+  NG_CUDA(h, voxel_filter_device(in, n, stride, leaf, h->sc, h->stream, &mm, &overflow));
+  int status = NGICP_OK;
+  if (overflow) {
+    // PCL: "Leaf size is too small for the input dataset. Integer indices would overflow." and output = input
+    vox_passthrough_kernel<<<blocks_for((int)n), 256, 0, h->stream->s>>>(h->sc.queries.as<float4>(), (int)n, h->sc.vox_out.as<float>());
+    NG_CUDA(h, cudaGetLastError());
+    mm = n;
+    status = NGICP_W_VOXEL_OVERFLOW;
+  }
+  if (mm > cap) return fail(h, NGICP_E_INVALID, "voxel filter: output capacity too small");
+  if (mm && out) NG_CUDA(h, cudaMemcpyAsync(out, h->sc.vox_out.p, 32 * mm, cudaMemcpyDefault, h->stream->s));
+  ph_end(h, PH_VOXEL);
+  NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
+  *m = mm;
+  return status;
+}
+
+int ngicp_voxel_assignment(ngicp_t* h, int* slot_of_point, size_t n) {
+  if (!h || !slot_of_point) return NGICP_E_INVALID;
+  if (!h->sc.vox_slot.p || h->sc.vox_slot.bytes < sizeof(int) * n) return fail(h, NGICP_E_STATE, "no voxel filter result");
+  DeviceGuard g(h->device);
+  NG_CUDA(h, cudaMemcpyAsync(slot_of_point, h->sc.vox_slot.p, sizeof(int) * n, cudaMemcpyDefault, h->stream->s));
+  NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
+  return NGICP_OK;
+}
+
+int ngicp_knn(ngicp_t* h, int which, const float* queries, size_t nq, size_t q_stride, int k, int* idx, float* d2) {
+  if (!h || (!queries && nq) || !idx || !d2 || q_stride < 12 || (q_stride & 3)) return NGICP_E_INVALID;
+  if (k < 1 || k > KNN_MAX_K) return fail(h, NGICP_E_UNSUPPORTED, "k must be in [1,32]");
+  DeviceGuard g(h->device);
+  CloudPtr& c = which == NGICP_SOURCE ? h->src : h->tgt;
+  if (!c) return fail(h, NGICP_E_STATE, "knn: cloud not set");
+  if (!c->indexed) return fail(h, NGICP_E_STATE, "knn: no search index (nanoflann throws here, nanoflann_impl.hpp:1235-1237)");
+  if (nq == 0) return NGICP_OK;
+  DevCloud qc;
+  NG_CUDA(h, upload_cloud(qc, queries, nq, q_stride, h->sc, h->stream));
+  NG_CUDA(h, h->sc.knn_idx.reserve(sizeof(int) * nq * k, h->stream));
+  NG_CUDA(h, h->sc.knn_d2.reserve(sizeof(float) * nq * k, h->stream));
+  NG_CUDA(h, launch_knn_queries(*c, qc.pts.as<float4>(), (int)nq, k, h->sc.knn_idx.as<int>(), h->sc.knn_d2.as<float>(), h->stream->s));
+  NG_CUDA(h, cudaMemcpyAsync(idx, h->sc.knn_idx.p, sizeof(int) * nq * k, cudaMemcpyDefault, h->stream->s));
+  NG_CUDA(h, cudaMemcpyAsync(d2, h->sc.knn_d2.p, sizeof(float) * nq * k, cudaMemcpyDefault, h->stream->s));
+  NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
+  return NGICP_OK;
+}
+
+int ngicp_linearize_partial(ngicp_t* h, const double* T16, double* out43) {
+  if (!h || !T16 || !out43) return NGICP_E_INVALID;
+  DeviceGuard g(h->device);
+  AlignBuffers ab;
+  int rc = prepare_align(h, false, ab);
+  if (rc) return rc;
+  NG_CUDA(h, launch_linearize(ab, T16, h->prm.max_correspondence_distance, h->stream->s));
+  rc = fetch_reduced(h, NRED);
+  if (rc) return rc;
+  double tmp[43];
+  unpack_H(h->red_pinned, tmp);
+  for (int i = 0; i < 6; i++) tmp[36 + i] = h->red_pinned[21 + i];
+  tmp[42] = h->red_pinned[27];
+  NG_CUDA(h, cudaMemcpy(out43, tmp, sizeof tmp, cudaMemcpyDefault));
+  h->lin_valid = true;
+  return NGICP_OK;
+}
+
+int ngicp_linearize(ngicp_t* h, const double* T16, double* H36, double* b6, double* err, int* corr, float* sqd, double* mahal) {
+  if (!h || !T16) return NGICP_E_INVALID;
+  double tmp[43];
+  int rc = ngicp_linearize_partial(h, T16, tmp);
+  if (rc) return rc;
+  DeviceGuard g(h->device);
+  if (H36) memcpy(H36, tmp, sizeof(double) * 36);
+  if (b6) memcpy(b6, tmp + 36, sizeof(double) * 6);
+  if (err) *err = tmp[42];
+  const size_t ns = (size_t)h->src->n;
+  if (corr) NG_CUDA(h, cudaMemcpyAsync(corr, h->sc.corr.p, sizeof(int) * ns, cudaMemcpyDefault, h->stream->s));
+  if (sqd) NG_CUDA(h, cudaMemcpyAsync(sqd, h->sc.sqd.p, sizeof(float) * ns, cudaMemcpyDefault, h->stream->s));
+  if (mahal) {
+    AlignBuffers ab;
+    rc = prepare_align(h, false, ab);
+    if (rc) return rc;
+    NG_CUDA(h, h->sc.cov_stage.reserve(sizeof(double) * 16 * ns, h->stream));
+    NG_CUDA(h, launch_export_mahal(ab, h->sc.cov_stage.as<double>(), h->stream->s));
+    NG_CUDA(h, cudaMemcpyAsync(mahal, h->sc.cov_stage.p, sizeof(double) * 16 * ns, cudaMemcpyDefault, h->stream->s));
+  }
+  NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
+  return NGICP_OK;
+}
+
+int ngicp_compute_error_partial(ngicp_t* h, const double* T16, double* out1) {
+  if (!h || !T16 || !out1) return NGICP_E_INVALID;
+  if (!h->lin_valid) return fail(h, NGICP_E_STATE, "compute_error needs a preceding linearize on the same clouds");
+  DeviceGuard g(h->device);
+  AlignBuffers ab;
+  int rc = prepare_align(h, false, ab);
+  if (rc) return rc;
+  NG_CUDA(h, launch_compute_error(ab, T16, h->stream->s));
+  rc = fetch_reduced(h, 1);
+  if (rc) return rc;
+  NG_CUDA(h, cudaMemcpy(out1, h->red_pinned, sizeof(double), cudaMemcpyDefault));
+  return NGICP_OK;
+}
+int ngicp_compute_error(ngicp_t* h, const double* T16, double* err) { return ngicp_compute_error_partial(h, T16, err); }
+
+}  // extern "C"

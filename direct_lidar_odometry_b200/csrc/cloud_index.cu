@@ -1,0 +1,194 @@
+// cloud_index.cu — K1: snapshot a caller cloud into HBM and build the uniform-grid search index that
+// replaces nanoflann's serial kd-tree build (reference include/nano_gicp/nanoflann.hpp:132-138 ->
+// impl/nanoflann_impl.hpp:1199-1211, divideTree :867-917).
+//
+// Layout produced (all in HBM, SURVEY §8d "canonical device layout"):
+//   pts[n]        float4 {x,y,z,1}            original order
+//   sorted[n]     float4 {x,y,z,bits(orig)}   ordered by cell key (x fastest, then y, then z), ties by original index
+//   cell_start[]  int32, ncells+1 entries     cell_start[c] = first sorted slot whose key >= c  (so any run of
+//                                              x-adjacent cells is ONE contiguous slot range)
+//   desc          GridDesc                    origin, cell edge, dims — computed on the device, no host round trip
+// Algorithmic bytes: 16 n read + 16 n sorted write + 4 n permutation = 36 B/point.
+#include "internal.h"
+
+namespace ngicp {
+
+cudaError_t DevBuf::alloc(size_t nbytes, const StreamPtr& stream) {
+  release();
+  if (nbytes == 0) nbytes = 16;
+  st = stream;
+  cudaError_t e;
+  if (st && st->owned) e = cudaMallocAsync(&p, nbytes, st->s);
+  else e = cudaMalloc(&p, nbytes);
+  if (e != cudaSuccess) { p = nullptr; bytes = 0; return e; }
+  bytes = nbytes;
+  return cudaSuccess;
+}
+cudaError_t DevBuf::reserve(size_t nbytes, const StreamPtr& stream) {
+  if (p && bytes >= nbytes) return cudaSuccess;
+  // grow geometrically so that streams of slightly different cloud sizes do not reallocate every call
+  size_t want = nbytes + nbytes / 4 + 256;
+  return alloc(want, stream);
+}
+void DevBuf::release() {
+  if (!p) return;
+  if (st && st->owned) cudaFreeAsync(p, st->s);
+  else cudaFree(p);
+  p = nullptr;
+  bytes = 0;
+}
+
+__global__ void desc_init_kernel(GridDesc* d) {
+  for (int i = 0; i < 3; i++) { d->bb_min[i] = f2ord(FLT_MAX); d->bb_max[i] = f2ord(-FLT_MAX); }
+  d->ncells = 0; d->n = 0; d->nfinite = 0; d->vcount = 0; d->voverflow = 0;
+}
+
+// raw records (x,y,z at the start of each stride) -> float4, fused with the bounding-box reduction
+__global__ void __launch_bounds__(256) pack_bbox_kernel(const unsigned char* __restrict__ raw, size_t stride, int n,
+                                                        float4* __restrict__ pts, GridDesc* __restrict__ d) {
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  int finite = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float* r = reinterpret_cast<const float*>(raw + (size_t)i * stride);
+    float x, y, z;
+    if ((stride & 15) == 0) { const float4 v = *reinterpret_cast<const float4*>(r); x = v.x; y = v.y; z = v.z; }
+    else { x = r[0]; y = r[1]; z = r[2]; }
+    pts[i] = make_float4(x, y, z, 1.0f);
+    if (isfinite(x) && isfinite(y) && isfinite(z)) {
+      finite++;
+      mn[0] = fminf(mn[0], x); mn[1] = fminf(mn[1], y); mn[2] = fminf(mn[2], z);
+      mx[0] = fmaxf(mx[0], x); mx[1] = fmaxf(mx[1], y); mx[2] = fmaxf(mx[2], z);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(FULL, mn[a], o));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(FULL, mx[a], o));
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) finite += __shfl_xor_sync(FULL, finite, o);
+  if ((threadIdx.x & 31) == 0 && finite > 0) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) { atomicMin(&d->bb_min[a], f2ord(mn[a])); atomicMax(&d->bb_max[a], f2ord(mx[a])); }
+    atomicAdd(&d->nfinite, finite);
+  }
+}
+
+// single thread: derive the grid from the bounding box; grow the cell until the dense table fits
+__global__ void grid_setup_kernel(GridDesc* d, float cell_req, int cap, int n) {
+  float lo[3], hi[3];
+  for (int a = 0; a < 3; a++) { lo[a] = ord2f(d->bb_min[a]); hi[a] = ord2f(d->bb_max[a]); }
+  if (d->nfinite == 0) { for (int a = 0; a < 3; a++) { lo[a] = 0.f; hi[a] = 0.f; } }
+  float cell = cell_req > 0.f ? cell_req : 1.0f;
+  int dim[3];
+  for (int it = 0; it < 64; it++) {
+    double prod = 1.0;
+    const float inv = 1.0f / cell;
+    for (int a = 0; a < 3; a++) {
+      float ext = (hi[a] - lo[a]) * inv;
+      if (!(ext < 2.0e9f)) ext = 2.0e9f;
+      dim[a] = (int)floorf(ext) + 1;
+      prod *= (double)dim[a];
+    }
+    if (prod <= (double)cap) break;
+    cell *= 2.0f;
+  }
+  for (int a = 0; a < 3; a++) { d->origin[a] = lo[a]; d->dim[a] = dim[a]; }
+  d->cell = cell;
+  d->inv_cell = 1.0f / cell;
+  d->ncells = dim[0] * dim[1] * dim[2];
+  d->n = n;
+  d->max_dim = max(dim[0], max(dim[1], dim[2]));
+  d->margin = cell * (0.01f + 1e-6f * (float)d->max_dim);
+}
+
+__global__ void __launch_bounds__(256) zero_cells_kernel(int* __restrict__ cell_start, const GridDesc* __restrict__ d) {
+  const int total = d->ncells + 1;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) cell_start[i] = 0;
+}
+
+__global__ void __launch_bounds__(256) bin_points_kernel(const float4* __restrict__ pts, int n, const GridDesc* __restrict__ d,
+                                                         unsigned* __restrict__ keys, unsigned* __restrict__ vals, int* __restrict__ cell_count) {
+  const float ox = d->origin[0], oy = d->origin[1], oz = d->origin[2], inv = d->inv_cell;
+  const int dx = d->dim[0], dy = d->dim[1], dz = d->dim[2];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = pts[i];
+    const int cx = cell_coord(p.x, ox, inv, dx), cy = cell_coord(p.y, oy, inv, dy), cz = cell_coord(p.z, oz, inv, dz);
+    const unsigned key = (unsigned)((cz * dy + cy) * dx + cx);
+    keys[i] = key;
+    vals[i] = (unsigned)i;
+    atomicAdd(&cell_count[key], 1);
+  }
+}
+
+__global__ void __launch_bounds__(256) gather_sorted_kernel(const float4* __restrict__ pts, const unsigned* __restrict__ perm, int n,
+                                                            float4* __restrict__ sorted) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned o = perm[i];
+    const float4 p = pts[o];
+    sorted[i] = make_float4(p.x, p.y, p.z, __uint_as_float(o));
+  }
+}
+
+static inline int grid_for(int n, int threads = 256, int max_blocks = 148 * 8) {
+  int g = (n + threads - 1) / threads;
+  if (g < 1) g = 1;
+  return g > max_blocks ? max_blocks : g;
+}
+
+cudaError_t upload_cloud(DevCloud& c, const void* pts, size_t n, size_t stride_bytes, Scratch& sc, const StreamPtr& st) {
+  cudaError_t e;
+  c.n = (int)n;
+  c.indexed = false;
+  if ((e = c.pts.alloc(sizeof(float4) * (n ? n : 1), st)) != cudaSuccess) return e;
+  if ((e = c.desc.alloc(sizeof(GridDesc), st)) != cudaSuccess) return e;
+  desc_init_kernel<<<1, 1, 0, st->s>>>(c.desc.as<GridDesc>());
+  if (n == 0) return cudaGetLastError();
+  const size_t raw_bytes = (n - 1) * stride_bytes + 12;  // last record may be shorter than the stride
+  if ((e = sc.staging.reserve(raw_bytes + 16, st)) != cudaSuccess) return e;
+  if ((e = cudaMemcpyAsync(sc.staging.p, pts, raw_bytes, cudaMemcpyDefault, st->s)) != cudaSuccess) return e;
+  pack_bbox_kernel<<<grid_for((int)n), 256, 0, st->s>>>(sc.staging.as<unsigned char>(), stride_bytes, (int)n, c.pts.as<float4>(), c.desc.as<GridDesc>());
+  return cudaGetLastError();
+}
+
+static int bits_for(int cap) {
+  int b = 1;
+  while (b < 31 && (1ll << b) < (long long)cap) b++;
+  return b;
+}
+
+cudaError_t build_index(DevCloud& c, float cell_req, int table_cap, Scratch& sc, const StreamPtr& st) {
+  cudaError_t e;
+  const int n = c.n;
+  if (table_cap < 64) table_cap = 64;
+  c.table_cap = table_cap;
+  if ((e = c.cell_start.alloc(sizeof(int) * ((size_t)table_cap + 1), st)) != cudaSuccess) return e;
+  if ((e = c.sorted.alloc(sizeof(float4) * (n ? n : 1), st)) != cudaSuccess) return e;
+  GridDesc* d = c.desc.as<GridDesc>();
+  grid_setup_kernel<<<1, 1, 0, st->s>>>(d, cell_req, table_cap, n);
+  zero_cells_kernel<<<148 * 4, 256, 0, st->s>>>(c.cell_start.as<int>(), d);
+  if (n > 0) {
+    const size_t nb = sizeof(unsigned) * (size_t)n;
+    if ((e = sc.keys_a.reserve(nb, st)) != cudaSuccess) return e;
+    if ((e = sc.keys_b.reserve(nb, st)) != cudaSuccess) return e;
+    if ((e = sc.vals_a.reserve(nb, st)) != cudaSuccess) return e;
+    if ((e = sc.vals_b.reserve(nb, st)) != cudaSuccess) return e;
+    if ((e = sc.hist.reserve(sizeof(int) * radix_sort_scratch_ints(n), st)) != cudaSuccess) return e;
+    bin_points_kernel<<<grid_for(n), 256, 0, st->s>>>(c.pts.as<float4>(), n, d, sc.keys_a.as<unsigned>(), sc.vals_a.as<unsigned>(), c.cell_start.as<int>());
+  }
+  if ((e = sc.tile_sums.reserve(sizeof(int) * scan_scratch_ints(table_cap + 1), st)) != cudaSuccess) return e;
+  // counts -> lower-bound table (exclusive scan over ncells+1 entries; ncells is read from the descriptor)
+  exclusive_scan_inplace(c.cell_start.as<int>(), &d->ncells, 1, table_cap + 1, sc.tile_sums.as<int>(), st->s);
+  if (n > 0) {
+    const int where = radix_sort_pairs(sc.keys_a.as<unsigned>(), sc.vals_a.as<unsigned>(), sc.keys_b.as<unsigned>(), sc.vals_b.as<unsigned>(),
+                                       n, bits_for(table_cap), sc.hist.as<int>(), st->s);
+    const unsigned* perm = where ? sc.vals_b.as<unsigned>() : sc.vals_a.as<unsigned>();
+    gather_sorted_kernel<<<grid_for(n), 256, 0, st->s>>>(c.pts.as<float4>(), perm, n, c.sorted.as<float4>());
+  }
+  c.indexed = true;
+  return cudaGetLastError();
+}
+
+}  // namespace ngicp

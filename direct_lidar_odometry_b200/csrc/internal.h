@@ -1,0 +1,126 @@
+// internal.h — host-side declarations shared by the translation units of libnanogicp_b200.
+#pragma once
+#include <cuda_runtime.h>
+#include <cstddef>
+#include <cstdint>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/nanogicp_c.h"
+#include "common.cuh"
+
+namespace ngicp {
+
+// ---- streams and device memory -----------------------------------------------------------------
+struct StreamRef {
+  cudaStream_t s = nullptr;
+  bool owned = false;
+  ~StreamRef() {
+    if (owned && s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+  }
+};
+typedef std::shared_ptr<StreamRef> StreamPtr;
+
+// stream-ordered device buffer (cudaMallocAsync on an owned stream, plain cudaMalloc/cudaFree otherwise)
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  StreamPtr st;
+  DevBuf() {}
+  DevBuf(const DevBuf&) = delete;
+  DevBuf& operator=(const DevBuf&) = delete;
+  ~DevBuf() { release(); }
+  cudaError_t alloc(size_t nbytes, const StreamPtr& stream);
+  // grow-only: keeps the allocation when it is already large enough
+  cudaError_t reserve(size_t nbytes, const StreamPtr& stream);
+  void release();
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
+// ---- device-resident cloud + index ---------------------------------------------------------------
+struct DevCloud {
+  int n = 0;
+  DevBuf pts;         // float4[n], original order, w = 1
+  bool indexed = false;
+  DevBuf desc;        // GridDesc
+  DevBuf cell_start;  // int[table_cap + 1]
+  DevBuf sorted;      // float4[n], cell order, w = original index bits
+  int table_cap = 0;
+  GridView view() const {
+    GridView v;
+    v.cell_start = cell_start.as<int>();
+    v.sorted = sorted.as<float4>();
+    v.desc = desc.as<GridDesc>();
+    return v;
+  }
+};
+typedef std::shared_ptr<DevCloud> CloudPtr;
+
+struct DevCovs {
+  int n = 0;
+  DevBuf c;  // double[n*6], original point order, {xx,xy,xz,yy,yz,zz}
+};
+typedef std::shared_ptr<DevCovs> CovsPtr;
+
+// grow-only scratch owned by a handle
+struct Scratch {
+  DevBuf staging;    // raw bytes of caller records
+  DevBuf keys_a, keys_b, vals_a, vals_b;
+  DevBuf hist, tile_sums;
+  DevBuf flags;      // voxel head flags / scanned slots
+  DevBuf vox_desc;   // GridDesc for the voxel filter
+  DevBuf vox_out;    // PointXYZI records
+  DevBuf vox_slot;   // int per input point
+  DevBuf knn_idx, knn_d2, queries;
+  DevBuf cov_stage;  // Matrix4d staging for import/export
+  // align state
+  DevBuf mahal;      // double[ns*6]
+  DevBuf corr;       // int[ns]   target ORIGINAL index or -1
+  DevBuf sqd;        // float[ns]
+  DevBuf tgt_pt;     // float4[ns] matched target point
+  DevBuf partials;   // double[blocks*NRED]
+  DevBuf reduced;    // double[64]
+  DevBuf lm_state;   // device-resident LM state / result of the fused kernel
+  DevBuf barrier;    // unsigned counters for the grid barrier
+};
+
+// ---- sort_scan.cu ---------------------------------------------------------------------------------
+void exclusive_scan_inplace(int* data, const int* n_dev, int n_add, int max_n, int* tile_sums, cudaStream_t st);
+size_t scan_scratch_ints(int max_n);
+size_t radix_sort_scratch_ints(int n);
+int radix_sort_pairs(unsigned* keys_a, unsigned* vals_a, unsigned* keys_b, unsigned* vals_b, int n, int bits, int* hist, cudaStream_t st);
+
+// ---- cloud_index.cu -------------------------------------------------------------------------------
+// snapshot caller records into cloud.pts (float4) and compute the bounding box into cloud.desc
+cudaError_t upload_cloud(DevCloud& c, const void* pts, size_t n, size_t stride_bytes, Scratch& sc, const StreamPtr& st);
+// build the uniform grid index of an uploaded cloud
+cudaError_t build_index(DevCloud& c, float cell_req, int table_cap, Scratch& sc, const StreamPtr& st);
+
+// ---- knn_cov.cu -----------------------------------------------------------------------------------
+cudaError_t launch_knn_queries(const DevCloud& c, const float4* queries, int nq, int k, int* idx, float* d2, cudaStream_t st);
+cudaError_t launch_covariances(const DevCloud& c, int k, int method, double* covs6, cudaStream_t st);
+constexpr int KNN_MAX_K = 32;
+
+// ---- align.cu -------------------------------------------------------------------------------------
+struct AlignBuffers {
+  const float4* src_pts; const double* src_cov; int ns;
+  GridView tgt; const double* tgt_cov; int nt;
+  double* mahal; int* corr; float* sqd; float4* tgt_pt;
+  double* partials; double* reduced; int max_blocks;
+};
+// one linearisation at T (row-major R + t as Iso3 passed by value inside); reduced[0..NRED) <- packed H,b,err
+cudaError_t launch_linearize(const AlignBuffers& ab, const double* T16_colmajor, double max_corr_dist, cudaStream_t st);
+cudaError_t launch_compute_error(const AlignBuffers& ab, const double* T16_colmajor, cudaStream_t st);
+cudaError_t launch_export_mahal(const AlignBuffers& ab, double* out16, cudaStream_t st);
+// the whole LM loop in one persistent cooperative kernel; result written to *res_dev (ngicp_result layout)
+cudaError_t launch_align_fused(const AlignBuffers& ab, const ngicp_params& prm, const float* guess16, ngicp_result* res_dev,
+                               unsigned* barrier, int device, cudaStream_t st);
+int align_fused_max_blocks(int device);
+
+// ---- voxel.cu -------------------------------------------------------------------------------------
+// returns cudaSuccess; *m_out and *overflow are valid after the call (it synchronises once to learn m)
+cudaError_t voxel_filter_device(const void* in, size_t n, size_t stride_bytes, float leaf, Scratch& sc, const StreamPtr& st,
+                                size_t* m_out, int* overflow);
+
+}  // namespace ngicp

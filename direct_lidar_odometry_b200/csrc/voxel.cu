@@ -1,0 +1,181 @@
+// voxel.cu — K0: pcl::VoxelGrid<PointXYZI>::filter as a sort-based voxel reduce
+// (third-party code in the reference; call sites src/dlo/odom.cc:460-463, 487-490, 1160-1163;
+// algorithm restated in SURVEY.md App. B1):
+//   bbox -> min_b = floor(min * inv), div_b -> per point idx = i + j*dx + k*dx*dy (int32) ->
+//   stable radix sort of (idx, point) -> one centroid per run of equal idx, emitted in ascending idx.
+// The within-voxel accumulation order is ascending input index (the sort is stable), float32 running
+// sums of x,y,z,intensity divided by the float count — the order the CPU oracle fixes as well.
+// Algorithmic bytes: 16 N read + 16 M written (records are 32 B at the boundary).
+#include "internal.h"
+
+namespace ngicp {
+
+constexpr unsigned VOX_INVALID = 0xFFFFFFFFu;
+
+__global__ void vox_desc_init_kernel(GridDesc* d) {
+  for (int i = 0; i < 3; i++) { d->bb_min[i] = f2ord(FLT_MAX); d->bb_max[i] = f2ord(-FLT_MAX); }
+  d->nfinite = 0; d->vcount = 0; d->voverflow = 0;
+}
+
+// raw records -> float4 {x,y,z,intensity}; bbox over finite points (pcl::getMinMax3D on a non-dense cloud)
+__global__ void __launch_bounds__(256) vox_pack_kernel(const unsigned char* __restrict__ raw, size_t stride, int n, int intensity_float,
+                                                       float4* __restrict__ pts, GridDesc* __restrict__ d) {
+  float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+  int finite = 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float* r = reinterpret_cast<const float*>(raw + (size_t)i * stride);
+    const float x = r[0], y = r[1], z = r[2];
+    const float it = intensity_float >= 0 ? r[intensity_float] : 0.f;
+    pts[i] = make_float4(x, y, z, it);
+    if (isfinite(x) && isfinite(y) && isfinite(z)) {
+      finite++;
+      mn[0] = fminf(mn[0], x); mn[1] = fminf(mn[1], y); mn[2] = fminf(mn[2], z);
+      mx[0] = fmaxf(mx[0], x); mx[1] = fmaxf(mx[1], y); mx[2] = fmaxf(mx[2], z);
+    }
+  }
+#pragma unroll
+  for (int a = 0; a < 3; a++)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[a] = fminf(mn[a], __shfl_xor_sync(FULL, mn[a], o));
+      mx[a] = fmaxf(mx[a], __shfl_xor_sync(FULL, mx[a], o));
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) finite += __shfl_xor_sync(FULL, finite, o);
+  if ((threadIdx.x & 31) == 0 && finite > 0) {
+#pragma unroll
+    for (int a = 0; a < 3; a++) { atomicMin(&d->bb_min[a], f2ord(mn[a])); atomicMax(&d->bb_max[a], f2ord(mx[a])); }
+    atomicAdd(&d->nfinite, finite);
+  }
+}
+
+__global__ void vox_setup_kernel(GridDesc* d, float inv) {
+  if (d->nfinite == 0) { d->voverflow = 0; for (int a = 0; a < 3; a++) { d->vmin_b[a] = 0; d->vdiv[a] = 1; } return; }
+  float lo[3], hi[3];
+  for (int a = 0; a < 3; a++) { lo[a] = ord2f(d->bb_min[a]); hi[a] = ord2f(d->bb_max[a]); }
+  // PCL: int64 dx = (int64)((max - min) * inverse_leaf) + 1 ...; if dx*dy*dz > INT32_MAX -> warn, output = input
+  const long long dx = (long long)(__fmul_rn(__fsub_rn(hi[0], lo[0]), inv)) + 1;
+  const long long dy = (long long)(__fmul_rn(__fsub_rn(hi[1], lo[1]), inv)) + 1;
+  const long long dz = (long long)(__fmul_rn(__fsub_rn(hi[2], lo[2]), inv)) + 1;
+  d->voverflow = (dx * dy * dz > 2147483647ll) ? 1 : 0;
+  for (int a = 0; a < 3; a++) {
+    const int mnb = (int)floorf(__fmul_rn(lo[a], inv));
+    const int mxb = (int)floorf(__fmul_rn(hi[a], inv));
+    d->vmin_b[a] = mnb;
+    d->vdiv[a] = mxb - mnb + 1;
+  }
+}
+
+__global__ void __launch_bounds__(256) vox_keys_kernel(const float4* __restrict__ pts, int n, const GridDesc* __restrict__ d, float inv,
+                                                       unsigned* __restrict__ keys, unsigned* __restrict__ vals) {
+  const int m0 = d->vmin_b[0], m1 = d->vmin_b[1], m2 = d->vmin_b[2];
+  const int mul1 = d->vdiv[0], mul2 = d->vdiv[0] * d->vdiv[1];
+  const bool bad = d->voverflow != 0;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = pts[i];
+    unsigned key = VOX_INVALID;
+    if (!bad && isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+      const int i0 = (int)(__fsub_rn(floorf(__fmul_rn(p.x, inv)), (float)m0));
+      const int i1 = (int)(__fsub_rn(floorf(__fmul_rn(p.y, inv)), (float)m1));
+      const int i2 = (int)(__fsub_rn(floorf(__fmul_rn(p.z, inv)), (float)m2));
+      key = (unsigned)(i0 + i1 * mul1 + i2 * mul2);
+    }
+    keys[i] = key;
+    vals[i] = (unsigned)i;
+  }
+}
+
+// flags[i] = 1 at the first element of every run of equal valid keys; flags[n] = 0 (sentinel for the total)
+__global__ void __launch_bounds__(256) vox_heads_kernel(const unsigned* __restrict__ keys, int n, int* __restrict__ flags) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += gridDim.x * blockDim.x) {
+    int f = 0;
+    if (i < n) {
+      const unsigned k = keys[i];
+      f = (k != VOX_INVALID && (i == 0 || keys[i - 1] != k)) ? 1 : 0;
+    }
+    flags[i] = f;
+  }
+}
+
+// one thread per run head: sequential float accumulation in sorted (= ascending input index) order
+__global__ void __launch_bounds__(128) vox_centroid_kernel(const unsigned* __restrict__ keys, const unsigned* __restrict__ perm, int n,
+                                                           const int* __restrict__ slots, const float4* __restrict__ pts,
+                                                           float* __restrict__ out, int* __restrict__ slot_of_point) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned k = keys[i];
+    if (k == VOX_INVALID) { slot_of_point[perm[i]] = -1; continue; }
+    if (i > 0 && keys[i - 1] == k) continue;
+    const int slot = slots[i];
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    int j = i;
+    for (; j < n && keys[j] == k; ++j) {
+      const unsigned o = perm[j];
+      const float4 p = pts[o];
+      sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); si = __fadd_rn(si, p.w);
+      slot_of_point[o] = slot;
+    }
+    const float cnt = (float)(j - i);
+    float4* o4 = reinterpret_cast<float4*>(out + (size_t)slot * 8);
+    o4[0] = make_float4(__fdiv_rn(sx, cnt), __fdiv_rn(sy, cnt), __fdiv_rn(sz, cnt), 1.0f);
+    o4[1] = make_float4(__fdiv_rn(si, cnt), 0.f, 0.f, 0.f);
+  }
+}
+
+static inline int vgrid(int n, int threads) {
+  int g = (n + threads - 1) / threads;
+  if (g < 1) g = 1;
+  return g > 148 * 16 ? 148 * 16 : g;
+}
+
+cudaError_t voxel_filter_device(const void* in, size_t n, size_t stride_bytes, float leaf, Scratch& sc, const StreamPtr& st,
+                                size_t* m_out, int* overflow) {
+  cudaError_t e;
+  *m_out = 0;
+  *overflow = 0;
+  if (n == 0) return cudaSuccess;
+  const int ni = (int)n;
+  const float inv = 1.0f / leaf;  // PCL: inverse_leaf_size_ = 1 / leaf_size_ in float
+  const int ifloat = stride_bytes >= 20 ? 4 : (stride_bytes >= 16 ? 3 : -1);
+  const size_t last = ifloat >= 0 ? (size_t)(ifloat + 1) * 4 : 12;
+  const size_t raw_bytes = (n - 1) * stride_bytes + last;
+  if ((e = sc.staging.reserve(raw_bytes + 16, st)) != cudaSuccess) return e;
+  if ((e = sc.queries.reserve(sizeof(float4) * n, st)) != cudaSuccess) return e;
+  if ((e = sc.vox_desc.reserve(sizeof(GridDesc), st)) != cudaSuccess) return e;
+  const size_t nb = sizeof(unsigned) * n;
+  if ((e = sc.keys_a.reserve(nb, st)) != cudaSuccess) return e;
+  if ((e = sc.keys_b.reserve(nb, st)) != cudaSuccess) return e;
+  if ((e = sc.vals_a.reserve(nb, st)) != cudaSuccess) return e;
+  if ((e = sc.vals_b.reserve(nb, st)) != cudaSuccess) return e;
+  if ((e = sc.hist.reserve(sizeof(int) * radix_sort_scratch_ints(ni), st)) != cudaSuccess) return e;
+  if ((e = sc.flags.reserve(sizeof(int) * (n + 1), st)) != cudaSuccess) return e;
+  if ((e = sc.tile_sums.reserve(sizeof(int) * scan_scratch_ints(ni + 1), st)) != cudaSuccess) return e;
+  if ((e = sc.vox_out.reserve(32 * n, st)) != cudaSuccess) return e;
+  if ((e = sc.vox_slot.reserve(sizeof(int) * n, st)) != cudaSuccess) return e;
+  if ((e = cudaMemcpyAsync(sc.staging.p, in, raw_bytes, cudaMemcpyDefault, st->s)) != cudaSuccess) return e;
+  GridDesc* d = sc.vox_desc.as<GridDesc>();
+  float4* pts = sc.queries.as<float4>();
+  vox_desc_init_kernel<<<1, 1, 0, st->s>>>(d);
+  vox_pack_kernel<<<vgrid(ni, 256), 256, 0, st->s>>>(sc.staging.as<unsigned char>(), stride_bytes, ni, ifloat, pts, d);
+  vox_setup_kernel<<<1, 1, 0, st->s>>>(d, inv);
+  vox_keys_kernel<<<vgrid(ni, 256), 256, 0, st->s>>>(pts, ni, d, inv, sc.keys_a.as<unsigned>(), sc.vals_a.as<unsigned>());
+  const int where = radix_sort_pairs(sc.keys_a.as<unsigned>(), sc.vals_a.as<unsigned>(), sc.keys_b.as<unsigned>(), sc.vals_b.as<unsigned>(),
+                                     ni, 32, sc.hist.as<int>(), st->s);
+  const unsigned* keys = where ? sc.keys_b.as<unsigned>() : sc.keys_a.as<unsigned>();
+  const unsigned* perm = where ? sc.vals_b.as<unsigned>() : sc.vals_a.as<unsigned>();
+  int* flags = sc.flags.as<int>();
+  vox_heads_kernel<<<vgrid(ni + 1, 256), 256, 0, st->s>>>(keys, ni, flags);
+  // the scan length (n+1) is known on the host; park it in the descriptor so the generic scan can read it
+  int len = ni + 1;
+  if ((e = cudaMemcpyAsync(&d->n, &len, sizeof(int), cudaMemcpyHostToDevice, st->s)) != cudaSuccess) return e;
+  exclusive_scan_inplace(flags, &d->n, 0, ni + 1, sc.tile_sums.as<int>(), st->s);
+  vox_centroid_kernel<<<vgrid(ni, 128), 128, 0, st->s>>>(keys, perm, ni, flags, pts, sc.vox_out.as<float>(), sc.vox_slot.as<int>());
+  int host[2] = {0, 0};
+  if ((e = cudaMemcpyAsync(&host[0], flags + ni, sizeof(int), cudaMemcpyDeviceToHost, st->s)) != cudaSuccess) return e;
+  if ((e = cudaMemcpyAsync(&host[1], &d->voverflow, sizeof(int), cudaMemcpyDeviceToHost, st->s)) != cudaSuccess) return e;
+  if ((e = cudaStreamSynchronize(st->s)) != cudaSuccess) return e;
+  *m_out = (size_t)host[0];
+  *overflow = host[1];
+  return cudaGetLastError();
+}
+
+}  // namespace ngicp

@@ -8,7 +8,7 @@ axis-aligned "buildings" on a 40 m lattice).  Points are emitted in the SENSOR
 frame as pcl::PointXYZI records (reference include/dlo/dlo.h:50): 8 float32 per
 point {x, y, z, 1.0, intensity, 0, 0, 0} = 32 bytes, row-major beam x col order.
 
-Pure numpy; no GPU, no oracle.  Used by tests/, bench.py and __graft_entry__.smoke().
+Pure numpy, no GPU.  Used by tests/, bench.py and __graft_entry__.smoke().
 """
 from __future__ import annotations
 

@@ -1,0 +1,184 @@
+/* nanogicp_c.h — C ABI of libnanogicp_b200.so: the NanoGICP registration hot path of
+ * Direct LiDAR Odometry re-built as hand-written sm_100a CUDA kernels.
+ *
+ * This is the drop-in boundary.  The reference has no FFI: OdomNode uses the C++ class
+ * nano_gicp::NanoGICP<PointXYZI,PointXYZI> directly (reference include/dlo/odom.h:119-120).
+ * include/nano_gicp/nano_gicp.hpp in this repo re-creates that class surface and forwards every
+ * call to the functions below; each entry point cites the reference member it replaces
+ * (paths relative to the reference tree).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no CUDA/torch types.  `pts` arguments point at n records of
+ *     `stride_bytes` each whose first three floats are x,y,z (stride 32 for pcl::PointXYZI, 16 for
+ *     float4, 12 for packed xyz).  They may be HOST or DEVICE pointers (unified addressing decides);
+ *     the call snapshots them into HBM, the caller keeps ownership and may free them on return.
+ *   - 4x4 matrices are column-major like Eigen (element (r,c) at [c*4+r]); covariances are
+ *     Eigen::Matrix4d records (16 doubles, 128 B) of which only the symmetric upper-left 3x3 is used.
+ *   - every function returns an int status: 0 ok, <0 error (ngicp_last_error() has the text),
+ *     >0 warning.  Nothing throws or aborts across the boundary.  "LM did not converge" is not an
+ *     error: it is reported in ngicp_result like the reference reports it via hasConverged().
+ *   - a handle owns one CUDA stream and is not thread-safe; different handles may be used from
+ *     different threads / devices concurrently.
+ *   - there is NO CPU fallback: every compute entry point launches CUDA kernels on the handle's
+ *     device and fails with NGICP_E_CUDA if that is impossible.
+ */
+#ifndef NANOGICP_C_H
+#define NANOGICP_C_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct ngicp_handle ngicp_t;
+
+enum {
+  NGICP_OK = 0,
+  NGICP_E_INVALID = -1,          /* bad argument */
+  NGICP_E_STATE = -2,            /* missing source/target/index (PCL prints an error and returns) */
+  NGICP_E_TOO_FEW_POINTS = -3,   /* cloud has fewer than k points (UB in the reference, nano_gicp_impl.hpp:315-318) */
+  NGICP_E_COV_SIZE = -4,         /* covariance count != point count (assert at nano_gicp_impl.hpp:175-176) */
+  NGICP_E_CUDA = -5,
+  NGICP_E_UNSUPPORTED = -6,
+  NGICP_W_VOXEL_OVERFLOW = 1     /* voxel index would overflow int32: input passed through, like PCL */
+};
+
+/* RegularizationMethod, include/nano_gicp/gicp/gicp_settings.hpp:47 */
+enum { NGICP_REG_NONE = 0, NGICP_REG_MIN_EIG = 1, NGICP_REG_NORMALIZED_MIN_EIG = 2, NGICP_REG_PLANE = 3, NGICP_REG_FROBENIUS = 4 };
+/* LSQ_OPTIMIZER_TYPE, include/nano_gicp/lsq_registration.hpp:54 */
+enum { NGICP_OPT_GAUSS_NEWTON = 0, NGICP_OPT_LEVENBERG_MARQUARDT = 1 };
+enum { NGICP_SOURCE = 0, NGICP_TARGET = 1 };
+/* how ngicp_align drives the LM loop */
+enum {
+  NGICP_ALIGN_FUSED = 0,   /* one persistent cooperative kernel runs the whole LM loop, state stays in HBM/registers */
+  NGICP_ALIGN_STEPPED = 1  /* one launch per linearize/compute_error, LM decisions on the host (debug + sharded mode) */
+};
+
+typedef struct {
+  /* reference parameters and their defaults */
+  int k_correspondences;               /* setCorrespondenceRandomness; nano_gicp_impl.hpp:57 (20) */
+  double max_correspondence_distance;  /* setMaxCorrespondenceDistance; nano_gicp_impl.hpp:59 (FLT_MAX) */
+  int max_iterations;                  /* setMaximumIterations; lsq_registration_impl.hpp:52 (64) */
+  double transformation_epsilon;       /* setTransformationEpsilon; lsq_registration_impl.hpp:54 (5e-4) */
+  double rotation_epsilon;             /* setRotationEpsilon; lsq_registration_impl.hpp:53 (2e-3) */
+  int optimizer;                       /* lsq_registration_impl.hpp:56 (LM) */
+  int lm_max_iterations;               /* lsq_registration_impl.hpp:58 (10) */
+  double lm_init_lambda_factor;        /* setInitialLambdaFactor; lsq_registration_impl.hpp:59 (1e-9) */
+  int regularization_method;           /* setRegularizationMethod; nano_gicp_impl.hpp:61 (PLANE) */
+  /* B200-side knobs without a reference counterpart */
+  float grid_cell_size;                /* uniform-grid cell edge in metres; 0 = choose from the data */
+  int grid_table_cells;                /* capacity of the dense cell table (cells); the cell edge grows to fit */
+  int align_mode;                      /* NGICP_ALIGN_FUSED / NGICP_ALIGN_STEPPED */
+} ngicp_params;
+
+/* what pcl::Registration / LsqRegistration expose after align() */
+typedef struct {
+  float final_transformation[16];  /* getFinalTransformation(): double state cast to float, lsq_registration_impl.hpp:113 */
+  double final_x[16];              /* the double state itself */
+  double final_hessian[36];        /* getFinalHessian(), lsq_registration_impl.hpp:84-86 */
+  double lm_lambda;
+  double last_error;               /* y0 of the last linearisation */
+  int nr_iterations;               /* index of the last outer iteration, lsq_registration_impl.hpp:102 */
+  int converged;                   /* hasConverged() */
+  int n_linearize;                 /* calls of linearize() */
+  int n_compute_error;             /* calls of compute_error() (LM trials) */
+  int lm_failed;                   /* 1 when "lm not converged!!" (lsq_registration_impl.hpp:105-108) */
+  int reserved;
+} ngicp_result;
+
+/* device time of the phases of the last calls on this handle, milliseconds (CUDA events) */
+typedef struct {
+  float set_source_ms, set_target_ms, source_covs_ms, target_covs_ms, align_ms, voxel_ms;
+  float reserved[10];
+} ngicp_timings;
+
+/* ---- lifetime ------------------------------------------------------------------------------- */
+/* NanoGICP::NanoGICP(), nano_gicp_impl.hpp:49-64 */
+int ngicp_create(int device, ngicp_t** out);
+void ngicp_destroy(ngicp_t* h);
+const char* ngicp_last_error(const ngicp_t* h);
+/* run this handle's work on an existing cudaStream_t (e.g. the caller's current stream); NULL = own stream */
+int ngicp_set_stream(ngicp_t* h, void* cuda_stream);
+void* ngicp_get_stream(const ngicp_t* h);
+int ngicp_sync(ngicp_t* h);
+int ngicp_get_timings(ngicp_t* h, ngicp_timings* out);
+
+/* ---- parameters: the setters at odom.cc:100-114 and nano_gicp.hpp:82-84 ----------------------- */
+void ngicp_params_default(ngicp_params* p);
+int ngicp_set_params(ngicp_t* h, const ngicp_params* p);
+int ngicp_get_params(const ngicp_t* h, ngicp_params* p);
+
+/* ---- clouds ----------------------------------------------------------------------------------- */
+/* NanoGICP::setInputSource, nano_gicp_impl.hpp:120-129: snapshot + build the search index, drop source covariances */
+int ngicp_set_source(ngicp_t* h, const void* pts, size_t n, size_t stride_bytes);
+/* NanoGICP::setInputTarget, nano_gicp_impl.hpp:131-139 */
+int ngicp_set_target(ngicp_t* h, const void* pts, size_t n, size_t stride_bytes);
+/* NanoGICP::registerInputSource, nano_gicp_impl.hpp:112-118: snapshot only, no index, covariances kept */
+int ngicp_register_source(ngicp_t* h, const void* pts, size_t n, size_t stride_bytes);
+/* `gicp.source_kdtree_ = gicp_s2s.source_kdtree_` (odom.cc:525): dst's source cloud+index alias src's, no copy */
+int ngicp_share_source(ngicp_t* dst, const ngicp_t* src);
+/* `gicp.source_covs_ = gicp_s2s.source_covs_` (odom.cc:815) without leaving HBM */
+int ngicp_share_source_covs(ngicp_t* dst, const ngicp_t* src);
+/* NanoGICP::swapSourceAndTarget, nano_gicp_impl.hpp:90-98: O(1) role swap of device buffers */
+int ngicp_swap(ngicp_t* h);
+/* NanoGICP::clearSource / clearTarget, nano_gicp_impl.hpp:100-110 */
+int ngicp_clear_source(ngicp_t* h);
+int ngicp_clear_target(ngicp_t* h);
+size_t ngicp_cloud_size(const ngicp_t* h, int which);
+
+/* ---- covariances ------------------------------------------------------------------------------ */
+/* NanoGICP::calculateSourceCovariances / calculateTargetCovariances, nano_gicp_impl.hpp:151-159,298-357 */
+int ngicp_calc_source_covs(ngicp_t* h);
+int ngicp_calc_target_covs(ngicp_t* h);
+/* NanoGICP::setSourceCovariances / setTargetCovariances, nano_gicp_impl.hpp:141-149 (n Matrix4d records, host or device) */
+int ngicp_set_source_covs(ngicp_t* h, const double* covs, size_t n);
+int ngicp_set_target_covs(ngicp_t* h, const double* covs, size_t n);
+/* `source_covs_.clear()` (odom.cc:526) */
+int ngicp_clear_covs(ngicp_t* h, int which);
+/* NanoGICP::getSourceCovariances / getTargetCovariances, nano_gicp.hpp:100-106: writes n*16 doubles */
+size_t ngicp_covs_size(const ngicp_t* h, int which);
+int ngicp_get_source_covs(ngicp_t* h, double* out, size_t n);
+int ngicp_get_target_covs(ngicp_t* h, double* out, size_t n);
+
+/* ---- registration ----------------------------------------------------------------------------- */
+/* pcl::Registration::align(output, guess) -> NanoGICP::computeTransformation (nano_gicp_impl.hpp:161-171)
+ * -> LsqRegistration::computeTransformation (lsq_registration_impl.hpp:89-115).  Lazily computes missing
+ * covariances like the reference.  `guess` NULL = identity (align(output)). */
+int ngicp_align(ngicp_t* h, const float* guess16, ngicp_result* out);
+/* pcl::transformPointCloud(*input_, output, final) at lsq_registration_impl.hpp:114: writes n packed
+ * {x,y,z,1} float4 records (host or device); the facade merges them into the output cloud's records */
+int ngicp_transform_source(ngicp_t* h, const float* T16, float* out_xyz1, size_t n);
+
+/* ---- voxel grid ------------------------------------------------------------------------------- */
+/* pcl::VoxelGrid<PointXYZI>::filter with leaf (l,l,l) (odom.cc:126-127,460-463,487-490,1160-1163).
+ * in: n PointXYZI-like records (x,y,z at floats 0..2, intensity at float 4 when stride_bytes >= 20);
+ * out: up to out_capacity 32-byte PointXYZI records {x,y,z,1,intensity,0,0,0}, ordered by voxel index;
+ * *m = number written.  in/out may be host or device memory. */
+int ngicp_voxel_filter(ngicp_t* h, const void* in, size_t n, size_t stride_bytes, float leaf, void* out,
+                       size_t out_capacity, size_t* m);
+/* test hook: the output slot every input point was averaged into (-1 for non-finite points) */
+int ngicp_voxel_assignment(ngicp_t* h, int* slot_of_point, size_t n);
+
+/* ---- introspection used by the parity tests --------------------------------------------------- */
+/* KdTreeFLANN::nearestKSearch (nanoflann.hpp:141-152) for nq queries against the source/target index:
+ * idx[nq*k] (original point order, -1 padded), d2[nq*k] ascending */
+int ngicp_knn(ngicp_t* h, int which, const float* queries, size_t nq, size_t q_stride_bytes, int k, int* idx, float* d2);
+/* NanoGICP::linearize (nano_gicp_impl.hpp:213-270): H 6x6 col-major, b, sum of errors; optional per-point
+ * correspondences_ (target index or -1), sq_distances_, and mahalanobis_ (n*16 doubles) */
+int ngicp_linearize(ngicp_t* h, const double* T16, double* H36, double* b6, double* err, int* corr, float* sqd, double* mahal);
+/* NanoGICP::compute_error (nano_gicp_impl.hpp:272-296) with the correspondences frozen by the last linearize */
+int ngicp_compute_error(ngicp_t* h, const double* T16, double* err);
+/* sharded-submap building block: like ngicp_linearize but returns the raw partial sums
+ * out43 = {H (36, col-major), b (6), err (1)} so that ranks can all-reduce them; out43 may be device memory */
+int ngicp_linearize_partial(ngicp_t* h, const double* T16, double* out43);
+int ngicp_compute_error_partial(ngicp_t* h, const double* T16, double* out1);
+
+/* library identification: "nanogicp-b200 <version> sm_100a" */
+const char* ngicp_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* NANOGICP_C_H */

@@ -1,0 +1,437 @@
+"""GPU parity tests: every stage of the CUDA path against the CPU oracle, called through the C ABI.
+
+Tolerances are the ones BASELINE.json's north_star states:
+  * voxel assignment and kNN indices bit-exact (indices compared wherever distances are not exactly tied),
+    kNN squared distances bit-identical
+  * covariances within 1e-5 relative
+  * final poses within 1e-4 m / 1e-5 rad, identical iteration counts
+"""
+import numpy as np
+import pytest
+
+from direct_lidar_odometry_b200 import synth
+from util import tie_free_mask, pose_delta
+
+pytestmark = pytest.mark.gpu
+
+COV_RTOL = 1e-5
+POSE_T_TOL = 1e-4
+POSE_R_TOL = 1e-5
+
+
+@pytest.fixture(scope="module")
+def G():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from direct_lidar_odometry_b200 import NanoGICP
+    return NanoGICP
+
+
+@pytest.fixture(scope="module")
+def O():
+    from oracle import oracle
+    oracle.load(prefer_ref=True)
+    return oracle
+
+
+@pytest.fixture(scope="module")
+def vox_pair(O, scan_pair):
+    v0 = O.voxel_filter(scan_pair["s0"], 0.25)
+    v1 = O.voxel_filter(scan_pair["s1"], 0.25)
+    return v0, v1
+
+
+def bits(a):
+    return np.ascontiguousarray(a).view(np.uint32)
+
+
+# ---------------------------------------------------------------------------------------------- K0
+@pytest.mark.parametrize("leaf", [0.25, 0.5, 2.0])
+def test_voxel_filter_bit_exact(G, O, scan_pair, leaf):
+    g = G()
+    s0 = scan_pair["s0"]
+    ref, ref_assign, rc = O.voxel_filter(s0, leaf, return_assignment=True)
+    out, st = g.voxel_filter(s0, leaf, return_status=True)
+    assert st == 0 and rc == 0
+    assert out.shape == ref.shape
+    assert np.array_equal(bits(out), bits(ref))                      # centroids, intensity, padding: bit-exact
+    assert np.array_equal(g.voxel_assignment(s0.shape[0]), ref_assign)  # voxel of every input point
+    # idempotence-style property at full size: re-filtering the centroids cannot add points
+    again = g.voxel_filter(out, leaf)
+    assert again.shape[0] <= out.shape[0]
+
+
+def test_voxel_filter_edge_cases(G, O, scan_pair):
+    g = G()
+    s0 = scan_pair["s0"]
+    assert g.voxel_filter(np.zeros((0, 8), np.float32), 0.25).shape[0] == 0
+    one = g.voxel_filter(s0[:1], 0.25)
+    assert one.shape[0] == 1 and np.array_equal(bits(one), bits(O.voxel_filter(s0[:1], 0.25)))
+    # non-finite points are skipped (is_dense=false path of PCL)
+    dirty = s0[:5000].copy()
+    dirty[::7, 0] = np.nan
+    dirty[3::11, 2] = np.inf
+    ref, ref_assign, _ = O.voxel_filter(dirty, 0.5, return_assignment=True)
+    out = g.voxel_filter(dirty, 0.5)
+    assert np.array_equal(bits(out), bits(ref))
+    assert np.array_equal(g.voxel_assignment(dirty.shape[0]), ref_assign)
+    # all points in one voxel
+    blob = s0[:300].copy()
+    blob[:, :3] = blob[:, :3] * 1e-3 + 5.0
+    assert np.array_equal(bits(g.voxel_filter(blob, 1.0)), bits(O.voxel_filter(blob, 1.0)))
+    # int32 voxel index overflow: PCL warns and passes the input through
+    far = s0[:100].copy()
+    far[0, :3] = 1e6
+    out, st = g.voxel_filter(far, 0.01, return_status=True)
+    assert st == 1 and out.shape[0] == 100 and np.array_equal(out[:, :3], far[:, :3])
+    # packed xyz input (stride 12) gives the same centroids with zero intensity
+    xyz = np.ascontiguousarray(s0[:4000, :3])
+    out = g.voxel_filter(xyz, 0.5)
+    ref = O.voxel_filter(xyz, 0.5)
+    assert np.array_equal(bits(out[:, :4]), bits(ref[:, :4]))
+
+
+# ---------------------------------------------------------------------------------------------- K1+K2
+@pytest.mark.parametrize("k", [1, 5, 10, 20])
+def test_knn_matches_reference_nanoflann_golden(G, golden_knn, k):
+    """Vectors produced by the reference's own vendored nanoflann (tests/golden/make_golden.py)."""
+    g = G()
+    cloud = golden_knn["cloud"]
+    g.setInputTarget(cloud)
+    idx, d2 = g.knn(1, golden_knn["queries"], k)
+    assert np.array_equal(bits(d2), bits(golden_knn[f"d2_k{k}"]))
+    # ties: compare indices only where the distance differs from both neighbours in the (k+1)-list
+    _, d2p = g.knn(1, golden_knn["queries"], k + 1)
+    m = tie_free_mask(d2p)
+    assert m.mean() > 0.9
+    assert np.array_equal(idx[m], golden_knn[f"idx_k{k}"][m])
+    # tied slots must still hold points at exactly that distance
+    q = golden_knn["queries"]
+    p = cloud[idx]
+    dx, dy, dz = q[:, None, 0] - p[..., 0], q[:, None, 1] - p[..., 1], q[:, None, 2] - p[..., 2]
+    recomputed = (dx * dx + dy * dy).astype(np.float32) + (dz * dz).astype(np.float32)
+    assert np.array_equal(bits(recomputed.astype(np.float32)), bits(d2))
+
+
+@pytest.mark.parametrize("cell,table", [(0.0, 1 << 23), (0.3, 1 << 23), (3.0, 1 << 23), (0.25, 4096)])
+def test_knn_scan_vs_oracle_kdtree(G, O, vox_pair, cell, table):
+    v0, v1 = vox_pair
+    g = G()
+    g.setGridCellSize(cell)
+    g.setGridTableCells(table)     # a tiny table forces the cell edge to grow on the device
+    g.setInputTarget(v0)
+    tree = O.Cloud(v0)
+    rng = np.random.default_rng(5)
+    far = rng.uniform(-150, 150, size=(300, 3)).astype(np.float32)   # queries far outside the cloud's bbox too
+    far[:, 2] *= 0.3
+    q = np.vstack([v1[:6000, :3], far])
+    for k in (1, 20):
+        idx, d2 = g.knn(1, q, k + 1)
+        ridx, rd2 = tree.knn(q, k + 1)
+        assert np.array_equal(bits(d2), bits(rd2))
+        m = tie_free_mask(rd2)
+        assert np.array_equal(idx[:, :k][m], ridx[:, :k][m])
+
+
+def test_knn_small_clouds(G, O):
+    g = G()
+    pts = synth.random_planes_cloud(7, seed=1)
+    g.setInputTarget(pts)
+    idx, d2 = g.knn(1, pts[:, :3].copy(), 10)     # fewer points than k: -1 padded like nanoflann's short result
+    ridx, rd2 = O.Cloud(pts).knn(pts[:, :3].copy(), 10)
+    assert np.array_equal(idx, ridx) and np.array_equal(bits(d2), bits(rd2))
+    from direct_lidar_odometry_b200 import NanoGICPError
+    g.setCorrespondenceRandomness(10)
+    with pytest.raises(NanoGICPError) as e:
+        g.calculateTargetCovariances()
+    assert e.value.code == -3
+    # duplicates and a single point
+    dup = np.repeat(pts[:2], 5, axis=0)
+    g2 = G()
+    g2.setInputTarget(dup)
+    idx, d2 = g2.knn(1, dup[:1, :3].copy(), 5)
+    assert (d2 == 0).all() and set(idx[0]) <= set(range(10))
+
+
+# ---------------------------------------------------------------------------------------------- K3
+@pytest.mark.parametrize("k,method", [(10, 3), (20, 3), (20, 0), (10, 1), (10, 2), (10, 4)])
+def test_covariances_vs_oracle(G, O, vox_pair, k, method):
+    v0, _ = vox_pair
+    g = G()
+    g.setCorrespondenceRandomness(k)
+    g.setRegularizationMethod(method)
+    g.setInputTarget(v0)
+    assert g.calculateTargetCovariances() is True
+    got = g.getTargetCovariances()
+    ref, ridx, rd2 = O.Cloud(v0).covariances(k, method=method, with_knn=True)
+    assert got.shape == ref.shape
+    assert np.abs(got[:, 3, :]).max() == 0 and np.abs(got[:, :, 3]).max() == 0
+    # exclude points whose k-th and (k+1)-th neighbour distances tie exactly (neighbour SET is then ambiguous)
+    _, d2p = O.Cloud(v0).knn(v0[:, :3].copy(), k + 1)
+    ok = d2p[:, k - 1] != d2p[:, k]
+    assert ok.mean() > 0.99
+    num = np.linalg.norm((got - ref)[ok].reshape(-1, 16), axis=1)
+    den = np.linalg.norm(ref[ok].reshape(-1, 16), axis=1)
+    rel = num / den
+    if method == 3:
+        # PLANE output is basis dependent when the two smallest singular values (nearly) coincide — collinear
+        # neighbourhoods; measure the gap from the raw covariance and require parity wherever it is resolvable
+        raw = O.Cloud(v0).covariances(k, method=0)[:, :3, :3]
+        w = np.linalg.eigvalsh(raw)[ok]
+        resolvable = (w[:, 1] - w[:, 0]) > 1e-6 * w[:, 2]
+        assert resolvable.mean() > 0.99
+        assert rel[resolvable].max() < COV_RTOL
+        ev = np.linalg.eigvalsh(0.5 * (got[:, :3, :3] + got[:, :3, :3].transpose(0, 2, 1)))
+        assert np.allclose(ev, [1e-3, 1, 1], atol=1e-9)   # holds for every point, ambiguous or not
+    else:
+        assert rel.max() < COV_RTOL
+
+
+# ---------------------------------------------------------------------------------------------- K4 / K5
+def _setup_pair(G, O, v_src, v_tgt, k, thr, **kw):
+    g = G()
+    g.setCorrespondenceRandomness(k)
+    g.setMaxCorrespondenceDistance(thr)
+    for name, val in kw.items():
+        getattr(g, name)(val)
+    g.setInputTarget(v_tgt)
+    g.setInputSource(v_src)
+    o = O.Gicp(k=k, max_corr_dist=thr, num_threads=0)
+    o.set_target(O.Cloud(v_tgt))
+    o.set_source(O.Cloud(v_src))
+    return g, o
+
+
+@pytest.mark.parametrize("thr", [1.0, float(np.finfo(np.float32).max)])
+def test_linearize_and_error_vs_oracle(G, O, vox_pair, thr):
+    v0, v1 = vox_pair
+    g, o = _setup_pair(G, O, v1, v0, 10, thr)
+    g.calculateTargetCovariances(); g.calculateSourceCovariances()
+    o.calc_target_covs(); o.calc_source_covs()
+    # feed the GPU the oracle's covariances so this test isolates K4/K5
+    g.setSourceCovariances(o.get_source_covs()); g.setTargetCovariances(o.get_target_covs())
+    T = synth.perturb_pose(np.eye(4), (0.08, -0.03, 0.02), 0.4)
+    lg = g.linearize(T, per_point=True)
+    lo = o.linearize(T, per_point=True)
+    matched = lo["corr"] >= 0
+    assert matched.mean() > 0.5
+    assert np.array_equal(lg["corr"] >= 0, matched)
+    assert np.array_equal(bits(lg["sqd"][matched]), bits(lo["sqd"][matched]))
+    same = lg["corr"] == lo["corr"]
+    assert same.mean() > 0.9995          # the rest are exact 1-NN distance ties
+    scale = np.abs(lo["H"]).max()
+    if same.all():
+        assert np.abs(lg["H"] - lo["H"]).max() < 1e-9 * scale
+        assert np.abs(lg["b"] - lo["b"]).max() < 1e-9 * max(1.0, np.abs(lo["b"]).max())
+        assert abs(lg["err"] - lo["err"]) < 1e-9 * abs(lo["err"])
+    else:
+        assert np.abs(lg["H"] - lo["H"]).max() < 1e-3 * scale
+    mm = lo["mahalanobis"][same & matched]
+    assert np.abs(lg["mahalanobis"][same & matched] - mm).max() < 1e-9 * np.abs(mm).max()
+    # frozen-correspondence error at another transform
+    T2 = synth.perturb_pose(T, (0.01, 0.01, 0.0), 0.05)
+    eg, eo = g.compute_error(T2), o.compute_error(T2)
+    assert abs(eg - eo) < (1e-9 if same.all() else 1e-3) * abs(eo)
+
+
+# ---------------------------------------------------------------------------------------------- LM
+CONFIGS = {
+    # cfg/params.yaml:54-58 (S2S) and :63-67 (S2M); library defaults nano_gicp_impl.hpp:57-59
+    "dlo_s2s": dict(k=10, thr=1.0, max_iter=32, trans_eps=0.01),
+    "dlo_s2m": dict(k=20, thr=0.5, max_iter=32, trans_eps=0.01),
+    "defaults": dict(k=20, thr=float(np.finfo(np.float32).max), max_iter=64, trans_eps=5e-4),
+}
+
+
+def _align_both(G, O, v_src, v_tgt, cfg, guess, mode, optimizer=1):
+    g = G()
+    g.setCorrespondenceRandomness(cfg["k"]); g.setMaxCorrespondenceDistance(cfg["thr"])
+    g.setMaximumIterations(cfg["max_iter"]); g.setTransformationEpsilon(cfg["trans_eps"])
+    g.setOptimizer(optimizer)
+    g.setAlignMode(mode)
+    g.setInputTarget(v_tgt); g.setInputSource(v_src)
+    g.align(guess)
+    o = O.Gicp(k=cfg["k"], max_corr_dist=cfg["thr"], max_iter=cfg["max_iter"], trans_eps=cfg["trans_eps"], optimizer=optimizer,
+               num_threads=1)
+    o.set_target(O.Cloud(v_tgt)); o.set_source(O.Cloud(v_src))
+    r = o.align(guess)
+    return g, r
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("cfg", ["dlo_s2s", "defaults"])
+def test_align_s2s_pose_and_iterations(G, O, vox_pair, scan_pair, cfg, mode):
+    v0, v1 = vox_pair
+    for guess in (None, synth.perturb_pose(np.eye(4), (0.3, 0.1, 0.0), 2.0).astype(np.float32)):
+        g, r = _align_both(G, O, v1, v0, CONFIGS[cfg], guess, mode)
+        res = g.result
+        assert (res.nr_iterations, res.converged, res.n_linearize, res.n_compute_error, res.lm_failed) == \
+               (r.nr_iterations, r.converged, r.n_linearize, r.n_compute_error, r.lm_failed)
+        dt, dr = pose_delta(g.final_state(), r.Tx())
+        assert dt < POSE_T_TOL and dr < POSE_R_TOL, (dt, dr)
+        dt, dr = pose_delta(g.getFinalTransformation(), r.T())
+        assert dt < POSE_T_TOL and dr < POSE_R_TOL
+        assert np.allclose(g.getFinalHessian(), r.H(), rtol=1e-6, atol=1e-6 * np.abs(r.H()).max())
+        assert g.hasConverged() == bool(r.converged)
+    truth = np.linalg.inv(scan_pair["T0"]) @ scan_pair["T1"]
+    assert np.abs(g.final_state()[:3, 3] - truth[:3, 3]).max() < 2e-2
+
+
+def test_align_gauss_newton(G, O, vox_pair):
+    v0, v1 = vox_pair
+    g, r = _align_both(G, O, v1, v0, CONFIGS["dlo_s2s"], None, 0, optimizer=0)
+    assert g.result.nr_iterations == r.nr_iterations and g.result.n_compute_error == 0
+    dt, dr = pose_delta(g.final_state(), r.Tx())
+    assert dt < POSE_T_TOL and dr < POSE_R_TOL
+
+
+@pytest.fixture(scope="module")
+def small_submap(O):
+    """A scaled-down S2M case: 6 keyframes 5 m apart voxelised at 0.5 m in the world frame (reference
+    odom.cc:484-490), and one scan voxelised at 0.25 m as the source."""
+    keys = []
+    for j in range(6):
+        i = j * 33
+        T = synth.trajectory_pose(i)
+        s = synth.crop_box_negative(synth.os1_like(i, T))
+        w = synth.transform_xyzi(O.voxel_filter(s, 0.25), T.astype(np.float32))
+        keys.append(O.voxel_filter(w, 0.5))
+    submap = np.ascontiguousarray(np.vstack(keys))
+    i = 90
+    T = synth.trajectory_pose(i)
+    scan = O.voxel_filter(synth.crop_box_negative(synth.os1_like(i, T)), 0.25)
+    return submap, scan, T
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_align_s2m_vs_oracle(G, O, small_submap, mode):
+    submap, scan, T = small_submap
+    guess = synth.perturb_pose(T, (0.2, 0.0, 0.0), 1.0).astype(np.float32)
+    g, r = _align_both(G, O, scan, submap, CONFIGS["dlo_s2m"], guess, mode)
+    res = g.result
+    assert (res.nr_iterations, res.converged, res.n_linearize, res.n_compute_error) == \
+           (r.nr_iterations, r.converged, r.n_linearize, r.n_compute_error)
+    dt, dr = pose_delta(g.final_state(), r.Tx())
+    assert dt < POSE_T_TOL and dr < POSE_R_TOL, (dt, dr)
+    dt, dr = pose_delta(g.final_state(), T)
+    assert dt < 0.05 and dr < 2e-3   # and it actually localises against the map
+
+
+def test_align_edge_cases(G, O):
+    from direct_lidar_odometry_b200 import NanoGICPError
+    a = synth.random_planes_cloud(500, seed=1)
+    b = a.copy(); b[:, :3] += 500.0
+    for mode in (0, 1):
+        g = G()
+        g.setCorrespondenceRandomness(10); g.setMaxCorrespondenceDistance(1.0); g.setAlignMode(mode)
+        g.setInputTarget(a); g.setInputSource(b)
+        g.align()
+        # no correspondence inside the threshold: H=b=0, d=0, rho=NaN -> accepted, converged at iteration 0
+        assert g.result.nr_iterations == 0 and g.result.converged == 1
+        assert np.array_equal(g.final_state(), np.eye(4))
+    g = G()
+    g.setInputSource(a)
+    assert g.align() is None            # no target: PCL prints an error and returns
+    g.setInputTarget(a[:5])
+    g.setCorrespondenceRandomness(10)
+    with pytest.raises(NanoGICPError):  # fewer than k points: UB in the reference, an error here
+        g.align()
+    # output cloud = source transformed by the final transformation
+    g2 = G()
+    g2.setCorrespondenceRandomness(10)
+    g2.setInputTarget(a); g2.setInputSource(a)
+    out = g2.align(want_output=True)
+    assert out.shape == (500, 4) and np.allclose(out[:, :3], a[:, :3], atol=1e-4) and (out[:, 3] == 1).all()
+
+
+# ---------------------------------------------------------------------------------------------- OdomNode call sequence
+def test_odom_call_sequence_matches_oracle(G, O):
+    """The S2S/S2M call pattern of OdomNode (reference src/dlo/odom.cc:472-528, 792-852) on 5 scans:
+    two registration objects, shared source index, covariance hand-over, swapSourceAndTarget."""
+    scans, poses = [], []
+    for i in range(5):
+        T = synth.trajectory_pose(i * 4)
+        scans.append(O.voxel_filter(synth.crop_box_negative(synth.os1_like(i * 4, T)), 0.25))
+        poses.append(T)
+    s2s, s2m = G(), G()
+    for obj, c in ((s2s, CONFIGS["dlo_s2s"]), (s2m, CONFIGS["dlo_s2m"])):
+        obj.setCorrespondenceRandomness(c["k"]); obj.setMaxCorrespondenceDistance(c["thr"])
+        obj.setMaximumIterations(c["max_iter"]); obj.setTransformationEpsilon(c["trans_eps"])
+    o_s2s = O.Gicp(k=10, max_corr_dist=1.0, max_iter=32, trans_eps=0.01, num_threads=0)
+    o_s2m = O.Gicp(k=20, max_corr_dist=0.5, max_iter=32, trans_eps=0.01, num_threads=0)
+
+    # initializeInputTarget (odom.cc:472-507)
+    s2s.setInputTarget(scans[0]); s2s.calculateTargetCovariances()
+    oc0 = O.Cloud(scans[0])
+    o_s2s.set_target(oc0); o_s2s.calc_target_covs()
+    T0 = poses[0].astype(np.float32)
+    key = s2s.voxel_filter(synth.transform_xyzi(scans[0], T0), 0.5)
+    key_ref = O.voxel_filter(synth.transform_xyzi(scans[0], T0), 0.5)
+    assert np.array_equal(bits(key), bits(key_ref))
+    s2s.setInputSource(key); s2s.calculateSourceCovariances()
+    key_covs = s2s.getSourceCovariances()
+    ock = O.Cloud(key_ref)
+    o_s2s.set_source(ock); o_s2s.calc_source_covs()
+    key_covs_ref = o_s2s.get_source_covs()
+    assert np.abs(key_covs - key_covs_ref).max() < 1e-5
+
+    T_s2s_prev = T0.copy()
+    T_s2s_prev_ref = T0.copy()
+    first = True
+    for i in range(1, 5):
+        cur = scans[i]
+        # setInputSources (odom.cc:514-528)
+        s2s.setInputSource(cur)
+        s2m.registerInputSource(cur)
+        s2m.source_kdtree_ = s2s.source_kdtree_
+        s2m.source_covs_.clear()
+        occ = O.Cloud(cur)
+        o_s2s.set_source(occ); o_s2m.set_source(occ)
+        # getNextPose (odom.cc:792-852)
+        s2s.align()
+        r = o_s2s.align()
+        assert (s2s.result.nr_iterations, s2s.result.n_compute_error) == (r.nr_iterations, r.n_compute_error)
+        dt, dr = pose_delta(s2s.final_state(), r.Tx())
+        assert dt < POSE_T_TOL and dr < POSE_R_TOL
+        T_s2s = T_s2s_prev @ s2s.getFinalTransformation()          # propagateS2S, float (odom.cc:928)
+        T_s2s_ref = T_s2s_prev_ref @ r.T()
+        s2m.source_covs_ = s2s.source_covs_                         # odom.cc:815, stays in HBM
+        o_s2m.set_source_covs(o_s2s.get_source_covs())
+        s2s.swapSourceAndTarget(); o_s2s.swap()
+        if first:                                                   # submap_hasChanged
+            s2m.setInputTarget(key); s2m.setTargetCovariances(key_covs)
+            o_s2m.set_target(ock); o_s2m.set_target_covs(key_covs_ref)
+            first = False
+        s2m.align(T_s2s)
+        r2 = o_s2m.align(T_s2s_ref)
+        assert (s2m.result.nr_iterations, s2m.result.n_compute_error) == (r2.nr_iterations, r2.n_compute_error)
+        dt, dr = pose_delta(s2m.final_state(), r2.Tx())
+        assert dt < 5 * POSE_T_TOL and dr < 5 * POSE_R_TOL   # the two chains start from slightly different float guesses
+        T_s2s_prev = s2m.getFinalTransformation()
+        T_s2s_prev_ref = r2.T()
+        dt, dr = pose_delta(T_s2s_prev, poses[i])
+        assert dt < 0.1 and dr < 5e-3                            # odometry stays on the true trajectory
+
+
+# ---------------------------------------------------------------------------------------------- full-size properties
+def test_full_size_submap_properties(G, O):
+    """BASELINE config C2 size (500k-point submap, k=20): properties that do not need the oracle at full size,
+    plus an oracle spot check on a sample of queries."""
+    rng = np.random.default_rng(11)
+    base = synth.random_planes_cloud(500_000, seed=4, extent=150.0, noise=0.02)
+    g = G()
+    g.setCorrespondenceRandomness(20)
+    g.setInputTarget(base)
+    sample = rng.permutation(base.shape[0])[:3000]
+    q = np.ascontiguousarray(base[sample, :3])
+    idx, d2 = g.knn(1, q, 20)
+    assert (idx[:, 0] == sample).mean() > 0.999 and (d2[:, 0] == 0).all()      # self first
+    assert (np.diff(d2, axis=1) >= 0).all()                                      # ascending
+    ridx, rd2 = O.Cloud(base).knn(q, 21)
+    assert np.array_equal(bits(d2), bits(rd2[:, :20]))
+    m = tie_free_mask(rd2)
+    assert np.array_equal(idx[m], ridx[:, :20][m])
+    g.calculateTargetCovariances()
+    covs = g.getTargetCovariances()
+    ev = np.linalg.eigvalsh(0.5 * (covs[:, :3, :3] + covs[:, :3, :3].transpose(0, 2, 1)))
+    assert np.allclose(ev, [1e-3, 1, 1], atol=1e-8)
