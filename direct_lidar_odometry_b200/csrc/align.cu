@@ -199,6 +199,7 @@ cudaError_t launch_linearize(const AlignBuffers& ab, const double* T16, double m
   iso_from_colmajor16(T16, T.x);
   linearize_kernel<<<blocks, AL_THREADS, 0, st>>>(a, T, cap_from(max_corr_dist), max_corr_dist * max_corr_dist);
   reduce_partials_kernel<<<1, 32, 0, st>>>(a.partials, blocks, NRED, ab.reduced);
+  note_launches(2);
   return cudaGetLastError();
 }
 
@@ -209,6 +210,7 @@ cudaError_t launch_compute_error(const AlignBuffers& ab, const double* T16, cuda
   iso_from_colmajor16(T16, T.x);
   compute_error_kernel<<<blocks, AL_THREADS, 0, st>>>(a, T);
   reduce_partials_kernel<<<1, 32, 0, st>>>(a.partials, blocks, 1, ab.reduced);
+  note_launches(2);
   return cudaGetLastError();
 }
 
@@ -227,6 +229,7 @@ __global__ void export_mahal_kernel(const double* __restrict__ mahal, const int*
 cudaError_t launch_export_mahal(const AlignBuffers& ab, double* out16, cudaStream_t st) {
   if (ab.ns <= 0) return cudaSuccess;
   export_mahal_kernel<<<(ab.ns + 255) / 256, 256, 0, st>>>(ab.mahal, ab.corr, ab.ns, out16);
+  note_launches(1);
   return cudaGetLastError();
 }
 
@@ -486,6 +489,7 @@ cudaError_t launch_align_fused(const AlignBuffers& ab, const ngicp_params& p, co
   cudaError_t e = cudaMemsetAsync(barrier, 0, sizeof(unsigned) * 4, st);
   if (e != cudaSuccess) return e;
   double* totals = ab.reduced;  // [2][NRED]
+  note_launches(1);
   void* args[] = {(void*)&a, (void*)&prm, (void*)&g, (void*)&res_dev, (void*)&barrier, (void*)&totals};
   return cudaLaunchCooperativeKernel((const void*)align_fused_kernel, dim3(blocks), dim3(AL_THREADS), args, 0, st);
 }

@@ -28,6 +28,11 @@ struct ngicp_handle {
   int align_max_blocks = 2048;
 };
 
+namespace ngicp {
+static unsigned long long g_launches = 0;
+void note_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
+}  // namespace ngicp
+
 namespace {
 
 int fail(ngicp_t* h, int code, const char* what, cudaError_t e = cudaSuccess) {
@@ -152,6 +157,7 @@ int set_covs(ngicp_t* h, int which, const double* covs, size_t n) {
     NG_CUDA(h, h->sc.cov_stage.reserve(sizeof(double) * 16 * n, h->stream));
     NG_CUDA(h, cudaMemcpyAsync(h->sc.cov_stage.p, covs, sizeof(double) * 16 * n, cudaMemcpyDefault, h->stream->s));
     mat4_to_sym6_kernel<<<blocks_for((int)n), 256, 0, h->stream->s>>>(h->sc.cov_stage.as<double>(), (int)n, cv->c.as<double>());
+    note_launches(1);
     NG_CUDA(h, cudaGetLastError());
   }
   (which == NGICP_SOURCE ? h->src_cov : h->tgt_cov) = cv;
@@ -167,6 +173,7 @@ int get_covs(ngicp_t* h, int which, double* out, size_t n) {
   if (n == 0) return NGICP_OK;
   NG_CUDA(h, h->sc.cov_stage.reserve(sizeof(double) * 16 * n, h->stream));
   sym6_to_mat4_kernel<<<blocks_for((int)n), 256, 0, h->stream->s>>>(cv->c.as<double>(), (int)n, h->sc.cov_stage.as<double>());
+  note_launches(1);
   NG_CUDA(h, cudaGetLastError());
   NG_CUDA(h, cudaMemcpyAsync(out, h->sc.cov_stage.p, sizeof(double) * 16 * n, cudaMemcpyDefault, h->stream->s));
   NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
@@ -303,6 +310,8 @@ int align_stepped(ngicp_t* h, const AlignBuffers& ab, const float* guess16, ngic
 }  // namespace
 
 extern "C" {
+
+unsigned long long ngicp_launch_count(void) { return __atomic_load_n(&ngicp::g_launches, __ATOMIC_RELAXED); }
 
 const char* ngicp_version(void) { return "nanogicp-b200 0.1 sm_100a"; }
 

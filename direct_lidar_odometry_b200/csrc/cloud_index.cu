@@ -145,11 +145,13 @@ cudaError_t upload_cloud(DevCloud& c, const void* pts, size_t n, size_t stride_b
   if ((e = c.pts.alloc(sizeof(float4) * (n ? n : 1), st)) != cudaSuccess) return e;
   if ((e = c.desc.alloc(sizeof(GridDesc), st)) != cudaSuccess) return e;
   desc_init_kernel<<<1, 1, 0, st->s>>>(c.desc.as<GridDesc>());
+  note_launches(1);
   if (n == 0) return cudaGetLastError();
   const size_t raw_bytes = (n - 1) * stride_bytes + 12;  // last record may be shorter than the stride
   if ((e = sc.staging.reserve(raw_bytes + 16, st)) != cudaSuccess) return e;
   if ((e = cudaMemcpyAsync(sc.staging.p, pts, raw_bytes, cudaMemcpyDefault, st->s)) != cudaSuccess) return e;
   pack_bbox_kernel<<<grid_for((int)n), 256, 0, st->s>>>(sc.staging.as<unsigned char>(), stride_bytes, (int)n, c.pts.as<float4>(), c.desc.as<GridDesc>());
+  note_launches(1);
   return cudaGetLastError();
 }
 
@@ -169,6 +171,7 @@ cudaError_t build_index(DevCloud& c, float cell_req, int table_cap, Scratch& sc,
   GridDesc* d = c.desc.as<GridDesc>();
   grid_setup_kernel<<<1, 1, 0, st->s>>>(d, cell_req, table_cap, n);
   zero_cells_kernel<<<148 * 4, 256, 0, st->s>>>(c.cell_start.as<int>(), d);
+  note_launches(2 + (n > 0 ? 2 : 0));
   if (n > 0) {
     const size_t nb = sizeof(unsigned) * (size_t)n;
     if ((e = sc.keys_a.reserve(nb, st)) != cudaSuccess) return e;

@@ -85,6 +85,9 @@ struct Scratch {
   DevBuf barrier;    // unsigned counters for the grid barrier
 };
 
+// number of kernels launched by this library since load (diagnostics; ngicp_launch_count())
+void note_launches(int n);
+
 // ---- sort_scan.cu ---------------------------------------------------------------------------------
 void exclusive_scan_inplace(int* data, const int* n_dev, int n_add, int max_n, int* tile_sums, cudaStream_t st);
 size_t scan_scratch_ints(int max_n);

@@ -92,6 +92,7 @@ cudaError_t launch_knn_queries(const DevCloud& c, const float4* queries, int nq,
   int blocks = (nq + KC_WARPS - 1) / KC_WARPS;
   if (blocks > 148 * 16) blocks = 148 * 16;
   knn_query_kernel<<<blocks, KC_THREADS, 0, st>>>(c.view(), queries, nq, k, idx, d2);
+  note_launches(1);
   return cudaGetLastError();
 }
 
@@ -102,6 +103,7 @@ cudaError_t launch_covariances(const DevCloud& c, int k, int method, double* cov
   if (blocks > 148 * 16) blocks = 148 * 16;
   const size_t smem = sizeof(int) * (size_t)KC_WARPS * k * KC_ROW;
   knn_cov_kernel<<<blocks, KC_THREADS, smem, st>>>(c.view(), c.n, k, method, covs6);
+  note_launches(1);
   return cudaGetLastError();
 }
 

@@ -104,6 +104,7 @@ void exclusive_scan_inplace(int* data, const int* n_dev, int n_add, int max_n, i
   scan_tile_sums<<<grid, SCAN_THREADS, 0, st>>>(data, n_dev, n_add, tile_sums);
   scan_tile_offsets<<<1, 1024, 0, st>>>(tile_sums, n_dev, n_add);
   scan_apply<<<grid, SCAN_THREADS, 0, st>>>(data, n_dev, n_add, tile_sums);
+  note_launches(3);
 }
 
 size_t scan_scratch_ints(int max_n) { return (size_t)(max_n + SCAN_TILE - 1) / SCAN_TILE + 1; }
@@ -239,6 +240,7 @@ int radix_sort_pairs(unsigned* keys_a, unsigned* vals_a, unsigned* keys_b, unsig
     rs_histogram<<<nblk, RS_THREADS, 0, st>>>(kin, n, p * 8, nblk, hist);
     rs_scan_hist<<<1, 1024, 0, st>>>(hist, 256 * nblk);
     rs_scatter<<<nblk, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, p * 8, nblk, hist);
+    note_launches(3);
     cur ^= 1;
   }
   return cur;

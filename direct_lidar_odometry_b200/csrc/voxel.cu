@@ -169,6 +169,7 @@ cudaError_t voxel_filter_device(const void* in, size_t n, size_t stride_bytes, f
   if ((e = cudaMemcpyAsync(&d->n, &len, sizeof(int), cudaMemcpyHostToDevice, st->s)) != cudaSuccess) return e;
   exclusive_scan_inplace(flags, &d->n, 0, ni + 1, sc.tile_sums.as<int>(), st->s);
   vox_centroid_kernel<<<vgrid(ni, 128), 128, 0, st->s>>>(keys, perm, ni, flags, pts, sc.vox_out.as<float>(), sc.vox_slot.as<int>());
+  note_launches(6);
   int host[2] = {0, 0};
   if ((e = cudaMemcpyAsync(&host[0], flags + ni, sizeof(int), cudaMemcpyDeviceToHost, st->s)) != cudaSuccess) return e;
   if ((e = cudaMemcpyAsync(&host[1], &d->voverflow, sizeof(int), cudaMemcpyDeviceToHost, st->s)) != cudaSuccess) return e;

@@ -175,6 +175,9 @@ int ngicp_compute_error(ngicp_t* h, const double* T16, double* err);
 int ngicp_linearize_partial(ngicp_t* h, const double* T16, double* out43);
 int ngicp_compute_error_partial(ngicp_t* h, const double* T16, double* out1);
 
+/* number of CUDA kernels this library has launched since it was loaded (all handles; diagnostics for bench.py) */
+unsigned long long ngicp_launch_count(void);
+
 /* library identification: "nanogicp-b200 <version> sm_100a" */
 const char* ngicp_version(void);
 
