@@ -2,7 +2,7 @@
 //
 // K4  linearize        = NanoGICP::update_correspondences + NanoGICP::linearize fused
 //                        (reference include/nano_gicp/impl/nano_gicp_impl.hpp:173-211, :213-270):
-//                        per source point  q = float(T) * p  ->  bounded 1-NN on the target grid  ->
+//                        one THREAD per source point:  q = float(T) * p  ->  bounded 1-NN on the target grid  ->
 //                        M = (C_B + R C_A R^T)^-1  ->  J^T M J / J^T M e / e^T M e, reduced with warp
 //                        shuffles and per-block partials into one packed {H(21), b(6), err} per call.
 // K5  compute_error    = NanoGICP::compute_error (:272-296) with correspondences and M frozen.
@@ -31,7 +31,6 @@ struct AlignArgs {
   double* mahal; int* corr; float* sqd; float4* tgt_pt;
   double* partials;  // [2][max_blocks][NRED]
   int max_blocks;
-  int batch;         // source points handled per warp batch (1..32)
 };
 
 __device__ __forceinline__ void make_xforms(const Iso3& x, XformF& f) {
@@ -48,50 +47,39 @@ __device__ __forceinline__ float xform_row(const float* m, float x, float y, flo
   return __fadd_rn(__fadd_rn(__fmul_rn(m[0], x), __fmul_rn(m[1], y)), __fadd_rn(__fmul_rn(m[2], z), __fmul_rn(m[3], 1.0f)));
 }
 
-// one warp: correspondences + Mahalanobis + H/b/err contributions of `cnt` source points starting at i0
-__device__ __forceinline__ void linearize_batch(const AlignArgs& a, const GridParams& gp, const XformF& Tf, const Iso3& Td,
-                                                float cap_d2, double thr2, int i0, int cnt, double* acc) {
-  const int lane = threadIdx.x & 31;
+// one thread: correspondence + Mahalanobis + H/b/err contribution of source point i
+__device__ __forceinline__ void linearize_point(const AlignArgs& a, const GridParams& gp, const XformF& Tf, const Iso3& Td,
+                                                float cap_d2, double thr2, int i, double* acc) {
+  const float4 p = __ldg(a.src_pts + i);
+  const float qx = xform_row(Tf.m + 0, p.x, p.y, p.z), qy = xform_row(Tf.m + 4, p.x, p.y, p.z), qz = xform_row(Tf.m + 8, p.x, p.y, p.z);
   float my_d = FLT_MAX;
   int my_p = -1;
-  for (int t = 0; t < cnt; ++t) {
-    const float4 p = __ldg(a.src_pts + i0 + t);
-    const float qx = xform_row(Tf.m + 0, p.x, p.y, p.z), qy = xform_row(Tf.m + 4, p.x, p.y, p.z), qz = xform_row(Tf.m + 8, p.x, p.y, p.z);
-    WarpBest1 rs;
-    rs.init();
-    if (isfinite(qx) && isfinite(qy) && isfinite(qz)) grid_search_warp(a.tgt, gp, qx, qy, qz, cap_d2, rs);
-    rs.finalize();
-    if (lane == t) { my_d = rs.d; my_p = rs.p; }
-  }
-  if (lane < cnt) {
-    const int i = i0 + lane;
-    int corr = -1;
-    if (my_p >= 0 && (double)my_d < thr2) {
-      const float4 p = __ldg(a.src_pts + i);
-      const float4 tp = __ldg(a.tgt.sorted + my_p);
-      corr = __float_as_int(tp.w);
-      double CA[6], CB[6], RCR[6], M[6];
-      const double* ca = a.src_cov + (size_t)i * 6;
-      const double* cb = a.tgt_cov + (size_t)corr * 6;
+  if (isfinite(qx) && isfinite(qy) && isfinite(qz)) grid_nn1_thread(a.tgt, gp, qx, qy, qz, cap_d2, my_d, my_p);
+  int corr = -1;
+  if (my_p >= 0 && (double)my_d < thr2) {
+    const float4 tp = __ldg(a.tgt.sorted + my_p);
+    corr = __float_as_int(tp.w);
+    double CA[6], CB[6], RCR[6], M[6];
+    const double* ca = a.src_cov + (size_t)i * 6;
+    const double* cb = a.tgt_cov + (size_t)corr * 6;
 #pragma unroll
-      for (int j = 0; j < 6; j++) { CA[j] = __ldg(ca + j); CB[j] = __ldg(cb + j); }
-      sym3_rcr(CB, Td.R, CA, RCR);
-      sym3_inverse(RCR, M);
-      const double px = (double)p.x, py = (double)p.y, pz = (double)p.z;
-      double tA[3], e[3];
-      tA[0] = Td.R[0] * px + Td.R[1] * py + Td.R[2] * pz + Td.t[0];
-      tA[1] = Td.R[3] * px + Td.R[4] * py + Td.R[5] * pz + Td.t[1];
-      tA[2] = Td.R[6] * px + Td.R[7] * py + Td.R[8] * pz + Td.t[2];
-      e[0] = (double)tp.x - tA[0]; e[1] = (double)tp.y - tA[1]; e[2] = (double)tp.z - tA[2];
-      gicp_accumulate(tA, e, M, acc);
-      double* md = a.mahal + (size_t)i * 6;
+    for (int j = 0; j < 6; j++) { CA[j] = __ldg(ca + j); CB[j] = __ldg(cb + j); }
+    sym3_rcr(CB, Td.R, CA, RCR);
+    sym3_inverse(RCR, M);
+    const double px = (double)p.x, py = (double)p.y, pz = (double)p.z;
+    double tA[3], e[3];
+    tA[0] = Td.R[0] * px + Td.R[1] * py + Td.R[2] * pz + Td.t[0];
+    tA[1] = Td.R[3] * px + Td.R[4] * py + Td.R[5] * pz + Td.t[1];
+    tA[2] = Td.R[6] * px + Td.R[7] * py + Td.R[8] * pz + Td.t[2];
+    e[0] = (double)tp.x - tA[0]; e[1] = (double)tp.y - tA[1]; e[2] = (double)tp.z - tA[2];
+    gicp_accumulate(tA, e, M, acc);
+    double* md = a.mahal + (size_t)i * 6;
 #pragma unroll
-      for (int j = 0; j < 6; j++) md[j] = M[j];
-      a.tgt_pt[i] = tp;
-    }
-    a.corr[i] = corr;
-    a.sqd[i] = my_d;
+    for (int j = 0; j < 6; j++) md[j] = M[j];
+    a.tgt_pt[i] = tp;
   }
+  a.corr[i] = corr;
+  a.sqd[i] = my_d;
 }
 
 __device__ __forceinline__ double error_point(const AlignArgs& a, const Iso3& Td, int i) {
@@ -142,12 +130,8 @@ __global__ void __launch_bounds__(AL_THREADS) linearize_kernel(AlignArgs a, IsoA
   double acc[NRED];
 #pragma unroll
   for (int j = 0; j < NRED; j++) acc[j] = 0.0;
-  const int nbatches = (a.ns + a.batch - 1) / a.batch;
-  const int gw = blockIdx.x * AL_WARPS + (threadIdx.x >> 5);
-  for (int bch = gw; bch < nbatches; bch += gridDim.x * AL_WARPS) {
-    const int i0 = bch * a.batch;
-    linearize_batch(a, gp, Tf, T.x, cap_d2, thr2, i0, min(a.batch, a.ns - i0), acc);
-  }
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.ns; i += gridDim.x * blockDim.x)
+    linearize_point(a, gp, Tf, T.x, cap_d2, thr2, i, acc);
   block_reduce_store<NRED>(acc, s_red, a.partials + (size_t)blockIdx.x * NRED);
 }
 
@@ -178,10 +162,7 @@ static AlignArgs make_args(const AlignBuffers& ab, int blocks_hint) {
   a.tgt = ab.tgt; a.tgt_cov = ab.tgt_cov;
   a.mahal = ab.mahal; a.corr = ab.corr; a.sqd = ab.sqd; a.tgt_pt = ab.tgt_pt;
   a.partials = ab.partials; a.max_blocks = ab.max_blocks;
-  // points per warp batch: spread the searches over all resident warps
-  const int warps = blocks_hint * AL_WARPS;
-  int b = (ab.ns + warps - 1) / warps;
-  a.batch = b < 1 ? 1 : (b > 32 ? 32 : b);
+  (void)blocks_hint;
   return a;
 }
 
@@ -309,9 +290,8 @@ __global__ void __launch_bounds__(AL_THREADS) align_fused_kernel(AlignArgs a, Lm
   __shared__ Iso3 s_x;        // transform used by the next phase
   __shared__ int s_decision;
   const GridParams gp = load_grid(a.tgt.desc);
-  const int nbatches = (a.ns + a.batch - 1) / a.batch;
-  const int gw = blockIdx.x * AL_WARPS + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  const int gstride = gridDim.x * blockDim.x;
   GridSync gs;
   gs.arrive = bar; gs.flag = bar + 1; gs.totals = totals; gs.phase = 0;
 
@@ -342,10 +322,7 @@ __global__ void __launch_bounds__(AL_THREADS) align_fused_kernel(AlignArgs a, Lm
       double acc[NRED];
 #pragma unroll
       for (int j = 0; j < NRED; j++) acc[j] = 0.0;
-      for (int bch = gw; bch < nbatches; bch += gridDim.x * AL_WARPS) {
-        const int i0 = bch * a.batch;
-        linearize_batch(a, gp, Tf, T, prm.cap_d2, prm.thr2, i0, min(a.batch, a.ns - i0), acc);
-      }
+      for (int i = gtid; i < a.ns; i += gstride) linearize_point(a, gp, Tf, T, prm.cap_d2, prm.thr2, i, acc);
       grid_reduce<NRED>(acc, s_red, s_tot, a.partials, gs);
     }
     int outcome = 0;  // 1: step returned true, 0: LM failed
@@ -395,10 +372,7 @@ __global__ void __launch_bounds__(AL_THREADS) align_fused_kernel(AlignArgs a, Lm
         {
           const Iso3 T = s_x;
           double acc[1] = {0.0};
-          for (int bch = gw; bch < nbatches; bch += gridDim.x * AL_WARPS) {
-            const int i0 = bch * a.batch;
-            if (lane < min(a.batch, a.ns - i0)) acc[0] += error_point(a, T, i0 + lane);
-          }
+          for (int i = gtid; i < a.ns; i += gstride) acc[0] += error_point(a, T, i);
           grid_reduce<1>(acc, s_red, s_tot, a.partials, gs);
         }
         if (threadIdx.x == 0) {
@@ -469,7 +443,7 @@ int align_fused_max_blocks(int device) {
 
 cudaError_t launch_align_fused(const AlignBuffers& ab, const ngicp_params& p, const float* guess16, ngicp_result* res_dev,
                                unsigned* barrier, int device, cudaStream_t st) {
-  int blocks = (ab.ns + 2 * AL_WARPS - 1) / (2 * AL_WARPS);   // aim at >= 2 searches per warp
+  int blocks = (ab.ns + AL_THREADS - 1) / AL_THREADS;   // one source point per thread when the grid can hold them
   const int lim = align_fused_max_blocks(device);
   if (blocks > lim) blocks = lim;
   if (blocks > ab.max_blocks) blocks = ab.max_blocks;

@@ -73,6 +73,7 @@ struct Scratch {
   DevBuf vox_out;    // PointXYZI records
   DevBuf vox_slot;   // int per input point
   DevBuf knn_idx, knn_d2, queries;
+  DevBuf nbr;        // int[n*k] neighbour slots between the kNN and covariance kernels
   DevBuf cov_stage;  // Matrix4d staging for import/export
   // align state
   DevBuf mahal;      // double[ns*6]
@@ -102,7 +103,7 @@ cudaError_t build_index(DevCloud& c, float cell_req, int table_cap, Scratch& sc,
 
 // ---- knn_cov.cu -----------------------------------------------------------------------------------
 cudaError_t launch_knn_queries(const DevCloud& c, const float4* queries, int nq, int k, int* idx, float* d2, cudaStream_t st);
-cudaError_t launch_covariances(const DevCloud& c, int k, int method, double* covs6, cudaStream_t st);
+cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_scratch /* n*k ints */, double* covs6, cudaStream_t st);
 constexpr int KNN_MAX_K = 32;
 
 // ---- align.cu -------------------------------------------------------------------------------------
