@@ -283,6 +283,7 @@ def main():
         barrier()
         t_wall = time.perf_counter() - t_wall0
     launches = (L.ngicp_launch_count() - launches0)
+    grids = {"target": g.grid_info(1), "source": g.grid_info(0)}
     # end to end: pinned host buffers in, result struct out, every step
     for _ in range(2):
         gpu_step(g, submap_h, scan_h, guess)
@@ -327,7 +328,7 @@ def main():
                              "share_of_step": kcov_ms / (tot_dev_ms / args.steps)},
                 "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": tot_e2e_ms / args.steps,
                         "h2d_bytes_per_step": int(submap_np.nbytes + scan_np.nbytes), "d2h_bytes_per_step": 496},
-                "gpu_launches": int(launches), "clocks": clk.summary()}
+                "gpu_launches": int(launches), "grids": grids, "clocks": clk.summary()}
         if world == 1:
             c = run_cpu(wl, args.cpu_steps, 0)
             line["cpu_baseline"] = {"value": 1e3 / c["ms"], "unit": "pairs/s", "cores": c["threads"], "kind": c["kind"],

@@ -25,7 +25,7 @@ EXPORTS = [
     "ngicp_set_source_covs", "ngicp_set_target_covs", "ngicp_clear_covs", "ngicp_covs_size", "ngicp_get_source_covs",
     "ngicp_get_target_covs", "ngicp_align", "ngicp_transform_source", "ngicp_voxel_filter", "ngicp_voxel_assignment",
     "ngicp_knn", "ngicp_linearize", "ngicp_compute_error", "ngicp_linearize_partial", "ngicp_compute_error_partial",
-    "ngicp_version", "ngicp_launch_count",
+    "ngicp_version", "ngicp_launch_count", "ngicp_grid_info",
 ]
 
 
@@ -102,5 +102,6 @@ def load() -> C.CDLL:
     proto("ngicp_compute_error_partial", i32, vp, dp, vp)
     proto("ngicp_version", C.c_char_p)
     proto("ngicp_launch_count", C.c_ulonglong)
+    proto("ngicp_grid_info", i32, vp, i32, fp, ip, ip)
     _LIB = L
     return L

@@ -21,7 +21,7 @@
 
 namespace ngicp {
 
-constexpr int AL_THREADS = 128;
+constexpr int AL_THREADS = 256;
 constexpr int AL_WARPS = AL_THREADS / 32;
 
 struct XformF { float m[12]; };   // rows: m[r*4+c], c=3 is translation; float cast of the double state
@@ -218,6 +218,7 @@ cudaError_t launch_export_mahal(const AlignBuffers& ab, double* out16, cudaStrea
 // fused mode: the whole optimisation in one persistent cooperative kernel
 // ------------------------------------------------------------------------------------------
 struct LmParams {
+  unsigned long long* trace;   // optional device buffer of %globaltimer stamps (debug, NGICP_ALIGN_TRACE=1)
   int max_iterations, lm_max_iterations, optimizer;
   double rot_eps, trans_eps, lm_init_lambda_factor, thr2;
   float cap_d2;
@@ -242,6 +243,12 @@ struct GridSync {
   unsigned phase;     // phases completed so far
 };
 
+__device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+
 template <int NV>
 __device__ __forceinline__ void grid_reduce(double* acc, double (*s_red)[NRED], double* s_tot, double* partials, GridSync& gs) {
   __shared__ int s_last;
@@ -255,11 +262,25 @@ __device__ __forceinline__ void grid_reduce(double* acc, double (*s_red)[NRED], 
   double* tot = gs.totals + (size_t)(gs.phase & 1u) * NRED;
   if (s_last) {
     __threadfence();
+    // warp `seg` sums blocks seg, seg+W, seg+2W, ... for column v = lane; 8 independent loads in flight,
+    // combined in a fixed order (the result does not depend on which block happens to arrive last)
     const int v = threadIdx.x & 31, seg = threadIdx.x >> 5;
     if (v < NV) {
-      double s = 0.0;
-      for (unsigned bk = seg; bk < gridDim.x; bk += AL_WARPS) s += __ldcg(partials + (size_t)bk * NRED + v);
-      s_red[seg][v] = s;
+      double part[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) part[u] = 0.0;
+      const unsigned nb = gridDim.x;
+      for (unsigned b0 = seg; b0 < nb; b0 += AL_WARPS * 8) {
+        double x[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const unsigned bk = b0 + u * AL_WARPS;
+          x[u] = bk < nb ? __ldcg(partials + (size_t)bk * NRED + v) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) part[u] += x[u];
+      }
+      s_red[seg][v] = ((part[0] + part[1]) + (part[2] + part[3])) + ((part[4] + part[5]) + (part[6] + part[7]));
     }
     __syncthreads();
     if (threadIdx.x < NV) {
@@ -273,9 +294,10 @@ __device__ __forceinline__ void grid_reduce(double* acc, double (*s_red)[NRED], 
     if (threadIdx.x == 0) {
       asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(gs.flag), "r"(gs.phase + 1u) : "memory");
     }
-  }
-  if (threadIdx.x == 0) {
-    while (ld_acquire_u32(gs.flag) < gs.phase + 1u) { }
+  } else if (threadIdx.x == 0) {
+    // poll with a relaxed load (no L1 invalidation per probe) and back off so that the reducing block is
+    // not starved of L2 bandwidth; one acquire fence once the flag is seen
+    while (ld_relaxed_u32(gs.flag) < gs.phase + 1u) __nanosleep(40);
     __threadfence();
   }
   __syncthreads();
@@ -284,7 +306,19 @@ __device__ __forceinline__ void grid_reduce(double* acc, double (*s_red)[NRED], 
   __syncthreads();
 }
 
+__device__ __forceinline__ void trace_stamp(const LmParams& prm, int& slot) {
+  if (prm.trace && blockIdx.x == 0 && threadIdx.x == 0 && slot < 250) {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    prm.trace[1 + slot] = t;
+    slot++;
+    prm.trace[0] = (unsigned long long)slot;
+  }
+}
+
 __global__ void __launch_bounds__(AL_THREADS) align_fused_kernel(AlignArgs a, LmParams prm, Guess16 guess, ngicp_result* __restrict__ res, unsigned* bar, double* totals) {
+  int tslot = 0;
+  trace_stamp(prm, tslot);
   __shared__ double s_red[AL_WARPS][NRED];
   __shared__ double s_tot[NRED];
   __shared__ Iso3 s_x;        // transform used by the next phase
@@ -323,7 +357,9 @@ __global__ void __launch_bounds__(AL_THREADS) align_fused_kernel(AlignArgs a, Lm
 #pragma unroll
       for (int j = 0; j < NRED; j++) acc[j] = 0.0;
       for (int i = gtid; i < a.ns; i += gstride) linearize_point(a, gp, Tf, T, prm.cap_d2, prm.thr2, i, acc);
+      trace_stamp(prm, tslot);
       grid_reduce<NRED>(acc, s_red, s_tot, a.partials, gs);
+      trace_stamp(prm, tslot);
     }
     int outcome = 0;  // 1: step returned true, 0: LM failed
     if (threadIdx.x == 0) {
@@ -337,7 +373,7 @@ __global__ void __launch_bounds__(AL_THREADS) align_fused_kernel(AlignArgs a, Lm
       if (threadIdx.x == 0) {
         double nb[6];
         for (int i = 0; i < 6; i++) nb[i] = -b6[i];
-        ldlt6_solve(H36, nb, d6);
+        lm_solve(H36, nb, d6);
         delta_from_step(d6, delta);
         iso_mul(delta, x0, xi);
         x0 = xi;
@@ -362,7 +398,7 @@ __global__ void __launch_bounds__(AL_THREADS) align_fused_kernel(AlignArgs a, Lm
           double A[36], nb[6];
           for (int i = 0; i < 36; i++) A[i] = H36[i];
           for (int i = 0; i < 6; i++) { A[i * 7] += lambda; nb[i] = -b6[i]; }
-          ldlt6_solve(A, nb, d6);
+          lm_solve(A, nb, d6);
           delta_from_step(d6, delta);
           iso_mul(delta, x0, xi);
           s_x = xi;
@@ -372,8 +408,11 @@ __global__ void __launch_bounds__(AL_THREADS) align_fused_kernel(AlignArgs a, Lm
         {
           const Iso3 T = s_x;
           double acc[1] = {0.0};
+          trace_stamp(prm, tslot);
           for (int i = gtid; i < a.ns; i += gstride) acc[0] += error_point(a, T, i);
+          trace_stamp(prm, tslot);
           grid_reduce<1>(acc, s_red, s_tot, a.partials, gs);
+          trace_stamp(prm, tslot);
         }
         if (threadIdx.x == 0) {
           n_err++;
@@ -388,7 +427,8 @@ __global__ void __launch_bounds__(AL_THREADS) align_fused_kernel(AlignArgs a, Lm
           } else {
             x0 = xi;
             // std::max(1/3, v) returns 1/3 unless 1/3 < v (same NaN behaviour)
-            const double v = 1.0 - pow(2.0 * rho - 1.0, 3.0);
+            const double w3 = 2.0 * rho - 1.0;
+            const double v = 1.0 - w3 * w3 * w3;
             lambda = lambda * ((1.0 / 3.0 < v) ? v : 1.0 / 3.0);
             for (int i = 0; i < 36; i++) final_H[i] = H36[i];
             dec = 1;
@@ -442,7 +482,7 @@ int align_fused_max_blocks(int device) {
 }
 
 cudaError_t launch_align_fused(const AlignBuffers& ab, const ngicp_params& p, const float* guess16, ngicp_result* res_dev,
-                               unsigned* barrier, int device, cudaStream_t st) {
+                               unsigned* barrier, int device, cudaStream_t st, unsigned long long* trace) {
   int blocks = (ab.ns + AL_THREADS - 1) / AL_THREADS;   // one source point per thread when the grid can hold them
   const int lim = align_fused_max_blocks(device);
   if (blocks > lim) blocks = lim;
@@ -450,6 +490,7 @@ cudaError_t launch_align_fused(const AlignBuffers& ab, const ngicp_params& p, co
   if (blocks < 1) blocks = 1;
   AlignArgs a = make_args(ab, blocks);
   LmParams prm;
+  prm.trace = trace;
   prm.max_iterations = p.max_iterations;
   prm.lm_max_iterations = p.lm_max_iterations;
   prm.optimizer = p.optimizer;

@@ -2,6 +2,7 @@
 // device-resident clouds / covariances with O(1) sharing and swapping, the stepped LM driver, and
 // the import/export of Eigen::Matrix4d covariance records.
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <cmath>
 #include <new>
@@ -248,7 +249,7 @@ int align_stepped(ngicp_t* h, const AlignBuffers& ab, const float* guess16, ngic
     if (p.optimizer == NGICP_OPT_GAUSS_NEWTON) {
       double nb[6];
       for (int i = 0; i < 6; i++) nb[i] = -b6[i];
-      ldlt6_solve(H36, nb, d6);
+      lm_solve(H36, nb, d6);
       delta_from_step(d6, delta);
       iso_mul(delta, x0, xi);
       x0 = xi;
@@ -265,7 +266,7 @@ int align_stepped(ngicp_t* h, const AlignBuffers& ab, const float* guess16, ngic
         double A[36], nb[6];
         memcpy(A, H36, sizeof A);
         for (int i = 0; i < 6; i++) { A[i * 7] += lambda; nb[i] = -b6[i]; }
-        ldlt6_solve(A, nb, d6);
+        lm_solve(A, nb, d6);
         delta_from_step(d6, delta);
         iso_mul(delta, x0, xi);
         iso_to_colmajor16(xi, T16);
@@ -284,7 +285,8 @@ int align_stepped(ngicp_t* h, const AlignBuffers& ab, const float* guess16, ngic
           continue;
         }
         x0 = xi;
-        const double v = 1.0 - pow(2.0 * rho - 1.0, 3.0);
+        const double w3 = 2.0 * rho - 1.0;
+            const double v = 1.0 - w3 * w3 * w3;
         lambda = lambda * ((1.0 / 3.0 < v) ? v : 1.0 / 3.0);
         memcpy(final_H, H36, sizeof final_H);
         ok = true;
@@ -312,6 +314,20 @@ int align_stepped(ngicp_t* h, const AlignBuffers& ab, const float* guess16, ngic
 
 extern "C" {
 
+int ngicp_grid_info(ngicp_t* h, int which, float* cell, int* dims3, int* ncells) {
+  if (!h) return NGICP_E_INVALID;
+  DeviceGuard g(h->device);
+  CloudPtr& c = which == NGICP_SOURCE ? h->src : h->tgt;
+  if (!c || !c->indexed) return fail(h, NGICP_E_STATE, "grid info: no search index");
+  GridDesc d;
+  NG_CUDA(h, cudaMemcpyAsync(&d, c->desc.p, sizeof d, cudaMemcpyDeviceToHost, h->stream->s));
+  NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
+  if (cell) *cell = d.cell;
+  if (dims3) { dims3[0] = d.dim[0]; dims3[1] = d.dim[1]; dims3[2] = d.dim[2]; }
+  if (ncells) *ncells = d.ncells;
+  return NGICP_OK;
+}
+
 unsigned long long ngicp_launch_count(void) { return __atomic_load_n(&ngicp::g_launches, __ATOMIC_RELAXED); }
 
 const char* ngicp_version(void) { return "nanogicp-b200 0.1 sm_100a"; }
@@ -328,7 +344,7 @@ void ngicp_params_default(ngicp_params* p) {
   p->lm_init_lambda_factor = 1e-9;
   p->regularization_method = NGICP_REG_PLANE;
   p->grid_cell_size = 0.f;
-  p->grid_table_cells = 1 << 23;
+  p->grid_table_cells = 1 << 25;
   p->align_mode = NGICP_ALIGN_FUSED;
 }
 
@@ -494,10 +510,24 @@ int ngicp_align(ngicp_t* h, const float* guess16, ngicp_result* out) {
     if (rc) return rc;
   } else {
     ngicp_result* res_dev = h->sc.lm_state.as<ngicp_result>();
-    NG_CUDA(h, launch_align_fused(ab, h->prm, guess16, res_dev, h->sc.barrier.as<unsigned>(), h->device, h->stream->s));
+    static const bool want_trace = getenv("NGICP_ALIGN_TRACE") != nullptr;
+    unsigned long long* trace = nullptr;
+    if (want_trace) {
+      NG_CUDA(h, h->sc.trace.reserve(sizeof(unsigned long long) * 256, h->stream));
+      trace = h->sc.trace.as<unsigned long long>();
+      NG_CUDA(h, cudaMemsetAsync(trace, 0, sizeof(unsigned long long) * 256, h->stream->s));
+    }
+    NG_CUDA(h, launch_align_fused(ab, h->prm, guess16, res_dev, h->sc.barrier.as<unsigned>(), h->device, h->stream->s, trace));
     NG_CUDA(h, cudaMemcpyAsync(h->res_pinned, res_dev, sizeof(ngicp_result), cudaMemcpyDeviceToHost, h->stream->s));
     NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
     *out = *h->res_pinned;
+    if (trace) {
+      unsigned long long t[256];
+      NG_CUDA(h, cudaMemcpy(t, trace, sizeof t, cudaMemcpyDeviceToHost));
+      fprintf(stderr, "[align trace, us since start]");
+      for (unsigned long long i = 1; i <= t[0] && i < 255; i++) fprintf(stderr, " %.1f", (double)(t[i] - t[1]) * 1e-3);
+      fprintf(stderr, "\n");
+    }
   }
   ph_end(h, PH_ALIGN);
   h->lin_valid = true;

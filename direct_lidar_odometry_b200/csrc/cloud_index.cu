@@ -9,6 +9,7 @@
 //                                              x-adjacent cells is ONE contiguous slot range)
 //   desc          GridDesc                    origin, cell edge, dims — computed on the device, no host round trip
 // Algorithmic bytes: 16 n read + 16 n sorted write + 4 n permutation = 36 B/point.
+#include <cstdlib>
 #include "internal.h"
 
 namespace ngicp {
@@ -76,12 +77,11 @@ __global__ void __launch_bounds__(256) pack_bbox_kernel(const unsigned char* __r
   }
 }
 
-// single thread: derive the grid from the bounding box; grow the cell until the dense table fits
-__global__ void grid_setup_kernel(GridDesc* d, float cell_req, int cap, int n) {
+// derive the grid from the bounding box; grow the cell until the dense table fits
+__device__ void grid_setup_device(GridDesc* d, float cell, int cap, int n) {
   float lo[3], hi[3];
   for (int a = 0; a < 3; a++) { lo[a] = ord2f(d->bb_min[a]); hi[a] = ord2f(d->bb_max[a]); }
   if (d->nfinite == 0) { for (int a = 0; a < 3; a++) { lo[a] = 0.f; hi[a] = 0.f; } }
-  float cell = cell_req > 0.f ? cell_req : 1.0f;
   int dim[3];
   for (int it = 0; it < 64; it++) {
     double prod = 1.0;
@@ -93,7 +93,7 @@ __global__ void grid_setup_kernel(GridDesc* d, float cell_req, int cap, int n) {
       prod *= (double)dim[a];
     }
     if (prod <= (double)cap) break;
-    cell *= 2.0f;
+    cell *= 1.25f;
   }
   for (int a = 0; a < 3; a++) { d->origin[a] = lo[a]; d->dim[a] = dim[a]; }
   d->cell = cell;
@@ -102,6 +102,49 @@ __global__ void grid_setup_kernel(GridDesc* d, float cell_req, int cap, int n) {
   d->n = n;
   d->max_dim = max(dim[0], max(dim[1], dim[2]));
   d->margin = cell * (0.01f + 1e-6f * (float)d->max_dim);
+  d->occ_sq = 0ull;
+}
+
+__global__ void grid_setup_kernel(GridDesc* d, float cell, int cap, int n) { grid_setup_device(d, cell, cap, n); }
+
+// Automatic cell edge.  A trial grid (edge c0) has been histogrammed; occ = sum n_c^2 / n is the mean number of
+// points sharing a cell with a point.  LiDAR clouds are surface-like (n_c ~ c^2), so the edge that gives the
+// wanted occupancy is c0 * sqrt(target / occ).
+__global__ void grid_autocell_kernel(GridDesc* d, float c0, float target_occ, int cap, int n) {
+  float cell = c0;
+  if (n > 0 && d->occ_sq > 0ull) {
+    const float occ = (float)((double)d->occ_sq / (double)n);
+    float f = sqrtf(target_occ / occ);
+    f = fminf(fmaxf(f, 0.125f), 2.0f);
+    cell = c0 * f;
+  }
+  grid_setup_device(d, cell, cap, n);
+}
+
+// trial histogram only (no keys)
+__global__ void __launch_bounds__(256) count_points_kernel(const float4* __restrict__ pts, int n, const GridDesc* __restrict__ d, int* __restrict__ cell_count) {
+  const float ox = d->origin[0], oy = d->origin[1], oz = d->origin[2], inv = d->inv_cell;
+  const int dx = d->dim[0], dy = d->dim[1], dz = d->dim[2];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = pts[i];
+    const int cx = cell_coord(p.x, ox, inv, dx), cy = cell_coord(p.y, oy, inv, dy), cz = cell_coord(p.z, oz, inv, dz);
+    atomicAdd(&cell_count[(cz * dy + cy) * dx + cx], 1);
+  }
+}
+
+// sum over points of the population of their trial cell
+__global__ void __launch_bounds__(256) occupancy_kernel(const float4* __restrict__ pts, int n, GridDesc* __restrict__ d, const int* __restrict__ cell_count) {
+  const float ox = d->origin[0], oy = d->origin[1], oz = d->origin[2], inv = d->inv_cell;
+  const int dx = d->dim[0], dy = d->dim[1], dz = d->dim[2];
+  unsigned long long s = 0ull;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = pts[i];
+    const int cx = cell_coord(p.x, ox, inv, dx), cy = cell_coord(p.y, oy, inv, dy), cz = cell_coord(p.z, oz, inv, dz);
+    s += (unsigned long long)cell_count[(cz * dy + cy) * dx + cx];
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(FULL, s, o);
+  if ((threadIdx.x & 31) == 0 && s) atomicAdd(&d->occ_sq, s);
 }
 
 __global__ void __launch_bounds__(256) zero_cells_kernel(int* __restrict__ cell_start, const GridDesc* __restrict__ d) {
@@ -155,6 +198,16 @@ cudaError_t upload_cloud(DevCloud& c, const void* pts, size_t n, size_t stride_b
   return cudaGetLastError();
 }
 
+static float auto_target_occupancy() {
+  static float v = -1.f;
+  if (v < 0.f) {
+    const char* e = getenv("NGICP_TARGET_OCC");
+    v = e ? (float)atof(e) : 8.0f;
+    if (!(v > 0.f)) v = 8.0f;
+  }
+  return v;
+}
+
 static int bits_for(int cap) {
   int b = 1;
   while (b < 31 && (1ll << b) < (long long)cap) b++;
@@ -169,9 +222,22 @@ cudaError_t build_index(DevCloud& c, float cell_req, int table_cap, Scratch& sc,
   if ((e = c.cell_start.alloc(sizeof(int) * ((size_t)table_cap + 1), st)) != cudaSuccess) return e;
   if ((e = c.sorted.alloc(sizeof(float4) * (n ? n : 1), st)) != cudaSuccess) return e;
   GridDesc* d = c.desc.as<GridDesc>();
-  grid_setup_kernel<<<1, 1, 0, st->s>>>(d, cell_req, table_cap, n);
+  if (cell_req > 0.f || n == 0) {
+    grid_setup_kernel<<<1, 1, 0, st->s>>>(d, cell_req > 0.f ? cell_req : 1.0f, table_cap, n);
+    note_launches(1);
+  } else {
+    // two-stage: histogram a coarse trial grid, derive the cell edge from the point-weighted occupancy
+    const float c0 = 1.0f;
+    const int trial_cap = table_cap < (1 << 22) ? table_cap : (1 << 22);
+    grid_setup_kernel<<<1, 1, 0, st->s>>>(d, c0, trial_cap, n);
+    zero_cells_kernel<<<148 * 4, 256, 0, st->s>>>(c.cell_start.as<int>(), d);
+    count_points_kernel<<<grid_for(n), 256, 0, st->s>>>(c.pts.as<float4>(), n, d, c.cell_start.as<int>());
+    occupancy_kernel<<<grid_for(n), 256, 0, st->s>>>(c.pts.as<float4>(), n, d, c.cell_start.as<int>());
+    grid_autocell_kernel<<<1, 1, 0, st->s>>>(d, c0, auto_target_occupancy(), table_cap, n);
+    note_launches(5);
+  }
   zero_cells_kernel<<<148 * 4, 256, 0, st->s>>>(c.cell_start.as<int>(), d);
-  note_launches(2 + (n > 0 ? 2 : 0));
+  note_launches(1 + (n > 0 ? 2 : 0));
   if (n > 0) {
     const size_t nb = sizeof(unsigned) * (size_t)n;
     if ((e = sc.keys_a.reserve(nb, st)) != cudaSuccess) return e;

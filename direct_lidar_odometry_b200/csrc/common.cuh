@@ -31,6 +31,7 @@ struct GridDesc {
   int voverflow;
   int vcount;
   int nfinite;
+  unsigned long long occ_sq;  // sum over points of the population of their (trial) cell
 };
 
 // Read-only view handed to search kernels by value.

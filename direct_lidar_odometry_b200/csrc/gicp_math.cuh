@@ -303,6 +303,53 @@ __host__ __device__ inline void ldlt6_solve(const double* Ain, const double* rhs
 #undef NG_A
 }
 
+// Fast path for the LM system: unpivoted LDL^T of a symmetric positive-definite 6x6 held in registers
+// (fully unrolled).  Returns false when a pivot is not safely positive — the caller then uses the pivoted
+// routine above, which also reproduces Eigen's behaviour on singular systems.
+NG_HD bool ldlt6_solve_spd(const double* A, const double* rhs, double* x) {
+  double L[6][6], D[6];
+  bool ok = true;
+#pragma unroll
+  for (int j = 0; j < 6; j++) {
+    double dj = A[j * 6 + j];
+#pragma unroll
+    for (int k = 0; k < j; k++) dj -= L[j][k] * L[j][k] * D[k];
+    D[j] = dj;
+    ok = ok && (dj > 1e-280) && (dj < 1e280);
+    const double inv = 1.0 / dj;
+#pragma unroll
+    for (int i = j + 1; i < 6; i++) {
+      double v = A[j * 6 + i];   // symmetric: (i,j) == (j,i)
+#pragma unroll
+      for (int k = 0; k < j; k++) v -= L[i][k] * L[j][k] * D[k];
+      L[i][j] = v * inv;
+    }
+  }
+  if (!ok) return false;
+  double y[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    double v = rhs[i];
+#pragma unroll
+    for (int k = 0; k < i; k++) v -= L[i][k] * y[k];
+    y[i] = v;
+  }
+#pragma unroll
+  for (int i = 0; i < 6; i++) y[i] /= D[i];
+#pragma unroll
+  for (int i = 5; i >= 0; i--) {
+    double v = y[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; k++) v -= L[k][i] * x[k];
+    x[i] = v;
+  }
+  return true;
+}
+
+NG_HD void lm_solve(const double* A, const double* rhs, double* x) {
+  if (!ldlt6_solve_spd(A, rhs, x)) ldlt6_solve(A, rhs, x);
+}
+
 // The reduced quantities of one linearisation: 21 upper-triangle H entries, 6 b entries, error.
 constexpr int NRED = 28;
 // index of H(r,c), r<=c, in the packed upper triangle

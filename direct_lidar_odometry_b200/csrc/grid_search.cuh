@@ -115,85 +115,112 @@ struct WarpBest1 {
   }
 };
 
+__device__ __forceinline__ float cube_face_distance(const GridParams& gp, int cx, int cy, int cz, int s, float qx, float qy, float qz) {
+  float m = FLT_MAX;
+  if (cx - s > 0) m = fminf(m, qx - (gp.ox + (float)(cx - s) * gp.cell));
+  if (cx + s + 1 < gp.dx) m = fminf(m, (gp.ox + (float)(cx + s + 1) * gp.cell) - qx);
+  if (cy - s > 0) m = fminf(m, qy - (gp.oy + (float)(cy - s) * gp.cell));
+  if (cy + s + 1 < gp.dy) m = fminf(m, (gp.oy + (float)(cy + s + 1) * gp.cell) - qy);
+  if (cz - s > 0) m = fminf(m, qz - (gp.oz + (float)(cz - s) * gp.cell));
+  if (cz + s + 1 < gp.dz) m = fminf(m, (gp.oz + (float)(cz + s + 1) * gp.cell) - qz);
+  return m - gp.margin;
+}
+
+// scan sorted slots [ra, rb) with the whole warp
+template <class RS>
+__device__ __forceinline__ void scan_range_warp(const GridView& g, int ra, int rb, int lane, float qx, float qy, float qz, RS& rs) {
+  for (int p0 = ra; p0 < rb; p0 += 32) {
+    const int p = p0 + lane;
+    const bool valid = p < rb;
+    float d = FLT_MAX;
+    if (valid) {
+      const float4 c = __ldg(g.sorted + p);
+      d = sqdist_unfused(qx, qy, qz, c.x, c.y, c.z);
+    }
+    rs.offer(valid, d, p);
+  }
+}
+
+// The search grows a cube of cells around the query cell: radius s0 (already scanned, -1 = nothing) ->
+// radius s1.  Each (y,z) row of the new cube is one lane's job: rows outside the old cube contribute the
+// x-run [cx-s1, cx+s1], rows inside it only the two side runs [cx-s1, cx-s0-1] and [cx+s0+1, cx+s1].
+// Radii go 0 (or 1 when `start1`), 1, 2, 3, 4, then grow by 50% per step so that isolated points in
+// sparse regions do not pay O(r^3) single-cell probes.
 template <class RS>
 __device__ __forceinline__ void grid_search_warp(const GridView& g, const GridParams& gp, float qx, float qy, float qz,
-                                                 float cap_d2, RS& rs) {
+                                                 float cap_d2, RS& rs, bool start1 = false) {
   const int lane = threadIdx.x & 31;
   const int cx = cell_coord(qx, gp.ox, gp.inv, gp.dx);
   const int cy = cell_coord(qy, gp.oy, gp.inv, gp.dy);
   const int cz = cell_coord(qz, gp.oz, gp.inv, gp.dz);
   const int rmax = max(max(max(cx, gp.dx - 1 - cx), max(cy, gp.dy - 1 - cy)), max(cz, gp.dz - 1 - cz));
-  for (int s = 0; s <= rmax; ++s) {
-    const int side = 2 * s - 1;
-    const int nfull = s == 0 ? 1 : 8 * s;
-    const int ncap = s == 0 ? 0 : side * side;
-    const int nslots = nfull + 2 * ncap;
-    for (int base = 0; base < nslots; base += 32) {
-      const int slot = base + lane;
-      int a = 0, b = 0;
-      if (slot < nslots) {
-        int yy, zz, x0, x1;
-        if (slot < nfull) {
-          if (s == 0) { yy = 0; zz = 0; }
-          else {
-            const int sd = slot / (2 * s), o = slot - sd * (2 * s);
-            if (sd == 0) { yy = -s + o; zz = -s; }
-            else if (sd == 1) { yy = s; zz = -s + o; }
-            else if (sd == 2) { yy = s - o; zz = s; }
-            else { yy = -s; zz = s - o; }
-          }
-          x0 = cx - s; x1 = cx + s;
-        } else {
-          const int u = slot - nfull;
-          const int v = u >> 1;
-          zz = v / side;
-          yy = v - zz * side - (s - 1);
-          zz -= (s - 1);
-          x0 = x1 = (u & 1) ? cx + s : cx - s;
-        }
+  int s0 = -1;
+  int s1 = start1 ? min(1, rmax) : 0;
+  for (;;) {
+    const int w = 2 * s1 + 1;
+    const int nrows = w * w;
+    const int xlo = max(cx - s1, 0), xhi = min(cx + s1, gp.dx - 1);
+    for (int base = 0; base < nrows; base += 32) {
+      const int r = base + lane;
+      int a1 = 0, b1 = 0, a2 = 0, b2 = 0;
+      if (r < nrows) {
+        const int rz = r / w;
+        const int yy = r - rz * w - s1, zz = rz - s1;
         const int y = cy + yy, z = cz + zz;
-        const int xa = max(x0, 0), xb = min(x1, gp.dx - 1);
-        if (y >= 0 && y < gp.dy && z >= 0 && z < gp.dz && xa <= xb) {
-          const int row = (z * gp.dy + y) * gp.dx;
-          a = __ldg(g.cell_start + row + xa);
-          b = __ldg(g.cell_start + row + xb + 1);
+        if (y >= 0 && y < gp.dy && z >= 0 && z < gp.dz) {
+          const int* row = g.cell_start + (z * gp.dy + y) * gp.dx;
+          if (max(abs(yy), abs(zz)) > s0) {
+            a1 = __ldg(row + xlo);
+            b1 = __ldg(row + xhi + 1);
+          } else {
+            const int xl = cx - s0 - 1, xr = cx + s0 + 1;
+            if (xlo <= xl) { a1 = __ldg(row + xlo); b1 = __ldg(row + xl + 1); }
+            if (xr <= xhi) { a2 = __ldg(row + xr); b2 = __ldg(row + xhi + 1); }
+          }
         }
       }
-      unsigned ne = __ballot_sync(FULL, b > a);
-      while (ne) {
-        const int l = __ffs(ne) - 1;
-        ne &= ne - 1;
-        const int ra = __shfl_sync(FULL, a, l), rb = __shfl_sync(FULL, b, l);
-        for (int p0 = ra; p0 < rb; p0 += 32) {
-          const int p = p0 + lane;
-          const bool valid = p < rb;
-          float d = FLT_MAX;
-          if (valid) {
-            const float4 c = __ldg(g.sorted + p);
-            d = sqdist_unfused(qx, qy, qz, c.x, c.y, c.z);
-          }
-          rs.offer(valid, d, p);
+      // flatten the (mostly short) runs of the 32 rows into one candidate stream: inclusive scan of the run
+      // lengths, then every lane finds the run its candidate index falls into (5-step search over lanes)
+      const int len1 = b1 - a1;
+      const int len = len1 + (b2 - a2);
+      int inc = len;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+      const int total = __shfl_sync(FULL, inc, 31);
+      const int excl = inc - len;
+      for (int t0 = 0; t0 < total; t0 += 32) {
+        const int t = t0 + lane;
+        const bool valid = t < total;
+        int j = 0;
+#pragma unroll
+        for (int step = 16; step > 0; step >>= 1) {
+          const int v = __shfl_sync(FULL, inc, j + step - 1);
+          if (v <= t) j += step;
         }
+        const int off = t - __shfl_sync(FULL, excl, j);
+        const int ja1 = __shfl_sync(FULL, a1, j), jl1 = __shfl_sync(FULL, len1, j), ja2 = __shfl_sync(FULL, a2, j);
+        const int p = off < jl1 ? ja1 + off : ja2 + (off - jl1);
+        float d = FLT_MAX;
+        if (valid) {
+          const float4 c = __ldg(g.sorted + p);
+          d = sqdist_unfused(qx, qy, qz, c.x, c.y, c.z);
+        }
+        rs.offer(valid, d, p);
       }
     }
-    if (s == rmax) break;
-    // distance from the query to the nearest face of the visited cube that still has cells behind it
-    float m = FLT_MAX;
-    if (cx - s > 0) m = fminf(m, qx - (gp.ox + (float)(cx - s) * gp.cell));
-    if (cx + s + 1 < gp.dx) m = fminf(m, (gp.ox + (float)(cx + s + 1) * gp.cell) - qx);
-    if (cy - s > 0) m = fminf(m, qy - (gp.oy + (float)(cy - s) * gp.cell));
-    if (cy + s + 1 < gp.dy) m = fminf(m, (gp.oy + (float)(cy + s + 1) * gp.cell) - qy);
-    if (cz - s > 0) m = fminf(m, qz - (gp.oz + (float)(cz - s) * gp.cell));
-    if (cz + s + 1 < gp.dz) m = fminf(m, (gp.oz + (float)(cz + s + 1) * gp.cell) - qz);
-    m -= gp.margin;
+    if (s1 >= rmax) break;
+    // distance from the query to the nearest face of the scanned cube that still has cells behind it
+    const float m = cube_face_distance(gp, cx, cy, cz, s1, qx, qy, qz);
     if (m > 0.f) {
       const float m2 = m * m * 0.999999f;
       if (cap_d2 <= m2) break;
       if (rs.bound() <= m2) break;
     }
+    s0 = s1;
+    s1 = (s1 < 4) ? s1 + 1 : s1 + (s1 >> 1);
+    if (s1 > rmax) s1 = rmax;
   }
 }
-
 
 // ---------------------------------------------------------------------------------------------
 // 1-NN with ONE THREAD per query (used by the registration kernels, where every source point needs
@@ -212,17 +239,6 @@ __device__ __forceinline__ void nn1_scan_range(const GridView& g, int a, int b, 
   }
 }
 
-__device__ __forceinline__ float cube_face_distance(const GridParams& gp, int cx, int cy, int cz, int s, float qx, float qy, float qz) {
-  float m = FLT_MAX;
-  if (cx - s > 0) m = fminf(m, qx - (gp.ox + (float)(cx - s) * gp.cell));
-  if (cx + s + 1 < gp.dx) m = fminf(m, (gp.ox + (float)(cx + s + 1) * gp.cell) - qx);
-  if (cy - s > 0) m = fminf(m, qy - (gp.oy + (float)(cy - s) * gp.cell));
-  if (cy + s + 1 < gp.dy) m = fminf(m, (gp.oy + (float)(cy + s + 1) * gp.cell) - qy);
-  if (cz - s > 0) m = fminf(m, qz - (gp.oz + (float)(cz - s) * gp.cell));
-  if (cz + s + 1 < gp.dz) m = fminf(m, (gp.oz + (float)(cz + s + 1) * gp.cell) - qz);
-  return m - gp.margin;
-}
-
 __device__ __forceinline__ void grid_nn1_thread(const GridView& g, const GridParams& gp, float qx, float qy, float qz,
                                                 float cap_d2, float& best_d, int& best_p) {
   best_d = FLT_MAX;
@@ -231,45 +247,93 @@ __device__ __forceinline__ void grid_nn1_thread(const GridView& g, const GridPar
   const int cy = cell_coord(qy, gp.oy, gp.inv, gp.dy);
   const int cz = cell_coord(qz, gp.oz, gp.inv, gp.dz);
   const int rmax = max(max(max(cx, gp.dx - 1 - cx), max(cy, gp.dy - 1 - cy)), max(cz, gp.dz - 1 - cz));
-  // cube of radius 1: nine x-runs, ranges loaded first so the table reads overlap
+  // cube of radius 1, cell by cell: the own cell first, then the 26 neighbours, each skipped when even its
+  // nearest face is farther than the best distance so far (exact: margin-shrunk face distances).
   {
-    int ra[9], rb[9];
-    const int xa = max(cx - 1, 0), xb = min(cx + 1, gp.dx - 1);
+    // per-row table entries: e0..e3 bound the cells x-1, x, x+1 (empty when outside the grid)
+    const int e0 = max(cx - 1, 0), e1 = cx, e2 = cx + 1, e3 = min(cx + 2, gp.dx);
+    int v[9][4];
 #pragma unroll
     for (int r = 0; r < 9; ++r) {
       const int y = cy + (r % 3) - 1, z = cz + (r / 3) - 1;
-      ra[r] = 0; rb[r] = 0;
-      if (y >= 0 && y < gp.dy && z >= 0 && z < gp.dz) {
-        const int row = (z * gp.dy + y) * gp.dx;
-        ra[r] = __ldg(g.cell_start + row + xa);
-        rb[r] = __ldg(g.cell_start + row + xb + 1);
+      const bool in = (y >= 0 && y < gp.dy && z >= 0 && z < gp.dz);
+      const int* row = g.cell_start + (in ? (z * gp.dy + y) * gp.dx : 0);
+      v[r][0] = in ? __ldg(row + e0) : 0;
+      v[r][1] = in ? __ldg(row + e1) : 0;
+      v[r][2] = in ? __ldg(row + e2) : 0;
+      v[r][3] = in ? __ldg(row + e3) : 0;
+    }
+    // distances from the query to the faces of its own cell (shrunk by the margin, clamped at 0)
+    const float fx0 = fmaxf(qx - (gp.ox + (float)cx * gp.cell) - gp.margin, 0.f);
+    const float fx1 = fmaxf((gp.ox + (float)(cx + 1) * gp.cell) - qx - gp.margin, 0.f);
+    const float fy0 = fmaxf(qy - (gp.oy + (float)cy * gp.cell) - gp.margin, 0.f);
+    const float fy1 = fmaxf((gp.oy + (float)(cy + 1) * gp.cell) - qy - gp.margin, 0.f);
+    const float fz0 = fmaxf(qz - (gp.oz + (float)cz * gp.cell) - gp.margin, 0.f);
+    const float fz1 = fmaxf((gp.oz + (float)(cz + 1) * gp.cell) - qz - gp.margin, 0.f);
+    const float gx[3] = {fx0 * fx0, 0.f, fx1 * fx1};
+    const float gy[3] = {fy0 * fy0, 0.f, fy1 * fy1};
+    const float gz[3] = {fz0 * fz0, 0.f, fz1 * fz1};
+    nn1_scan_range(g, v[4][1], v[4][2], qx, qy, qz, best_d, best_p);   // own cell
+#pragma unroll
+    for (int r = 0; r < 9; ++r) {
+      const float dyz = gy[r % 3] + gz[r / 3];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (r == 4 && c == 1) continue;
+        const float lb = (dyz + gx[c]) * 0.999999f;
+        if (lb < best_d && lb < cap_d2) nn1_scan_range(g, v[r][c], v[r][c + 1], qx, qy, qz, best_d, best_p);
       }
     }
-#pragma unroll
-    for (int r = 0; r < 9; ++r) nn1_scan_range(g, ra[r], rb[r], qx, qy, qz, best_d, best_p);
   }
-  for (int s = 1; s < rmax; ) {
-    const float m = cube_face_distance(gp, cx, cy, cz, s, qx, qy, qz);
+  // further growth (only when the cell edge is smaller than the cap, or the cap is unbounded): cube s0 -> s0+1,
+  // rows taken 8 at a time so that their table reads overlap, rows and side runs whose nearest point is already
+  // farther than min(best, cap) skipped without touching memory
+  const float fy0 = fmaxf(qy - (gp.oy + (float)cy * gp.cell) - gp.margin, 0.f);
+  const float fy1 = fmaxf((gp.oy + (float)(cy + 1) * gp.cell) - qy - gp.margin, 0.f);
+  const float fz0 = fmaxf(qz - (gp.oz + (float)cz * gp.cell) - gp.margin, 0.f);
+  const float fz1 = fmaxf((gp.oz + (float)(cz + 1) * gp.cell) - qz - gp.margin, 0.f);
+  const float fx0 = fmaxf(qx - (gp.ox + (float)cx * gp.cell) - gp.margin, 0.f);
+  const float fx1 = fmaxf((gp.ox + (float)(cx + 1) * gp.cell) - qx - gp.margin, 0.f);
+  for (int s0 = 1; s0 < rmax; ++s0) {
+    const float m = cube_face_distance(gp, cx, cy, cz, s0, qx, qy, qz);
     if (m > 0.f) {
       const float m2 = m * m * 0.999999f;
       if (cap_d2 <= m2 || best_d <= m2) break;
     }
-    ++s;
-    // shell s: rows with max(|yy|,|zz|) == s in full, the two end cells of the inner rows
-    for (int zz = -s; zz <= s; ++zz) {
-      const int z = cz + zz;
-      if (z < 0 || z >= gp.dz) continue;
-      for (int yy = -s; yy <= s; ++yy) {
-        const int y = cy + yy;
-        if (y < 0 || y >= gp.dy) continue;
-        const int row = (z * gp.dy + y) * gp.dx;
-        if (max(abs(yy), abs(zz)) == s) {
-          const int xa = max(cx - s, 0), xb = min(cx + s, gp.dx - 1);
-          nn1_scan_range(g, __ldg(g.cell_start + row + xa), __ldg(g.cell_start + row + xb + 1), qx, qy, qz, best_d, best_p);
+    const int s1 = s0 + 1;
+    const int w = 2 * s1 + 1, nrows = w * w;
+    const int xlo = max(cx - s1, 0), xhi = min(cx + s1, gp.dx - 1);
+    // lower bounds of the two side runs of an inner row (x distance to the cells cx -/+ s1)
+    const float sxl = fx0 + (float)(s1 - 1) * gp.cell, sxr = fx1 + (float)(s1 - 1) * gp.cell;
+    for (int base = 0; base < nrows; base += 8) {
+      int a1[8], b1[8], a2[8], b2[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        a1[u] = b1[u] = a2[u] = b2[u] = 0;
+        const int r = base + u;
+        if (r >= nrows) continue;
+        const int rz = r / w;
+        const int yy = r - rz * w - s1, zz = rz - s1;
+        const int y = cy + yy, z = cz + zz;
+        if (y < 0 || y >= gp.dy || z < 0 || z >= gp.dz) continue;
+        const float dy = yy == 0 ? 0.f : (yy < 0 ? fy0 + (float)(-yy - 1) * gp.cell : fy1 + (float)(yy - 1) * gp.cell);
+        const float dz = zz == 0 ? 0.f : (zz < 0 ? fz0 + (float)(-zz - 1) * gp.cell : fz1 + (float)(zz - 1) * gp.cell);
+        const float lim = fminf(best_d, cap_d2);
+        const float dyz = (dy * dy + dz * dz) * 0.999999f;
+        if (dyz >= lim) continue;
+        const int* row = g.cell_start + (z * gp.dy + y) * gp.dx;
+        if (max(abs(yy), abs(zz)) == s1) {
+          a1[u] = __ldg(row + xlo);
+          b1[u] = __ldg(row + xhi + 1);
         } else {
-          if (cx - s >= 0) nn1_scan_range(g, __ldg(g.cell_start + row + cx - s), __ldg(g.cell_start + row + cx - s + 1), qx, qy, qz, best_d, best_p);
-          if (cx + s < gp.dx) nn1_scan_range(g, __ldg(g.cell_start + row + cx + s), __ldg(g.cell_start + row + cx + s + 1), qx, qy, qz, best_d, best_p);
+          if (cx - s1 >= 0 && dyz + sxl * sxl * 0.999999f < lim) { a1[u] = __ldg(row + cx - s1); b1[u] = __ldg(row + cx - s1 + 1); }
+          if (cx + s1 < gp.dx && dyz + sxr * sxr * 0.999999f < lim) { a2[u] = __ldg(row + cx + s1); b2[u] = __ldg(row + cx + s1 + 1); }
         }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        nn1_scan_range(g, a1[u], b1[u], qx, qy, qz, best_d, best_p);
+        nn1_scan_range(g, a2[u], b2[u], qx, qy, qz, best_d, best_p);
       }
     }
   }

@@ -84,6 +84,7 @@ struct Scratch {
   DevBuf reduced;    // double[64]
   DevBuf lm_state;   // device-resident LM state / result of the fused kernel
   DevBuf barrier;    // unsigned counters for the grid barrier
+  DevBuf trace;      // debug: %globaltimer stamps of the fused kernel
 };
 
 // number of kernels launched by this library since load (diagnostics; ngicp_launch_count())
@@ -119,7 +120,7 @@ cudaError_t launch_compute_error(const AlignBuffers& ab, const double* T16_colma
 cudaError_t launch_export_mahal(const AlignBuffers& ab, double* out16, cudaStream_t st);
 // the whole LM loop in one persistent cooperative kernel; result written to *res_dev (ngicp_result layout)
 cudaError_t launch_align_fused(const AlignBuffers& ab, const ngicp_params& prm, const float* guess16, ngicp_result* res_dev,
-                               unsigned* barrier, int device, cudaStream_t st);
+                               unsigned* barrier, int device, cudaStream_t st, unsigned long long* trace = nullptr);
 int align_fused_max_blocks(int device);
 
 // ---- voxel.cu -------------------------------------------------------------------------------------

@@ -49,7 +49,7 @@ __global__ void __launch_bounds__(KC_THREADS) knn_lists_kernel(GridView g, int n
     const float4 qp = __ldg(g.sorted + q);
     WarpTopK rs;
     rs.init(k, lane);
-    if (isfinite(qp.x) && isfinite(qp.y) && isfinite(qp.z)) grid_search_warp(g, gp, qp.x, qp.y, qp.z, FLT_MAX, rs);
+    if (isfinite(qp.x) && isfinite(qp.y) && isfinite(qp.z)) grid_search_warp(g, gp, qp.x, qp.y, qp.z, FLT_MAX, rs, k >= 4);
     if (lane < k) nbr[(size_t)q * k + lane] = rs.p;
   }
 }

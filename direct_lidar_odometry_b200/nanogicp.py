@@ -403,6 +403,11 @@ class NanoGICP:
         self._check(self._L.ngicp_voxel_assignment(self._h, a.ctypes.data_as(C.POINTER(C.c_int)), n))
         return a
 
+    def grid_info(self, which: int) -> dict:
+        cell, dims, nc = C.c_float(0), (C.c_int * 3)(), C.c_int(0)
+        self._check(self._L.ngicp_grid_info(self._h, which, C.byref(cell), dims, C.byref(nc)))
+        return {"cell": cell.value, "dims": list(dims), "ncells": nc.value}
+
     # ------------------------------------------------------------------ plumbing
     def set_stream(self, cuda_stream_ptr: int | None):
         self._check(self._L.ngicp_set_stream(self._h, cuda_stream_ptr))

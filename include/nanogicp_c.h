@@ -175,6 +175,9 @@ int ngicp_compute_error(ngicp_t* h, const double* T16, double* err);
 int ngicp_linearize_partial(ngicp_t* h, const double* T16, double* out43);
 int ngicp_compute_error_partial(ngicp_t* h, const double* T16, double* out1);
 
+/* diagnostics: the uniform grid chosen for a cloud's search index (cell edge in metres, dims[3], cell count) */
+int ngicp_grid_info(ngicp_t* h, int which, float* cell, int* dims3, int* ncells);
+
 /* number of CUDA kernels this library has launched since it was loaded (all handles; diagnostics for bench.py) */
 unsigned long long ngicp_launch_count(void);
 
