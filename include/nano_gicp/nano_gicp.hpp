@@ -1,0 +1,362 @@
+// nano_gicp.hpp — drop-in C++ facade: the class surface of the reference's
+// nano_gicp::NanoGICP<PointSource,PointTarget> (reference include/nano_gicp/nano_gicp.hpp:58-137 on top of
+// include/nano_gicp/lsq_registration.hpp:54-116 and pcl::Registration), implemented as a thin forwarder to the C ABI
+// of libnanogicp_b200.so (include/nanogicp_c.h).  OdomNode's call sites (reference src/dlo/odom.cc:100-120,
+// 472-528, 792-852, 1160-1174) compile against it unchanged, including the public members they poke:
+//   gicp.source_kdtree_ = gicp_s2s.source_kdtree_;      -> ngicp_share_source      (no rebuild, no copy)
+//   gicp.source_covs_.clear();                          -> ngicp_clear_covs
+//   gicp.source_covs_   = gicp_s2s.source_covs_;        -> ngicp_share_source_covs (stays in HBM)
+//   keyframe_normals.push_back(gicp_s2s.getSourceCovariances());   host vector materialised on demand
+//   gicp.setTargetCovariances(submap_normals);          -> ngicp_set_target_covs   (H2D of Matrix4d records)
+//
+// Host code only (C++14, no CUDA headers needed).  With PCL and Eigen on the include path their types are
+// used; otherwise the minimal stand-ins of compat/pcl_eigen_min.hpp (same layouts).
+#ifndef NANO_GICP_NANO_GICP_HPP
+#define NANO_GICP_NANO_GICP_HPP
+
+#include <cfloat>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#if defined(__has_include)
+#if __has_include(<pcl/point_cloud.h>) && __has_include(<Eigen/Core>) && !defined(NANO_GICP_B200_FORCE_COMPAT)
+#define NANO_GICP_B200_HAVE_PCL 1
+#endif
+#endif
+#ifdef NANO_GICP_B200_HAVE_PCL
+#include <Eigen/Core>
+#include <Eigen/Geometry>
+#include <pcl/point_cloud.h>
+#include <pcl/point_types.h>
+#else
+#include "compat/pcl_eigen_min.hpp"
+#endif
+
+#include "../nanogicp_c.h"
+
+namespace nano_gicp {
+
+// include/nano_gicp/gicp/gicp_settings.hpp:47
+enum class RegularizationMethod { NONE, MIN_EIG, NORMALIZED_MIN_EIG, PLANE, FROBENIUS };
+// include/nano_gicp/lsq_registration.hpp:54
+enum class LSQ_OPTIMIZER_TYPE { GaussNewton, LevenbergMarquardt };
+
+typedef std::vector<Eigen::Matrix4d, Eigen::aligned_allocator<Eigen::Matrix4d>> CovarianceVectorHost;
+
+namespace detail {
+struct Handle {
+  ngicp_t* h = nullptr;
+  Handle(int device) {
+    int rc = ngicp_create(device, &h);
+    if (rc != NGICP_OK || !h) {
+      std::fprintf(stderr, "[NanoGICP-B200] ngicp_create failed (rc=%d): no CUDA device; this library has no CPU fallback\n", rc);
+      h = nullptr;
+    }
+  }
+  ~Handle() { if (h) ngicp_destroy(h); }
+  Handle(const Handle&) = delete;
+  Handle& operator=(const Handle&) = delete;
+};
+inline void report(ngicp_t* h, int rc, const char* where) {
+  if (rc < 0) std::fprintf(stderr, "[NanoGICP-B200] %s: %s\n", where, h ? ngicp_last_error(h) : "no handle");
+}
+}  // namespace detail
+
+// What `source_covs_` / `target_covs_` are in this build: a vector of Matrix4d that lives in HBM and is
+// mirrored to the host only when somebody reads it.  Assigning one to another shares the device buffer.
+class CovarianceVector {
+ public:
+  CovarianceVector() {}
+  void bind(ngicp_t* h, int which) { h_ = h; which_ = which; }
+
+  size_t size() const { return h_ ? ngicp_covs_size(h_, which_) : 0; }
+  bool empty() const { return size() == 0; }
+  void clear() {
+    if (h_) ngicp_clear_covs(h_, which_);
+    host_valid_ = false;
+  }
+  // device -> device (gicp.source_covs_ = gicp_s2s.source_covs_)
+  CovarianceVector& operator=(const CovarianceVector& o) {
+    if (this == &o || !h_) return *this;
+    if (which_ == NGICP_SOURCE && o.which_ == NGICP_SOURCE && o.h_) detail::report(h_, ngicp_share_source_covs(h_, o.h_), "source_covs_ =");
+    else *this = o.host();
+    host_valid_ = false;
+    return *this;
+  }
+  // host -> device
+  CovarianceVector& operator=(const CovarianceVectorHost& v) {
+    if (!h_) return *this;
+    const double* p = v.empty() ? nullptr : reinterpret_cast<const double*>(v.data());
+    int rc = which_ == NGICP_SOURCE ? ngicp_set_source_covs(h_, p, v.size()) : ngicp_set_target_covs(h_, p, v.size());
+    detail::report(h_, rc, "set covariances");
+    host_valid_ = false;
+    return *this;
+  }
+  // device -> host, on demand
+  const CovarianceVectorHost& host() const {
+    const size_t n = size();
+    if (!host_valid_ || host_.size() != n) {
+      host_.resize(n);
+      if (n) {
+        int rc = which_ == NGICP_SOURCE ? ngicp_get_source_covs(h_, reinterpret_cast<double*>(host_.data()), n)
+                                        : ngicp_get_target_covs(h_, reinterpret_cast<double*>(host_.data()), n);
+        detail::report(h_, rc, "get covariances");
+      }
+      host_valid_ = true;
+    }
+    return host_;
+  }
+  operator const CovarianceVectorHost&() const { return host(); }
+  CovarianceVectorHost::const_iterator begin() const { return host().begin(); }
+  CovarianceVectorHost::const_iterator end() const { return host().end(); }
+  const Eigen::Matrix4d& operator[](size_t i) const { return host()[i]; }
+  void invalidate_host() { host_valid_ = false; }
+  void swap_binding(CovarianceVector& o) { std::swap(host_valid_, o.host_valid_); host_.swap(o.host_); }
+
+ private:
+  ngicp_t* h_ = nullptr;
+  int which_ = NGICP_SOURCE;
+  mutable CovarianceVectorHost host_;
+  mutable bool host_valid_ = false;
+};
+
+}  // namespace nano_gicp
+
+namespace nanoflann {
+// Stand-in for the reference's kd-tree wrapper type (include/nano_gicp/nanoflann.hpp:54-108): in this build the
+// search index is the uniform grid inside the handle; this object only names "the index of that handle's
+// source/target cloud" so that the reference's shared_ptr assignments keep working.
+template <typename PointT>
+class KdTreeFLANN {
+ public:
+  typedef typename pcl::PointCloud<PointT>::ConstPtr PointCloudConstPtr;
+  ngicp_t* owner = nullptr;
+  PointCloudConstPtr cloud;
+  PointCloudConstPtr getInputCloud() const { return cloud; }
+};
+}  // namespace nanoflann
+
+namespace nano_gicp {
+
+// `source_kdtree_` / `target_kdtree_`: behaves like the reference's std::shared_ptr<KdTreeFLANN> for the
+// operations OdomNode performs; assigning another object's source index shares the device index at once.
+template <typename PointT>
+class IndexSlot {
+ public:
+  typedef nanoflann::KdTreeFLANN<PointT> Tree;
+  void bind(ngicp_t* h, int which) { h_ = h; which_ = which; p_.reset(new Tree()); p_->owner = h; }
+  IndexSlot& operator=(const IndexSlot& o) {
+    if (this == &o) return *this;
+    p_ = o.p_;
+    if (h_ && o.h_ && which_ == NGICP_SOURCE && o.which_ == NGICP_SOURCE && h_ != o.h_) detail::report(h_, ngicp_share_source(h_, o.h_), "source_kdtree_ =");
+    return *this;
+  }
+  Tree* operator->() const { return p_.get(); }
+  Tree& operator*() const { return *p_; }
+  Tree* get() const { return p_.get(); }
+  explicit operator bool() const { return (bool)p_; }
+  void reset(Tree* t = nullptr) { p_.reset(t); if (t) t->owner = h_; }
+  void swap(IndexSlot& o) { p_.swap(o.p_); }
+
+ private:
+  std::shared_ptr<Tree> p_;
+  ngicp_t* h_ = nullptr;
+  int which_ = NGICP_SOURCE;
+};
+
+template <typename PointSource, typename PointTarget>
+class NanoGICP {
+ public:
+  using Scalar = float;
+  using Matrix4 = Eigen::Matrix4f;
+  using PointCloudSource = pcl::PointCloud<PointSource>;
+  using PointCloudSourcePtr = typename PointCloudSource::Ptr;
+  using PointCloudSourceConstPtr = typename PointCloudSource::ConstPtr;
+  using PointCloudTarget = pcl::PointCloud<PointTarget>;
+  using PointCloudTargetPtr = typename PointCloudTarget::Ptr;
+  using PointCloudTargetConstPtr = typename PointCloudTarget::ConstPtr;
+
+  EIGEN_MAKE_ALIGNED_OPERATOR_NEW
+
+  explicit NanoGICP(int device = 0) : handle_(new detail::Handle(device)) {
+    ngicp_params_default(&prm_);   // k 20, FLT_MAX, PLANE (nano_gicp_impl.hpp:57-61); 64, 2e-3, 5e-4, LM, 10, 1e-9 (lsq_registration_impl.hpp:52-59)
+    source_kdtree_.bind(h(), NGICP_SOURCE);
+    target_kdtree_.bind(h(), NGICP_TARGET);
+    source_covs_.bind(h(), NGICP_SOURCE);
+    target_covs_.bind(h(), NGICP_TARGET);
+    final_transformation_ = Matrix4::Identity();
+    final_hessian_.setIdentity();
+  }
+  virtual ~NanoGICP() {}
+  NanoGICP(const NanoGICP&) = delete;
+  NanoGICP& operator=(const NanoGICP&) = delete;
+
+  // ---- nano_gicp.hpp:82-84 ----------------------------------------------------------------------
+  void setNumThreads(int) {}   // OpenMP knob; nothing to do on the GPU
+  void setCorrespondenceRandomness(int k) { prm_.k_correspondences = k; push(); }
+  void setRegularizationMethod(RegularizationMethod m) { prm_.regularization_method = (int)m; push(); }
+
+  // ---- pcl::Registration setters used at odom.cc:100-120 -----------------------------------------
+  void setMaxCorrespondenceDistance(double d) { prm_.max_correspondence_distance = d; push(); }
+  void setMaximumIterations(int n) { prm_.max_iterations = n; push(); }
+  void setTransformationEpsilon(double e) { prm_.transformation_epsilon = e; push(); }
+  void setEuclideanFitnessEpsilon(double) {}               // never read by NanoGICP
+  void setRANSACIterations(int) {}
+  void setRANSACOutlierRejectionThreshold(double) {}
+  template <class TreePtr> void setSearchMethodSource(const TreePtr&, bool = false) {}
+  template <class TreePtr> void setSearchMethodTarget(const TreePtr&, bool = false) {}
+  double getMaxCorrespondenceDistance() const { return prm_.max_correspondence_distance; }
+  int getMaximumIterations() const { return prm_.max_iterations; }
+
+  // ---- lsq_registration.hpp:81-85 ---------------------------------------------------------------
+  void setRotationEpsilon(double e) { prm_.rotation_epsilon = e; push(); }
+  void setInitialLambdaFactor(double f) { prm_.lm_init_lambda_factor = f; push(); }
+  void setDebugPrint(bool) {}
+  const Eigen::Matrix<double, 6, 6>& getFinalHessian() const { return final_hessian_; }
+
+  // ---- B200-side knobs ---------------------------------------------------------------------------
+  void setGridCellSize(float c) { prm_.grid_cell_size = c; push(); }
+  void setAlignMode(int mode) { prm_.align_mode = mode; push(); }
+  void setFillOutputCloud(bool f) { fill_output_ = f; }
+  ngicp_t* handle() const { return h(); }
+
+  // ---- clouds (nano_gicp_impl.hpp:90-139) --------------------------------------------------------
+  virtual void swapSourceAndTarget() {
+    input_.swap(target_);
+    source_kdtree_.swap(target_kdtree_);
+    source_covs_.swap_binding(target_covs_);
+    if (h()) ngicp_swap(h());
+  }
+  virtual void clearSource() { input_.reset(); if (h()) ngicp_clear_source(h()); source_covs_.invalidate_host(); }
+  virtual void clearTarget() { target_.reset(); if (h()) ngicp_clear_target(h()); target_covs_.invalidate_host(); }
+
+  virtual void setInputSource(const PointCloudSourceConstPtr& cloud) {
+    if (input_ == cloud) return;
+    if (!check_cloud(cloud, "setInputSource")) return;
+    input_ = cloud;
+    detail::report(h(), ngicp_set_source(h(), cloud->points.data(), cloud->points.size(), sizeof(PointSource)), "setInputSource");
+    source_kdtree_->cloud = cloud;
+    source_covs_.invalidate_host();
+  }
+  virtual void registerInputSource(const PointCloudSourceConstPtr& cloud) {
+    if (input_ == cloud) return;
+    if (!check_cloud(cloud, "setInputSource")) return;
+    input_ = cloud;
+    detail::report(h(), ngicp_register_source(h(), cloud->points.data(), cloud->points.size(), sizeof(PointSource)), "registerInputSource");
+  }
+  virtual void setInputTarget(const PointCloudTargetConstPtr& cloud) {
+    if (target_ == cloud) return;
+    if (!check_cloud(cloud, "setInputTarget")) return;
+    target_ = cloud;
+    detail::report(h(), ngicp_set_target(h(), cloud->points.data(), cloud->points.size(), sizeof(PointTarget)), "setInputTarget");
+    target_kdtree_->cloud = cloud;
+    target_covs_.invalidate_host();
+  }
+  PointCloudSourceConstPtr getInputSource() const { return input_; }
+  PointCloudTargetConstPtr getInputTarget() const { return target_; }
+
+  // ---- covariances (nano_gicp_impl.hpp:141-159) --------------------------------------------------
+  virtual void setSourceCovariances(const CovarianceVectorHost& covs) { source_covs_ = covs; }
+  virtual void setTargetCovariances(const CovarianceVectorHost& covs) { target_covs_ = covs; }
+  virtual bool calculateSourceCovariances() {
+    detail::report(h(), ngicp_calc_source_covs(h()), "calculateSourceCovariances");
+    source_covs_.invalidate_host();
+    return true;
+  }
+  virtual bool calculateTargetCovariances() {
+    detail::report(h(), ngicp_calc_target_covs(h()), "calculateTargetCovariances");
+    target_covs_.invalidate_host();
+    return true;
+  }
+  const CovarianceVectorHost& getSourceCovariances() const { return source_covs_.host(); }
+  const CovarianceVectorHost& getTargetCovariances() const { return target_covs_.host(); }
+
+  // ---- pcl::Registration::align -------------------------------------------------
+  void align(PointCloudSource& output) { align(output, Matrix4::Identity()); }
+  void align(PointCloudSource& output, const Matrix4& guess) {
+    converged_ = false;
+    final_transformation_ = Matrix4::Identity();
+    if (!target_) { std::fprintf(stderr, "[pcl::Registration::align] No input target dataset was given!\n"); return; }
+    if (!input_) { std::fprintf(stderr, "[pcl::Registration::align] No input source dataset was given!\n"); return; }
+    ngicp_result res;
+    int rc = ngicp_align(h(), guess.data(), &res);
+    detail::report(h(), rc, "align");
+    if (rc < 0) return;
+    std::memcpy(final_transformation_.data(), res.final_transformation, sizeof(float) * 16);
+    std::memcpy(final_hessian_.data(), res.final_hessian, sizeof(double) * 36);
+    converged_ = res.converged != 0;
+    nr_iterations_ = res.nr_iterations;
+    last_result_ = res;
+    source_covs_.invalidate_host();   // lazily computed covariances may now exist
+    target_covs_.invalidate_host();
+    if (fill_output_) {
+      // pcl::transformPointCloud(*input_, output, final_transformation_) (lsq_registration_impl.hpp:114)
+      const size_t n = input_->points.size();
+      if (&output != input_.get()) output = *input_;
+      scratch_.resize(n * 4);
+      if (n && ngicp_transform_source(h(), final_transformation_.data(), scratch_.data(), n) == NGICP_OK)
+        for (size_t i = 0; i < n; i++) { output.points[i].x = scratch_[4 * i]; output.points[i].y = scratch_[4 * i + 1]; output.points[i].z = scratch_[4 * i + 2]; }
+    }
+  }
+  Matrix4 getFinalTransformation() const { return final_transformation_; }
+  bool hasConverged() const { return converged_; }
+  const ngicp_result& getLastResult() const { return last_result_; }
+
+ public:
+  // public data members of the reference class (nano_gicp.hpp:121-125)
+  IndexSlot<PointSource> source_kdtree_;
+  IndexSlot<PointTarget> target_kdtree_;
+  CovarianceVector source_covs_;
+  CovarianceVector target_covs_;
+
+ protected:
+  ngicp_t* h() const { return handle_ ? handle_->h : nullptr; }
+  void push() { if (h()) detail::report(h(), ngicp_set_params(h(), &prm_), "set parameter"); }
+  template <class CloudPtr> bool check_cloud(const CloudPtr& c, const char* who) const {
+    if (!c || c->points.empty()) { std::fprintf(stderr, "[pcl::Registration::%s] Invalid or empty point cloud dataset given!\n", who); return false; }
+    return h() != nullptr;
+  }
+
+  std::unique_ptr<detail::Handle> handle_;
+  ngicp_params prm_;
+  PointCloudSourceConstPtr input_;
+  PointCloudTargetConstPtr target_;
+  Matrix4 final_transformation_;
+  Eigen::Matrix<double, 6, 6> final_hessian_;
+  ngicp_result last_result_;
+  bool converged_ = false;
+  int nr_iterations_ = 0;
+  bool fill_output_ = true;
+  std::vector<float> scratch_;
+};
+
+// pcl::VoxelGrid<PointT> with the three calls DLO makes (odom.cc:126-127, 460-463): setLeafSize, setInputCloud, filter
+template <typename PointT>
+class VoxelGrid {
+ public:
+  explicit VoxelGrid(int device = 0) : handle_(new detail::Handle(device)) {}
+  void setLeafSize(float lx, float, float) { leaf_ = lx; }   // DLO always passes (r, r, r)
+  void setInputCloud(const typename pcl::PointCloud<PointT>::ConstPtr& c) { in_ = c; }
+  void filter(pcl::PointCloud<PointT>& out) {
+    if (!in_ || !handle_->h) return;
+    const size_t n = in_->points.size();
+    std::vector<PointT> tmp(n ? n : 1);
+    size_t m = 0;
+    int rc = ngicp_voxel_filter(handle_->h, in_->points.data(), n, sizeof(PointT), leaf_, tmp.data(), tmp.size(), &m);
+    detail::report(handle_->h, rc, "VoxelGrid::filter");
+    if (rc == NGICP_W_VOXEL_OVERFLOW) std::fprintf(stderr, "[pcl::VoxelGrid::applyFilter] Leaf size is too small for the input dataset. Integer indices would overflow.\n");
+    tmp.resize(m);
+    out.points.swap(tmp);
+    out.width = (uint32_t)m; out.height = 1; out.is_dense = true;
+  }
+ private:
+  std::unique_ptr<detail::Handle> handle_;
+  typename pcl::PointCloud<PointT>::ConstPtr in_;
+  float leaf_ = 0.25f;
+};
+
+}  // namespace nano_gicp
+
+#endif
