@@ -25,7 +25,8 @@ EXPORTS = [
     "ngicp_set_source_covs", "ngicp_set_target_covs", "ngicp_clear_covs", "ngicp_covs_size", "ngicp_get_source_covs",
     "ngicp_get_target_covs", "ngicp_align", "ngicp_transform_source", "ngicp_voxel_filter", "ngicp_voxel_assignment",
     "ngicp_knn", "ngicp_linearize", "ngicp_compute_error", "ngicp_linearize_partial", "ngicp_compute_error_partial",
-    "ngicp_version", "ngicp_launch_count", "ngicp_grid_info",
+    "ngicp_version", "ngicp_launch_count", "ngicp_grid_info", "ngicp_set_owner_slab", "ngicp_lm_trial",
+    "ngicp_lm_is_converged",
 ]
 
 
@@ -103,5 +104,8 @@ def load() -> C.CDLL:
     proto("ngicp_version", C.c_char_p)
     proto("ngicp_launch_count", C.c_ulonglong)
     proto("ngicp_grid_info", i32, vp, i32, fp, ip, ip)
+    proto("ngicp_set_owner_slab", i32, vp, i32, f32, f32)
+    proto("ngicp_lm_trial", i32, dp, dp, C.c_double, dp, dp, dp, dp)
+    proto("ngicp_lm_is_converged", i32, dp, C.c_double, C.c_double)
     _LIB = L
     return L

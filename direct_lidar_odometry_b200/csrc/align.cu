@@ -29,8 +29,12 @@ struct AlignArgs {
   const float4* src_pts; const double* src_cov; int ns;
   GridView tgt; const double* tgt_cov;
   double* mahal; int* corr; float* sqd; float4* tgt_pt;
-  double* partials;  // [2][max_blocks][NRED]
+  double* partials;  // [max_blocks][NRED]
   int max_blocks;
+  // sharded-submap mode: this handle only counts source points whose transformed position falls in
+  // [slab_lo, slab_hi) along slab_axis (-1 = no filter); see direct_lidar_odometry_b200/sharded.py
+  int slab_axis;
+  float slab_lo, slab_hi;
 };
 
 __device__ __forceinline__ void make_xforms(const Iso3& x, XformF& f) {
@@ -54,7 +58,12 @@ __device__ __forceinline__ void linearize_point(const AlignArgs& a, const GridPa
   const float qx = xform_row(Tf.m + 0, p.x, p.y, p.z), qy = xform_row(Tf.m + 4, p.x, p.y, p.z), qz = xform_row(Tf.m + 8, p.x, p.y, p.z);
   float my_d = FLT_MAX;
   int my_p = -1;
-  if (isfinite(qx) && isfinite(qy) && isfinite(qz)) grid_nn1_thread(a.tgt, gp, qx, qy, qz, cap_d2, my_d, my_p);
+  bool mine = isfinite(qx) && isfinite(qy) && isfinite(qz);
+  if (a.slab_axis >= 0) {
+    const float qa = a.slab_axis == 0 ? qx : (a.slab_axis == 1 ? qy : qz);
+    mine = mine && qa >= a.slab_lo && qa < a.slab_hi;
+  }
+  if (mine) grid_nn1_thread(a.tgt, gp, qx, qy, qz, cap_d2, my_d, my_p);
   int corr = -1;
   if (my_p >= 0 && (double)my_d < thr2) {
     const float4 tp = __ldg(a.tgt.sorted + my_p);
@@ -162,6 +171,7 @@ static AlignArgs make_args(const AlignBuffers& ab, int blocks_hint) {
   a.tgt = ab.tgt; a.tgt_cov = ab.tgt_cov;
   a.mahal = ab.mahal; a.corr = ab.corr; a.sqd = ab.sqd; a.tgt_pt = ab.tgt_pt;
   a.partials = ab.partials; a.max_blocks = ab.max_blocks;
+  a.slab_axis = ab.slab_axis; a.slab_lo = ab.slab_lo; a.slab_hi = ab.slab_hi;
   (void)blocks_hint;
   return a;
 }

@@ -27,6 +27,8 @@ struct ngicp_handle {
   ngicp_timings tm;
   bool lin_valid = false;               // correspondences_/mahalanobis_ valid for compute_error
   int align_max_blocks = 2048;
+  int slab_axis = -1;
+  float slab_lo = 0.f, slab_hi = 0.f;
 };
 
 namespace ngicp {
@@ -212,6 +214,7 @@ int prepare_align(ngicp_t* h, bool lazy, AlignBuffers& ab) {
   ab.tgt = h->tgt->view(); ab.tgt_cov = h->tgt_cov->c.as<double>(); ab.nt = h->tgt->n;
   ab.mahal = sc.mahal.as<double>(); ab.corr = sc.corr.as<int>(); ab.sqd = sc.sqd.as<float>(); ab.tgt_pt = sc.tgt_pt.as<float4>();
   ab.partials = sc.partials.as<double>(); ab.reduced = sc.reduced.as<double>(); ab.max_blocks = h->align_max_blocks;
+  ab.slab_axis = h->slab_axis; ab.slab_lo = h->slab_lo; ab.slab_hi = h->slab_hi;
   return NGICP_OK;
 }
 
@@ -658,5 +661,34 @@ int ngicp_compute_error_partial(ngicp_t* h, const double* T16, double* out1) {
   return NGICP_OK;
 }
 int ngicp_compute_error(ngicp_t* h, const double* T16, double* err) { return ngicp_compute_error_partial(h, T16, err); }
+
+int ngicp_set_owner_slab(ngicp_t* h, int axis, float lo, float hi) {
+  if (!h || axis < -1 || axis > 2) return NGICP_E_INVALID;
+  h->slab_axis = axis; h->slab_lo = lo; h->slab_hi = hi;
+  h->lin_valid = false;
+  return NGICP_OK;
+}
+
+// host-only scalar side of one LM / GN trial, the same code the fused kernel runs on the device
+int ngicp_lm_trial(const double* H36, const double* b6, double lambda, const double* x0_16, double* d6, double* delta16, double* xi16) {
+  if (!H36 || !b6 || !x0_16 || !d6 || !delta16 || !xi16) return NGICP_E_INVALID;
+  double A[36], nb[6];
+  memcpy(A, H36, sizeof A);
+  for (int i = 0; i < 6; i++) { A[i * 7] += lambda; nb[i] = -b6[i]; }
+  lm_solve(A, nb, d6);
+  Iso3 x0, delta, xi;
+  iso_from_colmajor16(x0_16, x0);
+  delta_from_step(d6, delta);
+  iso_mul(delta, x0, xi);
+  iso_to_colmajor16(delta, delta16);
+  iso_to_colmajor16(xi, xi16);
+  return NGICP_OK;
+}
+int ngicp_lm_is_converged(const double* delta16, double rot_eps, double trans_eps) {
+  if (!delta16) return 0;
+  Iso3 d;
+  iso_from_colmajor16(delta16, d);
+  return lm_is_converged(d, rot_eps, trans_eps) ? 1 : 0;
+}
 
 }  // extern "C"

@@ -113,6 +113,7 @@ struct AlignBuffers {
   GridView tgt; const double* tgt_cov; int nt;
   double* mahal; int* corr; float* sqd; float4* tgt_pt;
   double* partials; double* reduced; int max_blocks;
+  int slab_axis = -1; float slab_lo = 0.f, slab_hi = 0.f;
 };
 // one linearisation at T (row-major R + t as Iso3 passed by value inside); reduced[0..NRED) <- packed H,b,err
 cudaError_t launch_linearize(const AlignBuffers& ab, const double* T16_colmajor, double max_corr_dist, cudaStream_t st);

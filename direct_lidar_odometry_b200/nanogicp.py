@@ -403,6 +403,9 @@ class NanoGICP:
         self._check(self._L.ngicp_voxel_assignment(self._h, a.ctypes.data_as(C.POINTER(C.c_int)), n))
         return a
 
+    def set_owner_slab(self, axis: int, lo: float = 0.0, hi: float = 0.0):
+        self._check(self._L.ngicp_set_owner_slab(self._h, axis, C.c_float(lo), C.c_float(hi)))
+
     def grid_info(self, which: int) -> dict:
         cell, dims, nc = C.c_float(0), (C.c_int * 3)(), C.c_int(0)
         self._check(self._L.ngicp_grid_info(self._h, which, C.byref(cell), dims, C.byref(nc)))

@@ -1,0 +1,162 @@
+"""Multi-GPU host logic for the two ways the NanoGICP path shards.
+
+1. Independent scan pairs: `partition_pairs` gives every rank a contiguous block of pairs; no collective.
+2. One big submap sharded over ranks (`ShardedSubmapAligner`): the target is cut into slabs along its longest axis
+   (equal point counts), every rank holds its slab plus a halo of the max-correspondence distance.  Because a match
+   farther than that distance is discarded anyway (reference include/nano_gicp/impl/nano_gicp_impl.hpp:195), the
+   rank whose slab contains a transformed source point finds exactly the nearest neighbour the unsharded search
+   finds.  Per linearisation every rank contributes the partial {H (36), b (6), err} of the source points it owns,
+   the 43 doubles are all-reduced (one tiny collective per phase: NCCL over NVLink on GPUs, gloo in the CPU tests)
+   and every rank takes the same Levenberg-Marquardt decision (reference impl/lsq_registration_impl.hpp:160-208)
+   from the same numbers.
+
+The per-rank compute is behind a small backend interface; the product backend is `CudaShardBackend` (the C ABI).
+Tests may inject another backend to exercise this host logic on machines without a GPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import numpy as np
+
+from . import _lib
+
+
+def partition_pairs(n_pairs: int, rank: int, world: int) -> range:
+    """Contiguous block partition of `n_pairs` independent registrations; sizes differ by at most one."""
+    base, extra = divmod(n_pairs, world)
+    start = rank * base + min(rank, extra)
+    return range(start, start + base + (1 if rank < extra else 0))
+
+
+def slab_bounds(points: np.ndarray, world: int):
+    """Axis with the largest extent and `world+1` boundaries giving equal point counts; outer bounds are +-inf."""
+    xyz = np.asarray(points)[:, :3]
+    axis = int(np.argmax(xyz.max(0) - xyz.min(0)))
+    q = np.quantile(xyz[:, axis].astype(np.float64), np.linspace(0, 1, world + 1)[1:-1]) if world > 1 else np.array([])
+    bounds = np.concatenate([[-np.inf], q.astype(np.float32).astype(np.float64), [np.inf]])
+    return axis, bounds
+
+
+def shard_target(points: np.ndarray, covs: np.ndarray, rank: int, world: int, halo: float):
+    """This rank's part of the submap: points (and their covariances) inside its slab widened by `halo`."""
+    axis, bounds = slab_bounds(points, world)
+    lo, hi = bounds[rank], bounds[rank + 1]
+    c = np.asarray(points)[:, axis]
+    keep = (c >= lo - halo) & (c < hi + halo)
+    return np.ascontiguousarray(points[keep]), np.ascontiguousarray(np.asarray(covs)[keep]), axis, float(lo), float(hi)
+
+
+class CudaShardBackend:
+    """One NanoGICP handle on this rank's GPU holding one slab of the target."""
+
+    def __init__(self, device: int, **params):
+        from .nanogicp import NanoGICP
+        self.g = NanoGICP(device)
+        self.g.setCorrespondenceRandomness(params.get("k", 20))
+        self.g.setMaxCorrespondenceDistance(params["max_corr_dist"])
+
+    def set_target(self, pts, covs, axis, lo, hi):
+        self.g.clearTarget()
+        self.g.setInputTarget(pts)
+        self.g.setTargetCovariances(covs)
+        f32 = np.finfo(np.float32)
+        self.g.set_owner_slab(axis, float(np.clip(lo, f32.min, f32.max)), float(np.clip(hi, f32.min, f32.max)))
+
+    def set_source(self, pts, covs):
+        self.g.clearSource()
+        self.g.registerInputSource(pts)
+        self.g.setSourceCovariances(covs)
+
+    def linearize_partial(self, T) -> np.ndarray:
+        return self.g.linearize_partial(T)
+
+    def compute_error_partial(self, T) -> float:
+        return float(self.g.compute_error_partial(T)[0])
+
+
+class ShardedSubmapAligner:
+    """Host-stepped LM over a target sharded across the ranks of a torch.distributed process group."""
+
+    def __init__(self, backend, max_corr_dist: float, max_iter: int = 64, trans_eps: float = 5e-4, rot_eps: float = 2e-3,
+                 lm_max_iter: int = 10, lm_init_lambda_factor: float = 1e-9, group=None, device=None):
+        self.be = backend
+        self.max_corr_dist = max_corr_dist
+        self.max_iter, self.trans_eps, self.rot_eps = max_iter, trans_eps, rot_eps
+        self.lm_max_iter, self.lm_init_lambda_factor = lm_max_iter, lm_init_lambda_factor
+        self.group = group
+        self.device = device
+        self._L = _lib.load()   # host-only LM helpers; the library loads without a GPU
+
+    # -- collective: sum of a few doubles over ranks -------------------------------------------------
+    def _allreduce(self, v: np.ndarray) -> np.ndarray:
+        import torch
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            return v
+        t = torch.from_numpy(np.ascontiguousarray(v, dtype=np.float64))
+        if self.device is not None:
+            t = t.to(self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=self.group)
+        return t.cpu().numpy()
+
+    def _trial(self, H, b, lam, x0):
+        dp = C.POINTER(C.c_double)
+        Hc = np.ascontiguousarray(H.T).reshape(36)
+        x0c = np.ascontiguousarray(x0.T).reshape(16)
+        d, delta, xi = np.zeros(6), np.zeros(16), np.zeros(16)
+        self._L.ngicp_lm_trial(Hc.ctypes.data_as(dp), np.ascontiguousarray(b).ctypes.data_as(dp), C.c_double(lam),
+                               x0c.ctypes.data_as(dp), d.ctypes.data_as(dp), delta.ctypes.data_as(dp), xi.ctypes.data_as(dp))
+        return d, delta.reshape(4, 4).T.copy(), xi.reshape(4, 4).T.copy()
+
+    def _converged(self, delta) -> bool:
+        dc = np.ascontiguousarray(delta.T).reshape(16)
+        return bool(self._L.ngicp_lm_is_converged(dc.ctypes.data_as(C.POINTER(C.c_double)), C.c_double(self.rot_eps),
+                                                   C.c_double(self.trans_eps)))
+
+    def linearize(self, T):
+        tot = self._allreduce(np.asarray(self.be.linearize_partial(T), dtype=np.float64))
+        return tot[:36].reshape(6, 6).T.copy(), tot[36:42].copy(), float(tot[42])
+
+    def compute_error(self, T) -> float:
+        return float(self._allreduce(np.array([self.be.compute_error_partial(T)], dtype=np.float64))[0])
+
+    def align(self, guess=None) -> dict:
+        """LsqRegistration::computeTransformation with step_lm (lsq_registration_impl.hpp:89-115,160-208)."""
+        x0 = np.eye(4) if guess is None else np.asarray(guess, dtype=np.float32).astype(np.float64)
+        lam, converged, nr_iterations, n_lin, n_err, lm_failed, y0 = -1.0, False, 0, 0, 0, 0, 0.0
+        final_H = np.eye(6)
+        for it in range(self.max_iter):
+            if converged:
+                break
+            nr_iterations = it
+            H, b, y0 = self.linearize(x0)
+            n_lin += 1
+            if lam < 0.0:
+                lam = self.lm_init_lambda_factor * np.abs(np.diag(H)).max()
+            nu, ok, delta = 2.0, False, np.eye(4)
+            for _ in range(self.lm_max_iter):
+                d, delta, xi = self._trial(H, b, lam, x0)
+                yi = self.compute_error(xi)
+                n_err += 1
+                with np.errstate(invalid="ignore", divide="ignore"):
+                    rho = (y0 - yi) / float(d @ (lam * d - b))
+                if rho < 0:
+                    if self._converged(delta):
+                        ok = True
+                        break
+                    lam, nu = nu * lam, 2 * nu
+                    continue
+                x0 = xi
+                w3 = 2.0 * rho - 1.0
+                v = 1.0 - w3 * w3 * w3
+                lam = lam * (v if 1.0 / 3.0 < v else 1.0 / 3.0)
+                final_H = H
+                ok = True
+                break
+            if not ok:
+                lm_failed = 1
+                break
+            converged = self._converged(delta)
+        return dict(final_x=x0, final_transformation=x0.astype(np.float32), final_hessian=final_H, nr_iterations=nr_iterations,
+                    converged=int(converged), n_linearize=n_lin, n_compute_error=n_err, lm_failed=lm_failed, last_error=y0,
+                    lm_lambda=lam)

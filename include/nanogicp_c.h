@@ -175,6 +175,16 @@ int ngicp_compute_error(ngicp_t* h, const double* T16, double* err);
 int ngicp_linearize_partial(ngicp_t* h, const double* T16, double* out43);
 int ngicp_compute_error_partial(ngicp_t* h, const double* T16, double* out1);
 
+/* sharded-submap mode (one handle per GPU holds one spatial slab of the target plus a halo of the max-correspondence
+ * distance): count only source points whose transformed position lies in [lo, hi) along `axis` (0/1/2; -1 = off) */
+int ngicp_set_owner_slab(ngicp_t* h, int axis, float lo, float hi);
+/* host-only: the scalar side of one LM trial (lsq_registration_impl.hpp:172-179): d = solve(H + lambda I, -b),
+ * delta = [so3_exp(d[0:3]) | d[3:6]], xi = delta * x0 — the same code the fused kernel runs; lambda = 0 gives the
+ * Gauss-Newton step (:147-154).  4x4 matrices column-major. */
+int ngicp_lm_trial(const double* H36, const double* b6, double lambda, const double* x0_16, double* d6, double* delta16, double* xi16);
+/* LsqRegistration::is_converged (lsq_registration_impl.hpp:118-127) */
+int ngicp_lm_is_converged(const double* delta16, double rot_eps, double trans_eps);
+
 /* diagnostics: the uniform grid chosen for a cloud's search index (cell edge in metres, dims[3], cell count) */
 int ngicp_grid_info(ngicp_t* h, int which, float* cell, int* dims3, int* ncells);
 

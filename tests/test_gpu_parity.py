@@ -435,3 +435,46 @@ def test_full_size_submap_properties(G, O):
     covs = g.getTargetCovariances()
     ev = np.linalg.eigvalsh(0.5 * (covs[:, :3, :3] + covs[:, :3, :3].transpose(0, 2, 1)))
     assert np.allclose(ev, [1e-3, 1, 1], atol=1e-8)
+
+
+# ---------------------------------------------------------------------------------------------- sharded submap (one GPU)
+def test_sharded_partials_sum_to_unsharded(G, O, small_submap):
+    """Two slabs of the target on two handles of ONE GPU (ranks emulated sequentially): the summed partial
+    {H,b,err} equal the unsharded linearisation and the host-stepped sharded LM reproduces the fused align."""
+    from direct_lidar_odometry_b200 import sharded
+    submap, scan, T = small_submap
+    thr = 0.5
+    tc = O.Cloud(submap).covariances(20)
+    sc = O.Cloud(scan).covariances(20)
+    guess = synth.perturb_pose(T, (0.2, 0.0, 0.0), 1.0).astype(np.float32)
+    world = 2
+    backs = []
+    for r in range(world):
+        pts, covs, axis, lo, hi = sharded.shard_target(submap, tc, r, world, halo=thr + 0.01)
+        assert pts.shape[0] < submap.shape[0]
+        be = sharded.CudaShardBackend(0, k=20, max_corr_dist=thr)
+        be.set_target(pts, covs, axis, lo, hi)
+        be.set_source(scan, sc)
+        backs.append(be)
+
+    class Both:
+        def linearize_partial(self, T_):
+            return sum(np.asarray(b.linearize_partial(T_)) for b in backs)
+
+        def compute_error_partial(self, T_):
+            return sum(b.compute_error_partial(T_) for b in backs)
+
+    g = G()
+    g.setCorrespondenceRandomness(20); g.setMaxCorrespondenceDistance(thr)
+    g.setMaximumIterations(32); g.setTransformationEpsilon(0.01)
+    g.setInputTarget(submap); g.setTargetCovariances(tc)
+    g.setInputSource(scan); g.setSourceCovariances(sc)
+    whole = g.linearize_partial(np.asarray(guess, dtype=np.float64))
+    parts = Both().linearize_partial(np.asarray(guess, dtype=np.float64))
+    assert np.abs(parts - whole).max() < 1e-9 * np.abs(whole).max()
+    al = sharded.ShardedSubmapAligner(Both(), max_corr_dist=thr, max_iter=32, trans_eps=0.01)
+    res = al.align(guess)
+    g.align(guess)
+    assert (res["nr_iterations"], res["n_linearize"], res["n_compute_error"], res["converged"]) == \
+           (g.result.nr_iterations, g.result.n_linearize, g.result.n_compute_error, g.result.converged)
+    assert np.abs(res["final_x"] - g.final_state()).max() < 1e-9
