@@ -107,7 +107,7 @@ def cpu_step(orc, submap, scan, guess, threads):
 def run_cpu(wl, steps, warmup, rank_scan=0):
     from oracle import oracle as orc
     L = orc.load(prefer_ref=True)
-    threads = L.orc_max_threads()
+    threads = os.cpu_count() or L.orc_max_threads()   # all host cores (torchrun pins OMP_NUM_THREADS=1 in the environment)
     submap, scan, guess = wl["submap"], wl[f"scan_{rank_scan}"], wl["guesses"][rank_scan]
     for _ in range(warmup):
         cpu_step(orc, submap, scan, guess, threads)
@@ -189,6 +189,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--cpu-steps", type=int, default=3, help="bounded CPU-baseline sample (full C2 steps)")
     ap.add_argument("--cell", type=float, default=0.0)
+    ap.add_argument("--table", type=int, default=0, help="grid table capacity in cells (0 = library default)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -226,6 +227,7 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")   # keep stdout to the one JSON line
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     g = NanoGICP(local_rank)
@@ -233,6 +235,8 @@ def main():
     g.setMaximumIterations(S2M["max_iter"]); g.setTransformationEpsilon(S2M["trans_eps"])
     if args.cell > 0:
         g.setGridCellSize(args.cell)
+    if args.table > 0:
+        g.setGridTableCells(args.table)
     if local_rank == 0:
         wl = make_workload(lambda p, leaf: g.voxel_filter(p, leaf), log=lambda *a: print(*a, file=sys.stderr))
     if world > 1:

@@ -10,6 +10,7 @@
 //   desc          GridDesc                    origin, cell edge, dims — computed on the device, no host round trip
 // Algorithmic bytes: 16 n read + 16 n sorted write + 4 n permutation = 36 B/point.
 #include <cstdlib>
+#include <cstdint>
 #include "internal.h"
 
 namespace ngicp {
@@ -148,12 +149,13 @@ __global__ void __launch_bounds__(256) occupancy_kernel(const float4* __restrict
 }
 
 __global__ void __launch_bounds__(256) zero_cells_kernel(int* __restrict__ cell_start, const GridDesc* __restrict__ d) {
-  const int total = d->ncells + 1;
+  const int total = d->ncells + 2;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) cell_start[i] = 0;
 }
 
+// histogram for the counting sort: counts of cell c go to table[c + 1] (see build_index)
 __global__ void __launch_bounds__(256) bin_points_kernel(const float4* __restrict__ pts, int n, const GridDesc* __restrict__ d,
-                                                         unsigned* __restrict__ keys, unsigned* __restrict__ vals, int* __restrict__ cell_count) {
+                                                         unsigned* __restrict__ keys, int* __restrict__ table) {
   const float ox = d->origin[0], oy = d->origin[1], oz = d->origin[2], inv = d->inv_cell;
   const int dx = d->dim[0], dy = d->dim[1], dz = d->dim[2];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -161,17 +163,40 @@ __global__ void __launch_bounds__(256) bin_points_kernel(const float4* __restric
     const int cx = cell_coord(p.x, ox, inv, dx), cy = cell_coord(p.y, oy, inv, dy), cz = cell_coord(p.z, oz, inv, dz);
     const unsigned key = (unsigned)((cz * dy + cy) * dx + cx);
     keys[i] = key;
-    vals[i] = (unsigned)i;
-    atomicAdd(&cell_count[key], 1);
+    atomicAdd(&table[key + 1], 1);
   }
 }
 
-__global__ void __launch_bounds__(256) gather_sorted_kernel(const float4* __restrict__ pts, const unsigned* __restrict__ perm, int n,
-                                                            float4* __restrict__ sorted) {
+// counting-sort scatter: table[c + 1] holds start(c) and is bumped to start(c + 1) by the atomics, which turns
+// `table` into the final lower-bound table; the order inside a cell is whatever the atomics produced ...
+__global__ void __launch_bounds__(256) scatter_points_kernel(const unsigned* __restrict__ keys, int n, int* __restrict__ table,
+                                                             unsigned* __restrict__ slot_orig) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const unsigned o = perm[i];
-    const float4 p = pts[o];
-    sorted[i] = make_float4(p.x, p.y, p.z, __uint_as_float(o));
+    const int pos = atomicAdd(&table[keys[i] + 1], 1);
+    slot_orig[pos] = (unsigned)i;
+  }
+}
+
+// ... and this pass makes it deterministic: every point is moved to (cell start + number of points of its cell
+// with a smaller original index), i.e. cells are ordered by original index exactly like a stable sort would.
+// Fused with the gather of the coordinates.  Cells with more than ORDER_FIX_MAX points keep the scatter order
+// (only the visiting order of equidistant neighbours could depend on it).
+constexpr int ORDER_FIX_MAX = 4096;
+__global__ void __launch_bounds__(256) order_gather_kernel(const float4* __restrict__ pts, const unsigned* __restrict__ keys,
+                                                           const unsigned* __restrict__ slot_orig, int n, const int* __restrict__ table,
+                                                           float4* __restrict__ sorted) {
+  for (int p = blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x) {
+    const unsigned o = slot_orig[p];
+    const unsigned key = keys[o];
+    const int a = table[key], b = table[key + 1];
+    int dst = p;
+    if (b - a <= ORDER_FIX_MAX) {
+      int rank = 0;
+      for (int j = a; j < b; ++j) rank += (slot_orig[j] < o) ? 1 : 0;
+      dst = a + rank;
+    }
+    const float4 v = pts[o];
+    sorted[dst] = make_float4(v.x, v.y, v.z, __uint_as_float(o));
   }
 }
 
@@ -191,9 +216,19 @@ cudaError_t upload_cloud(DevCloud& c, const void* pts, size_t n, size_t stride_b
   note_launches(1);
   if (n == 0) return cudaGetLastError();
   const size_t raw_bytes = (n - 1) * stride_bytes + 12;  // last record may be shorter than the stride
-  if ((e = sc.staging.reserve(raw_bytes + 16, st)) != cudaSuccess) return e;
-  if ((e = cudaMemcpyAsync(sc.staging.p, pts, raw_bytes, cudaMemcpyDefault, st->s)) != cudaSuccess) return e;
-  pack_bbox_kernel<<<grid_for((int)n), 256, 0, st->s>>>(sc.staging.as<unsigned char>(), stride_bytes, (int)n, c.pts.as<float4>(), c.desc.as<GridDesc>());
+  // records already in device memory (16-byte aligned) are read in place; host records go through a staging copy
+  const unsigned char* raw = nullptr;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, pts) == cudaSuccess && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) &&
+      (reinterpret_cast<uintptr_t>(pts) & 15) == 0 && (stride_bytes & 15) == 0 && stride_bytes >= 16) {
+    raw = static_cast<const unsigned char*>(pts);
+  } else {
+    cudaGetLastError();  // clear a possible "invalid value" from probing a plain host pointer
+    if ((e = sc.staging.reserve(raw_bytes + 16, st)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(sc.staging.p, pts, raw_bytes, cudaMemcpyDefault, st->s)) != cudaSuccess) return e;
+    raw = sc.staging.as<unsigned char>();
+  }
+  pack_bbox_kernel<<<grid_for((int)n), 256, 0, st->s>>>(raw, stride_bytes, (int)n, c.pts.as<float4>(), c.desc.as<GridDesc>());
   note_launches(1);
   return cudaGetLastError();
 }
@@ -219,8 +254,10 @@ cudaError_t build_index(DevCloud& c, float cell_req, int table_cap, Scratch& sc,
   const int n = c.n;
   if (table_cap < 64) table_cap = 64;
   c.table_cap = table_cap;
-  if ((e = c.cell_start.alloc(sizeof(int) * ((size_t)table_cap + 1), st)) != cudaSuccess) return e;
+  // table buffer: 3 ints of padding so that &table[1] (where the scan runs) is 16-byte aligned
+  if ((e = c.cell_start.alloc(sizeof(int) * ((size_t)table_cap + 8), st)) != cudaSuccess) return e;
   if ((e = c.sorted.alloc(sizeof(float4) * (n ? n : 1), st)) != cudaSuccess) return e;
+  int* table = c.cell_start.as<int>() + 3;
   GridDesc* d = c.desc.as<GridDesc>();
   if (cell_req > 0.f || n == 0) {
     grid_setup_kernel<<<1, 1, 0, st->s>>>(d, cell_req > 0.f ? cell_req : 1.0f, table_cap, n);
@@ -230,31 +267,26 @@ cudaError_t build_index(DevCloud& c, float cell_req, int table_cap, Scratch& sc,
     const float c0 = 1.0f;
     const int trial_cap = table_cap < (1 << 22) ? table_cap : (1 << 22);
     grid_setup_kernel<<<1, 1, 0, st->s>>>(d, c0, trial_cap, n);
-    zero_cells_kernel<<<148 * 4, 256, 0, st->s>>>(c.cell_start.as<int>(), d);
-    count_points_kernel<<<grid_for(n), 256, 0, st->s>>>(c.pts.as<float4>(), n, d, c.cell_start.as<int>());
-    occupancy_kernel<<<grid_for(n), 256, 0, st->s>>>(c.pts.as<float4>(), n, d, c.cell_start.as<int>());
+    zero_cells_kernel<<<148 * 4, 256, 0, st->s>>>(table, d);
+    count_points_kernel<<<grid_for(n), 256, 0, st->s>>>(c.pts.as<float4>(), n, d, table);
+    occupancy_kernel<<<grid_for(n), 256, 0, st->s>>>(c.pts.as<float4>(), n, d, table);
     grid_autocell_kernel<<<1, 1, 0, st->s>>>(d, c0, auto_target_occupancy(), table_cap, n);
     note_launches(5);
   }
-  zero_cells_kernel<<<148 * 4, 256, 0, st->s>>>(c.cell_start.as<int>(), d);
-  note_launches(1 + (n > 0 ? 2 : 0));
+  zero_cells_kernel<<<148 * 4, 256, 0, st->s>>>(table, d);
+  note_launches(1);
+  if ((e = sc.tile_sums.reserve(sizeof(int) * scan_scratch_ints(table_cap + 1), st)) != cudaSuccess) return e;
   if (n > 0) {
     const size_t nb = sizeof(unsigned) * (size_t)n;
     if ((e = sc.keys_a.reserve(nb, st)) != cudaSuccess) return e;
-    if ((e = sc.keys_b.reserve(nb, st)) != cudaSuccess) return e;
     if ((e = sc.vals_a.reserve(nb, st)) != cudaSuccess) return e;
-    if ((e = sc.vals_b.reserve(nb, st)) != cudaSuccess) return e;
-    if ((e = sc.hist.reserve(sizeof(int) * radix_sort_scratch_ints(n), st)) != cudaSuccess) return e;
-    bin_points_kernel<<<grid_for(n), 256, 0, st->s>>>(c.pts.as<float4>(), n, d, sc.keys_a.as<unsigned>(), sc.vals_a.as<unsigned>(), c.cell_start.as<int>());
-  }
-  if ((e = sc.tile_sums.reserve(sizeof(int) * scan_scratch_ints(table_cap + 1), st)) != cudaSuccess) return e;
-  // counts -> lower-bound table (exclusive scan over ncells+1 entries; ncells is read from the descriptor)
-  exclusive_scan_inplace(c.cell_start.as<int>(), &d->ncells, 1, table_cap + 1, sc.tile_sums.as<int>(), st->s);
-  if (n > 0) {
-    const int where = radix_sort_pairs(sc.keys_a.as<unsigned>(), sc.vals_a.as<unsigned>(), sc.keys_b.as<unsigned>(), sc.vals_b.as<unsigned>(),
-                                       n, bits_for(table_cap), sc.hist.as<int>(), st->s);
-    const unsigned* perm = where ? sc.vals_b.as<unsigned>() : sc.vals_a.as<unsigned>();
-    gather_sorted_kernel<<<grid_for(n), 256, 0, st->s>>>(c.pts.as<float4>(), perm, n, c.sorted.as<float4>());
+    // counting sort: histogram at table[c+1] -> exclusive scan (table[c+1] = start(c)) -> atomic scatter (table becomes
+    // the lower-bound table) -> deterministic in-cell order + gather
+    bin_points_kernel<<<grid_for(n), 256, 0, st->s>>>(c.pts.as<float4>(), n, d, sc.keys_a.as<unsigned>(), table);
+    exclusive_scan_inplace(table + 1, &d->ncells, 0, table_cap, sc.tile_sums.as<int>(), st->s);
+    scatter_points_kernel<<<grid_for(n), 256, 0, st->s>>>(sc.keys_a.as<unsigned>(), n, table, sc.vals_a.as<unsigned>());
+    order_gather_kernel<<<grid_for(n, 256, 148 * 16), 256, 0, st->s>>>(c.pts.as<float4>(), sc.keys_a.as<unsigned>(), sc.vals_a.as<unsigned>(), n, table, c.sorted.as<float4>());
+    note_launches(3);
   }
   c.indexed = true;
   return cudaGetLastError();

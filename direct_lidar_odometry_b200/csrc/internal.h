@@ -49,7 +49,7 @@ struct DevCloud {
   int table_cap = 0;
   GridView view() const {
     GridView v;
-    v.cell_start = cell_start.as<int>();
+    v.cell_start = cell_start.as<int>() + 3;   // see build_index: 3 ints of alignment padding
     v.sorted = sorted.as<float4>();
     v.desc = desc.as<GridDesc>();
     return v;

@@ -3,6 +3,7 @@
 //   * stable LSD radix sort of (uint32 key, uint32 value) pairs, 8 bits per pass
 // Stability matters: it makes "ascending original index inside a cell/voxel" the deterministic
 // within-bucket order (pcl::VoxelGrid's own sort is unstable).
+#include <cstdint>
 #include "internal.h"
 
 namespace ngicp {
@@ -35,11 +36,17 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_tile_sums(const int* __rest
   __shared__ int sm[8];
   const int n = *n_ptr + n_add;
   const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  const bool vec = (reinterpret_cast<uintptr_t>(data) & 15) == 0;
   for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int base = t * SCAN_TILE + threadIdx.x * SCAN_IPT;
     int s = 0;
+    if (vec && base + SCAN_IPT <= n) {
+      const int4 a = *reinterpret_cast<const int4*>(data + base), b = *reinterpret_cast<const int4*>(data + base + 4);
+      s = (a.x + a.y) + (a.z + a.w) + (b.x + b.y) + (b.z + b.w);
+    } else {
 #pragma unroll
-    for (int j = 0; j < SCAN_IPT; j++) s += (base + j < n) ? data[base + j] : 0;
+      for (int j = 0; j < SCAN_IPT; j++) s += (base + j < n) ? data[base + j] : 0;
+    }
     int total;
     block_exclusive_scan_256(s, sm, total);
     if (threadIdx.x == 0) tile_sums[t] = total;
@@ -84,16 +91,33 @@ __global__ void __launch_bounds__(SCAN_THREADS) scan_apply(int* __restrict__ dat
   __shared__ int sm[8];
   const int n = *n_ptr + n_add;
   const int ntiles = (n + SCAN_TILE - 1) / SCAN_TILE;
+  const bool vec = (reinterpret_cast<uintptr_t>(data) & 15) == 0;
   for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
     const int base = t * SCAN_TILE + threadIdx.x * SCAN_IPT;
     int v[SCAN_IPT];
     int s = 0;
+    const bool full = vec && base + SCAN_IPT <= n;
+    if (full) {
+      const int4 a = *reinterpret_cast<const int4*>(data + base), b = *reinterpret_cast<const int4*>(data + base + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
 #pragma unroll
-    for (int j = 0; j < SCAN_IPT; j++) { v[j] = (base + j < n) ? data[base + j] : 0; s += v[j]; }
+      for (int j = 0; j < SCAN_IPT; j++) s += v[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < SCAN_IPT; j++) { v[j] = (base + j < n) ? data[base + j] : 0; s += v[j]; }
+    }
     int total;
     int off = block_exclusive_scan_256(s, sm, total) + tile_sums[t];
+    if (full) {
+      int o[SCAN_IPT];
 #pragma unroll
-    for (int j = 0; j < SCAN_IPT; j++) { if (base + j < n) data[base + j] = off; off += v[j]; }
+      for (int j = 0; j < SCAN_IPT; j++) { o[j] = off; off += v[j]; }
+      *reinterpret_cast<int4*>(data + base) = make_int4(o[0], o[1], o[2], o[3]);
+      *reinterpret_cast<int4*>(data + base + 4) = make_int4(o[4], o[5], o[6], o[7]);
+    } else {
+#pragma unroll
+      for (int j = 0; j < SCAN_IPT; j++) { if (base + j < n) data[base + j] = off; off += v[j]; }
+    }
   }
 }
 
