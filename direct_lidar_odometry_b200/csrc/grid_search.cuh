@@ -164,8 +164,10 @@ __device__ __forceinline__ void grid_search_warp(const GridView& g, const GridPa
       const int r = base + lane;
       int a1 = 0, b1 = 0, a2 = 0, b2 = 0;
       if (r < nrows) {
-        const int rz = r / w;
-        const int yy = r - rz * w - s1, zz = rz - s1;
+        // first 3x3 step: own row first, then the edge-adjacent rows, then the corners (tighter bound earlier)
+        const int rr = (s0 < 0 && s1 == 1) ? (int)((0x620837154ULL >> (4 * r)) & 15ULL) : r;
+        const int rz = rr / w;
+        const int yy = rr - rz * w - s1, zz = rz - s1;
         const int y = cy + yy, z = cz + zz;
         if (y >= 0 && y < gp.dy && z >= 0 && z < gp.dz) {
           const int* row = g.cell_start + (z * gp.dy + y) * gp.dx;
