@@ -1,0 +1,330 @@
+#!/usr/bin/env python
+"""Secondary benchmarks for the other BASELINE.json configs (bench.py is the headline C2 run):
+
+  c1  single OS1-64-like scan pair, S2S align (shipped DLO cfg and library defaults), GPU vs CPU oracle
+  c3  odometry replay: the OdomNode S2S + S2M + keyframe/submap sequence over a synthetic trajectory
+  c4  independent scan-pair batch throughput (pairs/s), several handles/streams per GPU; under torchrun the pairs
+      are partitioned over ranks (direct_lidar_odometry_b200.sharded.partition_pairs)
+
+    python benchmarks/configs.py c1
+    python benchmarks/configs.py c3 --scans 300 --cpu-scans 40
+    python benchmarks/configs.py c4 --pairs 512 --handles 8
+
+Prints one JSON object per config.  Scan generation (numpy ray casting) is parallelised over host processes.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import time
+from concurrent.futures import ProcessPoolExecutor, ThreadPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from direct_lidar_odometry_b200 import synth  # noqa: E402
+
+S2S = dict(k=10, thr=1.0, max_iter=32, trans_eps=0.01)     # cfg/params.yaml:54-58
+S2M = dict(k=20, thr=0.5, max_iter=32, trans_eps=0.01)     # cfg/params.yaml:63-67
+DEFAULTS = dict(k=20, thr=float(np.finfo(np.float32).max), max_iter=64, trans_eps=5e-4)
+
+
+def _gen(i):
+    T = synth.trajectory_pose(i)
+    return i, T, synth.crop_box_negative(synth.os1_like(i, T))
+
+
+def gen_scans(indices):
+    with ProcessPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
+        out = list(ex.map(_gen, indices, chunksize=4))
+    return {i: (T, s) for i, T, s in out}
+
+
+def configure(g, cfg):
+    g.setCorrespondenceRandomness(cfg["k"]); g.setMaxCorrespondenceDistance(cfg["thr"])
+    g.setMaximumIterations(cfg["max_iter"]); g.setTransformationEpsilon(cfg["trans_eps"])
+
+
+def pose_err(Ta, Tb):
+    dt = float(np.linalg.norm(np.asarray(Ta, float)[:3, 3] - np.asarray(Tb, float)[:3, 3]))
+    dR = np.asarray(Ta, float)[:3, :3].T @ np.asarray(Tb, float)[:3, :3]
+    return dt, float(np.arccos(np.clip((np.trace(dR) - 1) / 2, -1, 1)))
+
+
+# ------------------------------------------------------------------------------------------------ C1
+def run_c1(args):
+    import torch
+    from direct_lidar_odometry_b200 import NanoGICP
+    from oracle import oracle as O
+    scans = gen_scans([0, 1])
+    (T0, s0), (T1, s1) = scans[0], scans[1]
+    truth = np.linalg.inv(T0) @ T1
+    out = {"config": "C1: single OS1-64-like scan pair, voxel 0.25 m, S2S align", "raw_points": [int(s0.shape[0]), int(s1.shape[0])]}
+    g = NanoGICP(0)
+    threads = os.cpu_count()
+    for name, cfg in (("dlo_s2s_cfg", S2S), ("library_defaults", DEFAULTS)):
+        configure(g, cfg)
+
+        def gpu_once():
+            g.clearSource(); g.clearTarget()
+            t0 = time.perf_counter()
+            v0 = g.voxel_filter(s0, 0.25); v1 = g.voxel_filter(s1, 0.25)
+            t1 = time.perf_counter()
+            g.setInputTarget(v0); g.calculateTargetCovariances()
+            g.setInputSource(v1); g.calculateSourceCovariances()
+            g.sync()
+            t2 = time.perf_counter()
+            g.align()
+            t3 = time.perf_counter()
+            return v0, v1, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3
+        for _ in range(5):
+            gpu_once()
+        reps = [gpu_once() for _ in range(20)]
+        v0, v1 = reps[0][0], reps[0][1]
+        tm = g.timings()
+        gpu = {"voxel_ms": float(np.median([r[2] for r in reps])), "index_and_covs_ms": float(np.median([r[3] for r in reps])),
+               "align_ms": float(np.median([r[4] for r in reps])), "align_kernel_ms": tm["align_ms"],
+               "iterations": int(g.result.nr_iterations), "trials": int(g.result.n_compute_error)}
+        gpu["total_ms"] = gpu["voxel_ms"] + gpu["index_and_covs_ms"] + gpu["align_ms"]
+
+        def cpu_once():
+            t0 = time.perf_counter()
+            c0 = O.voxel_filter(s0, 0.25); c1 = O.voxel_filter(s1, 0.25)
+            t1 = time.perf_counter()
+            tgt, src = O.Cloud(c0), O.Cloud(c1)
+            o = O.Gicp(k=cfg["k"], max_corr_dist=cfg["thr"], max_iter=cfg["max_iter"], trans_eps=cfg["trans_eps"], num_threads=threads)
+            o.set_target(tgt); o.set_source(src)
+            o.calc_target_covs(); o.calc_source_covs()
+            t2 = time.perf_counter()
+            r = o.align()
+            t3 = time.perf_counter()
+            return r, (t1 - t0) * 1e3, (t2 - t1) * 1e3, (t3 - t2) * 1e3
+        cpu_once()
+        creps = [cpu_once() for _ in range(10)]
+        r = creps[0][0]
+        cpu = {"voxel_ms": float(np.median([c[1] for c in creps])), "index_and_covs_ms": float(np.median([c[2] for c in creps])),
+               "align_ms": float(np.median([c[3] for c in creps])), "iterations": int(r.nr_iterations), "trials": int(r.n_compute_error),
+               "threads": threads}
+        cpu["total_ms"] = cpu["voxel_ms"] + cpu["index_and_covs_ms"] + cpu["align_ms"]
+        dt, dr = pose_err(g.final_state(), r.Tx())
+        et, er = pose_err(g.final_state(), truth)
+        out[name] = {"points": [int(v0.shape[0]), int(v1.shape[0])], "gpu": gpu, "cpu": cpu,
+                     "speedup_align": cpu["align_ms"] / gpu["align_ms"], "speedup_total": cpu["total_ms"] / gpu["total_ms"],
+                     "gpu_vs_cpu_pose": {"dt_m": dt, "dr_rad": dr}, "error_vs_truth": {"dt_m": et, "dr_rad": er}}
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------ C3
+class Replay:
+    """OdomNode's per-scan sequence (reference src/dlo/odom.cc:629-697) with the submap chosen as the `knn` nearest
+    keyframes (hull-based selection is out of scope).  `make()` builds a registration object."""
+
+    def __init__(self, make, voxel, get_T, thresh_d=5.0, knn=10):
+        self.s2s, self.s2m = make(S2S), make(S2M)
+        self.voxel, self.get_T = voxel, get_T
+        self.thresh_d, self.knn = thresh_d, knn
+        self.keyframes = []   # (position, cloud, covs)
+        self.prev_set = None
+        self.T = None
+
+    def first(self, scan, T0):
+        self.T = T0.astype(np.float32)
+        self.T_prev = self.T.copy()
+        self.s2s.setInputTarget(scan); self.s2s.calculateTargetCovariances()
+        self._add_keyframe(scan)
+
+    def _add_keyframe(self, scan):
+        kf = self.voxel(synth.transform_xyzi(scan, self.T), 0.5)
+        self.s2s.setInputSource(kf); self.s2s.calculateSourceCovariances()
+        self.keyframes.append((self.T[:3, 3].copy(), kf, self.s2s.getSourceCovariances()))
+
+    def step(self, scan):
+        self.s2s.setInputSource(scan)
+        self.s2m.registerInputSource(scan)
+        self.s2m.source_kdtree_ = self.s2s.source_kdtree_
+        self.s2m.source_covs_.clear()
+        self.s2s.align()
+        it_s2s = self.s2s.nr_iterations_
+        T_s2s = self.T_prev @ self.s2s.getFinalTransformation()
+        self.s2m.source_covs_ = self.s2s.source_covs_
+        self.s2s.swapSourceAndTarget()
+        d = [np.linalg.norm(T_s2s[:3, 3] - kf[0]) for kf in self.keyframes]
+        sel = tuple(sorted(np.argsort(d)[: self.knn].tolist()))
+        if sel != self.prev_set:
+            self.submap = np.ascontiguousarray(np.vstack([self.keyframes[i][1] for i in sel]))
+            self.submap_covs = np.concatenate([self.keyframes[i][2] for i in sel])
+            self.s2m.setInputTarget(self.submap); self.s2m.setTargetCovariances(self.submap_covs)
+            self.prev_set = sel
+        self.s2m.align(T_s2s)
+        self.T = self.s2m.getFinalTransformation()
+        self.T_prev = self.T
+        if min(np.linalg.norm(self.T[:3, 3] - kf[0]) for kf in self.keyframes) > self.thresh_d:
+            self._add_keyframe(scan)
+        return it_s2s, self.s2m.nr_iterations_
+
+
+class OracleGicp:
+    """Adapter giving the CPU oracle the method names Replay uses."""
+
+    def __init__(self, O, cfg, threads):
+        self.O, self.g = O, O.Gicp(k=cfg["k"], max_corr_dist=cfg["thr"], max_iter=cfg["max_iter"], trans_eps=cfg["trans_eps"], num_threads=threads)
+        self.nr_iterations_ = 0
+        self._src = self._tgt = None
+
+    def setInputTarget(self, c): self._tgt = self.O.Cloud(c); self.g.set_target(self._tgt)
+    def setInputSource(self, c): self._src = self.O.Cloud(c); self.g.set_source(self._src)
+    def registerInputSource(self, c): self._src = self.O.Cloud(c, build_index=False); self.g.set_source(self._src)
+    def calculateTargetCovariances(self): self.g.calc_target_covs()
+    def calculateSourceCovariances(self): self.g.calc_source_covs()
+    def getSourceCovariances(self): return self.g.get_source_covs()
+    def setTargetCovariances(self, c): self.g.set_target_covs(c)
+    def swapSourceAndTarget(self): self.g.swap(); self._src, self._tgt = self._tgt, self._src
+
+    class _Covs:
+        def __init__(self, outer): self.o = outer
+        def clear(self): self.o.g.set_source_covs(np.zeros((0, 4, 4)))
+
+    @property
+    def source_covs_(self): return OracleGicp._Covs(self)
+    @source_covs_.setter
+    def source_covs_(self, v): self.g.set_source_covs(v.o.g.get_source_covs() if isinstance(v, OracleGicp._Covs) else v)
+    @property
+    def source_kdtree_(self): return None
+    @source_kdtree_.setter
+    def source_kdtree_(self, v): pass
+
+    def align(self, guess=None):
+        self._r = self.g.align(guess)
+        self.nr_iterations_ = self._r.nr_iterations
+    def getFinalTransformation(self): return self._r.T()
+
+
+def run_c3(args):
+    from direct_lidar_odometry_b200 import NanoGICP
+    from oracle import oracle as O
+    idx = list(range(args.scans))
+    t0 = time.time()
+    scans = gen_scans(idx)
+    gen_s = time.time() - t0
+    vox = NanoGICP(0)
+
+    def make_gpu(cfg):
+        g = NanoGICP(0)
+        configure(g, cfg)
+        return g
+    rp = Replay(make_gpu, lambda p, l: vox.voxel_filter(p, l), None)
+    ms, iters, errs = [], [], []
+    for i in idx:
+        T_true, raw = scans[i]
+        t1 = time.perf_counter()
+        scan = vox.voxel_filter(raw, 0.25)        # preprocessPoints: vf_scan (crop box applied by the generator)
+        if i == 0:
+            rp.first(scan, T_true)
+            continue
+        its = rp.step(scan)
+        ms.append((time.perf_counter() - t1) * 1e3)
+        iters.append(its)
+        errs.append(pose_err(rp.T, T_true))
+    ms = np.array(ms)
+    out = {"config": f"C3: odometry replay, {args.scans} synthetic OS1-64 scans (S2S + S2M + keyframes every 5 m, knn-{rp.knn} submap)",
+           "gpu": {"ms_per_scan_mean": float(ms.mean()), "ms_per_scan_p50": float(np.percentile(ms, 50)), "ms_per_scan_p99": float(np.percentile(ms, 99)),
+                   "keyframes": len(rp.keyframes), "final_translation_error_m": errs[-1][0], "max_translation_error_m": float(max(e[0] for e in errs)),
+                   "max_rotation_error_rad": float(max(e[1] for e in errs)), "mean_iterations_s2s": float(np.mean([i[0] for i in iters])),
+                   "mean_iterations_s2m": float(np.mean([i[1] for i in iters]))},
+           "scan_generation_s": gen_s}
+    # CPU oracle over the first --cpu-scans scans with the same sequence: timing + iteration-count / pose parity
+    n_cpu = min(args.cpu_scans, args.scans)
+    if n_cpu > 1:
+        threads = os.cpu_count()
+        rc = Replay(lambda cfg: OracleGicp(O, cfg, threads), lambda p, l: O.voxel_filter(p, l), None)
+        cms, same_iters, dpose = [], 0, []
+        rg = Replay(make_gpu, lambda p, l: vox.voxel_filter(p, l), None)
+        for i in range(n_cpu):
+            T_true, raw = scans[i]
+            t1 = time.perf_counter()
+            scan = O.voxel_filter(raw, 0.25)
+            if i == 0:
+                rc.first(scan, T_true); rg.first(vox.voxel_filter(raw, 0.25), T_true)
+                continue
+            ic = rc.step(scan)
+            cms.append((time.perf_counter() - t1) * 1e3)
+            ig = rg.step(vox.voxel_filter(raw, 0.25))
+            same_iters += int(tuple(ic) == tuple(ig))
+            dpose.append(pose_err(rc.T, rg.T))
+        out["cpu"] = {"scans": n_cpu, "threads": threads, "ms_per_scan_mean": float(np.mean(cms)),
+                      "identical_iteration_counts": f"{same_iters}/{n_cpu - 1}", "max_gpu_vs_cpu_dt_m": float(max(d[0] for d in dpose)),
+                      "max_gpu_vs_cpu_dr_rad": float(max(d[1] for d in dpose))}
+        out["speedup_ms_per_scan"] = out["cpu"]["ms_per_scan_mean"] / float(ms[: n_cpu - 1].mean())
+    print(json.dumps(out))
+
+
+# ------------------------------------------------------------------------------------------------ C4
+def run_c4(args):
+    import torch
+    from direct_lidar_odometry_b200 import NanoGICP, sharded
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    # a pool of distinct pre-voxelised scans; pair i registers scan (i+1) against scan i of the pool (cyclic)
+    pool_n = args.pool
+    scans = gen_scans(list(range(0, pool_n * 3, 3)))
+    vox = NanoGICP(local)
+    pool = [vox.voxel_filter(scans[i][1], 0.25) for i in sorted(scans)]
+    dev = torch.device("cuda", local)
+    pool_d = [torch.from_numpy(p).to(dev) for p in pool]
+    mine = sharded.partition_pairs(args.pairs, rank, world)
+    handles = [NanoGICP(local) for _ in range(args.handles)]
+    for h in handles:
+        configure(h, S2S)
+
+    def work(hi):
+        h = handles[hi]
+        done = 0
+        for pi in list(mine)[hi::args.handles]:
+            a, b = pool_d[pi % pool_n], pool_d[(pi + 1) % pool_n]
+            h.clearSource(); h.clearTarget()
+            h.setInputTarget(a); h.setInputSource(b)      # index x2; covariances are computed lazily inside align
+            h.align()
+            done += 1
+        return done
+    # warm-up
+    with ThreadPoolExecutor(args.handles) as ex:
+        list(ex.map(lambda hi: [handles[hi].clearTarget(), handles[hi].setInputTarget(pool_d[0]), handles[hi].setInputSource(pool_d[1]), handles[hi].align()], range(args.handles)))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    with ThreadPoolExecutor(args.handles) as ex:
+        n_done = sum(ex.map(work, range(args.handles)))
+    torch.cuda.synchronize()
+    el = time.perf_counter() - t0
+    t = torch.tensor([el], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([n_done], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(cnt)
+    if rank == 0:
+        print(json.dumps({"config": f"C4: {args.pairs} independent S2S scan pairs (~{int(np.mean([p.shape[0] for p in pool]))} pts each, index + k=10 "
+                                    f"covariances for both clouds + align per pair), partitioned over {world} GPU(s)",
+                          "n_gpus": world, "pairs": int(cnt.item()), "handles_per_gpu": args.handles, "seconds": float(t.item()),
+                          "pairs_per_s": float(cnt.item() / t.item()), "ms_per_pair_per_gpu": float(t.item() * 1e3 * world / cnt.item())}))
+    if world > 1:
+        dist.barrier(); dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    ap = argparse.ArgumentParser()
+    ap.add_argument("which", choices=["c1", "c3", "c4"])
+    ap.add_argument("--scans", type=int, default=300)
+    ap.add_argument("--cpu-scans", type=int, default=40)
+    ap.add_argument("--pairs", type=int, default=512)
+    ap.add_argument("--pool", type=int, default=16)
+    ap.add_argument("--handles", type=int, default=8)
+    a = ap.parse_args()
+    {"c1": run_c1, "c3": run_c3, "c4": run_c4}[a.which](a)
