@@ -51,7 +51,8 @@ def configure(g, cfg):
 def pose_err(Ta, Tb):
     dt = float(np.linalg.norm(np.asarray(Ta, float)[:3, 3] - np.asarray(Tb, float)[:3, 3]))
     dR = np.asarray(Ta, float)[:3, :3].T @ np.asarray(Tb, float)[:3, :3]
-    return dt, float(np.arccos(np.clip((np.trace(dR) - 1) / 2, -1, 1)))
+    sk = 0.5 * np.array([dR[2, 1] - dR[1, 2], dR[0, 2] - dR[2, 0], dR[1, 0] - dR[0, 1]])   # well conditioned near identity
+    return dt, float(np.arcsin(min(1.0, float(np.linalg.norm(sk)))))
 
 
 # ------------------------------------------------------------------------------------------------ C1
@@ -142,6 +143,8 @@ class Replay:
         self.keyframes.append((self.T[:3, 3].copy(), kf, self.s2s.getSourceCovariances()))
 
     def step(self, scan):
+        self.events = []
+        t_ = time.perf_counter()
         self.s2s.setInputSource(scan)
         self.s2m.registerInputSource(scan)
         self.s2m.source_kdtree_ = self.s2s.source_kdtree_
@@ -153,16 +156,20 @@ class Replay:
         self.s2s.swapSourceAndTarget()
         d = [np.linalg.norm(T_s2s[:3, 3] - kf[0]) for kf in self.keyframes]
         sel = tuple(sorted(np.argsort(d)[: self.knn].tolist()))
+        self.events.append(("s2s", (time.perf_counter() - t_) * 1e3)); t_ = time.perf_counter()
         if sel != self.prev_set:
             self.submap = np.ascontiguousarray(np.vstack([self.keyframes[i][1] for i in sel]))
             self.submap_covs = np.concatenate([self.keyframes[i][2] for i in sel])
             self.s2m.setInputTarget(self.submap); self.s2m.setTargetCovariances(self.submap_covs)
             self.prev_set = sel
+            self.events.append(("submap_rebuild_%d" % self.submap.shape[0], (time.perf_counter() - t_) * 1e3)); t_ = time.perf_counter()
         self.s2m.align(T_s2s)
         self.T = self.s2m.getFinalTransformation()
         self.T_prev = self.T
+        self.events.append(("s2m", (time.perf_counter() - t_) * 1e3)); t_ = time.perf_counter()
         if min(np.linalg.norm(self.T[:3, 3] - kf[0]) for kf in self.keyframes) > self.thresh_d:
             self._add_keyframe(scan)
+            self.events.append(("new_keyframe", (time.perf_counter() - t_) * 1e3))
         return it_s2s, self.s2m.nr_iterations_
 
 
@@ -226,6 +233,9 @@ def run_c3(args):
             continue
         its = rp.step(scan)
         ms.append((time.perf_counter() - t1) * 1e3)
+        if ms[-1] > 5.0:
+            print(f"slow scan {i}: {ms[-1]:.1f} ms voxel+{[(n, round(v, 2)) for n, v in rp.events]} "
+                  f"s2s kernels {({k: round(v, 3) for k, v in rp.s2s.timings().items()})} grid {rp.s2s.grid_info(1)}", file=sys.stderr)
         iters.append(its)
         errs.append(pose_err(rp.T, T_true))
     ms = np.array(ms)

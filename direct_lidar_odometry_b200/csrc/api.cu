@@ -113,7 +113,7 @@ int set_cloud(ngicp_t* h, int which, const void* pts, size_t n, size_t stride, b
   const int ph = which == NGICP_SOURCE ? PH_SET_SRC : PH_SET_TGT;
   ph_begin(h, ph);
   NG_CUDA(h, upload_cloud(*c, pts, n, stride, h->sc, h->stream));
-  if (index) NG_CUDA(h, build_index(*c, h->prm.grid_cell_size, h->prm.grid_table_cells, h->sc, h->stream));
+  if (index) NG_CUDA(h, build_index(*c, h->prm.grid_cell_size, h->prm.grid_table_cells, h->sc, h->stream, h->device));
   ph_end(h, ph);
   if (which == NGICP_SOURCE) { h->src = c; if (index) h->src_cov.reset(); }
   else { h->tgt = c; h->tgt_cov.reset(); }
@@ -123,7 +123,7 @@ int set_cloud(ngicp_t* h, int which, const void* pts, size_t n, size_t stride, b
 
 int ensure_index(ngicp_t* h, CloudPtr& c) {
   if (c->indexed) return NGICP_OK;
-  NG_CUDA(h, build_index(*c, h->prm.grid_cell_size, h->prm.grid_table_cells, h->sc, h->stream));
+  NG_CUDA(h, build_index(*c, h->prm.grid_cell_size, h->prm.grid_table_cells, h->sc, h->stream, h->device));
   return NGICP_OK;
 }
 

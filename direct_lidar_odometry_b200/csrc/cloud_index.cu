@@ -10,6 +10,10 @@
 //   desc          GridDesc                    origin, cell edge, dims — computed on the device, no host round trip
 // Algorithmic bytes: 16 n read + 16 n sorted write + 4 n permutation = 36 B/point.
 #include <cstdlib>
+#include <mutex>
+#include <vector>
+#include <cstdio>
+#include <ctime>
 #include <cstdint>
 #include "internal.h"
 
@@ -20,8 +24,16 @@ cudaError_t DevBuf::alloc(size_t nbytes, const StreamPtr& stream) {
   if (nbytes == 0) nbytes = 16;
   st = stream;
   cudaError_t e;
+  static const bool trace = getenv("NGICP_HOST_TRACE") != nullptr;
+  timespec t0, t1;
+  if (trace) clock_gettime(CLOCK_MONOTONIC, &t0);
   if (st && st->owned) e = cudaMallocAsync(&p, nbytes, st->s);
   else e = cudaMalloc(&p, nbytes);
+  if (trace) {
+    clock_gettime(CLOCK_MONOTONIC, &t1);
+    const double ms = (t1.tv_sec - t0.tv_sec) * 1e3 + (t1.tv_nsec - t0.tv_nsec) * 1e-6;
+    if (ms > 0.5) fprintf(stderr, "[ngicp] slow alloc %.2f ms for %zu bytes\n", ms, nbytes);
+  }
   if (e != cudaSuccess) { p = nullptr; bytes = 0; return e; }
   bytes = nbytes;
   return cudaSuccess;
@@ -36,6 +48,57 @@ void DevBuf::release() {
   if (!p) return;
   if (st && st->owned) cudaFreeAsync(p, st->s);
   else cudaFree(p);
+  p = nullptr;
+  bytes = 0;
+}
+
+namespace {
+struct TableEntry { void* p; size_t bytes; int device; cudaEvent_t ready; };
+std::mutex g_table_mutex;
+std::vector<TableEntry> g_table_free;
+constexpr size_t TABLE_CACHE_MAX = 12;
+}  // namespace
+
+cudaError_t TableBuf::acquire(size_t nbytes, int dev, const StreamPtr& stream) {
+  release();
+  st = stream;
+  device = dev;
+  TableEntry got{nullptr, 0, 0, nullptr};
+  {
+    std::lock_guard<std::mutex> lock(g_table_mutex);
+    size_t best = (size_t)-1;
+    for (size_t i = 0; i < g_table_free.size(); i++) {
+      const TableEntry& e = g_table_free[i];
+      if (e.device == dev && e.bytes >= nbytes && (best == (size_t)-1 || e.bytes < g_table_free[best].bytes)) best = i;
+    }
+    if (best != (size_t)-1) { got = g_table_free[best]; g_table_free.erase(g_table_free.begin() + best); }
+  }
+  if (got.p) {
+    // everything enqueued on the previous owner's stream before the release must finish before this stream writes
+    if (got.ready) { cudaStreamWaitEvent(st->s, got.ready, 0); cudaEventDestroy(got.ready); }
+    p = got.p;
+    bytes = got.bytes;
+    return cudaSuccess;
+  }
+  cudaError_t e = cudaMalloc(&p, nbytes);
+  if (e != cudaSuccess) { p = nullptr; bytes = 0; return e; }
+  bytes = nbytes;
+  return cudaSuccess;
+}
+
+void TableBuf::release() {
+  if (!p) return;
+  TableEntry e{p, bytes, device, nullptr};
+  if (st && st->s && cudaEventCreateWithFlags(&e.ready, cudaEventDisableTiming) == cudaSuccess) cudaEventRecord(e.ready, st->s);
+  bool keep = false;
+  {
+    std::lock_guard<std::mutex> lock(g_table_mutex);
+    if (g_table_free.size() < TABLE_CACHE_MAX) { g_table_free.push_back(e); keep = true; }
+  }
+  if (!keep) {
+    if (e.ready) { cudaEventSynchronize(e.ready); cudaEventDestroy(e.ready); }
+    cudaFree(p);
+  }
   p = nullptr;
   bytes = 0;
 }
@@ -249,13 +312,13 @@ static int bits_for(int cap) {
   return b;
 }
 
-cudaError_t build_index(DevCloud& c, float cell_req, int table_cap, Scratch& sc, const StreamPtr& st) {
+cudaError_t build_index(DevCloud& c, float cell_req, int table_cap, Scratch& sc, const StreamPtr& st, int device) {
   cudaError_t e;
   const int n = c.n;
   if (table_cap < 64) table_cap = 64;
   c.table_cap = table_cap;
   // table buffer: 3 ints of padding so that &table[1] (where the scan runs) is 16-byte aligned
-  if ((e = c.cell_start.alloc(sizeof(int) * ((size_t)table_cap + 8), st)) != cudaSuccess) return e;
+  if ((e = c.cell_start.acquire(sizeof(int) * ((size_t)table_cap + 8), device, st)) != cudaSuccess) return e;
   if ((e = c.sorted.alloc(sizeof(float4) * (n ? n : 1), st)) != cudaSuccess) return e;
   int* table = c.cell_start.as<int>() + 3;
   GridDesc* d = c.desc.as<GridDesc>();

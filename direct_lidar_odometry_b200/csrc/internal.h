@@ -38,13 +38,30 @@ struct DevBuf {
   template <class T> T* as() const { return reinterpret_cast<T*>(p); }
 };
 
+// The dense cell table is by far the largest per-cloud buffer (capacity x 4 B, 128 MiB by default) and clouds come
+// and go once per scan, so tables are recycled through a small per-process free list instead of the allocator
+// (a fresh 128 MiB cudaMallocAsync costs 0.6-25 ms, measured; see benchmarks/exp_setsrc.py).
+struct TableBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+  int device = 0;
+  StreamPtr st;
+  TableBuf() {}
+  TableBuf(const TableBuf&) = delete;
+  TableBuf& operator=(const TableBuf&) = delete;
+  ~TableBuf() { release(); }
+  cudaError_t acquire(size_t nbytes, int dev, const StreamPtr& stream);
+  void release();
+  template <class T> T* as() const { return reinterpret_cast<T*>(p); }
+};
+
 // ---- device-resident cloud + index ---------------------------------------------------------------
 struct DevCloud {
   int n = 0;
   DevBuf pts;         // float4[n], original order, w = 1
   bool indexed = false;
   DevBuf desc;        // GridDesc
-  DevBuf cell_start;  // int[table_cap + 1]
+  TableBuf cell_start;  // int[table_cap + 8], recycled
   DevBuf sorted;      // float4[n], cell order, w = original index bits
   int table_cap = 0;
   GridView view() const {
@@ -100,7 +117,7 @@ int radix_sort_pairs(unsigned* keys_a, unsigned* vals_a, unsigned* keys_b, unsig
 // snapshot caller records into cloud.pts (float4) and compute the bounding box into cloud.desc
 cudaError_t upload_cloud(DevCloud& c, const void* pts, size_t n, size_t stride_bytes, Scratch& sc, const StreamPtr& st);
 // build the uniform grid index of an uploaded cloud
-cudaError_t build_index(DevCloud& c, float cell_req, int table_cap, Scratch& sc, const StreamPtr& st);
+cudaError_t build_index(DevCloud& c, float cell_req, int table_cap, Scratch& sc, const StreamPtr& st, int device);
 
 // ---- knn_cov.cu -----------------------------------------------------------------------------------
 cudaError_t launch_knn_queries(const DevCloud& c, const float4* queries, int nq, int k, int* idx, float* d2, cudaStream_t st);
