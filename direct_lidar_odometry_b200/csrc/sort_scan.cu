@@ -1,6 +1,6 @@
 // sort_scan.cu — hand-written device-wide primitives used by the grid index and the voxel reduce:
 //   * exclusive prefix sum over int32 (three-kernel tile scan, length read from device memory)
-//   * stable LSD radix sort of (uint32 key, uint32 value) pairs, 8 bits per pass
+//   * stable LSD radix sort of (uint32 key, uint32 value) pairs, 9 bits per pass
 // Stability matters: it makes "ascending original index inside a cell/voxel" the deterministic
 // within-bucket order (pcl::VoxelGrid's own sort is unstable).
 #include <cstdint>
@@ -138,25 +138,32 @@ size_t scan_scratch_ints(int max_n) { return (size_t)(max_n + SCAN_TILE - 1) / S
 // ------------------------------------------------------------------------------------------
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
-constexpr int RS_IPT = 16;
-constexpr int RS_TILE = RS_THREADS * RS_IPT;  // 4096 items per block
-constexpr int RS_WARP_ITEMS = 32 * RS_IPT;    // 512 contiguous items per warp
+constexpr int RS_BITS = 9;                    // 9-bit digits: 27-bit keys (cell / voxel indices) need 3 passes
+constexpr int RS_BINS = 1 << RS_BITS;
+constexpr unsigned RS_MASK = RS_BINS - 1;
 
+// per-block digit histogram, digit-major layout hist[d * nblk + blk].  Warps count with match_any (no contended
+// shared-memory atomics: voxel / cell keys arrive nearly sorted, so neighbouring items share their digit).
+template <int IPT>
 __global__ void __launch_bounds__(RS_THREADS) rs_histogram(const unsigned* __restrict__ keys, int n, int shift, int nblk, int* __restrict__ hist) {
-  __shared__ int cnt[256];
-  cnt[threadIdx.x] = 0;
+  __shared__ int cnt[RS_BINS];
+  for (int i = threadIdx.x; i < RS_BINS; i += RS_THREADS) cnt[i] = 0;
   __syncthreads();
-  const int base = blockIdx.x * RS_TILE;
-#pragma unroll 4
-  for (int j = 0; j < RS_IPT; j++) {
-    const int i = base + j * RS_THREADS + threadIdx.x;
-    if (i < n) atomicAdd(&cnt[(keys[i] >> shift) & 255u], 1);
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  const int wbase = blockIdx.x * (RS_THREADS * IPT) + w * (32 * IPT);
+#pragma unroll
+  for (int j = 0; j < IPT; j++) {
+    const int i = wbase + j * 32 + lane;
+    const bool valid = i < n;
+    const unsigned d = valid ? ((keys[i] >> shift) & RS_MASK) : (unsigned)RS_BINS;
+    const unsigned peers = __match_any_sync(FULL, d);
+    if (valid && lane == __ffs(peers) - 1) atomicAdd(&cnt[d], __popc(peers));
   }
   __syncthreads();
-  hist[threadIdx.x * nblk + blockIdx.x] = cnt[threadIdx.x];
+  for (int i = threadIdx.x; i < RS_BINS; i += RS_THREADS) hist[i * nblk + blockIdx.x] = cnt[i];
 }
 
-// exclusive scan of the digit-major histogram (256*nblk ints) by a single block
+// exclusive scan of the digit-major histogram (RS_BINS*nblk ints) by a single block
 __global__ void __launch_bounds__(1024) rs_scan_hist(int* __restrict__ hist, int total) {
   __shared__ int sm[32];
   __shared__ int carry_s;
@@ -191,25 +198,27 @@ __global__ void __launch_bounds__(1024) rs_scan_hist(int* __restrict__ hist, int
   }
 }
 
+// stable scatter: each warp owns 32*IPT contiguous items and ranks them in order with match_any
+template <int IPT>
 __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const unsigned* __restrict__ keys_in, const unsigned* __restrict__ vals_in,
                                                          unsigned* __restrict__ keys_out, unsigned* __restrict__ vals_out,
                                                          int n, int shift, int nblk, const int* __restrict__ hist) {
-  __shared__ int wcnt[RS_WARPS][256];
+  __shared__ int wcnt[RS_WARPS][RS_BINS];
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-  for (int i = threadIdx.x; i < RS_WARPS * 256; i += RS_THREADS) (&wcnt[0][0])[i] = 0;
+  for (int i = threadIdx.x; i < RS_WARPS * RS_BINS; i += RS_THREADS) (&wcnt[0][0])[i] = 0;
   __syncthreads();
-  const int wbase = blockIdx.x * RS_TILE + w * RS_WARP_ITEMS;
-  unsigned key[RS_IPT], val[RS_IPT];
-  int rank[RS_IPT];
+  const int wbase = blockIdx.x * (RS_THREADS * IPT) + w * (32 * IPT);
+  unsigned key[IPT], val[IPT];
+  int rank[IPT];
   const unsigned lt = (1u << lane) - 1u;
   // pass 1: per-warp digit counts in item order; remember each item's rank among equal digits of its warp
 #pragma unroll
-  for (int j = 0; j < RS_IPT; j++) {
+  for (int j = 0; j < IPT; j++) {
     const int i = wbase + j * 32 + lane;
     const bool valid = i < n;
     key[j] = valid ? keys_in[i] : 0u;
     val[j] = valid ? vals_in[i] : 0u;
-    const unsigned d = valid ? ((key[j] >> shift) & 255u) : 256u;
+    const unsigned d = valid ? ((key[j] >> shift) & RS_MASK) : (unsigned)RS_BINS;
     const unsigned peers = __match_any_sync(FULL, d);
     const int leader = __ffs(peers) - 1;
     int before = 0;
@@ -220,18 +229,17 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const unsigned* __restr
   }
   __syncthreads();
   // exclusive offsets: global digit base for this block, then earlier warps of this block
-  {
-    const int d = threadIdx.x;
+  for (int d = threadIdx.x; d < RS_BINS; d += RS_THREADS) {
     int run = hist[d * nblk + blockIdx.x];
 #pragma unroll
     for (int ww = 0; ww < RS_WARPS; ww++) { const int t = wcnt[ww][d]; wcnt[ww][d] = run; run += t; }
   }
   __syncthreads();
 #pragma unroll
-  for (int j = 0; j < RS_IPT; j++) {
+  for (int j = 0; j < IPT; j++) {
     const int i = wbase + j * 32 + lane;
     if (i < n) {
-      const unsigned d = (key[j] >> shift) & 255u;
+      const unsigned d = (key[j] >> shift) & RS_MASK;
       const int pos = wcnt[w][d] + rank[j];
       keys_out[pos] = key[j];
       vals_out[pos] = val[j];
@@ -239,31 +247,35 @@ __global__ void __launch_bounds__(RS_THREADS) rs_scatter(const unsigned* __restr
   }
 }
 
-// note: rs_histogram reads items striped over the whole 4096-item tile, rs_scatter reads them warp-contiguous;
-// both cover exactly [blockIdx.x*RS_TILE, +RS_TILE) so the per-block histograms agree.
+static inline int rs_ipt(int n) { return n <= (1 << 18) ? 4 : 16; }
 
 size_t radix_sort_scratch_ints(int n) {
-  int nblk = (n + RS_TILE - 1) / RS_TILE;
+  const int tile = RS_THREADS * rs_ipt(n);
+  int nblk = (n + tile - 1) / tile;
   if (nblk < 1) nblk = 1;
-  return (size_t)256 * nblk;
+  return (size_t)RS_BINS * nblk;
 }
 
 // Sorts (keys_a, vals_a) using (keys_b, vals_b) as the ping-pong partner.  `bits` = number of
-// significant key bits (rounded up to whole 8-bit passes).  Returns 0 if the sorted data ends in
+// significant key bits (rounded up to whole 9-bit passes).  Returns 0 if the sorted data ends in
 // the *_a buffers, 1 if in *_b.
 int radix_sort_pairs(unsigned* keys_a, unsigned* vals_a, unsigned* keys_b, unsigned* vals_b, int n, int bits, int* hist, cudaStream_t st) {
   if (n <= 0) return 0;
-  const int nblk = (n + RS_TILE - 1) / RS_TILE;
-  const int passes = (bits + 7) / 8;
+  const int ipt = rs_ipt(n);
+  const int tile = RS_THREADS * ipt;
+  const int nblk = (n + tile - 1) / tile;
+  const int passes = (bits + RS_BITS - 1) / RS_BITS;
   int cur = 0;
   for (int p = 0; p < passes; p++) {
     const unsigned* kin = cur ? keys_b : keys_a;
     const unsigned* vin = cur ? vals_b : vals_a;
     unsigned* kout = cur ? keys_a : keys_b;
     unsigned* vout = cur ? vals_a : vals_b;
-    rs_histogram<<<nblk, RS_THREADS, 0, st>>>(kin, n, p * 8, nblk, hist);
-    rs_scan_hist<<<1, 1024, 0, st>>>(hist, 256 * nblk);
-    rs_scatter<<<nblk, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, p * 8, nblk, hist);
+    if (ipt == 4) rs_histogram<4><<<nblk, RS_THREADS, 0, st>>>(kin, n, p * RS_BITS, nblk, hist);
+    else rs_histogram<16><<<nblk, RS_THREADS, 0, st>>>(kin, n, p * RS_BITS, nblk, hist);
+    rs_scan_hist<<<1, 1024, 0, st>>>(hist, RS_BINS * nblk);
+    if (ipt == 4) rs_scatter<4><<<nblk, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, p * RS_BITS, nblk, hist);
+    else rs_scatter<16><<<nblk, RS_THREADS, 0, st>>>(kin, vin, kout, vout, n, p * RS_BITS, nblk, hist);
     note_launches(3);
     cur ^= 1;
   }

@@ -10,7 +10,7 @@
 
 namespace ngicp {
 
-constexpr unsigned VOX_INVALID = 0xFFFFFFFFu;
+// non-finite points get the key one past the last voxel (sorted to the end, never emitted)
 
 __global__ void vox_desc_init_kernel(GridDesc* d) {
   for (int i = 0; i < 3; i++) { d->bb_min[i] = f2ord(FLT_MAX); d->bb_max[i] = f2ord(-FLT_MAX); }
@@ -71,6 +71,7 @@ __global__ void __launch_bounds__(256) vox_keys_kernel(const float4* __restrict_
   const int m0 = d->vmin_b[0], m1 = d->vmin_b[1], m2 = d->vmin_b[2];
   const int mul1 = d->vdiv[0], mul2 = d->vdiv[0] * d->vdiv[1];
   const bool bad = d->voverflow != 0;
+  const unsigned VOX_INVALID = d->voverflow ? 0u : (unsigned)(d->vdiv[0] * d->vdiv[1] * d->vdiv[2]);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float4 p = pts[i];
     unsigned key = VOX_INVALID;
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(256) vox_keys_kernel(const float4* __restrict_
 }
 
 // flags[i] = 1 at the first element of every run of equal valid keys; flags[n] = 0 (sentinel for the total)
-__global__ void __launch_bounds__(256) vox_heads_kernel(const unsigned* __restrict__ keys, int n, int* __restrict__ flags) {
+__global__ void __launch_bounds__(256) vox_heads_kernel(const unsigned* __restrict__ keys, int n, int* __restrict__ flags, unsigned VOX_INVALID) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += gridDim.x * blockDim.x) {
     int f = 0;
     if (i < n) {
@@ -100,7 +101,7 @@ __global__ void __launch_bounds__(256) vox_heads_kernel(const unsigned* __restri
 // one thread per run head: sequential float accumulation in sorted (= ascending input index) order
 __global__ void __launch_bounds__(128) vox_centroid_kernel(const unsigned* __restrict__ keys, const unsigned* __restrict__ perm, int n,
                                                            const int* __restrict__ slots, const float4* __restrict__ pts,
-                                                           float* __restrict__ out, int* __restrict__ slot_of_point) {
+                                                           float* __restrict__ out, int* __restrict__ slot_of_point, unsigned VOX_INVALID) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const unsigned k = keys[i];
     if (k == VOX_INVALID) { slot_of_point[perm[i]] = -1; continue; }
@@ -158,24 +159,33 @@ cudaError_t voxel_filter_device(const void* in, size_t n, size_t stride_bytes, f
   vox_pack_kernel<<<vgrid(ni, 256), 256, 0, st->s>>>(sc.staging.as<unsigned char>(), stride_bytes, ni, ifloat, pts, d);
   vox_setup_kernel<<<1, 1, 0, st->s>>>(d, inv);
   vox_keys_kernel<<<vgrid(ni, 256), 256, 0, st->s>>>(pts, ni, d, inv, sc.keys_a.as<unsigned>(), sc.vals_a.as<unsigned>());
+  // the voxel grid dimensions decide how many radix passes are needed: one small read-back (the call has to
+  // synchronise for the output count anyway) instead of always sorting 32 bits
+  int dims[4] = {1, 1, 1, 0};
+  if ((e = cudaMemcpyAsync(dims, d->vdiv, 3 * sizeof(int), cudaMemcpyDeviceToHost, st->s)) != cudaSuccess) return e;
+  if ((e = cudaMemcpyAsync(dims + 3, &d->voverflow, sizeof(int), cudaMemcpyDeviceToHost, st->s)) != cudaSuccess) return e;
+  if ((e = cudaStreamSynchronize(st->s)) != cudaSuccess) return e;
+  *overflow = dims[3];
+  if (dims[3]) { *m_out = 0; return cudaSuccess; }   // PCL passes the input through; the caller handles it
+  const unsigned invalid_key = (unsigned)((long long)dims[0] * dims[1] * dims[2]);
+  int bits = 1;
+  while (bits < 32 && (1ull << bits) <= (unsigned long long)invalid_key) bits++;
   const int where = radix_sort_pairs(sc.keys_a.as<unsigned>(), sc.vals_a.as<unsigned>(), sc.keys_b.as<unsigned>(), sc.vals_b.as<unsigned>(),
-                                     ni, 32, sc.hist.as<int>(), st->s);
+                                     ni, bits, sc.hist.as<int>(), st->s);
   const unsigned* keys = where ? sc.keys_b.as<unsigned>() : sc.keys_a.as<unsigned>();
   const unsigned* perm = where ? sc.vals_b.as<unsigned>() : sc.vals_a.as<unsigned>();
   int* flags = sc.flags.as<int>();
-  vox_heads_kernel<<<vgrid(ni + 1, 256), 256, 0, st->s>>>(keys, ni, flags);
+  vox_heads_kernel<<<vgrid(ni + 1, 256), 256, 0, st->s>>>(keys, ni, flags, invalid_key);
   // the scan length (n+1) is known on the host; park it in the descriptor so the generic scan can read it
   int len = ni + 1;
   if ((e = cudaMemcpyAsync(&d->n, &len, sizeof(int), cudaMemcpyHostToDevice, st->s)) != cudaSuccess) return e;
   exclusive_scan_inplace(flags, &d->n, 0, ni + 1, sc.tile_sums.as<int>(), st->s);
-  vox_centroid_kernel<<<vgrid(ni, 128), 128, 0, st->s>>>(keys, perm, ni, flags, pts, sc.vox_out.as<float>(), sc.vox_slot.as<int>());
+  vox_centroid_kernel<<<vgrid(ni, 128), 128, 0, st->s>>>(keys, perm, ni, flags, pts, sc.vox_out.as<float>(), sc.vox_slot.as<int>(), invalid_key);
   note_launches(6);
-  int host[2] = {0, 0};
-  if ((e = cudaMemcpyAsync(&host[0], flags + ni, sizeof(int), cudaMemcpyDeviceToHost, st->s)) != cudaSuccess) return e;
-  if ((e = cudaMemcpyAsync(&host[1], &d->voverflow, sizeof(int), cudaMemcpyDeviceToHost, st->s)) != cudaSuccess) return e;
+  int host_m = 0;
+  if ((e = cudaMemcpyAsync(&host_m, flags + ni, sizeof(int), cudaMemcpyDeviceToHost, st->s)) != cudaSuccess) return e;
   if ((e = cudaStreamSynchronize(st->s)) != cudaSuccess) return e;
-  *m_out = (size_t)host[0];
-  *overflow = host[1];
+  *m_out = (size_t)host_m;
   return cudaGetLastError();
 }
 
