@@ -143,8 +143,8 @@ int calc_covs(ngicp_t* h, int which) {
   NG_CUDA(h, cv->c.alloc(sizeof(double) * 6 * (size_t)c->n, h->stream));
   const int ph = which == NGICP_SOURCE ? PH_COV_SRC : PH_COV_TGT;
   ph_begin(h, ph);
-  NG_CUDA(h, h->sc.nbr.reserve(sizeof(int) * (size_t)c->n * k, h->stream));
-  NG_CUDA(h, launch_covariances(*c, k, h->prm.regularization_method, h->sc.nbr.as<int>(), cv->c.as<double>(), h->stream->s));
+  NG_CUDA(h, h->sc.nbr.reserve(sizeof(int) * covariance_scratch_ints(c->n, k), h->stream));
+  NG_CUDA(h, launch_covariances(*c, k, h->prm.regularization_method, h->sc.nbr.as<int>(), cv->c.as<double>(), c->table_cap, h->stream->s));
   ph_end(h, ph);
   (which == NGICP_SOURCE ? h->src_cov : h->tgt_cov) = cv;
   h->lin_valid = false;

@@ -121,7 +121,8 @@ cudaError_t build_index(DevCloud& c, float cell_req, int table_cap, Scratch& sc,
 
 // ---- knn_cov.cu -----------------------------------------------------------------------------------
 cudaError_t launch_knn_queries(const DevCloud& c, const float4* queries, int nq, int k, int* idx, float* d2, cudaStream_t st);
-cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_scratch /* n*k ints */, double* covs6, cudaStream_t st);
+size_t covariance_scratch_ints(int n, int k);   // neighbour lists + the work lists of the kNN kernels
+cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_scratch /* covariance_scratch_ints() */, double* covs6, int table_cap, cudaStream_t st);
 constexpr int KNN_MAX_K = 32;
 
 // ---- align.cu -------------------------------------------------------------------------------------

@@ -7,6 +7,7 @@
 // slots parked in HBM (4k B/point of scratch, L2 resident); cov_from_lists_kernel — one THREAD per
 // point for the fp64 statistics + 3x3 Jacobi SVD.  Algorithmic bytes of the pair: 16 B point read +
 // 48 B covariance write = 64 B/point.
+#include <cstdio>
 #include <cstdlib>
 #include "internal.h"
 #include "grid_search.cuh"
@@ -58,153 +59,470 @@ __global__ void __launch_bounds__(KC_THREADS, KNN_MIN_BLOCKS) knn_lists_kernel(G
   }
 }
 
-// K2, staged variant (the one launch_covariances uses): consecutive cell-ordered points mostly share their cell, so a
-// warp copies the 3x3x3 block of cells around the current cell into shared memory ONCE (9 coalesced runs, SoA) and
-// answers every query of that cell from there.  Selection is threshold-and-verify instead of list maintenance:
-// collect the candidates closer than a guessed T^2 (first guess from the block's population, then 1.3x the previous
-// query's k-th distance), accept when between k and 32 were collected — one bitonic sort of 32 then yields the
-// ascending k nearest — else bisect T^2.  T^2 never exceeds the squared distance to the nearest unexplored cell face,
-// so an accepted answer is exact; queries that cannot be decided inside the block (sparse regions, very dense
-// cells) fall back to the growing-cube search above.
-constexpr int ST_WARPS = 4;
-constexpr int ST_CMAX = 896;
-struct StageSmem {
-  float x[ST_CMAX], y[ST_CMAX], z[ST_CMAX];
-  float sel_d[32];
-  int sel_i[32];
-  int row_a[9];
-  int row_excl[9];
+// K2, tile variant (the one launch_covariances uses) — cell-major, one THREAD per query.
+// The cell grid is cut into boxes of TQ_CORE^3 cells.  knn_plan_kernel walks the boxes (skipping empty space 8 boxes at
+// a time), splits boxes whose surroundings would not fit a tile (dense cells) into 8 children, down to single cells,
+// and emits work items: (box, up to 64 of its points).  knn_lists_tile_kernel is persistent; a warp pulls an item,
+// copies the cells within radius s (1, then 2, then 4 for the points that need it) around the box into shared memory
+// ONCE — one coalesced x-run per (y,z) row, thanks to the x-fastest lower-bound table — and then answers the item's
+// points from that tile, 32 at a time, every lane working on ITS OWN query:
+//   threshold-and-verify   collect the tile points closer than a guessed T^2 into the lane's column of a
+//                          shared-memory list; accept when between k and TQ_LCAP were collected, otherwise rescale
+//                          T^2 by (k+8)/count (counts grow ~linearly in T^2 on surfaces) inside a bisection bracket;
+//   exactness              T^2 never exceeds the squared, margin-shrunk distance from the query to the nearest face
+//                          of the tile that still has cells behind it, so an accepted list contains every point that
+//                          can be among the k nearest (same stop rule as grid_search_warp);
+//   selection              the covariance only needs the SET of the k nearest, so the lane tightens the threshold on
+//                          its short list (secant steps on the count) until exactly k remain — no sorting network,
+//                          no dependent shuffles.  An exact tie at the k-th distance has no such threshold: those
+//                          (rare) points take the warp search.
+// One distance evaluation therefore costs one instruction slot per 32 queries instead of one per query.  Points that
+// cannot be decided inside a radius-4 tile are appended to a list and answered by the growing-cube warp search in a
+// last, fully parallel launch.
+#ifndef TQ_WARPS
+#define TQ_WARPS 2
+#endif
+#ifndef TQ_CMAX
+#define TQ_CMAX 384      // tile capacity (points)
+#endif
+#ifndef TQ_LCAP
+#define TQ_LCAP 40       // per-query collection capacity
+#endif
+#ifndef TQ_CORE
+#define TQ_CORE 4        // box edge in cells
+#endif
+#ifndef TQ_SMAX
+#define TQ_SMAX 16       // largest tile radius tried before a point goes to the warp search
+#endif
+constexpr int TQ_ITEM = 64;  // points per work item
+struct TileSmem {
+  float4 cand[TQ_CMAX];                  // x, y, z, bits(sorted slot)
+  uint2 lst[TQ_LCAP + 1][32];            // collected {bits(distance), tile position}, one column per lane; last row = dump
+  int cur[TQ_ITEM];                      // sorted slots of the points being answered from the current tile
+  float cur_t[TQ_ITEM];                  // their threshold guesses (0 = none yet) ...
+  float cur_lo[TQ_ITEM], cur_hi[TQ_ITEM];  // ... inside this bracket (hi < 0 = open)
+  int nxt[TQ_ITEM];                      // points that need a larger tile
+  int rowoff[68];                        // first tile position of every (y,z) row (radius <= 2 tiles: up to 64 rows)
 };
 
-__global__ void __launch_bounds__(ST_WARPS * 32) knn_lists_staged_kernel(GridView g, int n, int k, int qch, int* __restrict__ nbr) {
-  __shared__ StageSmem smem[ST_WARPS];
+// distance from q to the nearest face of the cell box [x0,x1]x[y0,y1]x[z0,z1] that still has cells behind it
+__device__ __forceinline__ float box_face_distance(const GridParams& gp, int x0, int x1, int y0, int y1, int z0, int z1,
+                                                   float qx, float qy, float qz) {
+  float m = FLT_MAX;
+  if (x0 > 0) m = fminf(m, qx - (gp.ox + (float)x0 * gp.cell));
+  if (x1 + 1 < gp.dx) m = fminf(m, (gp.ox + (float)(x1 + 1) * gp.cell) - qx);
+  if (y0 > 0) m = fminf(m, qy - (gp.oy + (float)y0 * gp.cell));
+  if (y1 + 1 < gp.dy) m = fminf(m, (gp.oy + (float)(y1 + 1) * gp.cell) - qy);
+  if (z0 > 0) m = fminf(m, qz - (gp.oz + (float)z0 * gp.cell));
+  if (z1 + 1 < gp.dz) m = fminf(m, (gp.oz + (float)(z1 + 1) * gp.cell) - qz);
+  return m == FLT_MAX ? FLT_MAX : m - gp.margin;
+}
+
+#ifdef TQ_DEBUG
+#define TQ_CHECK(cond, what, a, b) do { if (!(cond)) { printf("TQ_CHECK %s failed: %d %d (block %d thread %d)\n", what, (int)(a), (int)(b), blockIdx.x, threadIdx.x); __trap(); } } while (0)
+#else
+#define TQ_CHECK(cond, what, a, b) do { } while (0)
+#endif
+enum { ST_FALLBACK = 0, ST_TIES, ST_TILES, ST_PASSES, ST_LANES, ST_ITEMS, ST_N };
+// control words shared by the three launches
+enum { CT_ITEMS = 0, CT_NEXT, CT_REST, CT_N = 8 };
+
+// warp-aggregated append of the lanes in `mask` to the warp-search list
+__device__ __forceinline__ void fb_append(unsigned mask, int slot, int lane, int* __restrict__ fb_list, int* __restrict__ fb_count) {
+  if (!mask) return;
+  const int leader = __ffs(mask) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(fb_count, __popc(mask));
+  base = __shfl_sync(FULL, base, leader);
+  if ((mask >> lane) & 1u) fb_list[base + __popc(mask & ((1u << lane) - 1u))] = slot;
+}
+
+__device__ __forceinline__ int warp_incl_scan(int v, int lane) {
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, v, o); if (lane >= o) v += t; }
+  return v;
+}
+// index of the run that holds flattened position t, given the inclusive scan of the run lengths over the lanes
+__device__ __forceinline__ int run_of(int inc, int t) {
+  int j = 0;
+#pragma unroll
+  for (int step = 16; step > 0; step >>= 1) {
+    const int v = __shfl_sync(FULL, inc, j + step - 1);
+    if (v <= t) j += step;
+  }
+  return j;
+}
+
+// number of points in the cells [x0-s, x0+sz-1+s] x [y0-s, ..] x [z0-s, ..], computed by a group of `nsub` adjacent
+// lanes (power of two; `sub` = lane index inside the group); the result is uniform across the group
+__device__ __forceinline__ int box_population(const GridView& g, const GridParams& gp, int x0, int y0, int z0, int sz, int s, int sub, int nsub) {
+  const int ny = sz + 2 * s, nrows = ny * ny;
+  const int xl = max(x0 - s, 0), xr = min(x0 + sz - 1 + s, gp.dx - 1) + 1;
+  int c = 0;
+  for (int r = sub; r < nrows; r += nsub) {
+    const int y = y0 - s + (r % ny), z = z0 - s + (r / ny);
+    if (y >= 0 && y < gp.dy && z >= 0 && z < gp.dz && xl < xr) {
+      const int* row = g.cell_start + (z * gp.dy + y) * gp.dx;
+      c += __ldg(row + xr) - __ldg(row + xl);
+    }
+  }
+  for (int o = nsub >> 1; o > 0; o >>= 1) c += __shfl_xor_sync(FULL, c, o);
+  return c;
+}
+
+// emit the work items of the boxes held by the lanes with q > 0 (one box per such lane)
+__device__ __forceinline__ void emit_items(bool emit, int x0, int y0, int z0, int sz, int q, int lane, int4* __restrict__ items, int* __restrict__ ctrl) {
+  const int nit = emit ? (q + TQ_ITEM - 1) / TQ_ITEM : 0;
+  const int inc = warp_incl_scan(nit, lane);
+  const int total = __shfl_sync(FULL, inc, 31);
+  if (total == 0) return;
+  int base = 0;
+  if (lane == 0) base = atomicAdd(ctrl + CT_ITEMS, total);
+  base = __shfl_sync(FULL, base, 0) + inc - nit;
+  for (int i = 0; i < nit; ++i) items[base + i] = make_int4(x0, y0, z0, sz | (i << 8));
+}
+
+// one warp per run of x-adjacent boxes (8 on big grids, 1 on small ones): emits the work items of knn_lists_tile_kernel.
+// A box whose radius-1 tile would not fit is split into its 8 children (evaluated 4 lanes each, in parallel), and a
+// child that still does not fit into its 8 single cells.
+__global__ void __launch_bounds__(256) knn_plan_kernel(GridView g, int4* __restrict__ items, int* __restrict__ ctrl) {
   const int lane = threadIdx.x & 31;
-  StageSmem& S = smem[threadIdx.x >> 5];
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const GridParams gp = load_grid(g.desc);
-  const unsigned lt = (1u << lane) - 1u;
-  const int nchunks = (n + qch - 1) / qch;
-  for (int chunk = warp; chunk < nchunks; chunk += nwarps) {
-    int scx = -1, scy = -1, scz = -1, C = 0;
-    bool staged_ok = false;
-    float t2_prev = 0.f;
-    const int qend = min(n, (chunk + 1) * qch);
-    for (int q = chunk * qch; q < qend; ++q) {
-      const float4 qp = __ldg(g.sorted + q);
-      if (!(isfinite(qp.x) && isfinite(qp.y) && isfinite(qp.z))) {
-        if (lane < k) nbr[(size_t)q * k + lane] = -1;
+  const int nbx = (gp.dx + TQ_CORE - 1) / TQ_CORE, nby = (gp.dy + TQ_CORE - 1) / TQ_CORE, nbz = (gp.dz + TQ_CORE - 1) / TQ_CORE;
+  const int run = ((long long)nbx * nby * nbz > 32768) ? 8 : 1;
+  const int nrx = (nbx + run - 1) / run;
+  const int nruns = nrx * nby * nbz;
+  // the launch covers the usual run count; the stride loop covers flat grids, whose per-axis rounding makes more boxes
+  for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nruns; w += nwarps) {
+    const int rbx = (w % nrx) * run, rby = (w / nrx) % nby, rbz = w / (nrx * nby);
+    if (run > 1) {
+      // whole run empty?  (16 core rows, one lane each)
+      int e = 0;
+      if (lane < TQ_CORE * TQ_CORE) {
+        const int y = rby * TQ_CORE + (lane % TQ_CORE), z = rbz * TQ_CORE + (lane / TQ_CORE);
+        if (y < gp.dy && z < gp.dz) {
+          const int* row = g.cell_start + (z * gp.dy + y) * gp.dx;
+          e = __ldg(row + min((rbx + run) * TQ_CORE, gp.dx)) - __ldg(row + rbx * TQ_CORE);
+        }
+      }
+      if (!__any_sync(FULL, e != 0)) continue;
+    }
+    for (int bi = 0; bi < run; ++bi) {
+      const int bx = rbx + bi;
+      if (bx >= nbx) break;
+      const int x0 = bx * TQ_CORE, y0 = rby * TQ_CORE, z0 = rbz * TQ_CORE;
+      const int Q = box_population(g, gp, x0, y0, z0, TQ_CORE, 0, lane, 32);
+      if (Q == 0) continue;
+      if (box_population(g, gp, x0, y0, z0, TQ_CORE, 1, lane, 32) <= TQ_CMAX) {
+        emit_items(lane == 0, x0, y0, z0, TQ_CORE, Q, lane, items, ctrl);
         continue;
       }
-      const int cx = cell_coord(qp.x, gp.ox, gp.inv, gp.dx);
-      const int cy = cell_coord(qp.y, gp.oy, gp.inv, gp.dy);
-      const int cz = cell_coord(qp.z, gp.oz, gp.inv, gp.dz);
-      if (cx != scx || cy != scy || cz != scz) {
-        // ---- stage the block of cells around (cx,cy,cz) ----
-        __syncwarp();
-        int a = 0, b = 0;
-        if (lane < 9) {
-          const int y = cy + (lane % 3) - 1, z = cz + (lane / 3) - 1;
-          if (y >= 0 && y < gp.dy && z >= 0 && z < gp.dz) {
-            const int* row = g.cell_start + (z * gp.dy + y) * gp.dx;
-            a = __ldg(row + max(cx - 1, 0));
-            b = __ldg(row + min(cx + 1, gp.dx - 1) + 1);
-          }
-        }
-        const int len = b - a;
-        int inc = len;
-#pragma unroll
-        for (int o = 1; o < 16; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
-        C = __shfl_sync(FULL, inc, 8);
-        const int excl = inc - len;
-        staged_ok = C <= ST_CMAX;
-        if (staged_ok) {
-          if (lane < 9) { S.row_a[lane] = a; S.row_excl[lane] = excl; }
-          for (int t0 = 0; t0 < C; t0 += 32) {
-            const int t = t0 + lane;
-            int j = 0;
-#pragma unroll
-            for (int step = 8; step > 0; step >>= 1) {
-              const int v = __shfl_sync(FULL, inc, j + step - 1);
-              if (v <= t) j += step;
-            }
-            const int ja = __shfl_sync(FULL, a, j), je = __shfl_sync(FULL, excl, j);
-            if (t < C) {
-              const float4 c = __ldg(g.sorted + ja + (t - je));
-              S.x[t] = c.x; S.y[t] = c.y; S.z[t] = c.z;
-            }
-          }
-        }
-        __syncwarp();
-        scx = cx; scy = cy; scz = cz;
-        t2_prev = 0.f;
-      }
-      bool done = false;
-      if (staged_ok && C >= k) {
-        const int rmax = max(max(max(cx, gp.dx - 1 - cx), max(cy, gp.dy - 1 - cy)), max(cz, gp.dz - 1 - cz));
-        float m2 = FLT_MAX;   // the block already covers the whole grid
-        if (rmax > 1) {
-          const float m = cube_face_distance(gp, cx, cy, cz, 1, qp.x, qp.y, qp.z);
-          m2 = m > 0.f ? m * m * 0.999999f : 0.f;
-        }
-        float T2 = t2_prev > 0.f ? t2_prev * 1.3f : 2.865f * (float)(k + 6) * gp.cell * gp.cell / (float)C;
-        T2 = fminf(T2, m2);
-        float lo = 0.f, hi = -1.f;
-        for (int tries = 0; tries < 8; ++tries) {
-          int cnt = 0;
-          for (int t0 = 0; t0 < C; t0 += 32) {
-            const int t = t0 + lane;
-            float d = INFINITY;
-            if (t < C) d = sqdist_unfused(qp.x, qp.y, qp.z, S.x[t], S.y[t], S.z[t]);
-            const bool pass = d < T2;
-            const unsigned mk = __ballot_sync(FULL, pass);
-            if (pass) {
-              const int pos = cnt + __popc(mk & lt);
-              if (pos < 32) { S.sel_d[pos] = d; S.sel_i[pos] = t; }
-            }
-            cnt += __popc(mk);
-          }
-          __syncwarp();
-          if (cnt >= k && cnt <= 32) {
-            float d = lane < cnt ? S.sel_d[lane] : INFINITY;
-            int ci = lane < cnt ? S.sel_i[lane] : -1;
-#pragma unroll
-            for (int size = 2; size <= 32; size <<= 1) {
-              const bool asc = (size == 32) || ((lane & size) == 0);
-#pragma unroll
-              for (int stride = size >> 1; stride > 0; stride >>= 1) WarpTopK::cex(d, ci, stride, ((lane & stride) == 0) == asc);
-            }
-            t2_prev = __shfl_sync(FULL, d, k - 1);
-            if (lane < k) {
-              int j = 0;
-#pragma unroll
-              for (int r = 1; r < 9; ++r) if (ci >= S.row_excl[r]) j = r;
-              nbr[(size_t)q * k + lane] = S.row_a[j] + (ci - S.row_excl[j]);
-            }
-            done = true;
-            __syncwarp();
-            break;
-          }
-          if (cnt < k) {
-            if (T2 >= m2) { __syncwarp(); break; }   // not decidable inside the block
-            lo = T2;
-            T2 = hi > 0.f ? sqrtf(lo * hi) : T2 * 1.7f;
-            T2 = fminf(T2, m2);
-          } else {
-            hi = T2;
-            T2 = lo > 0.f ? sqrtf(lo * hi) : T2 * 0.6f;
-          }
-          __syncwarp();
-        }
-      }
-      if (!done) {
-        WarpTopK rs;
-        rs.init(k, lane);
-        grid_search_warp(g, gp, qp.x, qp.y, qp.z, FLT_MAX, rs, k >= 4);
-        if (lane < k) nbr[(size_t)q * k + lane] = rs.p;
-        t2_prev = (rs.kth < FLT_MAX) ? rs.kth : 0.f;
+      // 8 children of edge TQ_CORE/2, 4 lanes each
+      const int h = TQ_CORE / 2;
+      const int ch = lane >> 2, sub = lane & 3;
+      const int cx0 = x0 + (ch & 1) * h, cy0 = y0 + ((ch >> 1) & 1) * h, cz0 = z0 + (ch >> 2) * h;
+      const int Qc = box_population(g, gp, cx0, cy0, cz0, h, 0, sub, 4);
+      const int Cc = box_population(g, gp, cx0, cy0, cz0, h, 1, sub, 4);
+      const bool fits = Cc <= TQ_CMAX;
+      emit_items(sub == 0 && Qc > 0 && fits, cx0, cy0, cz0, h, Qc, lane, items, ctrl);
+      unsigned deep = __ballot_sync(FULL, sub == 0 && Qc > 0 && !fits);
+      for (; deep; deep &= deep - 1) {
+        const int l = __ffs(deep) - 1;
+        const int px = __shfl_sync(FULL, cx0, l), py = __shfl_sync(FULL, cy0, l), pz = __shfl_sync(FULL, cz0, l);
+        // 8 single cells of that child; whether their radius-1 tile fits is left to the tile kernel
+        const int gx = px + (ch & 1), gy = py + ((ch >> 1) & 1), gz = pz + (ch >> 2);
+        const int Qg = box_population(g, gp, gx, gy, gz, 1, 0, sub, 4);
+        emit_items(sub == 0 && Qg > 0, gx, gy, gz, 1, Qg, lane, items, ctrl);
       }
     }
+  }
+}
+
+// one pass over the tile positions [c, cend): every point closer than T2 is counted, the first TQ_LCAP are stored in the
+// lane's list column (branch-free: overflow and non-passing candidates land in the dump row).  T2 < 0 switches a lane off.
+__device__ __forceinline__ int collect_pass(TileSmem& S, int c, int cend, float qx, float qy, float qz, float T2, int lane, int cnt) {
+  uint2* const col = &S.lst[0][lane];
+#define TQ_OFFER(D, CI)                                                         \
+  {                                                                             \
+    const bool ps = (D) < T2;                                                   \
+    const int row = ps ? min(cnt, TQ_LCAP) : TQ_LCAP;                           \
+    col[row * 32] = make_uint2(__float_as_uint(D), (unsigned)(CI));             \
+    cnt += ps ? 1 : 0;                                                          \
+  }
+  for (; c + 4 <= cend; c += 4) {
+    const float4 p0 = S.cand[c], p1 = S.cand[c + 1], p2 = S.cand[c + 2], p3 = S.cand[c + 3];
+    const float d0 = sqdist_unfused(qx, qy, qz, p0.x, p0.y, p0.z);
+    const float d1 = sqdist_unfused(qx, qy, qz, p1.x, p1.y, p1.z);
+    const float d2 = sqdist_unfused(qx, qy, qz, p2.x, p2.y, p2.z);
+    const float d3 = sqdist_unfused(qx, qy, qz, p3.x, p3.y, p3.z);
+    TQ_OFFER(d0, c) TQ_OFFER(d1, c + 1) TQ_OFFER(d2, c + 2) TQ_OFFER(d3, c + 3)
+  }
+  for (; c < cend; ++c) {
+    const float4 p0 = S.cand[c];
+    const float d0 = sqdist_unfused(qx, qy, qz, p0.x, p0.y, p0.z);
+    TQ_OFFER(d0, c)
+  }
+#undef TQ_OFFER
+  return cnt;
+}
+
+__global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView g, int n, int k, int* __restrict__ nbr,
+                                                                        const int4* __restrict__ items, int* __restrict__ ctrl,
+                                                                        int* __restrict__ fb_list, unsigned long long* __restrict__ stats) {
+  extern __shared__ __align__(16) unsigned char tq_smem_raw[];
+  TileSmem& S = reinterpret_cast<TileSmem*>(tq_smem_raw)[threadIdx.x >> 5];
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  const GridParams gp = load_grid(g.desc);
+  const int nitems = ctrl[CT_ITEMS];
+  unsigned st_fb = 0, st_ties = 0, st_tiles = 0, st_passes = 0, st_lanes = 0, st_items = 0;
+
+  for (;;) {
+    int w = 0;
+    if (lane == 0) w = atomicAdd(ctrl + CT_NEXT, 1);
+    w = __shfl_sync(FULL, w, 0);
+    if (w >= nitems) break;
+    st_items++;
+    const int4 item = __ldg(items + w);
+    TQ_CHECK(nitems <= n, "nitems", nitems, n);
+    const int x0 = item.x, y0 = item.y, z0 = item.z, sz = item.w & 255, first = (item.w >> 8) * TQ_ITEM;
+    // ---- the item's points: positions [first, first + TQ_ITEM) of the box's sz*sz contiguous slot ranges ----
+    int ncur = 0;
+    {
+      int qa = 0, qlen = 0;
+      if (lane < sz * sz) {
+        const int y = y0 + (lane % sz), z = z0 + (lane / sz);
+        if (y < gp.dy && z < gp.dz && x0 < gp.dx) {
+          const int* row = g.cell_start + (z * gp.dy + y) * gp.dx;
+          qa = __ldg(row + x0);
+          qlen = __ldg(row + min(x0 + sz, gp.dx)) - qa;
+        }
+      }
+      const int qinc = warp_incl_scan(qlen, lane);
+      const int Q = __shfl_sync(FULL, qinc, 31);
+      const int qexcl = qinc - qlen;
+      ncur = min(TQ_ITEM, Q - first);
+      for (int t0 = 0; t0 < ncur; t0 += 32) {
+        const int t = first + t0 + lane;
+        const int j = run_of(qinc, t);
+        const int ja = __shfl_sync(FULL, qa, j), je = __shfl_sync(FULL, qexcl, j);
+        if (t0 + lane < ncur) { S.cur[t0 + lane] = ja + (t - je); S.cur_t[t0 + lane] = 0.f; S.cur_lo[t0 + lane] = 0.f; S.cur_hi[t0 + lane] = -1.f; }
+      }
+      __syncwarp();
+    }
+    for (int s = 1; s <= TQ_SMAX && ncur > 0; s *= 2) {
+      // ---- stage the tile: cells [x0-s, x0+sz-1+s] x [y0-s, ..] x [z0-s, ..], 32 rows per round ----
+      const int ny = sz + 2 * s, nrows = ny * ny;
+      const int xl = max(x0 - s, 0), xr = min(x0 + sz - 1 + s, gp.dx - 1) + 1;
+      int C = 0;
+      bool overflow = false;
+      for (int r0 = 0; r0 < nrows; r0 += 32) {
+        const int r = r0 + lane;
+        int a = 0, b = 0;
+        if (r < nrows) {
+          const int y = y0 - s + (r % ny), z = z0 - s + (r / ny);
+          if (y >= 0 && y < gp.dy && z >= 0 && z < gp.dz) {
+            const int* row = g.cell_start + (z * gp.dy + y) * gp.dx;
+            a = __ldg(row + xl); b = __ldg(row + xr);
+          }
+        }
+        if (!__any_sync(FULL, b != a)) {
+          if (s <= 2 && r < nrows) S.rowoff[r] = C;
+          continue;
+        }
+        const int inc = warp_incl_scan(b - a, lane);
+        const int Cr = __shfl_sync(FULL, inc, 31);
+        if (C + Cr > TQ_CMAX) { overflow = true; break; }
+        const int excl = inc - (b - a);
+        if (s <= 2 && r < nrows) S.rowoff[r] = C + excl;
+        for (int t0 = 0; t0 < Cr; t0 += 32) {
+          const int t = t0 + lane;
+          const int j = run_of(inc, t);
+          const int ja = __shfl_sync(FULL, a, j), je = __shfl_sync(FULL, excl, j);
+          if (t < Cr) {
+            int p = ja + (t - je);
+            float4 c = __ldg(g.sorted + p);
+            c.w = __int_as_float(p);
+            S.cand[C + t] = c;
+          }
+        }
+        C += Cr;
+      }
+      if (overflow) break;                                    // the tile does not fit: warp search for what is left
+      if (C < k) continue;                                    // too sparse at this radius
+      if (s <= 2 && lane == 0) S.rowoff[nrows] = C;
+      __syncwarp();
+      st_tiles++;
+      // ---- answer the points from the tile, 32 at a time, one collection pass each; a point whose count misses
+      //      the window re-queues itself with a rescaled threshold, so retries share passes with other points ----
+      const float guess0 = (float)(k + 8) * (float)(ny * ny) * gp.cell * gp.cell / (3.14159265f * (float)C);
+      int nnxt = 0;
+      float prevT = 0.f;
+      for (int round = 0; round < 8 && ncur > 0; ++round) {
+        int nre = 0;
+        for (int t0 = 0; t0 < ncur; t0 += 32) {
+          const int t = t0 + lane;
+          const bool has = t < ncur;
+          int slot = has ? S.cur[t] : -1;
+          float T2 = has ? S.cur_t[t] : 0.f;
+          float lo = has ? S.cur_lo[t] : 0.f, hi = has ? S.cur_hi[t] : -1.f;
+          float4 qp = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (has) qp = __ldg(g.sorted + slot);
+          const bool me = has && isfinite(qp.x) && isfinite(qp.y) && isfinite(qp.z);
+          if (has && !me)
+            for (int j = 0; j < k; ++j) nbr[(size_t)slot * k + j] = -1;
+          // the (y,z) rows of cells this batch's points lie in: only tile rows within s of them can hold neighbours
+          // closer than the provable radius, so the pass scans that sub-tile (whole tile above radius 2)
+          int ylo = 0, yhi = ny - 1, zlo = 0, zhi = ny - 1;
+          if (s <= 2) {
+            const int yy = cell_coord(qp.y, gp.oy, gp.inv, gp.dy) - (y0 - s), zz = cell_coord(qp.z, gp.oz, gp.inv, gp.dz) - (z0 - s);
+            ylo = max(__reduce_min_sync(FULL, me ? yy : ny) - s, 0);
+            yhi = min(__reduce_max_sync(FULL, me ? yy : -1) + s, ny - 1);
+            zlo = max(__reduce_min_sync(FULL, me ? zz : ny) - s, 0);
+            zhi = min(__reduce_max_sync(FULL, me ? zz : -1) + s, ny - 1);
+          }
+          float m2 = FLT_MAX;
+          {
+            const float m = box_face_distance(gp, x0 - s, x0 + sz - 1 + s, y0 - s + ylo, y0 - s + yhi, z0 - s + zlo, z0 - s + zhi, qp.x, qp.y, qp.z);
+            if (m != FLT_MAX) m2 = m > 0.f ? m * m * 0.999999f : 0.f;
+          }
+          // first guess: 1.4 x the k-th distance this lane found last in this tile, else the radius holding k+8
+          // points at the tile's surface density (a planar cut through the tile covers ~ny*ny cells)
+          if (!(T2 > 0.f)) T2 = prevT > 0.f ? prevT * 1.4f : guess0;
+          T2 = fminf(T2, m2);
+          const bool active = me && m2 > 0.f;
+          st_passes++;
+          st_lanes += __popc(__ballot_sync(FULL, active));
+          int c_now = 0;
+          {
+            if (s <= 2) {
+              for (int zr = zlo; zr <= zhi && yhi >= ylo; ++zr)
+                c_now = collect_pass(S, S.rowoff[zr * ny + ylo], S.rowoff[zr * ny + yhi + 1], qp.x, qp.y, qp.z, active ? T2 : -1.f, lane, c_now);
+            } else {
+              c_now = collect_pass(S, 0, C, qp.x, qp.y, qp.z, active ? T2 : -1.f, lane, 0);
+            }
+          }
+          const bool good = active && c_now >= k && c_now <= TQ_LCAP;
+          // too few even at the largest provable radius (or no provable radius at all): needs a larger tile
+          const bool grow = me && (!active || (c_now < k && T2 >= m2));
+          const bool retry = active && !good && !grow;
+          // ---- tighten the threshold on the lane's own list until exactly k remain (warp-uniform loops) ----
+          bool decided = good;
+          bool tie = false;
+          float Tk = T2;
+          {
+            bool searching = good && c_now > k;
+            float slo = 0.f, shi = T2;
+            int clo = 0, chi = c_now;
+            const int cmax = __reduce_max_sync(FULL, searching ? c_now : 0);
+            for (int it = 0; it < 16 && __any_sync(FULL, searching); ++it) {
+              float T = slo + (shi - slo) * (((float)(k - clo) + 0.5f) / (float)max(chi - clo, 1));
+              if (!(T > slo && T < shi)) T = 0.5f * (slo + shi);
+              if (searching && !(T > slo && T < shi)) { searching = false; tie = true; }   // adjacent floats: tie at the k-th distance
+              int c = 0;
+              for (int i = 0; i < cmax; ++i) c += (i < c_now && __uint_as_float(S.lst[i][lane].x) < T) ? 1 : 0;
+              if (searching) {
+                if (c == k) { searching = false; Tk = T; }
+                else if (c < k) { slo = T; clo = c; }
+                else { shi = T; chi = c; }
+              }
+            }
+            if (searching) tie = true;
+            if (tie) { decided = false; st_ties++; }
+            const bool compact = good && c_now > k && !tie;
+            int pos = 0;
+            for (int i = 0; i < cmax; ++i) {
+              const uint2 e = S.lst[i][lane];
+              if (compact && i < c_now && __uint_as_float(e.x) < Tk) { S.lst[pos][lane].y = e.y; ++pos; }
+            }
+          }
+          if (decided) prevT = Tk;
+          const unsigned dmask = __ballot_sync(FULL, decided);
+          __syncwarp();
+          // ---- coalesced write-out: one query per step, lane j writes the j-th neighbour ----
+          for (unsigned mm = dmask; mm; mm &= mm - 1) {
+            const int l = __ffs(mm) - 1;
+            const int sl = __shfl_sync(FULL, slot, l);
+            TQ_CHECK(lane >= k || S.lst[lane][l].y < (unsigned)C, "tilepos", (int)S.lst[lane][l].y, C);
+            if (lane < k) nbr[(size_t)sl * k + lane] = __float_as_int(S.cand[S.lst[lane][l].y].w);
+          }
+          __syncwarp();
+          // ---- the rest: ties to the warp search, growers to the next radius, retries back into the queue ----
+          const unsigned tm = __ballot_sync(FULL, tie);
+          st_fb += __popc(tm);
+          fb_append(tm, slot, lane, fb_list, ctrl + CT_REST);
+          const unsigned gm = __ballot_sync(FULL, grow);
+          if (grow) S.nxt[nnxt + __popc(gm & lt)] = slot;
+          nnxt += __popc(gm);
+          const unsigned rm = __ballot_sync(FULL, retry);
+          if (retry) {
+            // counts grow ~linearly in T^2 on surfaces: aim at k+8 again, inside the bracket; never above the provable radius
+            if (c_now < k) lo = T2; else hi = T2;
+            float Tn = T2 * (float)(k + 8) / (float)max(c_now, 2);
+            if (Tn <= lo || (hi > 0.f && Tn >= hi)) Tn = hi > 0.f ? 0.5f * (lo + hi) : T2 * 2.f;
+            Tn = fminf(Tn, m2);
+            const int pos = nre + __popc(rm & lt);          // nre <= t0: never overtakes the reads
+            S.cur[pos] = slot;
+            S.cur_t[pos] = Tn;
+            S.cur_lo[pos] = lo;
+            S.cur_hi[pos] = hi;
+          }
+          nre += __popc(rm);
+          __syncwarp();
+        }
+        ncur = nre;
+      }
+      // still retrying after 8 rounds (pathological distributions): let the next radius / the warp search decide
+      for (int t0 = 0; t0 < ncur; t0 += 32) {
+        const bool has = t0 + lane < ncur;
+        const int slot = has ? S.cur[t0 + lane] : -1;
+        const unsigned m = __ballot_sync(FULL, has);
+        if (has) S.nxt[nnxt + __popc(m & lt)] = slot;
+        nnxt += __popc(m);
+      }
+      __syncwarp();
+      for (int t = lane; t < nnxt; t += 32) { S.cur[t] = S.nxt[t]; S.cur_t[t] = 0.f; S.cur_lo[t] = 0.f; S.cur_hi[t] = -1.f; }
+      ncur = nnxt;
+      __syncwarp();
+    }
+    // could not be decided inside a tile: warp search
+    for (int t0 = 0; t0 < ncur; t0 += 32) {
+      const bool has = t0 + lane < ncur;
+      const int slot = has ? S.cur[t0 + lane] : -1;
+      const unsigned m = __ballot_sync(FULL, has);
+      st_fb += __popc(m);
+      fb_append(m, slot, lane, fb_list, ctrl + CT_REST);
+    }
+    __syncwarp();
+  }
+  if (stats != nullptr && lane == 0) {
+    atomicAdd(stats + ST_FALLBACK, (unsigned long long)st_fb);
+    atomicAdd(stats + ST_TIES, (unsigned long long)st_ties);
+    atomicAdd(stats + ST_TILES, (unsigned long long)st_tiles);
+    atomicAdd(stats + ST_PASSES, (unsigned long long)st_passes);
+    atomicAdd(stats + ST_LANES, (unsigned long long)st_lanes);
+    atomicAdd(stats + ST_ITEMS, (unsigned long long)st_items);
+  }
+}
+
+// second launch: the growing-cube warp search for the points the tiles could not decide (non-finite points included:
+// they get -1 neighbours)
+__global__ void __launch_bounds__(KC_THREADS, KNN_MIN_BLOCKS) knn_lists_rest_kernel(GridView g, int k, const int* __restrict__ fb_list,
+                                                                                    const int* __restrict__ fb_count, int* __restrict__ nbr) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int nfb = *fb_count;
+  if (warp >= nfb) return;
+  const GridParams gp = load_grid(g.desc);
+  for (int i = warp; i < nfb; i += nwarps) {
+    const int q = __ldg(fb_list + i);
+    const float4 qp = __ldg(g.sorted + q);
+    WarpTopK rs;
+    rs.init(k, lane);
+    if (isfinite(qp.x) && isfinite(qp.y) && isfinite(qp.z)) grid_search_warp(g, gp, qp.x, qp.y, qp.z, FLT_MAX, rs, k >= 4);
+    if (lane < k) nbr[(size_t)q * k + lane] = rs.p;
   }
 }
 
@@ -218,6 +536,7 @@ __global__ void __launch_bounds__(128) cov_from_lists_kernel(GridView g, int n, 
   double mx = 0.0, my_ = 0.0, mz = 0.0;
   for (int j = 0; j < k; ++j) {
     const int p = __ldg(my + j);
+    TQ_CHECK(p < n, "nbr", p, q);
     if (p >= 0) { const float4 c = __ldg(g.sorted + p); mx += (double)c.x; my_ += (double)c.y; mz += (double)c.z; }
   }
   const double kd = (double)k;
@@ -247,21 +566,83 @@ cudaError_t launch_knn_queries(const DevCloud& c, const float4* queries, int nq,
   return cudaGetLastError();
 }
 
-cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_scratch, double* covs6, cudaStream_t st) {
+// scratch layout (ints): nbr[n*k] | control words[8] | warp-search list[n] | (16-byte aligned) work items int4[n]
+static inline size_t items_offset_ints(int n, int k) { return (((size_t)n * k + CT_N + (size_t)n) + 3) & ~(size_t)3; }
+size_t covariance_scratch_ints(int n, int k) { return items_offset_ints(n, k) + 4 * (size_t)n + 16; }
+
+cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_scratch, double* covs6, int table_cap, cudaStream_t st) {
   if (c.n <= 0) return cudaSuccess;
-  // queries per warp chunk: long enough to reuse a staged block, short enough to fill the GPU on small clouds
-  int qch = c.n / (148 * 20);
-  qch = qch < 4 ? 4 : (qch > 32 ? 32 : qch);
-  const int nchunks = (c.n + qch - 1) / qch;
-  int blocks = (nchunks + ST_WARPS - 1) / ST_WARPS;
-  if (blocks > 148 * 64) blocks = 148 * 64;
-  // the shared-memory staged variant executes fewer instructions but (occupancy 14 warps/SM, frequent fall-backs in
-  // sparse cells) is slower end to end on the C2 submap (1.26 ms vs 0.85 ms, profiles/); kept behind a switch
-  static const bool use_legacy = getenv("NGICP_KNN_STAGED") == nullptr;
-  if (use_legacy) knn_lists_kernel<<<(c.n + KC_WARPS - 1) / KC_WARPS, KC_THREADS, 0, st>>>(c.view(), c.n, k, nbr_scratch);
-  else knn_lists_staged_kernel<<<blocks, ST_WARPS * 32, 0, st>>>(c.view(), c.n, k, qch, nbr_scratch);
+  // Default: one warp per point (knn_lists_kernel).  NGICP_KNN_TILE=1 selects the cell-major tile path (plan + tile +
+  // rest launches): measured on the C2 submap it executes half the instructions but, at 11 resident warps per SM and
+  // ~14 busy lanes per pass, takes the same 0.82 ms for 500k points and is slower on 22k-point scans;
+  // NGICP_KNN_STATS=1 prints how many points took which path (synchronises: diagnostics only)
+  static const bool warp_only = getenv("NGICP_KNN_TILE") == nullptr;
+  static const bool want_stats = getenv("NGICP_KNN_STATS") != nullptr;
+  if (warp_only) {
+    knn_lists_kernel<<<(c.n + KC_WARPS - 1) / KC_WARPS, KC_THREADS, 0, st>>>(c.view(), c.n, k, nbr_scratch);
+    note_launches(1);
+  } else {
+    static bool attr_set[64] = {};
+    static int blocks_per_sm[64] = {};
+    static int sm_count[64] = {};
+    const size_t smem = sizeof(TileSmem) * TQ_WARPS;
+    int dev = 0;
+    cudaGetDevice(&dev);
+    const int di = dev & 63;
+    if (!attr_set[di]) {
+      cudaError_t e = cudaFuncSetAttribute(knn_lists_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      if (e != cudaSuccess) return e;
+      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[di], knn_lists_tile_kernel, TQ_WARPS * 32, smem)) != cudaSuccess) return e;
+      if ((e = cudaDeviceGetAttribute(&sm_count[di], cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+      if (blocks_per_sm[di] < 1) blocks_per_sm[di] = 1;
+      attr_set[di] = true;
+    }
+    int* ctrl = nbr_scratch + (size_t)c.n * k;
+    int* fb_list = ctrl + CT_N;
+    int4* items = reinterpret_cast<int4*>(nbr_scratch + items_offset_ints(c.n, k));
+    items = reinterpret_cast<int4*>((reinterpret_cast<uintptr_t>(items) + 15) & ~(uintptr_t)15);
+    cudaError_t e = cudaMemsetAsync(ctrl, 0, CT_N * sizeof(int), st);
+    if (e != cudaSuccess) return e;
+    unsigned long long* stats = nullptr;
+    if (want_stats) {
+      if (cudaMalloc(&stats, ST_N * sizeof(unsigned long long)) != cudaSuccess) return cudaGetLastError();
+      cudaMemsetAsync(stats, 0, ST_N * sizeof(unsigned long long), st);
+    }
+    // plan: one warp per run of boxes; the grid dimensions live on the device, so cover the table capacity
+    // (runs of 8 boxes above 32768 boxes, single boxes below)
+    const long long max_boxes = ((long long)table_cap + 63) / 64;
+    long long plan_warps = max_boxes > 32768 ? (max_boxes + 7) / 8 + 1024 : max_boxes + 1024;
+    knn_plan_kernel<<<(unsigned)((plan_warps + 7) / 8), 256, 0, st>>>(c.view(), items, ctrl);
+    if (want_stats) {
+      cudaError_t se = cudaStreamSynchronize(st);
+      int hc[CT_N] = {};
+      cudaMemcpy(hc, ctrl, sizeof(hc), cudaMemcpyDeviceToHost);
+      fprintf(stderr, "[ngicp knn] plan: %s items=%d (n=%d, grid %u blocks)\n", cudaGetErrorString(se), hc[CT_ITEMS], c.n, (unsigned)((plan_warps + 7) / 8));
+    }
+    // persistent grid: every resident warp pulls work items until the counter runs out
+    knn_lists_tile_kernel<<<sm_count[di] * blocks_per_sm[di], TQ_WARPS * 32, smem, st>>>(c.view(), c.n, k, nbr_scratch, items, ctrl, fb_list, stats);
+    if (want_stats) {
+      cudaError_t se = cudaStreamSynchronize(st);
+      fprintf(stderr, "[ngicp knn] tile: %s (grid %d blocks, smem %zu)\n", cudaGetErrorString(se), sm_count[di] * blocks_per_sm[di], smem);
+    }
+    knn_lists_rest_kernel<<<sm_count[di] * KNN_MIN_BLOCKS * 4, KC_THREADS, 0, st>>>(c.view(), k, fb_list, ctrl + CT_REST, nbr_scratch);
+    if (want_stats) {
+      cudaError_t se = cudaStreamSynchronize(st);
+      fprintf(stderr, "[ngicp knn] rest: %s\n", cudaGetErrorString(se));
+    }
+    note_launches(3);
+    if (want_stats) {
+      unsigned long long h[ST_N] = {};
+      cudaMemcpyAsync(h, stats, sizeof(h), cudaMemcpyDeviceToHost, st);
+      cudaStreamSynchronize(st);
+      cudaFree(stats);
+      fprintf(stderr, "[ngicp knn] n=%d k=%d warp-search=%llu (%.1f%%, ties %llu) items=%llu tiles=%llu passes=%llu lanes/pass=%.1f\n",
+              c.n, k, h[ST_FALLBACK], 100.0 * (double)h[ST_FALLBACK] / (double)c.n, h[ST_TIES], h[ST_ITEMS], h[ST_TILES], h[ST_PASSES],
+              h[ST_PASSES] ? (double)h[ST_LANES] / (double)h[ST_PASSES] : 0.0);
+    }
+  }
   cov_from_lists_kernel<<<(c.n + 127) / 128, 128, 0, st>>>(c.view(), c.n, k, method, nbr_scratch, covs6);
-  note_launches(2);
+  note_launches(1);
   return cudaGetLastError();
 }
 
