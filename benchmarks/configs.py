@@ -5,6 +5,10 @@
   c3  odometry replay: the OdomNode S2S + S2M + keyframe/submap sequence over a synthetic trajectory
   c4  independent scan-pair batch throughput (pairs/s), several handles/streams per GPU; under torchrun the pairs
       are partitioned over ranks (direct_lidar_odometry_b200.sharded.partition_pairs)
+  c5  dense 128-beam scan (no voxel filter) against a multi-million-point submap sharded over the ranks of one box:
+      every rank holds one slab (+ halo) of the target, the LM loop runs as one persistent kernel per GPU and the
+      partial H/b/err meet in NVLink peer memory (ngicp_comm_*); run under torchrun, e.g.
+      python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 benchmarks/configs.py c5
 
     python benchmarks/configs.py c1
     python benchmarks/configs.py c3 --scans 300 --cpu-scans 40
@@ -328,13 +332,148 @@ def run_c4(args):
         dist.barrier(); dist.destroy_process_group()
 
 
+# ------------------------------------------------------------------------------------------------ C5
+def _gen_dense(i):
+    T = synth.trajectory_pose(i)
+    s = synth.crop_box_negative(synth.os1_like(i, T, beams=128, cols=2048))
+    return i, T, s
+
+
+def c5_workload(n_target, log):
+    cache = os.path.join(ROOT, ".bench_cache", f"c5_v2_{n_target}.npz")
+    if os.path.exists(cache):
+        z = np.load(cache)
+        return {k: z[k] for k in z.files}
+    t0 = time.time()
+    stride = 33                                            # keyframes 5 m apart
+    n_key = max(2, int(np.ceil(n_target / 200_000.0)) + 1)
+    src_i = (n_key // 2) * stride + 10                     # the scan sits in the middle of its submap, as in DLO
+    with ProcessPoolExecutor(max_workers=min(16, os.cpu_count() or 1)) as ex:
+        out = list(ex.map(_gen_dense, [j * stride for j in range(n_key)] + [src_i]))
+    keys = [synth.transform_xyzi(s, T.astype(np.float32)) for _, T, s in out[:-1]]
+    target = np.ascontiguousarray(np.vstack(keys)[:n_target])
+    _, Ts, src = out[-1]
+    wl = dict(target=target, source=np.ascontiguousarray(src), truth=Ts,
+              guess=synth.perturb_pose(Ts, (0.2, 0.0, 0.0), 1.0).astype(np.float32))
+    log(f"C5 workload: {n_key} dense keyframes -> {target.shape[0]} target pts, source {src.shape[0]} pts, {time.time() - t0:.1f}s")
+    try:
+        os.makedirs(os.path.dirname(cache), exist_ok=True)
+        tmp = cache + f".{os.getpid()}.npz"
+        np.savez(tmp, **wl)
+        os.replace(tmp, cache)
+    except OSError:
+        pass
+    return wl
+
+
+def run_c5(args):
+    import torch
+    import torch.distributed as dist
+    from direct_lidar_odometry_b200 import NanoGICP, sharded
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=dev)
+    log = (lambda *a: print(*a, file=sys.stderr)) if rank == 0 else (lambda *a: None)
+    if rank == 0:
+        wl = c5_workload(args.target_points, log)
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        wl = c5_workload(args.target_points, log)
+    target, source, guess, truth = wl["target"], wl["source"], wl["guess"], wl["truth"]
+    be = sharded.CudaShardBackend(local, k=S2M["k"], max_corr_dist=S2M["thr"])
+    be.set_align_params(S2M["max_iter"], S2M["trans_eps"])
+    g = be.g
+    stream = torch.cuda.ExternalStream(g._L.ngicp_get_stream(g._h), device=dev)
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+
+    # ---- target: this rank's slab, index + k=20 covariances on this GPU, halo grown until exact ----
+    sync_all()
+    t0 = time.perf_counter()
+    info = be.build_target_shard(target, rank, world, halo=S2M["thr"] + 0.01, k=S2M["k"], cov_halo=args.cov_halo)
+    sync_all()
+    t_build = time.perf_counter() - t0
+    tm = g.timings()
+    build_gpu_ms = tm["set_target_ms"] + tm["target_covs_ms"]          # last round of the halo loop
+    if world > 1:
+        be.connect_fused(rank, world)
+    src_d = torch.from_numpy(source).to(dev)
+
+    def step():
+        be.set_source(src_d)             # index + k=20 covariances of the dense scan (replicated on every rank)
+        return be.align_fused(guess)     # persistent LM kernel, exchange in peer memory
+
+    for _ in range(3):
+        res = step()
+    sync_all()
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    al = []
+    for a, b in ev:
+        sync_all()
+        a.record(stream)
+        res = step()
+        b.record(stream)
+        b.synchronize()
+        al.append(g.timings()["align_ms"])
+    ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev) / args.steps, float(np.mean(al)), build_gpu_ms],
+                      dtype=torch.float64, device=dev)
+    npts = torch.tensor([info["shard_points"]], dtype=torch.int64, device=dev)
+    fx = torch.from_numpy(res["final_x"]).to(dev)
+    fx_all = [torch.zeros_like(fx) for _ in range(world)]
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        dist.all_gather(fx_all, fx)
+        shard_pts = [torch.zeros_like(npts) for _ in range(world)]
+        dist.all_gather(shard_pts, npts)
+    else:
+        fx_all, shard_pts = [fx], [npts]
+    identical = all(bool(torch.equal(fx_all[0], f)) for f in fx_all)
+    if rank == 0:
+        dt, dr = pose_err(res["final_x"], truth)
+        line = {"config": f"C5: dense 128-beam scan ({source.shape[0]} pts, no voxel filter) vs {target.shape[0]}-pt submap sharded over "
+                          f"{world} GPU(s): slabs + halo, k=20 covariances per slab, fused LM with the H/b/err exchange in NVLink peer memory",
+                "n_gpus": world, "steps": args.steps, "ms_per_scan": float(ms[0].item()), "align_ms": float(ms[1].item()),
+                "target_build_gpu_ms": float(ms[2].item()), "target_build_wall_s": t_build, "cov_halo_m": info["cov_halo"],
+                "halo_rounds": info["rounds"], "shard_points": [int(x.item()) for x in shard_pts],
+                "iterations": res["nr_iterations"], "n_linearize": res["n_linearize"], "n_compute_error": res["n_compute_error"],
+                "converged": res["converged"], "ranks_bit_identical": identical, "pose_error_m": dt, "pose_error_rad": dr}
+        if args.check and world > 1:
+            # the same registration unsharded on this GPU: iteration counts and pose must agree
+            u = NanoGICP(local)
+            configure(u, S2M)
+            u.setInputTarget(target); u.calculateTargetCovariances()
+            u.setInputSource(src_d); u.calculateSourceCovariances()
+            t1 = time.perf_counter()
+            u.align(guess)
+            line["unsharded_align_ms"] = u.timings()["align_ms"]
+            line["unsharded_iterations"] = int(u.result.nr_iterations)
+            line["max_abs_dT_vs_unsharded"] = float(np.abs(u.final_state() - res["final_x"]).max())
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        be.g.comm_close()
+        dist.destroy_process_group()
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
-    ap.add_argument("which", choices=["c1", "c3", "c4"])
+    ap.add_argument("which", choices=["c1", "c3", "c4", "c5"])
+    ap.add_argument("--target-points", type=int, default=5_000_000)
+    ap.add_argument("--cov-halo", type=float, default=2.0)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--check", type=int, default=1)
     ap.add_argument("--scans", type=int, default=300)
     ap.add_argument("--cpu-scans", type=int, default=40)
     ap.add_argument("--pairs", type=int, default=512)
     ap.add_argument("--pool", type=int, default=16)
     ap.add_argument("--handles", type=int, default=8)
     a = ap.parse_args()
-    {"c1": run_c1, "c3": run_c3, "c4": run_c4}[a.which](a)
+    {"c1": run_c1, "c3": run_c3, "c4": run_c4, "c5": run_c5}[a.which](a)

@@ -10,7 +10,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "csrc", "libnanogicp_b200.so")
 
-OK, E_INVALID, E_STATE, E_TOO_FEW_POINTS, E_COV_SIZE, E_CUDA, E_UNSUPPORTED, W_VOXEL_OVERFLOW = 0, -1, -2, -3, -4, -5, -6, 1
+OK, E_INVALID, E_STATE, E_TOO_FEW_POINTS, E_COV_SIZE, E_CUDA, E_UNSUPPORTED, E_COMM, W_VOXEL_OVERFLOW = 0, -1, -2, -3, -4, -5, -6, -7, 1
 REG_NONE, REG_MIN_EIG, REG_NORMALIZED_MIN_EIG, REG_PLANE, REG_FROBENIUS = range(5)
 OPT_GAUSS_NEWTON, OPT_LEVENBERG_MARQUARDT = 0, 1
 SOURCE, TARGET = 0, 1
@@ -26,7 +26,7 @@ EXPORTS = [
     "ngicp_get_target_covs", "ngicp_align", "ngicp_transform_source", "ngicp_voxel_filter", "ngicp_voxel_assignment",
     "ngicp_knn", "ngicp_linearize", "ngicp_compute_error", "ngicp_linearize_partial", "ngicp_compute_error_partial",
     "ngicp_version", "ngicp_launch_count", "ngicp_grid_info", "ngicp_set_owner_slab", "ngicp_lm_trial",
-    "ngicp_lm_is_converged",
+    "ngicp_lm_is_converged", "ngicp_comm_export", "ngicp_comm_connect", "ngicp_comm_connect_local", "ngicp_comm_close",
 ]
 
 
@@ -107,5 +107,9 @@ def load() -> C.CDLL:
     proto("ngicp_set_owner_slab", i32, vp, i32, f32, f32)
     proto("ngicp_lm_trial", i32, dp, dp, C.c_double, dp, dp, dp, dp)
     proto("ngicp_lm_is_converged", i32, dp, C.c_double, C.c_double)
+    proto("ngicp_comm_export", i32, vp, vp)
+    proto("ngicp_comm_connect", i32, vp, i32, i32, vp)
+    proto("ngicp_comm_connect_local", i32, vp, i32, i32, C.POINTER(vp))
+    proto("ngicp_comm_close", i32, vp)
     _LIB = L
     return L

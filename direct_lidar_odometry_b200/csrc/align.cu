@@ -15,6 +15,8 @@
 //
 // Per source point K4 touches p_A 16 B + C_A 48 B + p_B 16 B + C_B 48 B + corr 4 B = 132 B of
 // compulsory traffic (+48 B M +16 B p_B stored for K5, which then reads 16+48+16+4 = 84 B).
+#include <cstdlib>
+#include <cstring>
 #include "internal.h"
 #include "grid_search.cuh"
 #include "gicp_math.cuh"
@@ -259,8 +261,69 @@ __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
   return v;
 }
 
+// ---- sharded-submap mode: the exchange step fused into the grid reduction -------------------------------------
+// Every rank (one process per GPU) owns one slab of the target; the block that finishes this rank's fixed-order sum
+// writes the totals straight into EVERY rank's exchange buffer over NVLink (peer stores to IPC-mapped memory), raises
+// a sequence flag there, waits until all ranks' flags for this exchange have arrived in its own buffer and adds the
+// contributions in rank order.  All ranks therefore hold bit-identical sums and take identical LM decisions; there is
+// no host round trip and no separate collective launch.  Slots are double-buffered by the parity of the exchange
+// number: a rank can only be one exchange ahead of the slowest one, because finishing exchange s needs every rank's
+// flag s.  A rank that does not show up within pc.timeout_ns trips a sticky error flag instead of hanging the GPU.
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_release_sys_u64(unsigned long long* p, unsigned long long v) {
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// called by all AL_THREADS threads of the reducing block; s = this rank's total of column threadIdx.x (threads < NV)
 template <int NV>
-__device__ __forceinline__ void grid_reduce(double* acc, double (*s_red)[NRED], double* s_tot, double* partials, GridSync& gs) {
+__device__ __forceinline__ double peer_exchange_sum(double s, const PeerComm& pc) {
+  __shared__ unsigned long long s_seq;
+  if (threadIdx.x == 0) s_seq = *pc.seq + 1ull;
+  __syncthreads();
+  const unsigned long long seq = s_seq;
+  const int par = (int)(seq & 1ull);
+  if (threadIdx.x < NV) {
+    for (int p = 0; p < pc.world; ++p) {
+      volatile double* dst = pc.data[p] + (size_t)(par * NGICP_MAX_RANKS + pc.rank) * PEER_SLOT_DOUBLES + threadIdx.x;
+      *dst = s;
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x < pc.world) {
+    st_release_sys_u64(pc.flag[threadIdx.x] + par * NGICP_MAX_RANKS + pc.rank, seq);
+    const unsigned long long* mine = pc.flag[pc.rank] + par * NGICP_MAX_RANKS + threadIdx.x;
+    const unsigned long long t0 = global_timer_ns();
+    while (ld_acquire_sys_u64(mine) < seq) {
+      if (*(volatile int*)pc.error) break;
+      __nanosleep(200);
+      if (global_timer_ns() - t0 > pc.timeout_ns) { *(volatile int*)pc.error = 1; break; }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  double t = s;
+  if (threadIdx.x < NV) {
+    t = 0.0;
+    for (int r = 0; r < pc.world; ++r)
+      t += __ldcv(pc.data[pc.rank] + (size_t)(par * NGICP_MAX_RANKS + r) * PEER_SLOT_DOUBLES + threadIdx.x);
+  }
+  if (threadIdx.x == 0) *pc.seq = seq;
+  return t;
+}
+
+template <int NV>
+__device__ __forceinline__ void grid_reduce(double* acc, double (*s_red)[NRED], double* s_tot, double* partials, GridSync& gs,
+                                            const PeerComm& pc) {
   __shared__ int s_last;
   block_reduce_store<NV>(acc, s_red, partials + (size_t)blockIdx.x * NRED);
   if (threadIdx.x == 0) {
@@ -293,12 +356,13 @@ __device__ __forceinline__ void grid_reduce(double* acc, double (*s_red)[NRED], 
       s_red[seg][v] = ((part[0] + part[1]) + (part[2] + part[3])) + ((part[4] + part[5]) + (part[6] + part[7]));
     }
     __syncthreads();
+    double s = 0.0;
     if (threadIdx.x < NV) {
-      double s = 0.0;
 #pragma unroll
       for (int sg = 0; sg < AL_WARPS; sg++) s += s_red[sg][threadIdx.x];
-      __stcg(tot + threadIdx.x, s);
     }
+    if (pc.world > 1) s = peer_exchange_sum<NV>(s, pc);
+    if (threadIdx.x < NV) __stcg(tot + threadIdx.x, s);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -326,7 +390,12 @@ __device__ __forceinline__ void trace_stamp(const LmParams& prm, int& slot) {
   }
 }
 
-__global__ void __launch_bounds__(AL_THREADS) align_fused_kernel(AlignArgs a, LmParams prm, Guess16 guess, ngicp_result* __restrict__ res, unsigned* bar, double* totals) {
+// MINB = resident blocks per SM the kernel is compiled for.  1: 255 registers, the scalar LM state of thread 0 lives in
+// registers (shortest critical path; scans up to ~38k points have one point per thread anyway).  2 / 3: 128 / 80
+// registers, that state spills to local memory but twice / three times as many source points are in flight — the
+// better trade for dense scans (C5).
+template <int MINB>
+__global__ void __launch_bounds__(AL_THREADS, MINB) align_fused_kernel(AlignArgs a, LmParams prm, Guess16 guess, ngicp_result* __restrict__ res, unsigned* bar, double* totals, PeerComm pc) {
   int tslot = 0;
   trace_stamp(prm, tslot);
   __shared__ double s_red[AL_WARPS][NRED];
@@ -368,7 +437,7 @@ __global__ void __launch_bounds__(AL_THREADS) align_fused_kernel(AlignArgs a, Lm
       for (int j = 0; j < NRED; j++) acc[j] = 0.0;
       for (int i = gtid; i < a.ns; i += gstride) linearize_point(a, gp, Tf, T, prm.cap_d2, prm.thr2, i, acc);
       trace_stamp(prm, tslot);
-      grid_reduce<NRED>(acc, s_red, s_tot, a.partials, gs);
+      grid_reduce<NRED>(acc, s_red, s_tot, a.partials, gs, pc);
       trace_stamp(prm, tslot);
     }
     int outcome = 0;  // 1: step returned true, 0: LM failed
@@ -421,7 +490,7 @@ __global__ void __launch_bounds__(AL_THREADS) align_fused_kernel(AlignArgs a, Lm
           trace_stamp(prm, tslot);
           for (int i = gtid; i < a.ns; i += gstride) acc[0] += error_point(a, T, i);
           trace_stamp(prm, tslot);
-          grid_reduce<1>(acc, s_red, s_tot, a.partials, gs);
+          grid_reduce<1>(acc, s_red, s_tot, a.partials, gs, pc);
           trace_stamp(prm, tslot);
         }
         if (threadIdx.x == 0) {
@@ -475,26 +544,42 @@ __global__ void __launch_bounds__(AL_THREADS) align_fused_kernel(AlignArgs a, Lm
     res->n_linearize = n_lin;
     res->n_compute_error = n_err;
     res->lm_failed = lm_failed;
-    res->reserved = 0;
+    res->reserved = (pc.world > 1) ? *(volatile int*)pc.error : 0;   // 1: a peer did not show up in time
   }
 }
 
-int align_fused_max_blocks(int device) {
-  static int cached[64] = {0};
-  if (device >= 0 && device < 64 && cached[device]) return cached[device];
-  int per_sm = 0, sms = 0;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, align_fused_kernel, AL_THREADS, 0);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
-  int v = per_sm * sms;
-  if (v < 1) v = 1;
-  if (device >= 0 && device < 64) cached[device] = v;
-  return v;
+static int fused_blocks_per_sm(int device, int minb) {
+  static int cached[64][4] = {};
+  if (device >= 0 && device < 64 && cached[device][minb]) return cached[device][minb];
+  int per_sm = 0;
+  if (minb == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, align_fused_kernel<1>, AL_THREADS, 0);
+  else if (minb == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, align_fused_kernel<2>, AL_THREADS, 0);
+  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, align_fused_kernel<3>, AL_THREADS, 0);
+  if (per_sm < 1) per_sm = 1;
+  if (device >= 0 && device < 64) cached[device][minb] = per_sm;
+  return per_sm;
 }
+static int sm_count_of(int device) {
+  static int cached[64] = {};
+  if (device >= 0 && device < 64 && cached[device]) return cached[device];
+  int sms = 0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+  if (sms < 1) sms = 1;
+  if (device >= 0 && device < 64) cached[device] = sms;
+  return sms;
+}
+int align_fused_max_blocks(int device) { return fused_blocks_per_sm(device, 1) * sm_count_of(device); }
 
 cudaError_t launch_align_fused(const AlignBuffers& ab, const ngicp_params& p, const float* guess16, ngicp_result* res_dev,
-                               unsigned* barrier, int device, cudaStream_t st, unsigned long long* trace) {
+                               unsigned* barrier, int device, cudaStream_t st, unsigned long long* trace, const PeerComm* comm) {
   int blocks = (ab.ns + AL_THREADS - 1) / AL_THREADS;   // one source point per thread when the grid can hold them
-  const int lim = align_fused_max_blocks(device);
+  // variant: more resident blocks per SM once the scan no longer fits one point per thread (NGICP_ALIGN_MINB overrides)
+  static const int minb_env = getenv("NGICP_ALIGN_MINB") ? atoi(getenv("NGICP_ALIGN_MINB")) : 0;
+  const int sms = sm_count_of(device);
+  int minb = 1;
+  while (minb < 3 && blocks > fused_blocks_per_sm(device, minb) * sms) ++minb;   // smallest variant that holds one point per thread
+  if (minb_env >= 1 && minb_env <= 3) minb = minb_env;
+  const int lim = fused_blocks_per_sm(device, minb) * sms;
   if (blocks > lim) blocks = lim;
   if (blocks > ab.max_blocks) blocks = ab.max_blocks;
   if (blocks < 1) blocks = 1;
@@ -515,8 +600,13 @@ cudaError_t launch_align_fused(const AlignBuffers& ab, const ngicp_params& p, co
   if (e != cudaSuccess) return e;
   double* totals = ab.reduced;  // [2][NRED]
   note_launches(1);
-  void* args[] = {(void*)&a, (void*)&prm, (void*)&g, (void*)&res_dev, (void*)&barrier, (void*)&totals};
-  return cudaLaunchCooperativeKernel((const void*)align_fused_kernel, dim3(blocks), dim3(AL_THREADS), args, 0, st);
+  PeerComm pc;
+  memset(&pc, 0, sizeof pc);
+  pc.world = 1;
+  if (comm && comm->world > 1) pc = *comm;
+  void* args[] = {(void*)&a, (void*)&prm, (void*)&g, (void*)&res_dev, (void*)&barrier, (void*)&totals, (void*)&pc};
+  const void* fn = minb == 1 ? (const void*)align_fused_kernel<1> : (minb == 2 ? (const void*)align_fused_kernel<2> : (const void*)align_fused_kernel<3>);
+  return cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(AL_THREADS), args, 0, st);
 }
 
 }  // namespace ngicp

@@ -29,6 +29,12 @@ struct ngicp_handle {
   int align_max_blocks = 2048;
   int slab_axis = -1;
   float slab_lo = 0.f, slab_hi = 0.f;
+  // sharded-submap mode: exchange buffers of all ranks (own one allocated here, peers IPC-mapped or in-process)
+  void* comm_buf = nullptr;
+  void* comm_peer[NGICP_MAX_RANKS] = {};
+  bool comm_peer_ipc[NGICP_MAX_RANKS] = {};
+  PeerComm comm;
+  bool comm_on = false;
 };
 
 namespace ngicp {
@@ -380,6 +386,9 @@ int ngicp_create(int device, ngicp_t** out) {
     ngicp_destroy(h);
     return NGICP_E_CUDA;
   }
+  // NGICP_ALIGN_MAX_BLOCKS caps the persistent LM kernel's grid (default: whatever is co-resident); needed when
+  // several handles run their cooperative kernels on ONE GPU at the same time (sharded-mode tests)
+  if (const char* e = getenv("NGICP_ALIGN_MAX_BLOCKS")) { const int v = atoi(e); if (v > 0 && v < h->align_max_blocks) h->align_max_blocks = v; }
   *out = h;
   return NGICP_OK;
 }
@@ -389,6 +398,8 @@ void ngicp_destroy(ngicp_t* h) {
   DeviceGuard g(h->device);
   if (h->stream && h->stream->s) cudaStreamSynchronize(h->stream->s);
   h->src.reset(); h->tgt.reset(); h->src_cov.reset(); h->tgt_cov.reset();
+  ngicp_comm_close(h);
+  if (h->comm_buf) cudaFree(h->comm_buf);
   if (h->res_pinned) cudaFreeHost(h->res_pinned);
   if (h->red_pinned) cudaFreeHost(h->red_pinned);
   for (int i = 0; i < PH_COUNT; i++)
@@ -520,10 +531,12 @@ int ngicp_align(ngicp_t* h, const float* guess16, ngicp_result* out) {
       trace = h->sc.trace.as<unsigned long long>();
       NG_CUDA(h, cudaMemsetAsync(trace, 0, sizeof(unsigned long long) * 256, h->stream->s));
     }
-    NG_CUDA(h, launch_align_fused(ab, h->prm, guess16, res_dev, h->sc.barrier.as<unsigned>(), h->device, h->stream->s, trace));
+    NG_CUDA(h, launch_align_fused(ab, h->prm, guess16, res_dev, h->sc.barrier.as<unsigned>(), h->device, h->stream->s, trace,
+                                  h->comm_on ? &h->comm : nullptr));
     NG_CUDA(h, cudaMemcpyAsync(h->res_pinned, res_dev, sizeof(ngicp_result), cudaMemcpyDeviceToHost, h->stream->s));
     NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
     *out = *h->res_pinned;
+    if (h->comm_on && out->reserved != 0) return fail(h, NGICP_E_COMM, "sharded align: a peer rank did not reach the exchange in time");
     if (trace) {
       unsigned long long t[256];
       NG_CUDA(h, cudaMemcpy(t, trace, sizeof t, cudaMemcpyDeviceToHost));
@@ -691,4 +704,99 @@ int ngicp_lm_is_converged(const double* delta16, double rot_eps, double trans_ep
   return lm_is_converged(d, rot_eps, trans_eps) ? 1 : 0;
 }
 
+// ---- sharded-submap exchange (align.cu: peer_exchange_sum) ----------------------------------------------------
+static int comm_alloc(ngicp_t* h) {
+  if (h->comm_buf) return NGICP_OK;
+  NG_CUDA(h, cudaMalloc(&h->comm_buf, PEER_BUF_BYTES));   // plain cudaMalloc: IPC cannot export pool memory
+  NG_CUDA(h, cudaMemset(h->comm_buf, 0, PEER_BUF_BYTES));
+  return NGICP_OK;
+}
+static void comm_fill(ngicp_t* h, int rank, int world) {
+  PeerComm& pc = h->comm;
+  memset(&pc, 0, sizeof pc);
+  pc.world = world; pc.rank = rank;
+  for (int p = 0; p < world; ++p) {
+    unsigned char* base = static_cast<unsigned char*>(h->comm_peer[p]);
+    pc.data[p] = reinterpret_cast<double*>(base);
+    pc.flag[p] = reinterpret_cast<unsigned long long*>(base + PEER_DATA_BYTES);
+  }
+  unsigned char* own = static_cast<unsigned char*>(h->comm_buf);
+  pc.seq = reinterpret_cast<unsigned long long*>(own + PEER_DATA_BYTES + PEER_FLAG_BYTES);
+  pc.error = reinterpret_cast<int*>(own + PEER_DATA_BYTES + PEER_FLAG_BYTES + 8);
+  const char* e = getenv("NGICP_COMM_TIMEOUT_MS");
+  const double ms = e ? atof(e) : 2000.0;
+  pc.timeout_ns = (unsigned long long)((ms > 0.0 ? ms : 2000.0) * 1e6);
+  h->comm_on = world > 1;
+}
+
+int ngicp_comm_export(ngicp_t* h, void* handle64) {
+  if (!h || !handle64) return NGICP_E_INVALID;
+  static_assert(sizeof(cudaIpcMemHandle_t) <= NGICP_COMM_HANDLE_BYTES, "IPC handle does not fit");
+  DeviceGuard g(h->device);
+  int rc = comm_alloc(h);
+  if (rc) return rc;
+  NG_CUDA(h, cudaMemset(h->comm_buf, 0, PEER_BUF_BYTES));
+  cudaIpcMemHandle_t ipc;
+  NG_CUDA(h, cudaIpcGetMemHandle(&ipc, h->comm_buf));
+  memset(handle64, 0, NGICP_COMM_HANDLE_BYTES);
+  memcpy(handle64, &ipc, sizeof ipc);
+  return NGICP_OK;
+}
+
+int ngicp_comm_close(ngicp_t* h) {
+  if (!h) return NGICP_E_INVALID;
+  DeviceGuard g(h->device);
+  if (h->stream) cudaStreamSynchronize(h->stream->s);
+  for (int p = 0; p < NGICP_MAX_RANKS; ++p) {
+    if (h->comm_peer[p] && h->comm_peer_ipc[p]) cudaIpcCloseMemHandle(h->comm_peer[p]);
+    h->comm_peer[p] = nullptr;
+    h->comm_peer_ipc[p] = false;
+  }
+  h->comm_on = false;
+  return NGICP_OK;
+}
+
+int ngicp_comm_connect(ngicp_t* h, int rank, int world, const void* handles) {
+  if (!h || !handles || world < 1 || world > NGICP_MAX_RANKS || rank < 0 || rank >= world) return NGICP_E_INVALID;
+  DeviceGuard g(h->device);
+  int rc = comm_alloc(h);
+  if (rc) return rc;
+  ngicp_comm_close(h);
+  for (int p = 0; p < world; ++p) {
+    if (p == rank) { h->comm_peer[p] = h->comm_buf; continue; }
+    cudaIpcMemHandle_t ipc;
+    memcpy(&ipc, static_cast<const unsigned char*>(handles) + (size_t)p * NGICP_COMM_HANDLE_BYTES, sizeof ipc);
+    NG_CUDA(h, cudaIpcOpenMemHandle(&h->comm_peer[p], ipc, cudaIpcMemLazyEnablePeerAccess));
+    h->comm_peer_ipc[p] = true;
+  }
+  comm_fill(h, rank, world);
+  return NGICP_OK;
+}
+
+int ngicp_comm_connect_local(ngicp_t* h, int rank, int world, ngicp_t* const* peers) {
+  if (!h || !peers || world < 1 || world > NGICP_MAX_RANKS || rank < 0 || rank >= world) return NGICP_E_INVALID;
+  DeviceGuard g(h->device);
+  int rc = comm_alloc(h);
+  if (rc) return rc;
+  ngicp_comm_close(h);
+  for (int p = 0; p < world; ++p) {
+    ngicp_t* o = peers[p];
+    if (!o) return fail(h, NGICP_E_INVALID, "comm_connect_local: null peer");
+    if (p == rank) { h->comm_peer[p] = h->comm_buf; continue; }
+    { DeviceGuard go(o->device); rc = comm_alloc(o); if (rc) return fail(h, NGICP_E_CUDA, "comm_connect_local: peer buffer"); }
+    if (o->device != h->device) {
+      int can = 0;
+      NG_CUDA(h, cudaDeviceCanAccessPeer(&can, h->device, o->device));
+      if (!can) return fail(h, NGICP_E_UNSUPPORTED, "comm_connect_local: no peer access between the devices");
+      cudaError_t e = cudaDeviceEnablePeerAccess(o->device, 0);
+      if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail(h, NGICP_E_CUDA, "cudaDeviceEnablePeerAccess", e);
+      cudaGetLastError();
+    }
+    h->comm_peer[p] = o->comm_buf;
+  }
+  comm_fill(h, rank, world);
+  return NGICP_OK;
+}
+
 }  // extern "C"
+

@@ -137,9 +137,24 @@ struct AlignBuffers {
 cudaError_t launch_linearize(const AlignBuffers& ab, const double* T16_colmajor, double max_corr_dist, cudaStream_t st);
 cudaError_t launch_compute_error(const AlignBuffers& ab, const double* T16_colmajor, cudaStream_t st);
 cudaError_t launch_export_mahal(const AlignBuffers& ab, double* out16, cudaStream_t st);
+// sharded-submap mode: where every rank's exchange buffer is mapped in this process (see align.cu, peer_exchange_sum)
+constexpr int NGICP_MAX_RANKS = 8;
+constexpr int PEER_SLOT_DOUBLES = 32;                       // >= NRED
+constexpr size_t PEER_DATA_BYTES = sizeof(double) * 2 * NGICP_MAX_RANKS * PEER_SLOT_DOUBLES;
+constexpr size_t PEER_FLAG_BYTES = sizeof(unsigned long long) * 2 * NGICP_MAX_RANKS;
+constexpr size_t PEER_BUF_BYTES = PEER_DATA_BYTES + PEER_FLAG_BYTES + 64;   // + local exchange counter and error flag
+struct PeerComm {
+  int world, rank;
+  double* data[NGICP_MAX_RANKS];               // [2][NGICP_MAX_RANKS][PEER_SLOT_DOUBLES] on each rank
+  unsigned long long* flag[NGICP_MAX_RANKS];   // [2][NGICP_MAX_RANKS] on each rank
+  unsigned long long* seq;                     // local: exchanges completed
+  int* error;                                  // local: sticky "peer timed out"
+  unsigned long long timeout_ns;
+};
 // the whole LM loop in one persistent cooperative kernel; result written to *res_dev (ngicp_result layout)
 cudaError_t launch_align_fused(const AlignBuffers& ab, const ngicp_params& prm, const float* guess16, ngicp_result* res_dev,
-                               unsigned* barrier, int device, cudaStream_t st, unsigned long long* trace = nullptr);
+                               unsigned* barrier, int device, cudaStream_t st, unsigned long long* trace = nullptr,
+                               const PeerComm* comm = nullptr);
 int align_fused_max_blocks(int device);
 
 // ---- voxel.cu -------------------------------------------------------------------------------------

@@ -406,6 +406,29 @@ class NanoGICP:
     def set_owner_slab(self, axis: int, lo: float = 0.0, hi: float = 0.0):
         self._check(self._L.ngicp_set_owner_slab(self._h, axis, C.c_float(lo), C.c_float(hi)))
 
+    # ------------------------------------------------------------------ sharded-submap exchange (fused into align)
+    def comm_export(self) -> bytes:
+        """This rank's exchange buffer as a 64-byte CUDA IPC handle (allocates it on first use)."""
+        buf = (C.c_ubyte * 64)()
+        self._check(self._L.ngicp_comm_export(self._h, buf))
+        return bytes(buf)
+
+    def comm_connect(self, rank: int, world: int, handles) -> None:
+        """Map the exchange buffers of all ranks (`handles[r]` = comm_export() of rank r, one process per GPU).
+        Barrier between this call and the first align()."""
+        blob = b"".join(bytes(h) for h in handles)
+        assert len(blob) == 64 * world
+        arr = (C.c_ubyte * len(blob)).from_buffer_copy(blob)
+        self._check(self._L.ngicp_comm_connect(self._h, rank, world, arr))
+
+    def comm_connect_local(self, rank: int, peers) -> None:
+        """Same for NanoGICP objects living in this process (several GPUs, or one GPU in tests)."""
+        arr = (C.c_void_p * len(peers))(*[p._h for p in peers])
+        self._check(self._L.ngicp_comm_connect_local(self._h, rank, len(peers), arr))
+
+    def comm_close(self) -> None:
+        self._check(self._L.ngicp_comm_close(self._h))
+
     def grid_info(self, which: int) -> dict:
         cell, dims, nc = C.c_float(0), (C.c_int * 3)(), C.c_int(0)
         self._check(self._L.ngicp_grid_info(self._h, which, C.byref(cell), dims, C.byref(nc)))

@@ -62,13 +62,83 @@ class CudaShardBackend:
         f32 = np.finfo(np.float32)
         self.g.set_owner_slab(axis, float(np.clip(lo, f32.min, f32.max)), float(np.clip(hi, f32.min, f32.max)))
 
-    def set_source(self, pts, covs):
+    def set_source(self, pts, covs=None):
         self.g.clearSource()
-        self.g.registerInputSource(pts)
-        self.g.setSourceCovariances(covs)
+        if covs is None:
+            self.g.setInputSource(pts)            # index + covariances on this GPU (every rank holds the whole scan)
+            self.g.calculateSourceCovariances()
+        else:
+            self.g.registerInputSource(pts)
+            self.g.setSourceCovariances(covs)
+
+    def build_target_shard(self, points: np.ndarray, rank: int, world: int, halo: float, k: int, cov_halo: float = 2.0,
+                           chunk: int = 1 << 18) -> dict:
+        """This rank's slab of `points` with covariances computed HERE, on the slab widened by a halo that is grown
+        until the result is exact: a point the rank can be asked to match (inside the slab widened by `halo`, the
+        max-correspondence distance) must have its k-th neighbour closer than the nearest cut plane, otherwise its
+        neighbourhood may continue on the other side of the cut.  The check reads back the k-th distances of those
+        points through the kNN entry of the C ABI, in chunks."""
+        from . import _lib
+        axis, bounds = slab_bounds(points, world)
+        lo, hi = float(bounds[rank]), float(bounds[rank + 1])
+        c = np.asarray(points)[:, axis].astype(np.float64)
+        H, rounds = max(float(cov_halo), float(halo)), 0
+        self.g.setCorrespondenceRandomness(k)
+        while True:
+            rounds += 1
+            keep = (c >= lo - H) & (c < hi + H)
+            sub = np.ascontiguousarray(points[keep])
+            self.g.clearTarget()
+            self.g.setInputTarget(sub)
+            self.g.calculateTargetCovariances()
+            if keep.all():
+                break
+            cs = c[keep]
+            cut_lo = lo - H if np.isfinite(lo) and (c < lo - H).any() else -np.inf
+            cut_hi = hi + H if np.isfinite(hi) and (c >= hi + H).any() else np.inf
+            margin = np.minimum(cs - cut_lo, cut_hi - cs)
+            band = np.nonzero((cs >= lo - halo) & (cs < hi + halo) & np.isfinite(margin))[0]
+            worst = 0.0
+            bad = 0
+            for i in range(0, band.size, chunk):
+                sel = band[i:i + chunk]
+                _, d2 = self.g.knn(_lib.TARGET, np.ascontiguousarray(sub[sel, :3]), k)
+                kth = np.sqrt(d2[:, k - 1].astype(np.float64))
+                bad += int((kth >= margin[sel]).sum())
+                worst = max(worst, float((kth - margin[sel]).max()))
+            if bad == 0:
+                break
+            H *= 2.0
+        f32 = np.finfo(np.float32)
+        self.g.set_owner_slab(axis, float(np.clip(lo, f32.min, f32.max)), float(np.clip(hi, f32.min, f32.max)))
+        return dict(axis=axis, lo=lo, hi=hi, cov_halo=H, rounds=rounds, shard_points=int(keep.sum()), keep=keep)
 
     def linearize_partial(self, T) -> np.ndarray:
         return self.g.linearize_partial(T)
+
+    # -- exchange fused into the persistent LM kernel (NVLink peer memory; include/nanogicp_c.h ngicp_comm_*) -----
+    def connect_fused(self, rank: int, world: int, group=None):
+        """One process per GPU: swap CUDA IPC handles of the exchange buffers over the process group, map them."""
+        import torch.distributed as dist
+        mine = self.g.comm_export()
+        handles = [None] * world
+        dist.all_gather_object(handles, mine, group=group)
+        self.g.comm_connect(rank, world, handles)
+        dist.barrier(group=group)
+
+    def set_align_params(self, max_iter: int, trans_eps: float, rot_eps: float = 2e-3):
+        self.g.setMaximumIterations(max_iter)
+        self.g.setTransformationEpsilon(trans_eps)
+        self.g.setRotationEpsilon(rot_eps)
+
+    def align_fused(self, guess=None) -> dict:
+        """Every rank calls this with the same guess; the LM loop runs on the GPUs, partial sums meet in peer memory."""
+        self.g.align(guess)
+        r = self.g.result
+        return dict(final_x=self.g.final_state(), final_transformation=self.g.getFinalTransformation(),
+                    final_hessian=np.array(r.final_hessian).reshape(6, 6).T.copy(), nr_iterations=int(r.nr_iterations),
+                    converged=int(r.converged), n_linearize=int(r.n_linearize), n_compute_error=int(r.n_compute_error),
+                    lm_failed=int(r.lm_failed), last_error=float(r.last_error), lm_lambda=float(r.lm_lambda))
 
     def compute_error_partial(self, T) -> float:
         return float(self.g.compute_error_partial(T)[0])

@@ -42,6 +42,7 @@ enum {
   NGICP_E_COV_SIZE = -4,         /* covariance count != point count (assert at nano_gicp_impl.hpp:175-176) */
   NGICP_E_CUDA = -5,
   NGICP_E_UNSUPPORTED = -6,
+  NGICP_E_COMM = -7,             /* sharded align: a peer rank did not reach the exchange in time */
   NGICP_W_VOXEL_OVERFLOW = 1     /* voxel index would overflow int32: input passed through, like PCL */
 };
 
@@ -178,6 +179,23 @@ int ngicp_compute_error_partial(ngicp_t* h, const double* T16, double* out1);
 /* sharded-submap mode (one handle per GPU holds one spatial slab of the target plus a halo of the max-correspondence
  * distance): count only source points whose transformed position lies in [lo, hi) along `axis` (0/1/2; -1 = off) */
 int ngicp_set_owner_slab(ngicp_t* h, int axis, float lo, float hi);
+/* The exchange step of the sharded mode, fused into ngicp_align: once connected, the persistent LM kernel of every rank
+ * writes its partial {H, b, err} (and each trial's error) into every rank's exchange buffer over NVLink / NVSwitch peer
+ * memory, waits for the others' flags and sums in rank order — the reference's serial merge of per-thread partials
+ * (nano_gicp_impl.hpp:260-267) stretched across GPUs, with no host round trip and no separate collective launch.
+ * All ranks must call ngicp_align with the same source, parameters and guess; they take identical LM decisions.
+ *   ngicp_comm_export        allocates this rank's exchange buffer and returns its 64-byte CUDA IPC handle
+ *   ngicp_comm_connect       maps the buffers of all `world` ranks (handles = world x 64 bytes, indexed by rank; one
+ *                            process per GPU); callers must barrier between connect and the first align
+ *   ngicp_comm_connect_local the same for handles living in THIS process (several GPUs, or one GPU for tests)
+ *   ngicp_comm_close         unmaps; ngicp_align is single-GPU again
+ * A rank that does not arrive within NGICP_COMM_TIMEOUT_MS (environment, default 2000) makes ngicp_align return
+ * NGICP_E_COMM on the waiting ranks instead of hanging the GPU; reconnect before the next align. */
+#define NGICP_COMM_HANDLE_BYTES 64
+int ngicp_comm_export(ngicp_t* h, void* handle64);
+int ngicp_comm_connect(ngicp_t* h, int rank, int world, const void* handles);
+int ngicp_comm_connect_local(ngicp_t* h, int rank, int world, ngicp_t* const* peers);
+int ngicp_comm_close(ngicp_t* h);
 /* host-only: the scalar side of one LM trial (lsq_registration_impl.hpp:172-179): d = solve(H + lambda I, -b),
  * delta = [so3_exp(d[0:3]) | d[3:6]], xi = delta * x0 — the same code the fused kernel runs; lambda = 0 gives the
  * Gauss-Newton step (:147-154).  4x4 matrices column-major. */

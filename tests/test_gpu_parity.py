@@ -478,3 +478,62 @@ def test_sharded_partials_sum_to_unsharded(G, O, small_submap):
     assert (res["nr_iterations"], res["n_linearize"], res["n_compute_error"], res["converged"]) == \
            (g.result.nr_iterations, g.result.n_linearize, g.result.n_compute_error, g.result.converged)
     assert np.abs(res["final_x"] - g.final_state()).max() < 1e-9
+
+
+def test_sharded_align_fused_exchange_one_gpu(O, small_submap, monkeypatch):
+    """The exchange fused into the persistent LM kernel (ngicp_comm_*): two handles on ONE GPU each hold one slab of
+    the target, their kernels run concurrently (grids capped so that both are co-resident) and meet in each other's
+    exchange buffers.  Both must return the same bits, and the same pose / iteration counts as the unsharded align."""
+    import threading
+    from direct_lidar_odometry_b200 import NanoGICP, sharded
+    monkeypatch.setenv("NGICP_ALIGN_MAX_BLOCKS", "24")      # read at handle creation
+    monkeypatch.setenv("NGICP_COMM_TIMEOUT_MS", "3000")
+    submap, scan, T = small_submap
+    thr = 0.5
+    tc = O.Cloud(submap).covariances(20)
+    sc = O.Cloud(scan).covariances(20)
+    guess = synth.perturb_pose(T, (0.2, 0.0, 0.0), 1.0).astype(np.float32)
+    world = 2
+    backs = []
+    for r in range(world):
+        pts, covs, axis, lo, hi = sharded.shard_target(submap, tc, r, world, halo=thr + 0.01)
+        be = sharded.CudaShardBackend(0, k=20, max_corr_dist=thr)
+        be.set_align_params(32, 0.01)
+        be.set_target(pts, covs, axis, lo, hi)
+        be.set_source(scan, sc)
+        backs.append(be)
+    for r, be in enumerate(backs):
+        be.g.comm_connect_local(r, [b.g for b in backs])
+    out, err = [None] * world, [None] * world
+
+    def run(r):
+        try:
+            out[r] = backs[r].align_fused(guess)
+        except Exception as e:  # noqa: BLE001
+            err[r] = e
+
+    for rep in range(3):   # the exchange counters carry over from one align to the next
+        th = [threading.Thread(target=run, args=(r,)) for r in range(world)]
+        [t.start() for t in th]
+        [t.join() for t in th]
+        assert err == [None, None], err
+        assert np.array_equal(out[0]["final_x"], out[1]["final_x"])
+        assert out[0]["nr_iterations"] == out[1]["nr_iterations"]
+    g = NanoGICP(0)
+    g.setCorrespondenceRandomness(20); g.setMaxCorrespondenceDistance(thr)
+    g.setMaximumIterations(32); g.setTransformationEpsilon(0.01)
+    g.setInputTarget(submap); g.setTargetCovariances(tc)
+    g.setInputSource(scan); g.setSourceCovariances(sc)
+    g.align(guess)
+    res = out[0]
+    assert (res["nr_iterations"], res["n_linearize"], res["n_compute_error"], res["converged"]) == \
+           (g.result.nr_iterations, g.result.n_linearize, g.result.n_compute_error, g.result.converged)
+    assert np.abs(res["final_x"] - g.final_state()).max() < 1e-9
+    # a rank that never shows up must not hang the GPU: the waiting rank gets NGICP_E_COMM after the timeout
+    monkeypatch.setenv("NGICP_COMM_TIMEOUT_MS", "200")
+    for r, be in enumerate(backs):
+        be.g.comm_connect_local(r, [b.g for b in backs])
+    with pytest.raises(Exception, match="peer rank"):
+        backs[0].align_fused(guess)
+    for be in backs:
+        be.g.comm_close()
