@@ -590,6 +590,26 @@ int ngicp_voxel_filter(ngicp_t* h, const void* in, size_t n, size_t stride, floa
   return status;
 }
 
+int ngicp_preprocess(ngicp_t* h, const void* in, size_t n, size_t stride, const float* crop_min, const float* crop_max, float leaf,
+                     void* out, size_t cap, size_t* m) {
+  if (!h || !m || (!in && n) || stride < 12 || (stride & 3) || n > 0x7fffff00u || ((crop_min == nullptr) != (crop_max == nullptr)))
+    return h ? fail(h, NGICP_E_INVALID, "bad preprocess arguments") : NGICP_E_INVALID;
+  DeviceGuard g(h->device);
+  *m = 0;
+  float crop6[6];
+  if (crop_min) for (int a = 0; a < 3; a++) { crop6[a] = crop_min[a]; crop6[3 + a] = crop_max[a]; }
+  ph_begin(h, PH_VOXEL);
+  size_t mm = 0;
+  int overflow = 0;
+  NG_CUDA(h, voxel_filter_device(in, n, stride, leaf, h->sc, h->stream, &mm, &overflow, crop_min ? crop6 : nullptr, true));
+  if (mm > cap) return fail(h, NGICP_E_INVALID, "preprocess: output capacity too small");
+  if (mm && out) NG_CUDA(h, cudaMemcpyAsync(out, h->sc.vox_out.p, 32 * mm, cudaMemcpyDefault, h->stream->s));
+  ph_end(h, PH_VOXEL);
+  NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
+  *m = mm;
+  return overflow ? NGICP_W_VOXEL_OVERFLOW : NGICP_OK;
+}
+
 int ngicp_voxel_assignment(ngicp_t* h, int* slot_of_point, size_t n) {
   if (!h || !slot_of_point) return NGICP_E_INVALID;
   if (!h->sc.vox_slot.p || h->sc.vox_slot.bytes < sizeof(int) * n) return fail(h, NGICP_E_STATE, "no voxel filter result");

@@ -17,15 +17,23 @@ __global__ void vox_desc_init_kernel(GridDesc* d) {
   d->nfinite = 0; d->vcount = 0; d->voverflow = 0;
 }
 
+// pcl::CropBox with setNegative(true) (reference odom.cc:122-124,454-457): a point with min <= p <= max on all three
+// axes is dropped.  Fused here as "treat it like a non-finite point", which is also how removeNaNFromPointCloud
+// (odom.cc:451) is honoured: such points never enter the bounding box, get the invalid key and are never emitted.
+struct CropBox { int on; float lo[3], hi[3]; };
+
 // raw records -> float4 {x,y,z,intensity}; bbox over finite points (pcl::getMinMax3D on a non-dense cloud)
 __global__ void __launch_bounds__(256) vox_pack_kernel(const unsigned char* __restrict__ raw, size_t stride, int n, int intensity_float,
-                                                       float4* __restrict__ pts, GridDesc* __restrict__ d) {
+                                                       float4* __restrict__ pts, GridDesc* __restrict__ d, CropBox crop) {
   float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   int finite = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float* r = reinterpret_cast<const float*>(raw + (size_t)i * stride);
-    const float x = r[0], y = r[1], z = r[2];
+    float x = r[0];
+    const float y = r[1], z = r[2];
     const float it = intensity_float >= 0 ? r[intensity_float] : 0.f;
+    if (crop.on && x >= crop.lo[0] && x <= crop.hi[0] && y >= crop.lo[1] && y <= crop.hi[1] && z >= crop.lo[2] && z <= crop.hi[2])
+      x = __int_as_float(0x7fc00000);   // cropped away
     pts[i] = make_float4(x, y, z, it);
     if (isfinite(x) && isfinite(y) && isfinite(z)) {
       finite++;
@@ -122,6 +130,29 @@ __global__ void __launch_bounds__(128) vox_centroid_kernel(const unsigned* __res
   }
 }
 
+// no voxel grid (vf_scan_use_ = false, odom.cc:460) or PCL's "leaf too small" pass-through: the surviving points in input
+// order.  flags = exclusive scan of "kept".
+__global__ void __launch_bounds__(256) vox_keep_flags_kernel(const float4* __restrict__ pts, int n, int* __restrict__ flags) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += gridDim.x * blockDim.x) {
+    int f = 0;
+    if (i < n) { const float4 p = pts[i]; f = (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) ? 1 : 0; }
+    flags[i] = f;
+  }
+}
+__global__ void __launch_bounds__(256) vox_compact_kernel(const float4* __restrict__ pts, int n, const int* __restrict__ slots,
+                                                          float* __restrict__ out, int* __restrict__ slot_of_point) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = pts[i];
+    const bool keep = isfinite(p.x) && isfinite(p.y) && isfinite(p.z);
+    slot_of_point[i] = keep ? slots[i] : -1;
+    if (keep) {
+      float4* o4 = reinterpret_cast<float4*>(out + (size_t)slots[i] * 8);
+      o4[0] = make_float4(p.x, p.y, p.z, 1.0f);
+      o4[1] = make_float4(p.w, 0.f, 0.f, 0.f);
+    }
+  }
+}
+
 static inline int vgrid(int n, int threads) {
   int g = (n + threads - 1) / threads;
   if (g < 1) g = 1;
@@ -129,13 +160,17 @@ static inline int vgrid(int n, int threads) {
 }
 
 cudaError_t voxel_filter_device(const void* in, size_t n, size_t stride_bytes, float leaf, Scratch& sc, const StreamPtr& st,
-                                size_t* m_out, int* overflow) {
+                                size_t* m_out, int* overflow, const float* crop6, bool compact_on_overflow) {
   cudaError_t e;
   *m_out = 0;
   *overflow = 0;
   if (n == 0) return cudaSuccess;
   const int ni = (int)n;
-  const float inv = 1.0f / leaf;  // PCL: inverse_leaf_size_ = 1 / leaf_size_ in float
+  const bool use_grid = leaf > 0.f;
+  const float inv = use_grid ? 1.0f / leaf : 1.0f;  // PCL: inverse_leaf_size_ = 1 / leaf_size_ in float
+  CropBox crop;
+  crop.on = crop6 != nullptr;
+  for (int a = 0; a < 3; a++) { crop.lo[a] = crop6 ? crop6[a] : 0.f; crop.hi[a] = crop6 ? crop6[3 + a] : 0.f; }
   const int ifloat = stride_bytes >= 20 ? 4 : (stride_bytes >= 16 ? 3 : -1);
   const size_t last = ifloat >= 0 ? (size_t)(ifloat + 1) * 4 : 12;
   const size_t raw_bytes = (n - 1) * stride_bytes + last;
@@ -156,7 +191,24 @@ cudaError_t voxel_filter_device(const void* in, size_t n, size_t stride_bytes, f
   GridDesc* d = sc.vox_desc.as<GridDesc>();
   float4* pts = sc.queries.as<float4>();
   vox_desc_init_kernel<<<1, 1, 0, st->s>>>(d);
-  vox_pack_kernel<<<vgrid(ni, 256), 256, 0, st->s>>>(sc.staging.as<unsigned char>(), stride_bytes, ni, ifloat, pts, d);
+  vox_pack_kernel<<<vgrid(ni, 256), 256, 0, st->s>>>(sc.staging.as<unsigned char>(), stride_bytes, ni, ifloat, pts, d, crop);
+  note_launches(2);
+  int* flags = sc.flags.as<int>();
+  auto compact = [&]() -> cudaError_t {
+    vox_keep_flags_kernel<<<vgrid(ni + 1, 256), 256, 0, st->s>>>(pts, ni, flags);
+    int len = ni + 1;
+    cudaError_t ce;
+    if ((ce = cudaMemcpyAsync(&d->n, &len, sizeof(int), cudaMemcpyHostToDevice, st->s)) != cudaSuccess) return ce;
+    exclusive_scan_inplace(flags, &d->n, 0, ni + 1, sc.tile_sums.as<int>(), st->s);
+    vox_compact_kernel<<<vgrid(ni, 256), 256, 0, st->s>>>(pts, ni, flags, sc.vox_out.as<float>(), sc.vox_slot.as<int>());
+    note_launches(2);
+    int host_m = 0;
+    if ((ce = cudaMemcpyAsync(&host_m, flags + ni, sizeof(int), cudaMemcpyDeviceToHost, st->s)) != cudaSuccess) return ce;
+    if ((ce = cudaStreamSynchronize(st->s)) != cudaSuccess) return ce;
+    *m_out = (size_t)host_m;
+    return cudaGetLastError();
+  };
+  if (!use_grid) return compact();
   vox_setup_kernel<<<1, 1, 0, st->s>>>(d, inv);
   vox_keys_kernel<<<vgrid(ni, 256), 256, 0, st->s>>>(pts, ni, d, inv, sc.keys_a.as<unsigned>(), sc.vals_a.as<unsigned>());
   // the voxel grid dimensions decide how many radix passes are needed: one small read-back (the call has to
@@ -166,7 +218,11 @@ cudaError_t voxel_filter_device(const void* in, size_t n, size_t stride_bytes, f
   if ((e = cudaMemcpyAsync(dims + 3, &d->voverflow, sizeof(int), cudaMemcpyDeviceToHost, st->s)) != cudaSuccess) return e;
   if ((e = cudaStreamSynchronize(st->s)) != cudaSuccess) return e;
   *overflow = dims[3];
-  if (dims[3]) { *m_out = 0; return cudaSuccess; }   // PCL passes the input through; the caller handles it
+  if (dims[3]) {                                     // PCL passes the input through
+    if (compact_on_overflow) return compact();       // ... which, after removeNaN + CropBox, is the surviving points
+    *m_out = 0;
+    return cudaSuccess;                              // plain voxel filter: the caller copies the raw input
+  }
   const unsigned invalid_key = (unsigned)((long long)dims[0] * dims[1] * dims[2]);
   int bits = 1;
   while (bits < 32 && (1ull << bits) <= (unsigned long long)invalid_key) bits++;
@@ -174,14 +230,13 @@ cudaError_t voxel_filter_device(const void* in, size_t n, size_t stride_bytes, f
                                      ni, bits, sc.hist.as<int>(), st->s);
   const unsigned* keys = where ? sc.keys_b.as<unsigned>() : sc.keys_a.as<unsigned>();
   const unsigned* perm = where ? sc.vals_b.as<unsigned>() : sc.vals_a.as<unsigned>();
-  int* flags = sc.flags.as<int>();
   vox_heads_kernel<<<vgrid(ni + 1, 256), 256, 0, st->s>>>(keys, ni, flags, invalid_key);
   // the scan length (n+1) is known on the host; park it in the descriptor so the generic scan can read it
   int len = ni + 1;
   if ((e = cudaMemcpyAsync(&d->n, &len, sizeof(int), cudaMemcpyHostToDevice, st->s)) != cudaSuccess) return e;
   exclusive_scan_inplace(flags, &d->n, 0, ni + 1, sc.tile_sums.as<int>(), st->s);
   vox_centroid_kernel<<<vgrid(ni, 128), 128, 0, st->s>>>(keys, perm, ni, flags, pts, sc.vox_out.as<float>(), sc.vox_slot.as<int>(), invalid_key);
-  note_launches(6);
+  note_launches(4);
   int host_m = 0;
   if ((e = cudaMemcpyAsync(&host_m, flags + ni, sizeof(int), cudaMemcpyDeviceToHost, st->s)) != cudaSuccess) return e;
   if ((e = cudaStreamSynchronize(st->s)) != cudaSuccess) return e;

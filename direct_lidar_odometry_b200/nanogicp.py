@@ -398,6 +398,27 @@ class NanoGICP:
             res = res.copy()
         return (res, rc) if return_status else res
 
+    def preprocess(self, cloud, crop_size: float | None = 1.0, leaf: float = 0.25, out=None, return_status: bool = False):
+        """OdomNode::preprocessPoints (odom.cc:443-465) in one device pass: removeNaN + negative CropBox(+-crop_size,
+        None = no crop) + scan voxel grid (leaf <= 0 = no voxel grid).  Same output convention as voxel_filter."""
+        p, n, st, keep = _ptr_n_stride(cloud)
+        m = C.c_size_t(0)
+        if out is None:
+            buf = np.zeros((max(n, 1), 8), dtype=np.float32)
+            optr, cap = buf.ctypes.data, buf.shape[0]
+        else:
+            buf = out
+            optr, cap = out.data_ptr(), int(out.shape[0])
+        lo = hi = None
+        if crop_size is not None:
+            lo = (C.c_float * 3)(-crop_size, -crop_size, -crop_size)
+            hi = (C.c_float * 3)(crop_size, crop_size, crop_size)
+        rc = self._check(self._L.ngicp_preprocess(self._h, p, n, st, lo, hi, C.c_float(leaf), optr, cap, C.byref(m)))
+        res = buf[: m.value]
+        if out is None:
+            res = res.copy()
+        return (res, rc) if return_status else res
+
     def voxel_assignment(self, n: int) -> np.ndarray:
         a = np.zeros(n, dtype=np.int32)
         self._check(self._L.ngicp_voxel_assignment(self._h, a.ctypes.data_as(C.POINTER(C.c_int)), n))

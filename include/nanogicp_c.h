@@ -159,6 +159,12 @@ int ngicp_transform_source(ngicp_t* h, const float* T16, float* out_xyz1, size_t
  * *m = number written.  in/out may be host or device memory. */
 int ngicp_voxel_filter(ngicp_t* h, const void* in, size_t n, size_t stride_bytes, float leaf, void* out,
                        size_t out_capacity, size_t* m);
+/* OdomNode::preprocessPoints (odom.cc:443-465) in one pass over the raw scan: pcl::removeNaNFromPointCloud (:451),
+ * the negative pcl::CropBox (:122-124,454-457; a point with crop_min <= p <= crop_max on all axes is dropped; pass NULL
+ * for both to skip it) and the scan voxel grid (:460-463; leaf <= 0 skips it, as vf_scan_use_ = false does).  Output
+ * records as ngicp_voxel_filter; without a voxel grid the surviving points keep their input order. */
+int ngicp_preprocess(ngicp_t* h, const void* in, size_t n, size_t stride_bytes, const float* crop_min, const float* crop_max,
+                     float leaf, void* out, size_t out_capacity, size_t* m);
 /* test hook: the output slot every input point was averaged into (-1 for non-finite points) */
 int ngicp_voxel_assignment(ngicp_t* h, int* slot_of_point, size_t n);
 

@@ -111,6 +111,24 @@ def as_xyzi(pts: np.ndarray) -> np.ndarray:
     return out
 
 
+def preprocess_points(pts: np.ndarray, crop_size, leaf: float, lib=None):
+    """OdomNode::preprocessPoints restated (reference src/dlo/odom.cc:443-465): removeNaNFromPointCloud (:451), the
+    negative pcl::CropBox of +-crop_size (:122-124,454-457; PCL keeps a point as "inside" when min <= p <= max on all
+    axes and setNegative(true) drops those), then the scan voxel grid (:460-463) unless leaf <= 0."""
+    pts = as_xyzi(pts)
+    keep = np.isfinite(pts[:, :3]).all(axis=1)
+    if crop_size is not None:
+        inside = ((pts[:, :3] >= -np.float32(crop_size)) & (pts[:, :3] <= np.float32(crop_size))).all(axis=1)
+        keep &= ~inside
+    kept = np.ascontiguousarray(pts[keep])
+    if leaf <= 0:
+        out = kept.copy()
+        out[:, 3] = 1.0
+        out[:, 5:] = 0.0
+        return out
+    return voxel_filter(kept, leaf, lib=lib)
+
+
 def voxel_filter(pts: np.ndarray, leaf: float, lib=None, return_assignment: bool = False):
     L = lib or load()
     pts = as_xyzi(pts)

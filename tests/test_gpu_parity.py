@@ -91,6 +91,32 @@ def test_voxel_filter_edge_cases(G, O, scan_pair):
     assert np.array_equal(bits(out[:, :4]), bits(ref[:, :4]))
 
 
+def test_preprocess_fused_crop_nan_voxel(G, O, scan_pair):
+    """ngicp_preprocess = removeNaN + negative CropBox + voxel grid in one pass (odom.cc:443-465), bit-exact against
+    the three steps done one after the other by the oracle."""
+    g = G()
+    raw = scan_pair["raw0"] if "raw0" in scan_pair else scan_pair["s0"]
+    dirty = raw.copy()
+    dirty[::13, 1] = np.nan
+    dirty[5::17, 0] = -np.inf
+    dirty[:50, :3] *= 0.01                      # a few points well inside the +-1 m box
+    dirty[50, :3] = (1.0, -1.0, 1.0)            # exactly on the box: PCL counts it as inside
+    for crop, leaf in ((1.0, 0.25), (1.0, 0.5), (None, 0.25), (2.5, 0.0), (None, 0.0)):
+        ref = O.preprocess_points(dirty, crop, leaf)
+        out = g.preprocess(dirty, crop, leaf)
+        assert out.shape == ref.shape, (crop, leaf, out.shape, ref.shape)
+        assert np.array_equal(bits(out), bits(ref)), (crop, leaf)
+    assert g.preprocess(np.zeros((0, 8), np.float32), 1.0, 0.25).shape[0] == 0
+    # everything cropped away
+    assert g.preprocess(dirty[:50], 1.0, 0.25).shape[0] == 0
+    # index overflow after the crop: the surviving points pass through, as PCL's VoxelGrid does with its input
+    far = dirty[:200].copy()
+    far[60, :3] = 1e6
+    out, st = g.preprocess(far, 1.0, 0.01, return_status=True)
+    ref = O.preprocess_points(far, 1.0, 0.0)
+    assert st == 1 and np.array_equal(bits(out), bits(ref))
+
+
 # ---------------------------------------------------------------------------------------------- K1+K2
 @pytest.mark.parametrize("k", [1, 5, 10, 20])
 def test_knn_matches_reference_nanoflann_golden(G, golden_knn, k):

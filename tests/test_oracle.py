@@ -228,3 +228,24 @@ def test_align_without_correspondences_is_identity_step(orc):
     r = g.align()
     assert r.nr_iterations == 0 and r.converged == 1
     assert np.array_equal(r.Tx(), np.eye(4))
+
+
+def test_preprocess_points_restatement():
+    """removeNaN + negative CropBox + voxel grid (odom.cc:443-465): box membership is inclusive like pcl::CropBox."""
+    from oracle import oracle as orc
+    rng = np.random.default_rng(3)
+    pts = np.zeros((2000, 8), np.float32)
+    pts[:, :3] = rng.uniform(-4, 4, size=(2000, 3))
+    pts[:, 3] = 1.0
+    pts[:, 4] = rng.uniform(0, 1, 2000)
+    pts[0, :3] = (1.0, 1.0, -1.0)      # on the box -> inside -> dropped
+    pts[1, :3] = (1.0000001, 0.0, 0.0)  # just outside -> kept
+    pts[2, 0] = np.nan
+    kept = orc.preprocess_points(pts, 1.0, 0.0)
+    inside = (np.abs(pts[:, :3]) <= 1.0).all(axis=1)
+    finite = np.isfinite(pts[:, :3]).all(axis=1)
+    assert kept.shape[0] == int((finite & ~inside).sum())
+    assert not ((np.abs(kept[:, :3]) <= 1.0).all(axis=1)).any()
+    assert (kept[:, :3] == pts[1, :3]).all(axis=1).any() and not (kept[:, :3] == pts[0, :3]).all(axis=1).any()
+    v = orc.preprocess_points(pts, 1.0, 0.5)
+    assert np.array_equal(v, orc.voxel_filter(pts[finite & ~inside], 0.5))
