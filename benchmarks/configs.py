@@ -146,6 +146,12 @@ class Replay:
         self.s2s.setInputSource(kf); self.s2s.calculateSourceCovariances()
         self.keyframes.append((self.T[:3, 3].copy(), kf, self.s2s.getSourceCovariances()))
 
+    def _set_submap(self, sel):
+        self.submap = np.ascontiguousarray(np.vstack([self.keyframes[i][1] for i in sel]))
+        self.submap_covs = np.concatenate([self.keyframes[i][2] for i in sel])
+        self.s2m.setInputTarget(self.submap); self.s2m.setTargetCovariances(self.submap_covs)
+        return self.submap.shape[0]
+
     def step(self, scan):
         self.events = []
         t_ = time.perf_counter()
@@ -162,11 +168,9 @@ class Replay:
         sel = tuple(sorted(np.argsort(d)[: self.knn].tolist()))
         self.events.append(("s2s", (time.perf_counter() - t_) * 1e3)); t_ = time.perf_counter()
         if sel != self.prev_set:
-            self.submap = np.ascontiguousarray(np.vstack([self.keyframes[i][1] for i in sel]))
-            self.submap_covs = np.concatenate([self.keyframes[i][2] for i in sel])
-            self.s2m.setInputTarget(self.submap); self.s2m.setTargetCovariances(self.submap_covs)
+            npts = self._set_submap(sel)
             self.prev_set = sel
-            self.events.append(("submap_rebuild_%d" % self.submap.shape[0], (time.perf_counter() - t_) * 1e3)); t_ = time.perf_counter()
+            self.events.append(("submap_rebuild_%d" % npts, (time.perf_counter() - t_) * 1e3)); t_ = time.perf_counter()
         self.s2m.align(T_s2s)
         self.T = self.s2m.getFinalTransformation()
         self.T_prev = self.T
@@ -175,6 +179,30 @@ class Replay:
             self._add_keyframe(scan)
             self.events.append(("new_keyframe", (time.perf_counter() - t_) * 1e3))
         return it_s2s, self.s2m.nr_iterations_
+
+
+class DeviceReplay(Replay):
+    """The same sequence with the additive device-resident pieces: keyframe clouds are made by the
+    fused transform + voxel pass and stay on the GPU, keyframes and their covariances live in a KeyframeStore, and a
+    changed submap is assembled device-to-device — no 160 B/point round trip over PCIe."""
+
+    def __init__(self, make, pre, thresh_d=5.0, knn=10):
+        import torch
+        from direct_lidar_odometry_b200 import KeyframeStore
+        super().__init__(make, None, None, thresh_d, knn)
+        self.pre = pre
+        self.store = KeyframeStore(0)
+        self.kf_buf = torch.empty((1 << 17, 8), dtype=torch.float32, device="cuda")
+
+    def _add_keyframe(self, scan):
+        kf = self.pre.transform_voxel_filter(scan, self.T, 0.5, out=self.kf_buf)
+        self.s2s.setInputSource(kf); self.s2s.calculateSourceCovariances()
+        self.store.push(self.s2s)
+        self.keyframes.append((self.T[:3, 3].copy(), None, None))
+
+    def _set_submap(self, sel):
+        self.store.set_target(self.s2m, list(sel))
+        return sum(self.store.points(i) for i in sel)
 
 
 class OracleGicp:
@@ -226,12 +254,20 @@ def run_c3(args):
         g = NanoGICP(0)
         configure(g, cfg)
         return g
-    rp = Replay(make_gpu, lambda p, l: vox.voxel_filter(p, l), None)
-    ms, iters, errs = [], [], []
+    import torch
+    if args.device_store:
+        rp = DeviceReplay(make_gpu, vox)
+        scan_buf = [torch.empty((1 << 17, 8), dtype=torch.float32, device="cuda") for _ in range(2)]
+    else:
+        rp = Replay(make_gpu, lambda p, l: vox.voxel_filter(p, l), None)
+    ms, iters, errs, traj = [], [], [], []
     for i in idx:
         T_true, raw = scans[i]
         t1 = time.perf_counter()
-        scan = vox.voxel_filter(raw, 0.25)        # preprocessPoints: vf_scan (crop box applied by the generator)
+        if args.device_store:                     # preprocessPoints fused, output stays on the device
+            scan = vox.preprocess(raw, 1.0, 0.25, out=scan_buf[i & 1])
+        else:
+            scan = vox.voxel_filter(raw, 0.25)    # preprocessPoints: vf_scan (crop box applied by the generator)
         if i == 0:
             rp.first(scan, T_true)
             continue
@@ -242,13 +278,28 @@ def run_c3(args):
                   f"s2s kernels {({k: round(v, 3) for k, v in rp.s2s.timings().items()})} grid {rp.s2s.grid_info(1)}", file=sys.stderr)
         iters.append(its)
         errs.append(pose_err(rp.T, T_true))
+        traj.append(np.array(rp.T, dtype=np.float32).copy())
     ms = np.array(ms)
-    out = {"config": f"C3: odometry replay, {args.scans} synthetic OS1-64 scans (S2S + S2M + keyframes every 5 m, knn-{rp.knn} submap)",
+    out = {"config": f"C3: odometry replay, {args.scans} synthetic OS1-64 scans (S2S + S2M + keyframes every 5 m, knn-{rp.knn} submap)"
+                     + (", device-resident keyframes + fused preprocess (N1/N2)" if args.device_store else ", host keyframes as in OdomNode"),
            "gpu": {"ms_per_scan_mean": float(ms.mean()), "ms_per_scan_p50": float(np.percentile(ms, 50)), "ms_per_scan_p99": float(np.percentile(ms, 99)),
                    "keyframes": len(rp.keyframes), "final_translation_error_m": errs[-1][0], "max_translation_error_m": float(max(e[0] for e in errs)),
                    "max_rotation_error_rad": float(max(e[1] for e in errs)), "mean_iterations_s2s": float(np.mean([i[0] for i in iters])),
                    "mean_iterations_s2m": float(np.mean([i[1] for i in iters]))},
            "scan_generation_s": gen_s}
+    if args.device_store:
+        # the additive path must reproduce the OdomNode-style host path bit for bit
+        rh = Replay(make_gpu, lambda p, l: vox.voxel_filter(p, l), None)
+        same = 0
+        for i in idx:
+            T_true, raw = scans[i]
+            scan = vox.voxel_filter(raw, 0.25)
+            if i == 0:
+                rh.first(scan, T_true)
+                continue
+            rh.step(scan)
+            same += int(np.array_equal(np.array(rh.T, dtype=np.float32), traj[i - 1]))
+        out["gpu"]["poses_bit_identical_to_host_keyframe_path"] = f"{same}/{len(traj)}"
     # CPU oracle over the first --cpu-scans scans with the same sequence: timing + iteration-count / pose parity
     n_cpu = min(args.cpu_scans, args.scans)
     if n_cpu > 1:
@@ -466,6 +517,7 @@ def run_c5(args):
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("which", choices=["c1", "c3", "c4", "c5"])
+    ap.add_argument("--device-store", type=int, default=0, help="c3: device-resident keyframes + fused preprocess (N1/N2)")
     ap.add_argument("--target-points", type=int, default=5_000_000)
     ap.add_argument("--cov-halo", type=float, default=2.0)
     ap.add_argument("--steps", type=int, default=10)

@@ -8,11 +8,11 @@ The compute lives in csrc/ (hand-written CUDA behind the C ABI of include/nanogi
 """
 from . import synth  # noqa: F401  (pure numpy)
 
-__all__ = ["NanoGICP", "NanoGICPError", "CovarianceView", "synth", "lib_path"]
+__all__ = ["NanoGICP", "NanoGICPError", "CovarianceView", "KeyframeStore", "synth", "lib_path"]
 
 
 def __getattr__(name):
-    if name in ("NanoGICP", "NanoGICPError", "CovarianceView"):
+    if name in ("NanoGICP", "NanoGICPError", "CovarianceView", "KeyframeStore"):
         from . import nanogicp
         return getattr(nanogicp, name)
     if name == "lib_path":

@@ -37,6 +37,18 @@ struct ngicp_handle {
   bool comm_on = false;
 };
 
+// N1: device-resident keyframe store.  A keyframe is the pair DLO keeps on the host — the voxelised
+// world-frame cloud (keyframes[i].second, odom.cc:503,1177) and its covariances (keyframe_normals[i], :500,1174) — held
+// here as references to the immutable device buffers the S2S object already made for them.
+struct ngicp_kfstore {
+  int device = 0;
+  // points are copied (16 B each) so that the keyframe does not pin the S2S object's search index (a 128 MiB cell
+  // table per cloud); the covariance buffer is immutable and simply shared
+  struct Keyframe { std::shared_ptr<DevBuf> pts; int n = 0; CovsPtr covs; cudaEvent_t ready = nullptr; };
+  std::vector<Keyframe> kf;
+  std::string err;
+};
+
 namespace ngicp {
 static unsigned long long g_launches = 0;
 void note_launches(int n) { __atomic_fetch_add(&g_launches, (unsigned long long)n, __ATOMIC_RELAXED); }
@@ -386,6 +398,34 @@ int ngicp_create(int device, ngicp_t** out) {
     ngicp_destroy(h);
     return NGICP_E_CUDA;
   }
+  // Working-set priming, once per device and process: grow the stream-ordered pool to NGICP_POOL_PRIME_MB (default 512)
+  // and park NGICP_TABLE_PRIME (default 3) cell tables in the free list, so that the first scans of a stream do not pay
+  // for driver-level allocations (a fresh 128 MiB cudaMalloc costs 0.6-25 ms, pool growth ~10 ms per step; measured
+  // with benchmarks/configs.py c3).  Both are one-time costs of ngicp_create.
+  {
+    static bool primed[64] = {};
+    if (device < 64 && !primed[device]) {
+      primed[device] = true;
+      const char* e1 = getenv("NGICP_POOL_PRIME_MB");
+      const long mb = e1 ? atol(e1) : 512;
+      if (mb > 0) {
+        void* p = nullptr;
+        if (cudaMallocAsync(&p, (size_t)mb << 20, h->stream->s) == cudaSuccess) cudaFreeAsync(p, h->stream->s);
+        cudaGetLastError();
+      }
+      const char* e2 = getenv("NGICP_TABLE_PRIME");
+      const int nt = e2 ? atoi(e2) : 3;
+      const size_t tb = sizeof(int) * ((size_t)h->prm.grid_table_cells + 8);
+      std::vector<TableBuf*> tmp;
+      for (int i = 0; i < nt && i < 8; i++) {
+        TableBuf* t = new (std::nothrow) TableBuf();
+        if (!t || t->acquire(tb, device, h->stream) != cudaSuccess) { delete t; cudaGetLastError(); break; }
+        tmp.push_back(t);
+      }
+      for (TableBuf* t : tmp) delete t;   // release() parks them in the free list
+      cudaStreamSynchronize(h->stream->s);
+    }
+  }
   // NGICP_ALIGN_MAX_BLOCKS caps the persistent LM kernel's grid (default: whatever is co-resident); needed when
   // several handles run their cooperative kernels on ONE GPU at the same time (sharded-mode tests)
   if (const char* e = getenv("NGICP_ALIGN_MAX_BLOCKS")) { const int v = atoi(e); if (v > 0 && v < h->align_max_blocks) h->align_max_blocks = v; }
@@ -588,6 +628,24 @@ int ngicp_voxel_filter(ngicp_t* h, const void* in, size_t n, size_t stride, floa
   NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
   *m = mm;
   return status;
+}
+
+int ngicp_transform_voxel_filter(ngicp_t* h, const void* in, size_t n, size_t stride, const float* T16, float leaf, void* out, size_t cap,
+                                 size_t* m) {
+  if (!h || !m || !T16 || (!in && n) || stride < 12 || (stride & 3) || n > 0x7fffff00u)
+    return h ? fail(h, NGICP_E_INVALID, "bad transform+voxel arguments") : NGICP_E_INVALID;
+  DeviceGuard g(h->device);
+  *m = 0;
+  ph_begin(h, PH_VOXEL);
+  size_t mm = 0;
+  int overflow = 0;
+  NG_CUDA(h, voxel_filter_device(in, n, stride, leaf, h->sc, h->stream, &mm, &overflow, nullptr, true, T16));
+  if (mm > cap) return fail(h, NGICP_E_INVALID, "transform+voxel: output capacity too small");
+  if (mm && out) NG_CUDA(h, cudaMemcpyAsync(out, h->sc.vox_out.p, 32 * mm, cudaMemcpyDefault, h->stream->s));
+  ph_end(h, PH_VOXEL);
+  NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
+  *m = mm;
+  return overflow ? NGICP_W_VOXEL_OVERFLOW : NGICP_OK;
 }
 
 int ngicp_preprocess(ngicp_t* h, const void* in, size_t n, size_t stride, const float* crop_min, const float* crop_max, float leaf,
@@ -818,5 +876,89 @@ int ngicp_comm_connect_local(ngicp_t* h, int rank, int world, ngicp_t* const* pe
   return NGICP_OK;
 }
 
+// ---- N1: device-resident keyframes / submap assembly -------------------------------------------------------------
+int ngicp_kfstore_create(int device, ngicp_kfstore_t** out) {
+  if (!out) return NGICP_E_INVALID;
+  ngicp_kfstore* s = new (std::nothrow) ngicp_kfstore();
+  if (!s) return NGICP_E_INVALID;
+  s->device = device;
+  *out = s;
+  return NGICP_OK;
+}
+
+void ngicp_kfstore_destroy(ngicp_kfstore_t* s) {
+  if (!s) return;
+  DeviceGuard g(s->device);
+  for (auto& k : s->kf) if (k.ready) { cudaEventSynchronize(k.ready); cudaEventDestroy(k.ready); }
+  delete s;
+}
+
+size_t ngicp_kfstore_size(const ngicp_kfstore_t* s) { return s ? s->kf.size() : 0; }
+
+size_t ngicp_kfstore_points(const ngicp_kfstore_t* s, size_t index) {
+  return (s && index < s->kf.size()) ? (size_t)s->kf[index].n : 0;
+}
+
+int ngicp_kfstore_push(ngicp_kfstore_t* s, ngicp_t* from, size_t* index_out) {
+  if (!s || !from) return NGICP_E_INVALID;
+  if (from->device != s->device) return fail(from, NGICP_E_INVALID, "keyframe store lives on another device");
+  if (!from->src || !from->src_cov || from->src_cov->n != from->src->n)
+    return fail(from, NGICP_E_STATE, "keyframe push: source cloud and its covariances must be set (setInputSource + calculateSourceCovariances)");
+  DeviceGuard g(s->device);
+  ngicp_kfstore::Keyframe k;
+  k.n = from->src->n;
+  k.pts.reset(new (std::nothrow) DevBuf());
+  if (!k.pts) return fail(from, NGICP_E_INVALID, "out of host memory");
+  NG_CUDA(from, k.pts->alloc(sizeof(float4) * (size_t)(k.n ? k.n : 1), from->stream));
+  if (k.n) NG_CUDA(from, cudaMemcpyAsync(k.pts->p, from->src->pts.p, sizeof(float4) * (size_t)k.n, cudaMemcpyDeviceToDevice, from->stream->s));
+  k.covs = from->src_cov;
+  NG_CUDA(from, cudaEventCreateWithFlags(&k.ready, cudaEventDisableTiming));
+  NG_CUDA(from, cudaEventRecord(k.ready, from->stream->s));
+  s->kf.push_back(k);
+  if (index_out) *index_out = s->kf.size() - 1;
+  return NGICP_OK;
+}
+
+int ngicp_kfstore_set_target(ngicp_kfstore_t* s, ngicp_t* to, const int* indices, size_t n_indices) {
+  if (!s || !to || (!indices && n_indices)) return NGICP_E_INVALID;
+  if (to->device != s->device) return fail(to, NGICP_E_INVALID, "keyframe store lives on another device");
+  size_t total = 0;
+  for (size_t i = 0; i < n_indices; ++i) {
+    if (indices[i] < 0 || (size_t)indices[i] >= s->kf.size()) return fail(to, NGICP_E_INVALID, "keyframe index out of range");
+    total += (size_t)s->kf[indices[i]].n;
+  }
+  if (total == 0) return fail(to, NGICP_E_STATE, "submap without points");
+  if (total > 0x7fffff00u) return fail(to, NGICP_E_INVALID, "submap too large");
+  DeviceGuard g(to->device);
+  cudaStream_t st = to->stream->s;
+  CloudPtr c(new (std::nothrow) DevCloud());
+  CovsPtr cv(new (std::nothrow) DevCovs());
+  if (!c || !cv) return fail(to, NGICP_E_INVALID, "out of host memory");
+  ph_begin(to, PH_SET_TGT);
+  // submap_cloud += *keyframes[k].second; submap_normals.insert(...) (odom.cc:1315-1328), device to device
+  NG_CUDA(to, to->sc.staging.reserve(sizeof(float4) * total + 16, to->stream));
+  cv->n = (int)total;
+  NG_CUDA(to, cv->c.alloc(sizeof(double) * 6 * total, to->stream));
+  size_t off = 0;
+  for (size_t i = 0; i < n_indices; ++i) {
+    const ngicp_kfstore::Keyframe& k = s->kf[indices[i]];
+    const size_t n = (size_t)k.n;
+    if (n == 0) continue;
+    NG_CUDA(to, cudaStreamWaitEvent(st, k.ready, 0));
+    NG_CUDA(to, cudaMemcpyAsync(to->sc.staging.as<float4>() + off, k.pts->p, sizeof(float4) * n, cudaMemcpyDeviceToDevice, st));
+    NG_CUDA(to, cudaMemcpyAsync(cv->c.as<double>() + 6 * off, k.covs->c.p, sizeof(double) * 6 * n, cudaMemcpyDeviceToDevice, st));
+    off += n;
+  }
+  // gicp.setInputTarget(submap_cloud) (:830): snapshot + bounding box + search index
+  NG_CUDA(to, upload_cloud(*c, to->sc.staging.p, total, sizeof(float4), to->sc, to->stream));
+  NG_CUDA(to, build_index(*c, to->prm.grid_cell_size, to->prm.grid_table_cells, to->sc, to->stream, to->device));
+  ph_end(to, PH_SET_TGT);
+  to->tgt = c;
+  to->tgt_cov = cv;            // gicp.setTargetCovariances(submap_normals) (:833)
+  to->lin_valid = false;
+  return NGICP_OK;
+}
+
 }  // extern "C"
+
 

@@ -162,6 +162,7 @@ int align_fused_max_blocks(int device);
 // crop6 = {min xyz, max xyz} of a negative pcl::CropBox or nullptr; leaf <= 0 skips the voxel grid (compaction only);
 // compact_on_overflow: on PCL's index-overflow pass-through emit the surviving points instead of leaving it to the caller
 cudaError_t voxel_filter_device(const void* in, size_t n, size_t stride_bytes, float leaf, Scratch& sc, const StreamPtr& st,
-                                size_t* m_out, int* overflow, const float* crop6 = nullptr, bool compact_on_overflow = false);
+                                size_t* m_out, int* overflow, const float* crop6 = nullptr, bool compact_on_overflow = false,
+                                const float* T16_colmajor = nullptr /* transformPointCloud first */);
 
 }  // namespace ngicp

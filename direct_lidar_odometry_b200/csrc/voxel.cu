@@ -21,17 +21,25 @@ __global__ void vox_desc_init_kernel(GridDesc* d) {
 // axes is dropped.  Fused here as "treat it like a non-finite point", which is also how removeNaNFromPointCloud
 // (odom.cc:451) is honoured: such points never enter the bounding box, get the invalid key and are never emitted.
 struct CropBox { int on; float lo[3], hi[3]; };
+// pcl::transformPointCloud(*cloud, *cloud, T) in front of the submap voxel grid (odom.cc:484-490,1157-1163), fused into the
+// same pass: x' = ((m00 x + m01 y) + m02 z) + m03, float, unfused — the order the CPU oracle fixes (synth.transform_xyzi)
+struct RigidXf { int on; float m[12]; };
 
 // raw records -> float4 {x,y,z,intensity}; bbox over finite points (pcl::getMinMax3D on a non-dense cloud)
 __global__ void __launch_bounds__(256) vox_pack_kernel(const unsigned char* __restrict__ raw, size_t stride, int n, int intensity_float,
-                                                       float4* __restrict__ pts, GridDesc* __restrict__ d, CropBox crop) {
+                                                       float4* __restrict__ pts, GridDesc* __restrict__ d, CropBox crop, RigidXf xf) {
   float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   int finite = 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const float* r = reinterpret_cast<const float*>(raw + (size_t)i * stride);
-    float x = r[0];
-    const float y = r[1], z = r[2];
+    float x = r[0], y = r[1], z = r[2];
     const float it = intensity_float >= 0 ? r[intensity_float] : 0.f;
+    if (xf.on) {
+      const float tx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(xf.m[0], x), __fmul_rn(xf.m[1], y)), __fmul_rn(xf.m[2], z)), xf.m[3]);
+      const float ty = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(xf.m[4], x), __fmul_rn(xf.m[5], y)), __fmul_rn(xf.m[6], z)), xf.m[7]);
+      const float tz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(xf.m[8], x), __fmul_rn(xf.m[9], y)), __fmul_rn(xf.m[10], z)), xf.m[11]);
+      x = tx; y = ty; z = tz;
+    }
     if (crop.on && x >= crop.lo[0] && x <= crop.hi[0] && y >= crop.lo[1] && y <= crop.hi[1] && z >= crop.lo[2] && z <= crop.hi[2])
       x = __int_as_float(0x7fc00000);   // cropped away
     pts[i] = make_float4(x, y, z, it);
@@ -160,7 +168,7 @@ static inline int vgrid(int n, int threads) {
 }
 
 cudaError_t voxel_filter_device(const void* in, size_t n, size_t stride_bytes, float leaf, Scratch& sc, const StreamPtr& st,
-                                size_t* m_out, int* overflow, const float* crop6, bool compact_on_overflow) {
+                                size_t* m_out, int* overflow, const float* crop6, bool compact_on_overflow, const float* T16) {
   cudaError_t e;
   *m_out = 0;
   *overflow = 0;
@@ -171,6 +179,10 @@ cudaError_t voxel_filter_device(const void* in, size_t n, size_t stride_bytes, f
   CropBox crop;
   crop.on = crop6 != nullptr;
   for (int a = 0; a < 3; a++) { crop.lo[a] = crop6 ? crop6[a] : 0.f; crop.hi[a] = crop6 ? crop6[3 + a] : 0.f; }
+  RigidXf xf;
+  xf.on = T16 != nullptr;
+  for (int r = 0; r < 3; r++)
+    for (int c = 0; c < 4; c++) xf.m[r * 4 + c] = T16 ? T16[c * 4 + r] : 0.f;   // column-major 4x4 in
   const int ifloat = stride_bytes >= 20 ? 4 : (stride_bytes >= 16 ? 3 : -1);
   const size_t last = ifloat >= 0 ? (size_t)(ifloat + 1) * 4 : 12;
   const size_t raw_bytes = (n - 1) * stride_bytes + last;
@@ -191,7 +203,7 @@ cudaError_t voxel_filter_device(const void* in, size_t n, size_t stride_bytes, f
   GridDesc* d = sc.vox_desc.as<GridDesc>();
   float4* pts = sc.queries.as<float4>();
   vox_desc_init_kernel<<<1, 1, 0, st->s>>>(d);
-  vox_pack_kernel<<<vgrid(ni, 256), 256, 0, st->s>>>(sc.staging.as<unsigned char>(), stride_bytes, ni, ifloat, pts, d, crop);
+  vox_pack_kernel<<<vgrid(ni, 256), 256, 0, st->s>>>(sc.staging.as<unsigned char>(), stride_bytes, ni, ifloat, pts, d, crop, xf);
   note_launches(2);
   int* flags = sc.flags.as<int>();
   auto compact = [&]() -> cudaError_t {

@@ -419,6 +419,22 @@ class NanoGICP:
             res = res.copy()
         return (res, rc) if return_status else res
 
+    def transform_voxel_filter(self, cloud, T, leaf: float, out=None):
+        """pcl::transformPointCloud(cloud, T) + pcl::VoxelGrid(leaf) in one device pass (keyframes, odom.cc:484-490)."""
+        p, n, st, keep = _ptr_n_stride(cloud)
+        m = C.c_size_t(0)
+        if out is None:
+            buf = np.zeros((max(n, 1), 8), dtype=np.float32)
+            optr, cap = buf.ctypes.data, buf.shape[0]
+        else:
+            buf = out
+            optr, cap = out.data_ptr(), int(out.shape[0])
+        Tc = _mat_to_abi(T, np.float32)
+        self._check(self._L.ngicp_transform_voxel_filter(self._h, p, n, st, Tc.ctypes.data_as(C.POINTER(C.c_float)), C.c_float(leaf),
+                                                         optr, cap, C.byref(m)))
+        res = buf[: m.value]
+        return res.copy() if out is None else res
+
     def voxel_assignment(self, n: int) -> np.ndarray:
         a = np.zeros(n, dtype=np.int32)
         self._check(self._L.ngicp_voxel_assignment(self._h, a.ctypes.data_as(C.POINTER(C.c_int)), n))
@@ -466,3 +482,40 @@ class NanoGICP:
         t = Timings()
         self._check(self._L.ngicp_get_timings(self._h, C.byref(t)))
         return {k: getattr(t, k) for k, _ in Timings._fields_ if k != "reserved"}
+
+
+class KeyframeStore:
+    """Device-resident keyframes (include/nanogicp_c.h, ngicp_kfstore_*): what OdomNode keeps in `keyframes` /
+    `keyframe_normals` on the host, and the submap concatenation of getSubmapKeyframes, without leaving the GPU."""
+
+    def __init__(self, device: int = 0):
+        self._L = _lib.load()
+        h = C.c_void_p()
+        rc = self._L.ngicp_kfstore_create(device, C.byref(h))
+        if rc != _lib.OK:
+            raise NanoGICPError(rc, "ngicp_kfstore_create failed")
+        self._h = h
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            self._L.ngicp_kfstore_destroy(h)
+            self._h = None
+
+    def __len__(self):
+        return int(self._L.ngicp_kfstore_size(self._h))
+
+    def points(self, index: int) -> int:
+        return int(self._L.ngicp_kfstore_points(self._h, index))
+
+    def push(self, gicp: NanoGICP) -> int:
+        """keyframes.push_back / keyframe_normals.push_back: the current SOURCE cloud + covariances of `gicp`."""
+        idx = C.c_size_t(0)
+        gicp._check(self._L.ngicp_kfstore_push(self._h, gicp._h, C.byref(idx)))
+        return int(idx.value)
+
+    def set_target(self, gicp: NanoGICP, indices) -> None:
+        """submap concat + setInputTarget + setTargetCovariances for the selected keyframes, on the device."""
+        arr = (C.c_int * len(indices))(*[int(i) for i in indices])
+        gicp._check(self._L.ngicp_kfstore_set_target(self._h, gicp._h, arr, len(indices)))
+        gicp._target = object()    # a cloud no caller holds: the next setInputTarget(cloud) is never an identity hit

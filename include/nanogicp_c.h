@@ -165,6 +165,11 @@ int ngicp_voxel_filter(ngicp_t* h, const void* in, size_t n, size_t stride_bytes
  * records as ngicp_voxel_filter; without a voxel grid the surviving points keep their input order. */
 int ngicp_preprocess(ngicp_t* h, const void* in, size_t n, size_t stride_bytes, const float* crop_min, const float* crop_max,
                      float leaf, void* out, size_t out_capacity, size_t* m);
+/* The keyframe path: pcl::transformPointCloud(*cloud, *cloud, T) followed by vf_submap.filter (odom.cc:484-490,
+ * 1157-1163) in one pass; T16 = column-major float 4x4; leaf <= 0 only transforms.  With non-finite inputs or PCL's
+ * index overflow the surviving transformed points are emitted in input order. */
+int ngicp_transform_voxel_filter(ngicp_t* h, const void* in, size_t n, size_t stride_bytes, const float* T16, float leaf,
+                                 void* out, size_t out_capacity, size_t* m);
 /* test hook: the output slot every input point was averaged into (-1 for non-finite points) */
 int ngicp_voxel_assignment(ngicp_t* h, int* slot_of_point, size_t n);
 
@@ -208,6 +213,23 @@ int ngicp_comm_close(ngicp_t* h);
 int ngicp_lm_trial(const double* H36, const double* b6, double lambda, const double* x0_16, double* d6, double* delta16, double* xi16);
 /* LsqRegistration::is_converged (lsq_registration_impl.hpp:118-127) */
 int ngicp_lm_is_converged(const double* delta16, double rot_eps, double trans_eps);
+
+/* ---- device-resident keyframes (additive) ------------------------------------------------------
+ * OdomNode keeps every keyframe's voxelised world-frame cloud and covariances on the host (keyframes / keyframe_normals,
+ * include/dlo/odom.h:80-82), concatenates the selected ones into submap_cloud / submap_normals (odom.cc:1315-1328) and
+ * hands both back through setInputTarget + setTargetCovariances (:830-833) — 160 bytes per submap point over PCIe each
+ * time the submap changes.  The store keeps the device buffers instead:
+ *   ngicp_kfstore_push        right after gicp_s2s.setInputSource(keyframe_cloud) + calculateSourceCovariances()
+ *                             (:498-500,1172-1174): keeps a device copy of that cloud's points and shares its covariance buffer
+ *   ngicp_kfstore_set_target  target of `to` = the selected keyframes concatenated in the given order (device-to-device)
+ *                             + search index; equivalent to the host concatenation followed by :830-833 */
+typedef struct ngicp_kfstore ngicp_kfstore_t;
+int ngicp_kfstore_create(int device, ngicp_kfstore_t** out);
+void ngicp_kfstore_destroy(ngicp_kfstore_t* s);
+size_t ngicp_kfstore_size(const ngicp_kfstore_t* s);
+size_t ngicp_kfstore_points(const ngicp_kfstore_t* s, size_t index);
+int ngicp_kfstore_push(ngicp_kfstore_t* s, ngicp_t* from, size_t* index_out);
+int ngicp_kfstore_set_target(ngicp_kfstore_t* s, ngicp_t* to, const int* indices, size_t n_indices);
 
 /* diagnostics: the uniform grid chosen for a cloud's search index (cell edge in metres, dims[3], cell count) */
 int ngicp_grid_info(ngicp_t* h, int which, float* cell, int* dims3, int* ncells);

@@ -117,6 +117,20 @@ def test_preprocess_fused_crop_nan_voxel(G, O, scan_pair):
     assert st == 1 and np.array_equal(bits(out), bits(ref))
 
 
+def test_transform_voxel_filter_fused(G, O, scan_pair):
+    """transformPointCloud + vf_submap in one pass (keyframes, odom.cc:484-490) == the two steps of the oracle."""
+    g = G()
+    s0 = scan_pair["s0"]
+    T = synth.trajectory_pose(57).astype(np.float32)
+    for leaf in (0.5, 0.25):
+        ref = O.voxel_filter(synth.transform_xyzi(s0, T), leaf)
+        out = g.transform_voxel_filter(s0, T, leaf)
+        assert out.shape == ref.shape and np.array_equal(bits(out), bits(ref))
+    moved = g.transform_voxel_filter(s0[:1000], T, 0.0)
+    ref = synth.transform_xyzi(s0[:1000], T)
+    assert np.array_equal(bits(moved[:, :3]), bits(ref[:, :3])) and np.array_equal(bits(moved[:, 4]), bits(ref[:, 4]))
+
+
 # ---------------------------------------------------------------------------------------------- K1+K2
 @pytest.mark.parametrize("k", [1, 5, 10, 20])
 def test_knn_matches_reference_nanoflann_golden(G, golden_knn, k):
@@ -461,6 +475,43 @@ def test_full_size_submap_properties(G, O):
     covs = g.getTargetCovariances()
     ev = np.linalg.eigvalsh(0.5 * (covs[:, :3, :3] + covs[:, :3, :3].transpose(0, 2, 1)))
     assert np.allclose(ev, [1e-3, 1, 1], atol=1e-8)
+
+
+# ---------------------------------------------------------------------------------------------- N1 keyframe store
+def test_keyframe_store_submap_equals_host_concat(G, O, scan_pair):
+    """Submap assembled on the device from stored keyframes (ngicp_kfstore_*) == OdomNode's host concatenation of
+    keyframe clouds + keyframe_normals followed by setInputTarget/setTargetCovariances (odom.cc:1315-1328,830-833)."""
+    from direct_lidar_odometry_b200 import KeyframeStore
+    s2s, a, b = G(), G(), G()
+    s2s.setCorrespondenceRandomness(10)
+    for g in (a, b):
+        g.setCorrespondenceRandomness(20); g.setMaxCorrespondenceDistance(0.5)
+        g.setMaximumIterations(32); g.setTransformationEpsilon(0.01)
+    store = KeyframeStore(0)
+    host = []
+    for i in range(4):
+        T = synth.trajectory_pose(33 * i)
+        kf = O.voxel_filter(synth.transform_xyzi(synth.crop_box_negative(synth.os1_like(33 * i, T)), T.astype(np.float32)), 0.5)
+        s2s.setInputSource(kf)
+        s2s.calculateSourceCovariances()
+        assert store.push(s2s) == i and store.points(i) == kf.shape[0]
+        host.append((kf, s2s.getSourceCovariances()))
+    assert len(store) == 4
+    Ts = synth.trajectory_pose(40)
+    scan = O.voxel_filter(synth.crop_box_negative(synth.os1_like(40, Ts)), 0.25)
+    guess = synth.perturb_pose(Ts, (0.15, 0.0, 0.0), 0.5).astype(np.float32)
+    for sel in ([0, 1, 2, 3], [2, 0], [3]):
+        store.set_target(a, sel)
+        b.clearTarget()
+        b.setInputTarget(np.ascontiguousarray(np.vstack([host[i][0] for i in sel])))
+        b.setTargetCovariances(np.concatenate([host[i][1] for i in sel]))
+        assert np.array_equal(a.getTargetCovariances(), b.getTargetCovariances())
+        for g in (a, b):
+            g.clearSource(); g.setInputSource(scan); g.calculateSourceCovariances(); g.align(guess)
+        assert np.array_equal(a.final_state(), b.final_state())
+        assert (a.result.nr_iterations, a.result.n_compute_error) == (b.result.nr_iterations, b.result.n_compute_error)
+    with pytest.raises(Exception):
+        store.set_target(a, [7])
 
 
 # ---------------------------------------------------------------------------------------------- sharded submap (one GPU)
