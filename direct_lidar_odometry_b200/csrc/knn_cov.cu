@@ -239,14 +239,31 @@ __global__ void __launch_bounds__(256) knn_plan_kernel(GridView g, int4* __restr
   }
 }
 
-// one pass over the tile positions [c, cend): every point closer than T2 is counted, the first TQ_LCAP are stored in the
-// lane's list column (branch-free: overflow and non-passing candidates land in the dump row).  T2 < 0 switches a lane off.
-__device__ __forceinline__ int collect_pass(TileSmem& S, int c, int cend, float qx, float qy, float qz, float T2, int lane, int cnt) {
+// one pass over the tile positions [c, cend): every point closer than T2 goes into the lane's list column (branch-free:
+// non-passing candidates land in the dump row).  When a lane's list is about to fill up it LOWERS its own threshold and
+// keeps the entries below it — everything dropped, and everything rejected from then on, is farther than the final T2,
+// so the list still holds every tile point below the threshold the lane ends with.  T2 < 0 switches a lane off.
+#ifndef TQ_TARGET_EXTRA
+#define TQ_TARGET_EXTRA 12     // first guesses aim at k + this many collected points
+#endif
+__device__ __noinline__ int shrink_list(uint2* col, float& T2, int cnt) {
+  do {
+    T2 *= 0.75f;                              // counts grow ~linearly in T^2 on surfaces: about 3/4 survive
+    int pos = 0;
+    for (int i = 0; i < cnt; ++i) {
+      const uint2 e = col[i * 32];
+      if (__uint_as_float(e.x) < T2) { col[pos * 32] = e; ++pos; }
+    }
+    cnt = pos;
+  } while (cnt > TQ_LCAP - 4);
+  return cnt;
+}
+__device__ __forceinline__ int collect_pass(TileSmem& S, int c, int cend, float qx, float qy, float qz, float& T2, int lane, int cnt) {
   uint2* const col = &S.lst[0][lane];
 #define TQ_OFFER(D, CI)                                                         \
   {                                                                             \
     const bool ps = (D) < T2;                                                   \
-    const int row = ps ? min(cnt, TQ_LCAP) : TQ_LCAP;                           \
+    const int row = ps ? cnt : TQ_LCAP;                                         \
     col[row * 32] = make_uint2(__float_as_uint(D), (unsigned)(CI));             \
     cnt += ps ? 1 : 0;                                                          \
   }
@@ -257,11 +274,13 @@ __device__ __forceinline__ int collect_pass(TileSmem& S, int c, int cend, float 
     const float d2 = sqdist_unfused(qx, qy, qz, p2.x, p2.y, p2.z);
     const float d3 = sqdist_unfused(qx, qy, qz, p3.x, p3.y, p3.z);
     TQ_OFFER(d0, c) TQ_OFFER(d1, c + 1) TQ_OFFER(d2, c + 2) TQ_OFFER(d3, c + 3)
+    if (cnt > TQ_LCAP - 4) cnt = shrink_list(col, T2, cnt);     // room for the next four is guaranteed
   }
   for (; c < cend; ++c) {
     const float4 p0 = S.cand[c];
     const float d0 = sqdist_unfused(qx, qy, qz, p0.x, p0.y, p0.z);
     TQ_OFFER(d0, c)
+    if (cnt > TQ_LCAP - 4) cnt = shrink_list(col, T2, cnt);
   }
 #undef TQ_OFFER
   return cnt;
@@ -356,7 +375,7 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
       st_tiles++;
       // ---- answer the points from the tile, 32 at a time, one collection pass each; a point whose count misses
       //      the window re-queues itself with a rescaled threshold, so retries share passes with other points ----
-      const float guess0 = (float)(k + 8) * (float)(ny * ny) * gp.cell * gp.cell / (3.14159265f * (float)C);
+      const float guess0 = (float)(k + TQ_TARGET_EXTRA) * (float)(ny * ny) * gp.cell * gp.cell / (3.14159265f * (float)C);
       int nnxt = 0;
       float prevT = 0.f;
       for (int round = 0; round < 8 && ncur > 0; ++round) {
@@ -389,39 +408,49 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
           }
           // first guess: 1.4 x the k-th distance this lane found last in this tile, else the radius holding k+8
           // points at the tile's surface density (a planar cut through the tile covers ~ny*ny cells)
-          if (!(T2 > 0.f)) T2 = prevT > 0.f ? prevT * 1.4f : guess0;
+          if (!(T2 > 0.f)) T2 = prevT > 0.f ? prevT * (float)(k + TQ_TARGET_EXTRA) / (float)k : guess0;
           T2 = fminf(T2, m2);
           const bool active = me && m2 > 0.f;
           st_passes++;
           st_lanes += __popc(__ballot_sync(FULL, active));
           int c_now = 0;
+          const float T2_asked = T2;
           {
+            float Tc = active ? T2 : -1.f;      // may come back lower: the lane shrank its list on the way
             if (s <= 2) {
               for (int zr = zlo; zr <= zhi && yhi >= ylo; ++zr)
-                c_now = collect_pass(S, S.rowoff[zr * ny + ylo], S.rowoff[zr * ny + yhi + 1], qp.x, qp.y, qp.z, active ? T2 : -1.f, lane, c_now);
+                c_now = collect_pass(S, S.rowoff[zr * ny + ylo], S.rowoff[zr * ny + yhi + 1], qp.x, qp.y, qp.z, Tc, lane, c_now);
             } else {
-              c_now = collect_pass(S, 0, C, qp.x, qp.y, qp.z, active ? T2 : -1.f, lane, 0);
+              c_now = collect_pass(S, 0, C, qp.x, qp.y, qp.z, Tc, lane, 0);
             }
+            if (active) T2 = Tc;
           }
           const bool good = active && c_now >= k && c_now <= TQ_LCAP;
           // too few even at the largest provable radius (or no provable radius at all): needs a larger tile
           const bool grow = me && (!active || (c_now < k && T2 >= m2));
           const bool retry = active && !good && !grow;
-          // ---- tighten the threshold on the lane's own list until exactly k remain (warp-uniform loops) ----
+          // ---- tighten the threshold on the lane's own list until exactly k remain: the distances move into
+          //      registers once, the secant steps on the count then run without touching memory (warp-uniform loops) ----
           bool decided = good;
           bool tie = false;
           float Tk = T2;
           {
             bool searching = good && c_now > k;
+            const bool any_search = __any_sync(FULL, searching);
+            float dl[TQ_LCAP];
+            if (any_search) {
+#pragma unroll
+              for (int i = 0; i < TQ_LCAP; ++i) dl[i] = (searching && i < c_now) ? __uint_as_float(S.lst[i][lane].x) : INFINITY;
+            }
             float slo = 0.f, shi = T2;
             int clo = 0, chi = c_now;
-            const int cmax = __reduce_max_sync(FULL, searching ? c_now : 0);
             for (int it = 0; it < 16 && __any_sync(FULL, searching); ++it) {
               float T = slo + (shi - slo) * (((float)(k - clo) + 0.5f) / (float)max(chi - clo, 1));
               if (!(T > slo && T < shi)) T = 0.5f * (slo + shi);
               if (searching && !(T > slo && T < shi)) { searching = false; tie = true; }   // adjacent floats: tie at the k-th distance
               int c = 0;
-              for (int i = 0; i < cmax; ++i) c += (i < c_now && __uint_as_float(S.lst[i][lane].x) < T) ? 1 : 0;
+#pragma unroll
+              for (int i = 0; i < TQ_LCAP; ++i) c += (dl[i] < T) ? 1 : 0;
               if (searching) {
                 if (c == k) { searching = false; Tk = T; }
                 else if (c < k) { slo = T; clo = c; }
@@ -431,10 +460,12 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
             if (searching) tie = true;
             if (tie) { decided = false; st_ties++; }
             const bool compact = good && c_now > k && !tie;
-            int pos = 0;
-            for (int i = 0; i < cmax; ++i) {
-              const uint2 e = S.lst[i][lane];
-              if (compact && i < c_now && __uint_as_float(e.x) < Tk) { S.lst[pos][lane].y = e.y; ++pos; }
+            if (any_search) {
+              int pos = 0;
+#pragma unroll
+              for (int i = 0; i < TQ_LCAP; ++i) {
+                if (compact && dl[i] < Tk) { S.lst[pos][lane].y = S.lst[i][lane].y; ++pos; }
+              }
             }
           }
           if (decided) prevT = Tk;
@@ -458,8 +489,9 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
           const unsigned rm = __ballot_sync(FULL, retry);
           if (retry) {
             // counts grow ~linearly in T^2 on surfaces: aim at k+8 again, inside the bracket; never above the provable radius
-            if (c_now < k) lo = T2; else hi = T2;
-            float Tn = T2 * (float)(k + 8) / (float)max(c_now, 2);
+            // the count at T2 was too small; if the lane lowered its threshold on the way, the asked one was too large
+            if (c_now < k) { lo = T2; if (T2 < T2_asked) hi = hi > 0.f ? fminf(hi, T2_asked) : T2_asked; } else hi = T2;
+            float Tn = T2 * (float)(k + TQ_TARGET_EXTRA) / (float)max(c_now, 2);
             if (Tn <= lo || (hi > 0.f && Tn >= hi)) Tn = hi > 0.f ? 0.5f * (lo + hi) : T2 * 2.f;
             Tn = fminf(Tn, m2);
             const int pos = nre + __popc(rm & lt);          // nre <= t0: never overtakes the reads
@@ -572,11 +604,14 @@ size_t covariance_scratch_ints(int n, int k) { return items_offset_ints(n, k) + 
 
 cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_scratch, double* covs6, int table_cap, cudaStream_t st) {
   if (c.n <= 0) return cudaSuccess;
-  // Default: one warp per point (knn_lists_kernel).  NGICP_KNN_TILE=1 selects the cell-major tile path (plan + tile +
-  // rest launches): measured on the C2 submap it executes half the instructions but, at 11 resident warps per SM and
-  // ~14 busy lanes per pass, takes the same 0.82 ms for 500k points and is slower on 22k-point scans;
-  // NGICP_KNN_STATS=1 prints how many points took which path (synchronises: diagnostics only)
-  static const bool warp_only = getenv("NGICP_KNN_TILE") == nullptr;
+  // Two exact paths.  One warp per point (knn_lists_kernel): massively parallel, best for scans.  Cell-major tiles
+  // (plan + tile + rest launches): half the instructions per point but a longer serial path per warp, best for
+  // submaps — measured on the C2 submap (500k points, k=20) 0.63 ms against 0.82 ms, on a 22k-point scan 0.19 ms against
+  // 0.10 ms.  NGICP_KNN_TILE=0/1 forces a path; by default clouds of NGICP_KNN_TILE_MIN
+  // (131072) points or more take the tiles.
+  static const int tile_env = getenv("NGICP_KNN_TILE") ? atoi(getenv("NGICP_KNN_TILE")) : -1;
+  static const int tile_min = getenv("NGICP_KNN_TILE_MIN") ? atoi(getenv("NGICP_KNN_TILE_MIN")) : 131072;
+  const bool warp_only = tile_env == 0 || (tile_env < 0 && c.n < tile_min);
   static const bool want_stats = getenv("NGICP_KNN_STATS") != nullptr;
   if (warp_only) {
     knn_lists_kernel<<<(c.n + KC_WARPS - 1) / KC_WARPS, KC_THREADS, 0, st>>>(c.view(), c.n, k, nbr_scratch);

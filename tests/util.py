@@ -28,3 +28,21 @@ def pose_delta(Ta: np.ndarray, Tb: np.ndarray):
     # small-angle robust: use the skew part
     s = 0.5 * np.array([dR[2, 1] - dR[1, 2], dR[0, 2] - dR[2, 0], dR[1, 0] - dR[0, 1]])
     return dt, float(np.arcsin(min(1.0, np.linalg.norm(s))))
+
+
+def make_small_submap(O):
+    """A scaled-down S2M case: 6 keyframes 5 m apart voxelised at 0.5 m in the world frame (reference
+    odom.cc:484-490), and one scan voxelised at 0.25 m as the source.  `O` = the oracle module."""
+    from direct_lidar_odometry_b200 import synth
+    keys = []
+    for j in range(6):
+        i = j * 33
+        T = synth.trajectory_pose(i)
+        s = synth.crop_box_negative(synth.os1_like(i, T))
+        w = synth.transform_xyzi(O.voxel_filter(s, 0.25), T.astype(np.float32))
+        keys.append(O.voxel_filter(w, 0.5))
+    submap = np.ascontiguousarray(np.vstack(keys))
+    i = 90
+    T = synth.trajectory_pose(i)
+    scan = O.voxel_filter(synth.crop_box_negative(synth.os1_like(i, T)), 0.25)
+    return submap, scan, T
