@@ -77,8 +77,8 @@ __global__ void __launch_bounds__(KC_THREADS, KNN_MIN_BLOCKS) knn_lists_kernel(G
 //                          no dependent shuffles.  An exact tie at the k-th distance has no such threshold: those
 //                          (rare) points take the warp search.
 // One distance evaluation therefore costs one instruction slot per 32 queries instead of one per query.  Points that
-// cannot be decided inside a radius-4 tile are appended to a list and answered by the growing-cube warp search in a
-// last, fully parallel launch.
+// cannot be decided inside a radius-TQ_SMAX tile (isolated points, ties at the k-th distance) are appended to a list;
+// warps that run out of tiles drain it with the growing-cube warp search while the others are still at work.
 #ifndef TQ_WARPS
 #define TQ_WARPS 2
 #endif
@@ -124,8 +124,8 @@ __device__ __forceinline__ float box_face_distance(const GridParams& gp, int x0,
 #define TQ_CHECK(cond, what, a, b) do { } while (0)
 #endif
 enum { ST_FALLBACK = 0, ST_TIES, ST_TILES, ST_PASSES, ST_LANES, ST_ITEMS, ST_N };
-// control words shared by the three launches
-enum { CT_ITEMS = 0, CT_NEXT, CT_REST, CT_N = 8 };
+// control words shared by the plan and tile launches
+enum { CT_ITEMS = 0, CT_NEXT, CT_REST, CT_REST_NEXT, CT_DONE, CT_N = 8 };
 
 // warp-aggregated append of the lanes in `mask` to the warp-search list
 __device__ __forceinline__ void fb_append(unsigned mask, int slot, int lane, int* __restrict__ fb_list, int* __restrict__ fb_count) {
@@ -246,7 +246,8 @@ __global__ void __launch_bounds__(256) knn_plan_kernel(GridView g, int4* __restr
 #ifndef TQ_TARGET_EXTRA
 #define TQ_TARGET_EXTRA 12     // first guesses aim at k + this many collected points
 #endif
-__device__ __noinline__ int shrink_list(uint2* col, float& T2, int cnt) {
+struct Shrunk { float T2; int cnt; };
+__device__ __noinline__ Shrunk shrink_list(uint2* col, float T2, int cnt) {
   do {
     T2 *= 0.75f;                              // counts grow ~linearly in T^2 on surfaces: about 3/4 survive
     int pos = 0;
@@ -256,16 +257,29 @@ __device__ __noinline__ int shrink_list(uint2* col, float& T2, int cnt) {
     }
     cnt = pos;
   } while (cnt > TQ_LCAP - 4);
-  return cnt;
+  Shrunk r;
+  r.T2 = T2; r.cnt = cnt;
+  return r;
 }
-__device__ __forceinline__ int collect_pass(TileSmem& S, int c, int cend, float qx, float qy, float qz, float& T2, int lane, int cnt) {
+// "write, then advance if it passed": the slot after the last accepted entry is simply overwritten by the next
+// candidate, so an offer is one 64-bit shared store plus one predicated pointer bump (row stride 256 B)
+__device__ __forceinline__ int collect_pass(TileSmem& S, int c, int cend, float qx, float qy, float qz, float& T2_io, int lane, int cnt) {
   uint2* const col = &S.lst[0][lane];
-#define TQ_OFFER(D, CI)                                                         \
-  {                                                                             \
-    const bool ps = (D) < T2;                                                   \
-    const int row = ps ? cnt : TQ_LCAP;                                         \
-    col[row * 32] = make_uint2(__float_as_uint(D), (unsigned)(CI));             \
-    cnt += ps ? 1 : 0;                                                          \
+  float T2 = T2_io;
+  // 32-bit shared-window addresses: the bump is one predicated integer add
+  const unsigned a0 = (unsigned)__cvta_generic_to_shared(col);
+  unsigned p = a0 + (unsigned)cnt * 256u;
+  const unsigned plim = a0 + (unsigned)(TQ_LCAP - 4) * 256u;
+#define TQ_OFFER(D, CI)                                                                                      \
+  {                                                                                                          \
+    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(p), "r"(__float_as_uint(D)), "r"((unsigned)(CI)) : "memory"); \
+    if ((D) < T2) p += 256u;                                                                                 \
+  }
+#define TQ_MAYBE_SHRINK()                                                       \
+  if (p > plim) {                                                               \
+    const Shrunk r = shrink_list(col, T2, (int)((p - a0) >> 8));                \
+    T2 = r.T2;                                                                  \
+    p = a0 + (unsigned)r.cnt * 256u;                                            \
   }
   for (; c + 4 <= cend; c += 4) {
     const float4 p0 = S.cand[c], p1 = S.cand[c + 1], p2 = S.cand[c + 2], p3 = S.cand[c + 3];
@@ -274,16 +288,18 @@ __device__ __forceinline__ int collect_pass(TileSmem& S, int c, int cend, float 
     const float d2 = sqdist_unfused(qx, qy, qz, p2.x, p2.y, p2.z);
     const float d3 = sqdist_unfused(qx, qy, qz, p3.x, p3.y, p3.z);
     TQ_OFFER(d0, c) TQ_OFFER(d1, c + 1) TQ_OFFER(d2, c + 2) TQ_OFFER(d3, c + 3)
-    if (cnt > TQ_LCAP - 4) cnt = shrink_list(col, T2, cnt);     // room for the next four is guaranteed
+    TQ_MAYBE_SHRINK()                                           // room for the next four is guaranteed
   }
   for (; c < cend; ++c) {
     const float4 p0 = S.cand[c];
     const float d0 = sqdist_unfused(qx, qy, qz, p0.x, p0.y, p0.z);
     TQ_OFFER(d0, c)
-    if (cnt > TQ_LCAP - 4) cnt = shrink_list(col, T2, cnt);
+    TQ_MAYBE_SHRINK()
   }
 #undef TQ_OFFER
-  return cnt;
+#undef TQ_MAYBE_SHRINK
+  T2_io = T2;
+  return (int)((p - a0) >> 8);
 }
 
 __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView g, int n, int k, int* __restrict__ nbr,
@@ -528,6 +544,34 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
     }
     __syncwarp();
   }
+  // ---- drain: warps that ran out of tiles answer the listed points with the growing-cube warp search while other
+  //      warps are still producing; an entry is -1 until its producer has written it ----
+  __threadfence();
+  if (lane == 0) atomicAdd(ctrl + CT_DONE, 1);
+  {
+    const int total_warps = (int)gridDim.x * TQ_WARPS;
+    for (;;) {
+      int i = 0;
+      if (lane == 0) i = atomicAdd(ctrl + CT_REST_NEXT, 1);
+      i = __shfl_sync(FULL, i, 0);
+      int q = -1;
+      if (lane == 0 && i < n) {
+        for (;;) {
+          q = *(volatile int*)(fb_list + i);
+          if (q >= 0) break;
+          if (*(volatile int*)(ctrl + CT_DONE) == total_warps) { q = *(volatile int*)(fb_list + i); break; }
+          __nanosleep(200);
+        }
+      }
+      q = __shfl_sync(FULL, q, 0);
+      if (q < 0) break;
+      const float4 qp = __ldg(g.sorted + q);
+      WarpTopK rs;
+      rs.init(k, lane);
+      if (isfinite(qp.x) && isfinite(qp.y) && isfinite(qp.z)) grid_search_warp(g, gp, qp.x, qp.y, qp.z, FLT_MAX, rs, k >= 4);
+      if (lane < k) nbr[(size_t)q * k + lane] = rs.p;
+    }
+  }
   if (stats != nullptr && lane == 0) {
     atomicAdd(stats + ST_FALLBACK, (unsigned long long)st_fb);
     atomicAdd(stats + ST_TIES, (unsigned long long)st_ties);
@@ -535,26 +579,6 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
     atomicAdd(stats + ST_PASSES, (unsigned long long)st_passes);
     atomicAdd(stats + ST_LANES, (unsigned long long)st_lanes);
     atomicAdd(stats + ST_ITEMS, (unsigned long long)st_items);
-  }
-}
-
-// second launch: the growing-cube warp search for the points the tiles could not decide (non-finite points included:
-// they get -1 neighbours)
-__global__ void __launch_bounds__(KC_THREADS, KNN_MIN_BLOCKS) knn_lists_rest_kernel(GridView g, int k, const int* __restrict__ fb_list,
-                                                                                    const int* __restrict__ fb_count, int* __restrict__ nbr) {
-  const int lane = threadIdx.x & 31;
-  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  const int nfb = *fb_count;
-  if (warp >= nfb) return;
-  const GridParams gp = load_grid(g.desc);
-  for (int i = warp; i < nfb; i += nwarps) {
-    const int q = __ldg(fb_list + i);
-    const float4 qp = __ldg(g.sorted + q);
-    WarpTopK rs;
-    rs.init(k, lane);
-    if (isfinite(qp.x) && isfinite(qp.y) && isfinite(qp.z)) grid_search_warp(g, gp, qp.x, qp.y, qp.z, FLT_MAX, rs, k >= 4);
-    if (lane < k) nbr[(size_t)q * k + lane] = rs.p;
   }
 }
 
@@ -605,7 +629,7 @@ size_t covariance_scratch_ints(int n, int k) { return items_offset_ints(n, k) + 
 cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_scratch, double* covs6, int table_cap, cudaStream_t st) {
   if (c.n <= 0) return cudaSuccess;
   // Two exact paths.  One warp per point (knn_lists_kernel): massively parallel, best for scans.  Cell-major tiles
-  // (plan + tile + rest launches): half the instructions per point but a longer serial path per warp, best for
+  // (plan + tile launches): half the instructions per point but a longer serial path per warp, best for
   // submaps — measured on the C2 submap (500k points, k=20) 0.63 ms against 0.82 ms, on a 22k-point scan 0.19 ms against
   // 0.10 ms.  NGICP_KNN_TILE=0/1 forces a path; by default clouds of NGICP_KNN_TILE_MIN
   // (131072) points or more take the tiles.
@@ -638,6 +662,7 @@ cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_sc
     items = reinterpret_cast<int4*>((reinterpret_cast<uintptr_t>(items) + 15) & ~(uintptr_t)15);
     cudaError_t e = cudaMemsetAsync(ctrl, 0, CT_N * sizeof(int), st);
     if (e != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(fb_list, 0xff, (size_t)c.n * sizeof(int), st)) != cudaSuccess) return e;   // -1 = not written yet
     unsigned long long* stats = nullptr;
     if (want_stats) {
       if (cudaMalloc(&stats, ST_N * sizeof(unsigned long long)) != cudaSuccess) return cudaGetLastError();
@@ -656,16 +681,7 @@ cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_sc
     }
     // persistent grid: every resident warp pulls work items until the counter runs out
     knn_lists_tile_kernel<<<sm_count[di] * blocks_per_sm[di], TQ_WARPS * 32, smem, st>>>(c.view(), c.n, k, nbr_scratch, items, ctrl, fb_list, stats);
-    if (want_stats) {
-      cudaError_t se = cudaStreamSynchronize(st);
-      fprintf(stderr, "[ngicp knn] tile: %s (grid %d blocks, smem %zu)\n", cudaGetErrorString(se), sm_count[di] * blocks_per_sm[di], smem);
-    }
-    knn_lists_rest_kernel<<<sm_count[di] * KNN_MIN_BLOCKS * 4, KC_THREADS, 0, st>>>(c.view(), k, fb_list, ctrl + CT_REST, nbr_scratch);
-    if (want_stats) {
-      cudaError_t se = cudaStreamSynchronize(st);
-      fprintf(stderr, "[ngicp knn] rest: %s\n", cudaGetErrorString(se));
-    }
-    note_launches(3);
+    note_launches(2);
     if (want_stats) {
       unsigned long long h[ST_N] = {};
       cudaMemcpyAsync(h, stats, sizeof(h), cudaMemcpyDeviceToHost, st);
