@@ -10,7 +10,7 @@
 `value`  : scan pairs per second, inputs already resident in HBM (device pointers into the C ABI)
 `e2e`    : same through the public API with pinned HOST buffers (H2D of both clouds and D2H of the result inside the
            timed region)
-`roofline`: dominant kernel (fused kNN + covariance over the 500k submap) — algorithmic 64 B/point / its CUDA-event time
+`roofline`: dominant kernel group (exact kNN + covariance over the 500k submap) — algorithmic 64 B/point / its CUDA-event time
 `cpu_baseline`: the CPU oracle (reference's vendored nanoflann + restated GICP math, OpenMP) on this host's cores
 --impl reference: that CPU path alone, same workload/metric.
 N>1: one process per GPU (torchrun), every rank registers its own scans against the submap (weak scaling), no collective
@@ -326,7 +326,7 @@ def main():
                 "n_compute_error": int(res.n_compute_error), "converged": int(res.converged),
                 "pose_error_m": float(np.linalg.norm(np.array(res.final_x).reshape(4, 4).T[:3, 3] - wl["truths"][rank % 8][:3, 3])),
                 "wall_s_timed_region": t_wall,
-                "roofline": {"kernel": "knn_cov_kernel (fused kNN k=20 + plane covariance, 500k-pt submap)", "bound": "hbm",
+                "roofline": {"kernel": "K2+K3 over the 500k-pt submap: knn_plan_kernel + knn_lists_tile_kernel (exact kNN, k=20) + cov_from_lists_kernel (plane covariances)", "bound": "hbm",
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                              "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kcov_ms, "peak_source": peak_src,
                              "share_of_step": kcov_ms / (tot_dev_ms / args.steps)},
