@@ -505,6 +505,7 @@ int ngicp_share_source(ngicp_t* dst, const ngicp_t* src) {
   if (!dst || !src) return NGICP_E_INVALID;
   if (dst->device != src->device) return fail(dst, NGICP_E_INVALID, "handles live on different devices");
   if (!src->src) return fail(dst, NGICP_E_STATE, "share: source not set");
+  DeviceGuard g(dst->device);             // dropping the previous cloud frees stream-ordered memory of that device
   cudaStreamSynchronize(src->stream->s);  // the index must be complete before another stream reads it
   dst->src = src->src;
   dst->lin_valid = false;
@@ -513,6 +514,7 @@ int ngicp_share_source(ngicp_t* dst, const ngicp_t* src) {
 int ngicp_share_source_covs(ngicp_t* dst, const ngicp_t* src) {
   if (!dst || !src) return NGICP_E_INVALID;
   if (dst->device != src->device) return fail(dst, NGICP_E_INVALID, "handles live on different devices");
+  DeviceGuard g(dst->device);
   cudaStreamSynchronize(src->stream->s);
   dst->src_cov = src->src_cov;
   dst->lin_valid = false;
@@ -526,8 +528,9 @@ int ngicp_swap(ngicp_t* h) {
   h->lin_valid = false;
   return NGICP_OK;
 }
-int ngicp_clear_source(ngicp_t* h) { if (!h) return NGICP_E_INVALID; h->src.reset(); h->src_cov.reset(); h->lin_valid = false; return NGICP_OK; }
-int ngicp_clear_target(ngicp_t* h) { if (!h) return NGICP_E_INVALID; h->tgt.reset(); h->tgt_cov.reset(); h->lin_valid = false; return NGICP_OK; }
+// (releasing a cloud frees stream-ordered memory and records events: the handle's device must be current)
+int ngicp_clear_source(ngicp_t* h) { if (!h) return NGICP_E_INVALID; DeviceGuard g(h->device); h->src.reset(); h->src_cov.reset(); h->lin_valid = false; return NGICP_OK; }
+int ngicp_clear_target(ngicp_t* h) { if (!h) return NGICP_E_INVALID; DeviceGuard g(h->device); h->tgt.reset(); h->tgt_cov.reset(); h->lin_valid = false; return NGICP_OK; }
 size_t ngicp_cloud_size(const ngicp_t* h, int which) {
   if (!h) return 0;
   const CloudPtr& c = which == NGICP_SOURCE ? h->src : h->tgt;
@@ -540,6 +543,7 @@ int ngicp_set_source_covs(ngicp_t* h, const double* covs, size_t n) { return set
 int ngicp_set_target_covs(ngicp_t* h, const double* covs, size_t n) { return set_covs(h, NGICP_TARGET, covs, n); }
 int ngicp_clear_covs(ngicp_t* h, int which) {
   if (!h) return NGICP_E_INVALID;
+  DeviceGuard g(h->device);
   (which == NGICP_SOURCE ? h->src_cov : h->tgt_cov).reset();
   h->lin_valid = false;
   return NGICP_OK;
