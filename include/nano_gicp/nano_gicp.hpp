@@ -230,7 +230,9 @@ class NanoGICP {
     if (h()) ngicp_swap(h());
   }
   virtual void clearSource() { input_.reset(); if (h()) ngicp_clear_source(h()); source_covs_.invalidate_host(); }
-  virtual void clearTarget() { target_.reset(); if (h()) ngicp_clear_target(h()); target_covs_.invalidate_host(); }
+  virtual void clearTarget() { target_.reset(); device_target_ = false; if (h()) ngicp_clear_target(h()); target_covs_.invalidate_host(); }
+  // the target was replaced behind the facade (KeyframeStore::setTarget): drop the cached host pointer and host covariances
+  void forgetTarget() { target_.reset(); target_covs_.invalidate_host(); device_target_ = true; }
 
   virtual void setInputSource(const PointCloudSourceConstPtr& cloud) {
     if (input_ == cloud) return;
@@ -250,6 +252,7 @@ class NanoGICP {
     if (target_ == cloud) return;
     if (!check_cloud(cloud, "setInputTarget")) return;
     target_ = cloud;
+    device_target_ = false;
     detail::report(h(), ngicp_set_target(h(), cloud->points.data(), cloud->points.size(), sizeof(PointTarget)), "setInputTarget");
     target_kdtree_->cloud = cloud;
     target_covs_.invalidate_host();
@@ -278,7 +281,7 @@ class NanoGICP {
   void align(PointCloudSource& output, const Matrix4& guess) {
     converged_ = false;
     final_transformation_ = Matrix4::Identity();
-    if (!target_) { std::fprintf(stderr, "[pcl::Registration::align] No input target dataset was given!\n"); return; }
+    if (!target_ && !device_target_) { std::fprintf(stderr, "[pcl::Registration::align] No input target dataset was given!\n"); return; }
     if (!input_) { std::fprintf(stderr, "[pcl::Registration::align] No input source dataset was given!\n"); return; }
     ngicp_result res;
     int rc = ngicp_align(h(), guess.data(), &res);
@@ -329,6 +332,7 @@ class NanoGICP {
   bool converged_ = false;
   int nr_iterations_ = 0;
   bool fill_output_ = true;
+  bool device_target_ = false;   // target assembled on the device by KeyframeStore::setTarget (no host cloud)
   std::vector<float> scratch_;
 };
 
@@ -355,6 +359,59 @@ class VoxelGrid {
   std::unique_ptr<detail::Handle> handle_;
   typename pcl::PointCloud<PointT>::ConstPtr in_;
   float leaf_ = 0.25f;
+};
+
+// ---- additive helpers (not part of the reference class) ---------------------------------
+
+// OdomNode::preprocessPoints (odom.cc:443-465) in one device pass: removeNaN + negative CropBox(+-crop_size; <= 0 skips
+// it) + scan voxel grid (leaf <= 0 skips it)
+template <typename PointT>
+class Preprocessor {
+ public:
+  explicit Preprocessor(int device = 0) : handle_(new detail::Handle(device)) {}
+  void setCropSize(float s) { crop_ = s; }
+  void setLeafSize(float l) { leaf_ = l; }
+  void filter(const pcl::PointCloud<PointT>& in, pcl::PointCloud<PointT>& out) {
+    if (!handle_->h) return;
+    const size_t n = in.points.size();
+    std::vector<PointT> tmp(n ? n : 1);
+    size_t m = 0;
+    const float lo[3] = {-crop_, -crop_, -crop_}, hi[3] = {crop_, crop_, crop_};
+    int rc = ngicp_preprocess(handle_->h, in.points.data(), n, sizeof(PointT), crop_ > 0.f ? lo : nullptr, crop_ > 0.f ? hi : nullptr, leaf_,
+                              tmp.data(), tmp.size(), &m);
+    detail::report(handle_->h, rc, "Preprocessor::filter");
+    tmp.resize(m);
+    out.points.swap(tmp);
+    out.width = (uint32_t)m; out.height = 1; out.is_dense = true;
+  }
+ private:
+  std::unique_ptr<detail::Handle> handle_;
+  float crop_ = 1.0f, leaf_ = 0.25f;
+};
+
+// Device-resident keyframes: what OdomNode keeps in `keyframes` / `keyframe_normals` and concatenates on the host
+// (odom.cc:498-504, 1172-1178, 1315-1328), kept on the GPU (ngicp_kfstore_*).
+class KeyframeStore {
+ public:
+  explicit KeyframeStore(int device = 0) { if (ngicp_kfstore_create(device, &s_) != NGICP_OK) s_ = nullptr; }
+  ~KeyframeStore() { if (s_) ngicp_kfstore_destroy(s_); }
+  KeyframeStore(const KeyframeStore&) = delete;
+  KeyframeStore& operator=(const KeyframeStore&) = delete;
+  size_t size() const { return s_ ? ngicp_kfstore_size(s_) : 0; }
+  // after gicp_s2s.setInputSource(keyframe_cloud); gicp_s2s.calculateSourceCovariances();
+  template <class Gicp> int push(Gicp& gicp_s2s) {
+    size_t idx = 0;
+    detail::report(gicp_s2s.handle(), ngicp_kfstore_push(s_, gicp_s2s.handle(), &idx), "KeyframeStore::push");
+    return (int)idx;
+  }
+  // instead of gicp.setInputTarget(submap_cloud); gicp.setTargetCovariances(submap_normals);
+  template <class Gicp> void setTarget(Gicp& gicp, const std::vector<int>& keyframe_indices) {
+    detail::report(gicp.handle(), ngicp_kfstore_set_target(s_, gicp.handle(), keyframe_indices.data(), keyframe_indices.size()),
+                   "KeyframeStore::setTarget");
+    gicp.forgetTarget();
+  }
+ private:
+  ngicp_kfstore_t* s_ = nullptr;
 };
 
 }  // namespace nano_gicp

@@ -5,6 +5,7 @@
 // Output: one JSON line per scan with the S2S / S2M transforms and iteration counts.
 #include <cmath>
 #include <cstdio>
+#include <string>
 #include <cstdlib>
 #include <memory>
 #include <vector>
@@ -33,6 +34,8 @@ struct OdomNodeLike {
   nano_gicp::NanoGICP<PointType, PointType> gicp_s2s;
   nano_gicp::NanoGICP<PointType, PointType> gicp;
   nano_gicp::VoxelGrid<PointType> vf_submap;
+  nano_gicp::KeyframeStore store;     // additive: device-resident keyframes
+  bool use_store = false;
   pcl::PointCloud<PointType>::Ptr current_scan, target_cloud, keyframe_cloud, submap_cloud;
   std::vector<std::vector<Eigen::Matrix4d, Eigen::aligned_allocator<Eigen::Matrix4d>>> keyframe_normals;
   std::vector<Eigen::Matrix4d, Eigen::aligned_allocator<Eigen::Matrix4d>> submap_normals;
@@ -76,6 +79,7 @@ struct OdomNodeLike {
     gicp_s2s.setInputSource(keyframe_cloud);
     gicp_s2s.calculateSourceCovariances();
     keyframe_normals.push_back(gicp_s2s.getSourceCovariances());
+    store.push(gicp_s2s);
     submap_cloud = first_keyframe;
     submap_normals = keyframe_normals[0];
   }
@@ -96,8 +100,12 @@ struct OdomNodeLike {
     gicp.source_covs_ = gicp_s2s.source_covs_;
     gicp_s2s.swapSourceAndTarget();
     if (submap_hasChanged) {
-      gicp.setInputTarget(submap_cloud);
-      gicp.setTargetCovariances(submap_normals);
+      if (use_store) {
+        store.setTarget(gicp, std::vector<int>{0});       // additive path: submap assembled on the device
+      } else {
+        gicp.setInputTarget(submap_cloud);
+        gicp.setTargetCovariances(submap_normals);
+      }
       submap_hasChanged = false;
     }
     gicp.align(*aligned, T_s2s);
@@ -122,6 +130,7 @@ int main(int argc, char** argv) {
   if (std::fread(&nscans, 4, 1, f) != 1 || std::fread(T0, 4, 16, f) != 16) return 2;
   OdomNodeLike node;
   if (!node.gicp.handle() || !node.gicp_s2s.handle()) return 3;   // no GPU: fail loudly
+  node.use_store = argc > 2 && std::string(argv[2]) == "store";
   for (int i = 0; i < 16; i++) node.T.data()[i] = T0[i];
   node.T_s2s = node.T;
   node.T_s2s_prev = node.T;

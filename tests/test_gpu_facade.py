@@ -38,6 +38,10 @@ def test_facade_runs_odom_sequence(tmp_path):
     assert out.returncode == 0, out.stderr
     rows = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(rows) == 4
+    # the additive device-resident keyframe store (nano_gicp::KeyframeStore) must give the same output, bit for bit
+    out2 = subprocess.run([BIN, str(path), "store"], capture_output=True, text=True, timeout=120)
+    assert out2.returncode == 0, out2.stderr
+    assert [l for l in out2.stdout.splitlines() if l.startswith("{")] == [l for l in out.stdout.splitlines() if l.startswith("{")]
 
     # the same sequence through the Python mirror (same library, same inputs)
     s2s, s2m = NanoGICP(0), NanoGICP(0)
