@@ -53,19 +53,20 @@ __device__ __forceinline__ float xform_row(const float* m, float x, float y, flo
   return __fadd_rn(__fadd_rn(__fmul_rn(m[0], x), __fmul_rn(m[1], y)), __fadd_rn(__fmul_rn(m[2], z), __fmul_rn(m[3], 1.0f)));
 }
 
-// one thread: correspondence + Mahalanobis + H/b/err contribution of source point i
-__device__ __forceinline__ void linearize_point(const AlignArgs& a, const GridParams& gp, const XformF& Tf, const Iso3& Td,
-                                                float cap_d2, double thr2, int i, double* acc) {
-  const float4 p = __ldg(a.src_pts + i);
-  const float qx = xform_row(Tf.m + 0, p.x, p.y, p.z), qy = xform_row(Tf.m + 4, p.x, p.y, p.z), qz = xform_row(Tf.m + 8, p.x, p.y, p.z);
-  float my_d = FLT_MAX;
-  int my_p = -1;
-  bool mine = isfinite(qx) && isfinite(qy) && isfinite(qz);
-  if (a.slab_axis >= 0) {
-    const float qa = a.slab_axis == 0 ? qx : (a.slab_axis == 1 ? qy : qz);
-    mine = mine && qa >= a.slab_lo && qa < a.slab_hi;
-  }
-  if (mine) grid_nn1_thread(a.tgt, gp, qx, qy, qz, cap_d2, my_d, my_p);
+// The 1-NN of most source points is settled inside the 3x3x3 cells around them by their own thread.  The rest — points
+// whose nearest neighbour may lie farther than one cell (cell edge < max-correspondence distance, or no neighbour
+// nearby at all) — used to walk up to 5^3 cells alone and the whole grid waited at the reduction for that one thread.
+// They are queued in shared memory instead and the block's warps pull them one by one and finish the search
+// cooperatively (grid_search_warp resumed at radius 1, 32 candidates per step).
+struct TailQuery { float qx, qy, qz, d; int p; };
+struct TailQueue {
+  TailQuery q[AL_THREADS];          // slot = threadIdx.x of the owning thread (results are written back in place)
+  unsigned short list[AL_THREADS];  // owning threads, in arrival order (the order does not influence any result)
+  int n, next;
+};
+
+// after the search: Mahalanobis + H/b/err contribution of source point i with nearest sorted slot my_p at my_d
+__device__ __forceinline__ void finish_point(const AlignArgs& a, const Iso3& Td, double thr2, int i, const float4 p, float my_d, int my_p, double* acc) {
   int corr = -1;
   if (my_p >= 0 && (double)my_d < thr2) {
     const float4 tp = __ldg(a.tgt.sorted + my_p);
@@ -108,15 +109,85 @@ __device__ __forceinline__ double error_point(const AlignArgs& a, const Iso3& Td
   return e0 * m0 + e1 * m1 + e2 * m2;
 }
 
+// One block's share of a linearize pass.  LPP = lanes per source point: 1 = one thread per point; 2 / 4 = a group of
+// adjacent lanes shares the point's candidate scans (a 20k-point scan cannot fill the GPU with one thread per point,
+// and the search is a chain of dependent round trips — a group reads LPP x 8 candidates per round trip) and lane 0
+// of the group does the fp64 part.  The block handles points base + threadIdx.x / LPP for base = first,
+// first + stride, ... (block-uniform trip count: the loop contains barriers).
+template <int LPP>
+__device__ __forceinline__ void linearize_block(const AlignArgs& a, const GridParams& gp, const XformF& Tf, const Iso3& Td,
+                                                float cap_d2, double thr2, int first, int stride, TailQueue& tq, double& wtot) {
+  const int lane = threadIdx.x & 31;
+  const int sub = threadIdx.x & (LPP - 1), gi = threadIdx.x / LPP;
+  const unsigned gmask = (LPP == 1) ? 0u : (((1u << LPP) - 1u) << (lane & ~(LPP - 1)));
+  for (int base = first; base < a.ns; base += stride) {
+    if (threadIdx.x == 0) { tq.n = 0; tq.next = 0; }
+    __syncthreads();
+    const int i = base + gi;
+    const bool active = i < a.ns;
+    float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+    float my_d = FLT_MAX;
+    int my_p = -1;
+    bool queued = false;
+    if (active) {
+      p = __ldg(a.src_pts + i);
+      const float qx = xform_row(Tf.m + 0, p.x, p.y, p.z), qy = xform_row(Tf.m + 4, p.x, p.y, p.z), qz = xform_row(Tf.m + 8, p.x, p.y, p.z);
+      bool mine = isfinite(qx) && isfinite(qy) && isfinite(qz);
+      if (a.slab_axis >= 0) {
+        const float qa = a.slab_axis == 0 ? qx : (a.slab_axis == 1 ? qy : qz);
+        mine = mine && qa >= a.slab_lo && qa < a.slab_hi;
+      }
+      bool more = false;
+      if (mine) {
+        if (LPP == 1) more = grid_nn1_cube1(a.tgt, gp, qx, qy, qz, cap_d2, my_d, my_p);
+        else more = grid_nn1_cube1_group<LPP>(a.tgt, gp, sub, gmask, qx, qy, qz, cap_d2, my_d, my_p);
+      }
+      if (more && sub == 0) {
+        queued = true;
+        TailQuery& t = tq.q[gi];
+        t.qx = qx; t.qy = qy; t.qz = qz; t.d = my_d; t.p = my_p;
+        tq.list[atomicAdd(&tq.n, 1)] = (unsigned short)gi;
+      }
+    }
+    __syncthreads();
+    const int nq = tq.n;
+    if (nq > 0) {
+      for (;;) {
+        int e = 0;
+        if (lane == 0) e = atomicAdd(&tq.next, 1);
+        e = __shfl_sync(FULL, e, 0);
+        if (e >= nq) break;
+        TailQuery& t = tq.q[tq.list[e]];
+        WarpBest1 rs;
+        rs.d = t.d; rs.p = t.p;
+        grid_search_warp<WarpBest1, true>(a.tgt, gp, t.qx, t.qy, t.qz, cap_d2, rs, false, 1);
+        rs.finalize();
+        if (lane == 0) { t.d = rs.d; t.p = rs.p; }
+      }
+      __syncthreads();
+      if (queued) { my_d = tq.q[gi].d; my_p = tq.q[gi].p; }
+    }
+    // The 28 sums of this pass are reduced over the warp right away (lane j keeps the running total of value j):
+    // one live register across the search instead of 28 accumulators.
+    double contrib[NRED];
+#pragma unroll
+    for (int j = 0; j < NRED; j++) contrib[j] = 0.0;
+    if (active && sub == 0) finish_point(a, Td, thr2, i, p, my_d, my_p, contrib);
+    wtot += warp_sum_transposed<NRED>(contrib);
+    __syncthreads();
+  }
+}
+
 // block-level fixed-order reduction of NV values per thread -> out[0..NV) (written by threads < NV)
+// NV == 1: acc[0] is a per-thread value; NV > 1: acc[0] of lane j is already the warp's total of value j
 template <int NV>
 __device__ __forceinline__ void block_reduce_store(double* acc, double (*s_red)[NRED], double* out) {
   const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-#pragma unroll
-  for (int j = 0; j < NV; j++) acc[j] = warp_sum(acc[j]);
-  if (lane == 0) {
-#pragma unroll
-    for (int j = 0; j < NV; j++) s_red[w][j] = acc[j];
+  if (NV == 1) {
+    const double s = warp_sum(acc[0]);
+    if (lane == 0) s_red[w][0] = s;
+  } else {
+    if (lane < NV) s_red[w][lane] = acc[0];
   }
   __syncthreads();
   if (threadIdx.x < NV) {
@@ -135,14 +206,12 @@ struct IsoArg { Iso3 x; };
 
 __global__ void __launch_bounds__(AL_THREADS) linearize_kernel(AlignArgs a, IsoArg T, float cap_d2, double thr2) {
   __shared__ double s_red[AL_WARPS][NRED];
+  __shared__ TailQueue s_tq;
   const GridParams gp = load_grid(a.tgt.desc);
   XformF Tf;
   make_xforms(T.x, Tf);
-  double acc[NRED];
-#pragma unroll
-  for (int j = 0; j < NRED; j++) acc[j] = 0.0;
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < a.ns; i += gridDim.x * blockDim.x)
-    linearize_point(a, gp, Tf, T.x, cap_d2, thr2, i, acc);
+  double acc[1] = {0.0};
+  linearize_block<1>(a, gp, Tf, T.x, cap_d2, thr2, blockIdx.x * blockDim.x, gridDim.x * blockDim.x, s_tq, acc[0]);
   block_reduce_store<NRED>(acc, s_red, a.partials + (size_t)blockIdx.x * NRED);
 }
 
@@ -394,12 +463,13 @@ __device__ __forceinline__ void trace_stamp(const LmParams& prm, int& slot) {
 // registers (shortest critical path; scans up to ~38k points have one point per thread anyway).  2 / 3: 128 / 80
 // registers, that state spills to local memory but twice / three times as many source points are in flight — the
 // better trade for dense scans (C5).
-template <int MINB>
+template <int MINB, int LPP>
 __global__ void __launch_bounds__(AL_THREADS, MINB) align_fused_kernel(AlignArgs a, LmParams prm, Guess16 guess, ngicp_result* __restrict__ res, unsigned* bar, double* totals, PeerComm pc) {
   int tslot = 0;
   trace_stamp(prm, tslot);
   __shared__ double s_red[AL_WARPS][NRED];
   __shared__ double s_tot[NRED];
+  __shared__ TailQueue s_tq;
   __shared__ Iso3 s_x;        // transform used by the next phase
   __shared__ int s_decision;
   const GridParams gp = load_grid(a.tgt.desc);
@@ -432,11 +502,10 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) align_fused_kernel(AlignArgs
       const Iso3 T = s_x;
       XformF Tf;
       make_xforms(T, Tf);
-      double acc[NRED];
-#pragma unroll
-      for (int j = 0; j < NRED; j++) acc[j] = 0.0;
-      for (int i = gtid; i < a.ns; i += gstride) linearize_point(a, gp, Tf, T, prm.cap_d2, prm.thr2, i, acc);
+      double acc[1] = {0.0};
+      linearize_block<LPP>(a, gp, Tf, T, prm.cap_d2, prm.thr2, blockIdx.x * (AL_THREADS / LPP), gridDim.x * (AL_THREADS / LPP), s_tq, acc[0]);
       trace_stamp(prm, tslot);
+      if (prm.trace && it == 1 && threadIdx.x == 0 && blockIdx.x < 1024) prm.trace[256 + blockIdx.x] = global_timer_ns();
       grid_reduce<NRED>(acc, s_red, s_tot, a.partials, gs, pc);
       trace_stamp(prm, tslot);
     }
@@ -546,17 +615,25 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) align_fused_kernel(AlignArgs
     res->lm_failed = lm_failed;
     res->reserved = (pc.world > 1) ? *(volatile int*)pc.error : 0;   // 1: a peer did not show up in time
   }
+  // leave the barrier words zeroed for the next launch: the last block to depart does it (nobody polls any more)
+  if (threadIdx.x == 0) {
+    const unsigned prev = atomicAdd(bar + 2, 1u);
+    if (prev == gridDim.x - 1u) { bar[0] = 0u; bar[1] = 0u; bar[2] = 0u; }
+  }
 }
 
-static int fused_blocks_per_sm(int device, int minb) {
-  static int cached[64][4] = {};
-  if (device >= 0 && device < 64 && cached[device][minb]) return cached[device][minb];
+// compiled variants: (resident blocks per SM, lanes per source point)
+static const void* fused_variant(int minb, int lpp) {
+  if (lpp == 2) return minb <= 2 ? (const void*)align_fused_kernel<2, 2> : (const void*)align_fused_kernel<3, 2>;
+  return minb == 1 ? (const void*)align_fused_kernel<1, 1> : (minb == 2 ? (const void*)align_fused_kernel<2, 1> : (const void*)align_fused_kernel<3, 1>);
+}
+static int fused_blocks_per_sm(int device, int minb, int lpp = 1) {
+  static int cached[64][4][5] = {};
+  if (device >= 0 && device < 64 && cached[device][minb][lpp]) return cached[device][minb][lpp];
   int per_sm = 0;
-  if (minb == 1) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, align_fused_kernel<1>, AL_THREADS, 0);
-  else if (minb == 2) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, align_fused_kernel<2>, AL_THREADS, 0);
-  else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, align_fused_kernel<3>, AL_THREADS, 0);
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fused_variant(minb, lpp), AL_THREADS, 0);
   if (per_sm < 1) per_sm = 1;
-  if (device >= 0 && device < 64) cached[device][minb] = per_sm;
+  if (device >= 0 && device < 64) cached[device][minb][lpp] = per_sm;
   return per_sm;
 }
 static int sm_count_of(int device) {
@@ -572,14 +649,27 @@ int align_fused_max_blocks(int device) { return fused_blocks_per_sm(device, 1) *
 
 cudaError_t launch_align_fused(const AlignBuffers& ab, const ngicp_params& p, const float* guess16, ngicp_result* res_dev,
                                unsigned* barrier, int device, cudaStream_t st, unsigned long long* trace, const PeerComm* comm) {
-  int blocks = (ab.ns + AL_THREADS - 1) / AL_THREADS;   // one source point per thread when the grid can hold them
-  // variant: more resident blocks per SM once the scan no longer fits one point per thread (NGICP_ALIGN_MINB overrides)
+  // Variant.  Lanes per source point: 2 when the target is much larger than the scan (scan-to-map against a submap of
+  // overlapping keyframes: hundreds of candidates per query, the pair halves the chain of round trips; measured on C2:
+  // align 0.207 -> 0.178 ms) and the grid can still give every point its own pair; 1 otherwise (scan-to-scan: 0.092 vs
+  // 0.096 ms, the 255-register variant wins).  4 lanes per point need the 80-register variant and lose (0.123 ms).
+  // Then the fewest resident blocks per SM (= most registers) that hold the grid.  NGICP_ALIGN_LPP / _MINB override.
   static const int minb_env = getenv("NGICP_ALIGN_MINB") ? atoi(getenv("NGICP_ALIGN_MINB")) : 0;
+  static const int lpp_env = getenv("NGICP_ALIGN_LPP") ? atoi(getenv("NGICP_ALIGN_LPP")) : 0;
   const int sms = sm_count_of(device);
-  int minb = 1;
-  while (minb < 3 && blocks > fused_blocks_per_sm(device, minb) * sms) ++minb;   // smallest variant that holds one point per thread
+  int lpp = 1, minb = 1;
+  if (lpp_env == 1 || lpp_env == 2) lpp = lpp_env;
+  else if ((long long)ab.nt >= 4ll * ab.ns) {
+    const int need = (ab.ns + AL_THREADS / 2 - 1) / (AL_THREADS / 2);
+    if (need <= fused_blocks_per_sm(device, 2, 2) * sms && need <= ab.max_blocks) lpp = 2;
+  }
+  const int ppb = AL_THREADS / lpp;                      // source points per block and pass
+  int blocks = (ab.ns + ppb - 1) / ppb;
+  minb = lpp == 2 ? 2 : 1;
+  while (minb < 3 && blocks > fused_blocks_per_sm(device, minb, lpp) * sms) ++minb;
   if (minb_env >= 1 && minb_env <= 3) minb = minb_env;
-  const int lim = fused_blocks_per_sm(device, minb) * sms;
+  if (lpp == 2 && minb < 2) minb = 2;
+  const int lim = fused_blocks_per_sm(device, minb, lpp) * sms;
   if (blocks > lim) blocks = lim;
   if (blocks > ab.max_blocks) blocks = ab.max_blocks;
   if (blocks < 1) blocks = 1;
@@ -596,8 +686,6 @@ cudaError_t launch_align_fused(const AlignBuffers& ab, const ngicp_params& p, co
   prm.cap_d2 = cap_from(p.max_correspondence_distance);
   Guess16 g;
   for (int i = 0; i < 16; i++) g.g[i] = guess16 ? guess16[i] : ((i % 5 == 0) ? 1.0f : 0.0f);
-  cudaError_t e = cudaMemsetAsync(barrier, 0, sizeof(unsigned) * 4, st);
-  if (e != cudaSuccess) return e;
   double* totals = ab.reduced;  // [2][NRED]
   note_launches(1);
   PeerComm pc;
@@ -605,7 +693,7 @@ cudaError_t launch_align_fused(const AlignBuffers& ab, const ngicp_params& p, co
   pc.world = 1;
   if (comm && comm->world > 1) pc = *comm;
   void* args[] = {(void*)&a, (void*)&prm, (void*)&g, (void*)&res_dev, (void*)&barrier, (void*)&totals, (void*)&pc};
-  const void* fn = minb == 1 ? (const void*)align_fused_kernel<1> : (minb == 2 ? (const void*)align_fused_kernel<2> : (const void*)align_fused_kernel<3>);
+  const void* fn = fused_variant(minb, lpp);
   return cudaLaunchCooperativeKernel(fn, dim3(blocks), dim3(AL_THREADS), args, 0, st);
 }
 

@@ -20,7 +20,8 @@ struct ngicp_handle {
   CloudPtr src, tgt;
   CovsPtr src_cov, tgt_cov;
   Scratch sc;
-  ngicp_result* res_pinned = nullptr;   // pinned host mirror of the fused kernel's result
+  ngicp_result* res_pinned = nullptr;   // pinned + mapped host memory the fused kernel writes its result to
+  ngicp_result* res_mapped = nullptr;   // device-side address of res_pinned
   double* red_pinned = nullptr;         // pinned host mirror of reduced[]
   cudaEvent_t ev[6][2] = {};            // one begin/end pair per timed phase
   bool ev_used[6] = {false, false, false, false, false, false};
@@ -226,8 +227,10 @@ int prepare_align(ngicp_t* h, bool lazy, AlignBuffers& ab) {
   NG_CUDA(h, sc.tgt_pt.reserve(sizeof(float4) * ns, h->stream));
   NG_CUDA(h, sc.partials.reserve(sizeof(double) * NRED * (size_t)h->align_max_blocks, h->stream));
   NG_CUDA(h, sc.reduced.reserve(sizeof(double) * 64, h->stream));
-  NG_CUDA(h, sc.lm_state.reserve(sizeof(ngicp_result), h->stream));
-  NG_CUDA(h, sc.barrier.reserve(64, h->stream));
+  if (!sc.barrier.p) {   // zeroed once; the fused kernel leaves it zeroed (last departing block)
+    NG_CUDA(h, sc.barrier.reserve(64, h->stream));
+    NG_CUDA(h, cudaMemsetAsync(sc.barrier.p, 0, 64, h->stream->s));
+  }
   ab.src_pts = h->src->pts.as<float4>(); ab.src_cov = h->src_cov->c.as<double>(); ab.ns = h->src->n;
   ab.tgt = h->tgt->view(); ab.tgt_cov = h->tgt_cov->c.as<double>(); ab.nt = h->tgt->n;
   ab.mahal = sc.mahal.as<double>(); ab.corr = sc.corr.as<int>(); ab.sqd = sc.sqd.as<float>(); ab.tgt_pt = sc.tgt_pt.as<float4>();
@@ -390,7 +393,9 @@ int ngicp_create(int device, ngicp_t** out) {
     uint64_t thr = UINT64_MAX;
     cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
   }
-  bool ok = cudaMallocHost(&h->res_pinned, sizeof(ngicp_result)) == cudaSuccess &&
+  // mapped: the fused kernel stores its 496-byte result straight into host memory (no D2H copy node after it)
+  bool ok = cudaHostAlloc(&h->res_pinned, sizeof(ngicp_result), cudaHostAllocMapped) == cudaSuccess &&
+            cudaHostGetDevicePointer(&h->res_mapped, h->res_pinned, 0) == cudaSuccess &&
             cudaMallocHost(&h->red_pinned, sizeof(double) * 64) == cudaSuccess;
   for (int i = 0; ok && i < PH_COUNT; i++)
     ok = cudaEventCreate(&h->ev[i][0]) == cudaSuccess && cudaEventCreate(&h->ev[i][1]) == cudaSuccess;
@@ -567,25 +572,26 @@ int ngicp_align(ngicp_t* h, const float* guess16, ngicp_result* out) {
     rc = align_stepped(h, ab, guess16, out);
     if (rc) return rc;
   } else {
-    ngicp_result* res_dev = h->sc.lm_state.as<ngicp_result>();
+    ngicp_result* res_dev = h->res_mapped;
     static const bool want_trace = getenv("NGICP_ALIGN_TRACE") != nullptr;
     unsigned long long* trace = nullptr;
     if (want_trace) {
-      NG_CUDA(h, h->sc.trace.reserve(sizeof(unsigned long long) * 256, h->stream));
+      NG_CUDA(h, h->sc.trace.reserve(sizeof(unsigned long long) * 1280, h->stream));
       trace = h->sc.trace.as<unsigned long long>();
-      NG_CUDA(h, cudaMemsetAsync(trace, 0, sizeof(unsigned long long) * 256, h->stream->s));
+      NG_CUDA(h, cudaMemsetAsync(trace, 0, sizeof(unsigned long long) * 1280, h->stream->s));
     }
     NG_CUDA(h, launch_align_fused(ab, h->prm, guess16, res_dev, h->sc.barrier.as<unsigned>(), h->device, h->stream->s, trace,
                                   h->comm_on ? &h->comm : nullptr));
-    NG_CUDA(h, cudaMemcpyAsync(h->res_pinned, res_dev, sizeof(ngicp_result), cudaMemcpyDeviceToHost, h->stream->s));
     NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
     *out = *h->res_pinned;
     if (h->comm_on && out->reserved != 0) return fail(h, NGICP_E_COMM, "sharded align: a peer rank did not reach the exchange in time");
     if (trace) {
-      unsigned long long t[256];
+      static unsigned long long t[1280];
       NG_CUDA(h, cudaMemcpy(t, trace, sizeof t, cudaMemcpyDeviceToHost));
       fprintf(stderr, "[align trace, us since start]");
       for (unsigned long long i = 1; i <= t[0] && i < 255; i++) fprintf(stderr, " %.1f", (double)(t[i] - t[1]) * 1e-3);
+      fprintf(stderr, "\n[second linearize done per block, us since start]");
+      for (int b = 0; b < 1024; b++) if (t[256 + b]) fprintf(stderr, " %.1f", (double)(t[256 + b] - t[1]) * 1e-3);
       fprintf(stderr, "\n");
     }
   }

@@ -77,6 +77,31 @@ __device__ __forceinline__ double warp_sum(double v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
   return v;
 }
+// Sum NV (<= 32) per-lane values across the warp at once: at every butterfly step a lane keeps one half of its values,
+// hands the other half to its partner and adds what it receives, so 32 + 16 + ... = 31 exchanges do the work of
+// NV x 5.  Afterwards lane j holds the warp total of value j in v[0] (j < NV).  Fixed summation tree: deterministic.
+template <int NV>
+__device__ __forceinline__ double warp_sum_transposed(const double* acc) {
+  const int lane = threadIdx.x & 31;
+  double v[32];
+#pragma unroll
+  for (int j = 0; j < 32; j++) v[j] = j < NV ? acc[j] : 0.0;
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool up = (lane & half) != 0;
+#pragma unroll
+    for (int j = 0; j < half; j++) {
+      if (j >= NV) continue;                       // both halves are padding: nothing to move
+      const bool upper_real = j + half < NV;       // compile-time after unrolling
+      const double lo = v[j], hi = upper_real ? v[j + half] : 0.0;
+      const double send = up ? lo : hi;
+      const double keep = up ? hi : lo;
+      v[j] = keep + __shfl_xor_sync(FULL, send, half);
+    }
+  }
+  return v[0];
+}
+
 __device__ __forceinline__ float warp_min(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v = fminf(v, __shfl_xor_sync(FULL, v, o));

@@ -146,9 +146,11 @@ __device__ __forceinline__ void scan_range_warp(const GridView& g, int ra, int r
 // x-run [cx-s1, cx+s1], rows inside it only the two side runs [cx-s1, cx-s0-1] and [cx+s0+1, cx+s1].
 // Radii go 0 (or 1 when `start1`), 1, 2, 3, 4, then grow by 50% per step so that isolated points in
 // sparse regions do not pay O(r^3) single-cell probes.
-template <class RS>
+// PRUNE (used by the 1-NN tail of the registration kernels): rows and side runs whose nearest possible point is already
+// farther than min(current bound, cap) are skipped without touching memory — exact, the bounds are margin-shrunk.
+template <class RS, bool PRUNE = false>
 __device__ __forceinline__ void grid_search_warp(const GridView& g, const GridParams& gp, float qx, float qy, float qz,
-                                                 float cap_d2, RS& rs, bool start1 = false) {
+                                                 float cap_d2, RS& rs, bool start1 = false, int resume_s0 = -1) {
   const int lane = threadIdx.x & 31;
   const int cx = cell_coord(qx, gp.ox, gp.inv, gp.dx);
   const int cy = cell_coord(qy, gp.oy, gp.inv, gp.dy);
@@ -156,10 +158,24 @@ __device__ __forceinline__ void grid_search_warp(const GridView& g, const GridPa
   const int rmax = max(max(max(cx, gp.dx - 1 - cx), max(cy, gp.dy - 1 - cy)), max(cz, gp.dz - 1 - cz));
   int s0 = -1;
   int s1 = start1 ? min(1, rmax) : 0;
+  if (resume_s0 >= 0) {   // the cube of radius resume_s0 was scanned by the caller, who also applied the stop test
+    s0 = resume_s0;
+    s1 = min((s0 < 4) ? s0 + 1 : s0 + (s0 >> 1), rmax);
+  }
   for (;;) {
     const int w = 2 * s1 + 1;
     const int nrows = w * w;
     const int xlo = max(cx - s1, 0), xhi = min(cx + s1, gp.dx - 1);
+    float lim = FLT_MAX, fx0 = 0.f, fx1 = 0.f, fy0 = 0.f, fy1 = 0.f, fz0 = 0.f, fz1 = 0.f;
+    if (PRUNE) {
+      lim = fminf(rs.bound(), cap_d2);
+      fx0 = fmaxf(qx - (gp.ox + (float)cx * gp.cell) - gp.margin, 0.f);
+      fx1 = fmaxf((gp.ox + (float)(cx + 1) * gp.cell) - qx - gp.margin, 0.f);
+      fy0 = fmaxf(qy - (gp.oy + (float)cy * gp.cell) - gp.margin, 0.f);
+      fy1 = fmaxf((gp.oy + (float)(cy + 1) * gp.cell) - qy - gp.margin, 0.f);
+      fz0 = fmaxf(qz - (gp.oz + (float)cz * gp.cell) - gp.margin, 0.f);
+      fz1 = fmaxf((gp.oz + (float)(cz + 1) * gp.cell) - qz - gp.margin, 0.f);
+    }
     for (int base = 0; base < nrows; base += 32) {
       const int r = base + lane;
       int a1 = 0, b1 = 0, a2 = 0, b2 = 0;
@@ -169,15 +185,29 @@ __device__ __forceinline__ void grid_search_warp(const GridView& g, const GridPa
         const int rz = rr / w;
         const int yy = rr - rz * w - s1, zz = rz - s1;
         const int y = cy + yy, z = cz + zz;
-        if (y >= 0 && y < gp.dy && z >= 0 && z < gp.dz) {
+        bool keep = (y >= 0 && y < gp.dy && z >= 0 && z < gp.dz);
+        float dyz = 0.f;
+        if (PRUNE) {
+          const float dy = yy == 0 ? 0.f : (yy < 0 ? fy0 + (float)(-yy - 1) * gp.cell : fy1 + (float)(yy - 1) * gp.cell);
+          const float dz = zz == 0 ? 0.f : (zz < 0 ? fz0 + (float)(-zz - 1) * gp.cell : fz1 + (float)(zz - 1) * gp.cell);
+          dyz = (dy * dy + dz * dz) * 0.999999f;
+          keep = keep && dyz < lim;
+        }
+        if (keep) {
           const int* row = g.cell_start + (z * gp.dy + y) * gp.dx;
           if (max(abs(yy), abs(zz)) > s0) {
             a1 = __ldg(row + xlo);
             b1 = __ldg(row + xhi + 1);
           } else {
             const int xl = cx - s0 - 1, xr = cx + s0 + 1;
-            if (xlo <= xl) { a1 = __ldg(row + xlo); b1 = __ldg(row + xl + 1); }
-            if (xr <= xhi) { a2 = __ldg(row + xr); b2 = __ldg(row + xhi + 1); }
+            bool kl = xlo <= xl, kr = xr <= xhi;
+            if (PRUNE) {   // nearest x distance to the side runs [.., cx-s0-1] and [cx+s0+1, ..]
+              const float sxl = fx0 + (float)s0 * gp.cell, sxr = fx1 + (float)s0 * gp.cell;
+              kl = kl && dyz + sxl * sxl * 0.999999f < lim;
+              kr = kr && dyz + sxr * sxr * 0.999999f < lim;
+            }
+            if (kl) { a1 = __ldg(row + xlo); b1 = __ldg(row + xl + 1); }
+            if (kr) { a2 = __ldg(row + xr); b2 = __ldg(row + xhi + 1); }
           }
         }
       }
@@ -232,17 +262,26 @@ __device__ __forceinline__ void grid_search_warp(const GridView& g, const GridPa
 // the cap or the cap is unbounded) are walked slot by slot.
 // Strict '<' keeps the first visited of equidistant points, like nanoflann's result set does.
 // ---------------------------------------------------------------------------------------------
+// Candidates are fetched eight at a time with clamped addresses (no remainder loop: a one-by-one tail would be a chain
+// of dependent round trips to L1/L2) and compared in slot order.
 __device__ __forceinline__ void nn1_scan_range(const GridView& g, int a, int b, float qx, float qy, float qz, float& bd, int& bp) {
-#pragma unroll 4
-  for (int p = a; p < b; ++p) {
-    const float4 c = __ldg(g.sorted + p);
-    const float d = sqdist_unfused(qx, qy, qz, c.x, c.y, c.z);
-    if (d < bd) { bd = d; bp = p; }
+  for (int p0 = a; p0 < b; p0 += 8) {
+    float4 c[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) c[u] = __ldg(g.sorted + min(p0 + u, b - 1));
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const float d = sqdist_unfused(qx, qy, qz, c[u].x, c[u].y, c[u].z);
+      if (p0 + u < b && d < bd) { bd = d; bp = p0 + u; }
+    }
   }
 }
 
-__device__ __forceinline__ void grid_nn1_thread(const GridView& g, const GridParams& gp, float qx, float qy, float qz,
-                                                float cap_d2, float& best_d, int& best_p) {
+// Radius-1 cube only.  Returns true when the search is NOT finished (a closer point may exist outside the cube and
+// within the cap): the caller continues with grid_nn1_grow_thread or hands the query to a warp
+// (grid_search_warp with resume_s0 = 1).
+__device__ __forceinline__ bool grid_nn1_cube1(const GridView& g, const GridParams& gp, float qx, float qy, float qz,
+                                               float cap_d2, float& best_d, int& best_p) {
   best_d = FLT_MAX;
   best_p = -1;
   const int cx = cell_coord(qx, gp.ox, gp.inv, gp.dx);
@@ -287,9 +326,108 @@ __device__ __forceinline__ void grid_nn1_thread(const GridView& g, const GridPar
       }
     }
   }
-  // further growth (only when the cell edge is smaller than the cap, or the cap is unbounded): cube s0 -> s0+1,
-  // rows taken 8 at a time so that their table reads overlap, rows and side runs whose nearest point is already
-  // farther than min(best, cap) skipped without touching memory
+  if (rmax <= 1) return false;
+  const float m = cube_face_distance(gp, cx, cy, cz, 1, qx, qy, qz);
+  if (m > 0.f) {
+    const float m2 = m * m * 0.999999f;
+    if (cap_d2 <= m2 || best_d <= m2) return false;
+  }
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The same radius-1 search by a GROUP of LPP (2 or 4) adjacent lanes per query.  One thread per query leaves the
+// GPU almost empty for a 20k-point scan and every thread walks its candidates as a chain of dependent round trips;
+// a group reads LPP x 8 candidates per round trip.  Visiting order and tie rule are those of grid_nn1_cube1 (own
+// cell, then the rest row by row; strictly closer wins, among equals the lowest slot of the earliest range), so the
+// result is the same.  All lanes of a group must call this together with the same query; results are group-uniform.
+// ---------------------------------------------------------------------------------------------
+template <int LPP>
+__device__ __forceinline__ void nn1_group_scan(const GridView& g, int a, int b, int sub, unsigned gmask, float qx, float qy, float qz, float& bd, int& bp) {
+  if (a >= b) return;                     // group-uniform
+  float md = bd;
+  int mp = bp;
+  for (int p0 = a; p0 < b; p0 += 8 * LPP) {
+    float4 c[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) c[u] = __ldg(g.sorted + min(p0 + u * LPP + sub, b - 1));
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      const int p = p0 + u * LPP + sub;
+      const float d = sqdist_unfused(qx, qy, qz, c[u].x, c[u].y, c[u].z);
+      if (p < b && d < md) { md = d; mp = p; }
+    }
+  }
+  // combine the group: smallest distance, lowest slot among equals.  (A lane that found nothing strictly closer still
+  // holds the incumbent, so an incumbent at the minimum distance survives: every lane at that distance holds it.)
+#pragma unroll
+  for (int o = 1; o < LPP; o <<= 1) {
+    const float od = __shfl_xor_sync(gmask, md, o);
+    const int op = __shfl_xor_sync(gmask, mp, o);
+    if (od < md || (od == md && op < mp)) { md = od; mp = op; }
+  }
+  bd = md; bp = mp;
+}
+
+template <int LPP>
+__device__ __forceinline__ bool grid_nn1_cube1_group(const GridView& g, const GridParams& gp, int sub, unsigned gmask, float qx, float qy, float qz,
+                                                     float cap_d2, float& best_d, int& best_p) {
+  best_d = FLT_MAX;
+  best_p = -1;
+  const int cx = cell_coord(qx, gp.ox, gp.inv, gp.dx);
+  const int cy = cell_coord(qy, gp.oy, gp.inv, gp.dy);
+  const int cz = cell_coord(qz, gp.oz, gp.inv, gp.dz);
+  const int rmax = max(max(max(cx, gp.dx - 1 - cx), max(cy, gp.dy - 1 - cy)), max(cz, gp.dz - 1 - cz));
+  const int e0 = max(cx - 1, 0), e1 = cx, e2 = cx + 1, e3 = min(cx + 2, gp.dx);
+  int v[9][4];
+#pragma unroll
+  for (int r = 0; r < 9; ++r) {
+    const int y = cy + (r % 3) - 1, z = cz + (r / 3) - 1;
+    const bool in = (y >= 0 && y < gp.dy && z >= 0 && z < gp.dz);
+    const int* row = g.cell_start + (in ? (z * gp.dy + y) * gp.dx : 0);
+    v[r][0] = in ? __ldg(row + e0) : 0;
+    v[r][1] = in ? __ldg(row + e1) : 0;
+    v[r][2] = in ? __ldg(row + e2) : 0;
+    v[r][3] = in ? __ldg(row + e3) : 0;
+  }
+  const float fx0 = fmaxf(qx - (gp.ox + (float)cx * gp.cell) - gp.margin, 0.f);
+  const float fx1 = fmaxf((gp.ox + (float)(cx + 1) * gp.cell) - qx - gp.margin, 0.f);
+  const float fy0 = fmaxf(qy - (gp.oy + (float)cy * gp.cell) - gp.margin, 0.f);
+  const float fy1 = fmaxf((gp.oy + (float)(cy + 1) * gp.cell) - qy - gp.margin, 0.f);
+  const float fz0 = fmaxf(qz - (gp.oz + (float)cz * gp.cell) - gp.margin, 0.f);
+  const float fz1 = fmaxf((gp.oz + (float)(cz + 1) * gp.cell) - qz - gp.margin, 0.f);
+  const float gx[3] = {fx0 * fx0, 0.f, fx1 * fx1};
+  const float gy[3] = {fy0 * fy0, 0.f, fy1 * fy1};
+  const float gz[3] = {fz0 * fz0, 0.f, fz1 * fz1};
+  nn1_group_scan<LPP>(g, v[4][1], v[4][2], sub, gmask, qx, qy, qz, best_d, best_p);   // own cell
+#pragma unroll
+  for (int r = 0; r < 9; ++r) {
+    const float dyz = gy[r % 3] + gz[r / 3];
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      if (r == 4 && c == 1) continue;
+      const float lb = (dyz + gx[c]) * 0.999999f;
+      if (lb < best_d && lb < cap_d2) nn1_group_scan<LPP>(g, v[r][c], v[r][c + 1], sub, gmask, qx, qy, qz, best_d, best_p);
+    }
+  }
+  if (rmax <= 1) return false;
+  const float m = cube_face_distance(gp, cx, cy, cz, 1, qx, qy, qz);
+  if (m > 0.f) {
+    const float m2 = m * m * 0.999999f;
+    if (cap_d2 <= m2 || best_d <= m2) return false;
+  }
+  return true;
+}
+
+// further growth by the same thread (only when the cell edge is smaller than the cap, or the cap is unbounded):
+// cube s0 -> s0+1, rows taken 8 at a time so that their table reads overlap, rows and side runs whose nearest point
+// is already farther than min(best, cap) skipped without touching memory
+__device__ __forceinline__ void grid_nn1_grow_thread(const GridView& g, const GridParams& gp, float qx, float qy, float qz,
+                                                     float cap_d2, float& best_d, int& best_p) {
+  const int cx = cell_coord(qx, gp.ox, gp.inv, gp.dx);
+  const int cy = cell_coord(qy, gp.oy, gp.inv, gp.dy);
+  const int cz = cell_coord(qz, gp.oz, gp.inv, gp.dz);
+  const int rmax = max(max(max(cx, gp.dx - 1 - cx), max(cy, gp.dy - 1 - cy)), max(cz, gp.dz - 1 - cz));
   const float fy0 = fmaxf(qy - (gp.oy + (float)cy * gp.cell) - gp.margin, 0.f);
   const float fy1 = fmaxf((gp.oy + (float)(cy + 1) * gp.cell) - qy - gp.margin, 0.f);
   const float fz0 = fmaxf(qz - (gp.oz + (float)cz * gp.cell) - gp.margin, 0.f);
@@ -339,6 +477,11 @@ __device__ __forceinline__ void grid_nn1_thread(const GridView& g, const GridPar
       }
     }
   }
+}
+
+__device__ __forceinline__ void grid_nn1_thread(const GridView& g, const GridParams& gp, float qx, float qy, float qz,
+                                                float cap_d2, float& best_d, int& best_p) {
+  if (grid_nn1_cube1(g, gp, qx, qy, qz, cap_d2, best_d, best_p)) grid_nn1_grow_thread(g, gp, qx, qy, qz, cap_d2, best_d, best_p);
 }
 
 }  // namespace ngicp
