@@ -7,8 +7,9 @@ The compute lives in csrc/ (hand-written CUDA behind the C ABI of include/nanogi
 `NanoGICP` mirrors the reference class nano_gicp::NanoGICP member for member.
 """
 from . import synth  # noqa: F401  (pure numpy)
+from . import pointcloud2  # noqa: F401  (plain data + field mapping, no ROS)
 
-__all__ = ["NanoGICP", "NanoGICPError", "CovarianceView", "KeyframeStore", "synth", "lib_path"]
+__all__ = ["NanoGICP", "NanoGICPError", "CovarianceView", "KeyframeStore", "synth", "pointcloud2", "lib_path"]
 
 
 def __getattr__(name):

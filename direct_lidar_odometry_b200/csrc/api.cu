@@ -678,6 +678,44 @@ int ngicp_preprocess(ngicp_t* h, const void* in, size_t n, size_t stride, const 
   return overflow ? NGICP_W_VOXEL_OVERFLOW : NGICP_OK;
 }
 
+int ngicp_preprocess_pointcloud2(ngicp_t* h, const void* data, const ngicp_pc2_layout* L, const float* crop_min, const float* crop_max,
+                                 float leaf, void* out, size_t cap, size_t* m) {
+  if (!h || !m || !L) return h ? fail(h, NGICP_E_INVALID, "bad PointCloud2 arguments") : NGICP_E_INVALID;
+  *m = 0;
+  const unsigned long long n64 = (unsigned long long)L->width * (unsigned long long)L->height;
+  if ((!data && n64) || n64 > 0x7fffff00ull || ((crop_min == nullptr) != (crop_max == nullptr)))
+    return fail(h, NGICP_E_INVALID, "bad PointCloud2 arguments");
+  if (L->is_bigendian) return fail(h, NGICP_E_UNSUPPORTED, "PointCloud2: big-endian data (PCL reinterprets the bytes as they are; refuse instead)");
+  if (L->offset_x < 0 || L->offset_y < 0 || L->offset_z < 0)
+    return fail(h, NGICP_E_INVALID, "PointCloud2: no FLOAT32 x/y/z fields");      // pcl::fromROSMsg leaves them unset and warns
+  const int offs[4] = {L->offset_x, L->offset_y, L->offset_z, L->offset_intensity};
+  for (int f = 0; f < 4; f++)
+    if (offs[f] >= 0 && (unsigned long long)offs[f] + 4ull > (unsigned long long)L->point_step)
+      return fail(h, NGICP_E_INVALID, "PointCloud2: field beyond point_step");
+  if (n64 && (unsigned long long)L->row_step < (unsigned long long)L->width * L->point_step && L->height > 1)
+    return fail(h, NGICP_E_INVALID, "PointCloud2: row_step smaller than width * point_step");
+  if (n64 == 0) return NGICP_OK;
+  DeviceGuard g(h->device);
+  RecordLayout lay;
+  lay.width = (int)L->width;
+  lay.point_step = L->point_step;
+  lay.row_step = L->row_step;
+  lay.aligned = ((L->point_step | L->row_step) & 3u) == 0;
+  for (int f = 0; f < 4; f++) { lay.off[f] = offs[f] >= 0 ? offs[f] : -1; if (offs[f] >= 0 && (offs[f] & 3)) lay.aligned = 0; }
+  float crop6[6];
+  if (crop_min) for (int a = 0; a < 3; a++) { crop6[a] = crop_min[a]; crop6[3 + a] = crop_max[a]; }
+  ph_begin(h, PH_VOXEL);
+  size_t mm = 0;
+  int overflow = 0;
+  NG_CUDA(h, voxel_filter_records(data, (size_t)n64, lay, leaf, h->sc, h->stream, &mm, &overflow, crop_min ? crop6 : nullptr, true));
+  if (mm > cap) return fail(h, NGICP_E_INVALID, "preprocess: output capacity too small");
+  if (mm && out) NG_CUDA(h, cudaMemcpyAsync(out, h->sc.vox_out.p, 32 * mm, cudaMemcpyDefault, h->stream->s));
+  ph_end(h, PH_VOXEL);
+  NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
+  *m = mm;
+  return overflow ? NGICP_W_VOXEL_OVERFLOW : NGICP_OK;
+}
+
 int ngicp_voxel_assignment(ngicp_t* h, int* slot_of_point, size_t n) {
   if (!h || !slot_of_point) return NGICP_E_INVALID;
   if (!h->sc.vox_slot.p || h->sc.vox_slot.bytes < sizeof(int) * n) return fail(h, NGICP_E_STATE, "no voxel filter result");

@@ -161,6 +161,16 @@ int align_fused_max_blocks(int device);
 // returns cudaSuccess; *m_out and *overflow are valid after the call (it synchronises once to learn m)
 // crop6 = {min xyz, max xyz} of a negative pcl::CropBox or nullptr; leaf <= 0 skips the voxel grid (compaction only);
 // compact_on_overflow: on PCL's index-overflow pass-through emit the surviving points instead of leaving it to the caller
+// where record i of a raw cloud lives and where its FLOAT32 fields are (byte offsets; off[3] = intensity, -1 = absent)
+struct RecordLayout {
+  int width;                 // records per row (>= n: one row)
+  size_t point_step, row_step;
+  int off[4];
+  int aligned;               // every field address is 4-byte aligned (offsets, steps; the staging copy itself is)
+};
+cudaError_t voxel_filter_records(const void* in, size_t n, RecordLayout lay, float leaf, Scratch& sc, const StreamPtr& st,
+                                 size_t* m_out, int* overflow, const float* crop6 = nullptr, bool compact_on_overflow = false,
+                                 const float* T16 = nullptr);
 cudaError_t voxel_filter_device(const void* in, size_t n, size_t stride_bytes, float leaf, Scratch& sc, const StreamPtr& st,
                                 size_t* m_out, int* overflow, const float* crop6 = nullptr, bool compact_on_overflow = false,
                                 const float* T16_colmajor = nullptr /* transformPointCloud first */);

@@ -25,15 +25,27 @@ struct CropBox { int on; float lo[3], hi[3]; };
 // same pass: x' = ((m00 x + m01 y) + m02 z) + m03, float, unfused — the order the CPU oracle fixes (synth.transform_xyzi)
 struct RigidXf { int on; float m[12]; };
 
-// raw records -> float4 {x,y,z,intensity}; bbox over finite points (pcl::getMinMax3D on a non-dense cloud)
-__global__ void __launch_bounds__(256) vox_pack_kernel(const unsigned char* __restrict__ raw, size_t stride, int n, int intensity_float,
+// a FLOAT32 field at any byte address (sensor_msgs::PointCloud2 layouts need not be 4-byte aligned: Velodyne's
+// point_step is 22)
+__device__ __forceinline__ float load_f32(const unsigned char* p, bool aligned) {
+  if (aligned) return *reinterpret_cast<const float*>(p);
+  const unsigned u = (unsigned)p[0] | ((unsigned)p[1] << 8) | ((unsigned)p[2] << 16) | ((unsigned)p[3] << 24);
+  return __uint_as_float(u);
+}
+
+// raw records -> float4 {x,y,z,intensity}; bbox over finite points (pcl::getMinMax3D on a non-dense cloud).
+// Record i lives at (i / width) * row_step + (i % width) * point_step; its fields at the byte offsets of `lay`
+// (plain PointXYZI arrays: one row, offsets 0/4/8/16) — pcl::fromROSMsg's field mapping done on the fly.
+__global__ void __launch_bounds__(256) vox_pack_kernel(const unsigned char* __restrict__ raw, RecordLayout lay, int n,
                                                        float4* __restrict__ pts, GridDesc* __restrict__ d, CropBox crop, RigidXf xf) {
   float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
   int finite = 0;
+  const bool al = lay.aligned != 0;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
-    const float* r = reinterpret_cast<const float*>(raw + (size_t)i * stride);
-    float x = r[0], y = r[1], z = r[2];
-    const float it = intensity_float >= 0 ? r[intensity_float] : 0.f;
+    const int row = lay.width >= n ? 0 : i / lay.width;
+    const unsigned char* r = raw + (size_t)row * lay.row_step + (size_t)(i - row * lay.width) * lay.point_step;
+    float x = load_f32(r + lay.off[0], al), y = load_f32(r + lay.off[1], al), z = load_f32(r + lay.off[2], al);
+    const float it = lay.off[3] >= 0 ? load_f32(r + lay.off[3], al) : 0.f;
     if (xf.on) {
       const float tx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(xf.m[0], x), __fmul_rn(xf.m[1], y)), __fmul_rn(xf.m[2], z)), xf.m[3]);
       const float ty = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(xf.m[4], x), __fmul_rn(xf.m[5], y)), __fmul_rn(xf.m[6], z)), xf.m[7]);
@@ -169,6 +181,18 @@ static inline int vgrid(int n, int threads) {
 
 cudaError_t voxel_filter_device(const void* in, size_t n, size_t stride_bytes, float leaf, Scratch& sc, const StreamPtr& st,
                                 size_t* m_out, int* overflow, const float* crop6, bool compact_on_overflow, const float* T16) {
+  RecordLayout lay;
+  lay.width = (int)(n < 0x7fffffffu ? n : 0x7fffffffu);
+  lay.point_step = stride_bytes;
+  lay.row_step = 0;
+  lay.off[0] = 0; lay.off[1] = 4; lay.off[2] = 8;
+  lay.off[3] = stride_bytes >= 20 ? 16 : (stride_bytes >= 16 ? 12 : -1);
+  lay.aligned = 1;
+  return voxel_filter_records(in, n, lay, leaf, sc, st, m_out, overflow, crop6, compact_on_overflow, T16);
+}
+
+cudaError_t voxel_filter_records(const void* in, size_t n, RecordLayout lay, float leaf, Scratch& sc, const StreamPtr& st,
+                                 size_t* m_out, int* overflow, const float* crop6, bool compact_on_overflow, const float* T16) {
   cudaError_t e;
   *m_out = 0;
   *overflow = 0;
@@ -183,9 +207,11 @@ cudaError_t voxel_filter_device(const void* in, size_t n, size_t stride_bytes, f
   xf.on = T16 != nullptr;
   for (int r = 0; r < 3; r++)
     for (int c = 0; c < 4; c++) xf.m[r * 4 + c] = T16 ? T16[c * 4 + r] : 0.f;   // column-major 4x4 in
-  const int ifloat = stride_bytes >= 20 ? 4 : (stride_bytes >= 16 ? 3 : -1);
-  const size_t last = ifloat >= 0 ? (size_t)(ifloat + 1) * 4 : 12;
-  const size_t raw_bytes = (n - 1) * stride_bytes + last;
+  int last = 0;
+  for (int f = 0; f < 4; f++) last = lay.off[f] + 4 > last ? lay.off[f] + 4 : last;
+  const size_t rows = (n + (size_t)lay.width - 1) / (size_t)lay.width;
+  const size_t cols_last = n - (rows - 1) * (size_t)lay.width;
+  const size_t raw_bytes = (rows - 1) * lay.row_step + (cols_last - 1) * lay.point_step + (size_t)last;
   if ((e = sc.staging.reserve(raw_bytes + 16, st)) != cudaSuccess) return e;
   if ((e = sc.queries.reserve(sizeof(float4) * n, st)) != cudaSuccess) return e;
   if ((e = sc.vox_desc.reserve(sizeof(GridDesc), st)) != cudaSuccess) return e;
@@ -203,7 +229,7 @@ cudaError_t voxel_filter_device(const void* in, size_t n, size_t stride_bytes, f
   GridDesc* d = sc.vox_desc.as<GridDesc>();
   float4* pts = sc.queries.as<float4>();
   vox_desc_init_kernel<<<1, 1, 0, st->s>>>(d);
-  vox_pack_kernel<<<vgrid(ni, 256), 256, 0, st->s>>>(sc.staging.as<unsigned char>(), stride_bytes, ni, ifloat, pts, d, crop, xf);
+  vox_pack_kernel<<<vgrid(ni, 256), 256, 0, st->s>>>(sc.staging.as<unsigned char>(), lay, ni, pts, d, crop, xf);
   note_launches(2);
   int* flags = sc.flags.as<int>();
   auto compact = [&]() -> cudaError_t {

@@ -419,6 +419,35 @@ class NanoGICP:
             res = res.copy()
         return (res, rc) if return_status else res
 
+    def preprocess_pointcloud2(self, msg, crop_size: float | None = 1.0, leaf: float = 0.25, out=None, data_ptr: int | None = None,
+                               return_status: bool = False):
+        """pcl::fromROSMsg (odom.cc:636-637) + preprocessPoints (:443-465) in one device pass over the message bytes.
+        msg: anything with sensor_msgs/PointCloud2's members (see pointcloud2.PointCloud2); data_ptr: address of the
+        byte array when it already sits in pinned or device memory (msg.data is then not touched)."""
+        from .pointcloud2 import xyzi_layout
+        lay = xyzi_layout(msg)
+        n = int(msg.width) * int(msg.height)
+        keep = None
+        if data_ptr is None:
+            keep = np.frombuffer(msg.data, dtype=np.uint8)
+            data_ptr = keep.ctypes.data if keep.size else None
+        m = C.c_size_t(0)
+        if out is None:
+            buf = np.zeros((max(n, 1), 8), dtype=np.float32)
+            optr, cap = buf.ctypes.data, buf.shape[0]
+        else:
+            buf = out
+            optr, cap = out.data_ptr(), int(out.shape[0])
+        lo = hi = None
+        if crop_size is not None:
+            lo = (C.c_float * 3)(-crop_size, -crop_size, -crop_size)
+            hi = (C.c_float * 3)(crop_size, crop_size, crop_size)
+        rc = self._check(self._L.ngicp_preprocess_pointcloud2(self._h, data_ptr, C.byref(lay), lo, hi, C.c_float(leaf), optr, cap, C.byref(m)))
+        res = buf[: m.value]
+        if out is None:
+            res = res.copy()
+        return (res, rc) if return_status else res
+
     def transform_voxel_filter(self, cloud, T, leaf: float, out=None):
         """pcl::transformPointCloud(cloud, T) + pcl::VoxelGrid(leaf) in one device pass (keyframes, odom.cc:484-490)."""
         p, n, st, keep = _ptr_n_stride(cloud)

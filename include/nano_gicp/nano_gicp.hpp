@@ -384,6 +384,35 @@ class Preprocessor {
     out.points.swap(tmp);
     out.width = (uint32_t)m; out.height = 1; out.is_dense = true;
   }
+  // pcl::fromROSMsg(*pc, *current_scan) (odom.cc:636-637) + preprocessPoints in the same device pass.  Msg is
+  // sensor_msgs::PointCloud2 or anything with its members (width, height, point_step, row_step, is_bigendian, data,
+  // fields[] with name / offset / datatype / count); the members of PointXYZI are matched as PCL does: same name,
+  // datatype FLOAT32 (7), count 1.
+  template <class Msg>
+  void filterMsg(const Msg& msg, pcl::PointCloud<PointT>& out) {
+    if (!handle_->h) return;
+    ngicp_pc2_layout lay;
+    lay.width = (unsigned)msg.width; lay.height = (unsigned)msg.height;
+    lay.point_step = (unsigned)msg.point_step; lay.row_step = (unsigned)msg.row_step;
+    lay.offset_x = lay.offset_y = lay.offset_z = lay.offset_intensity = -1;
+    lay.is_bigendian = msg.is_bigendian ? 1 : 0;
+    for (const auto& f : msg.fields) {
+      if ((int)f.datatype != 7 || ((int)f.count != 1 && (int)f.count != 0)) continue;
+      int* dst = f.name == "x" ? &lay.offset_x : f.name == "y" ? &lay.offset_y : f.name == "z" ? &lay.offset_z
+                 : f.name == "intensity" ? &lay.offset_intensity : nullptr;
+      if (dst && *dst < 0) *dst = (int)f.offset;
+    }
+    const size_t n = (size_t)lay.width * lay.height;
+    std::vector<PointT> tmp(n ? n : 1);
+    size_t m = 0;
+    const float lo[3] = {-crop_, -crop_, -crop_}, hi[3] = {crop_, crop_, crop_};
+    int rc = ngicp_preprocess_pointcloud2(handle_->h, msg.data.data(), &lay, crop_ > 0.f ? lo : nullptr, crop_ > 0.f ? hi : nullptr, leaf_,
+                                          tmp.data(), tmp.size(), &m);
+    detail::report(handle_->h, rc, "Preprocessor::filterMsg");
+    tmp.resize(m);
+    out.points.swap(tmp);
+    out.width = (uint32_t)m; out.height = 1; out.is_dense = true;
+  }
  private:
   std::unique_ptr<detail::Handle> handle_;
   float crop_ = 1.0f, leaf_ = 0.25f;

@@ -170,6 +170,19 @@ int ngicp_preprocess(ngicp_t* h, const void* in, size_t n, size_t stride_bytes, 
  * index overflow the surviving transformed points are emitted in input order. */
 int ngicp_transform_voxel_filter(ngicp_t* h, const void* in, size_t n, size_t stride_bytes, const float* T16, float leaf,
                                  void* out, size_t out_capacity, size_t* m);
+/* pcl::fromROSMsg (odom.cc:636-637) + preprocessPoints in the same pass: `data` is the byte array of a
+ * sensor_msgs::PointCloud2 (host or device), the layout carries the message's geometry and the byte offsets of its
+ * FLOAT32 fields named "x", "y", "z", "intensity" (what pcl::fromROSMsg's field mapping matches for pcl::PointXYZI:
+ * same name, datatype FLOAT32, count 1; offset_intensity = -1 when the message has no such field — PCL then leaves
+ * intensity 0).  Offsets and steps need not be 4-byte aligned.  Output as ngicp_preprocess. */
+typedef struct ngicp_pc2_layout {
+  unsigned width, height;        /* points per row, rows (n = width * height) */
+  unsigned point_step, row_step; /* bytes per point / per row */
+  int offset_x, offset_y, offset_z, offset_intensity;
+  int is_bigendian;              /* must be 0 */
+} ngicp_pc2_layout;
+int ngicp_preprocess_pointcloud2(ngicp_t* h, const void* data, const ngicp_pc2_layout* layout, const float* crop_min,
+                                 const float* crop_max, float leaf, void* out, size_t out_capacity, size_t* m);
 /* test hook: the output slot every input point was averaged into (-1 for non-finite points) */
 int ngicp_voxel_assignment(ngicp_t* h, int* slot_of_point, size_t n);
 

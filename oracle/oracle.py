@@ -111,6 +111,32 @@ def as_xyzi(pts: np.ndarray) -> np.ndarray:
     return out
 
 
+def from_ros_msg(msg) -> np.ndarray:
+    """pcl::fromROSMsg(msg, pcl::PointCloud<pcl::PointXYZI>) restated (reference src/dlo/odom.cc:636-637; PCL
+    conversions.h: createMapping + fromPCLPointCloud2): every PointXYZI member (x, y, z, intensity — all FLOAT32) is
+    copied from the message field of the same name, the same datatype and count 1; a member without such a field
+    keeps the default-constructed value (0; data[3] = 1).  Point (row, col) starts at row * row_step + col *
+    point_step.  Byte order is taken as the host's (PCL ignores is_bigendian).  Returns (n, 8) float32 records
+    {x, y, z, 1, intensity, 0, 0, 0}."""
+    n = int(msg.width) * int(msg.height)
+    out = np.zeros((n, 8), dtype=np.float32)
+    out[:, 3] = 1.0
+    raw = np.frombuffer(msg.data, dtype=np.uint8)
+    member = {"x": 0, "y": 1, "z": 2, "intensity": 4}
+    done = set()
+    for f in msg.fields:
+        if f.name not in member or f.name in done or int(f.datatype) != 7 or int(f.count) not in (0, 1):
+            continue
+        done.add(f.name)
+        col = np.empty(n, dtype=np.float32)
+        for r in range(int(msg.height)):
+            base = r * int(msg.row_step) + int(f.offset)
+            idx = base + np.arange(int(msg.width), dtype=np.int64)[:, None] * int(msg.point_step) + np.arange(4)[None, :]
+            col[r * int(msg.width):(r + 1) * int(msg.width)] = raw[idx].copy().view("<f4").reshape(-1)
+        out[:, member[f.name]] = col
+    return out
+
+
 def preprocess_points(pts: np.ndarray, crop_size, leaf: float, lib=None):
     """OdomNode::preprocessPoints restated (reference src/dlo/odom.cc:443-465): removeNaNFromPointCloud (:451), the
     negative pcl::CropBox of +-crop_size (:122-124,454-457; PCL keeps a point as "inside" when min <= p <= max on all

@@ -7,6 +7,7 @@
 #include <cstdio>
 #include <string>
 #include <cstdlib>
+#include <cstring>
 #include <memory>
 #include <vector>
 
@@ -121,6 +122,35 @@ struct OdomNodeLike {
   }
 };
 
+// a sensor_msgs::PointCloud2 stand-in (ROS is not installed here): Ouster-style 48-byte records, 64 rows
+struct FieldLike { std::string name; uint32_t offset; uint8_t datatype; uint32_t count; };
+struct Pc2Like {
+  uint32_t height = 0, width = 0, point_step = 0, row_step = 0;
+  bool is_bigendian = false;
+  std::vector<FieldLike> fields;
+  std::vector<uint8_t> data;
+};
+static int check_pointcloud2_path(const pcl::PointCloud<PointType>& scan) {
+  Pc2Like msg;
+  const size_t n = (scan.points.size() / 64) * 64;
+  msg.height = 64; msg.width = (uint32_t)(n / 64); msg.point_step = 48; msg.row_step = msg.width * 48;
+  msg.fields = {{"x", 0, 7, 1}, {"y", 4, 7, 1}, {"z", 8, 7, 1}, {"intensity", 16, 7, 1}, {"t", 20, 6, 1}, {"ring", 26, 2, 1}};
+  msg.data.assign(n * 48, 0xab);
+  pcl::PointCloud<PointType> plain;
+  plain.points.assign(scan.points.begin(), scan.points.begin() + (long)n);
+  for (size_t i = 0; i < n; i++) {
+    std::memcpy(&msg.data[i * 48], &scan.points[i].x, 12);
+    std::memcpy(&msg.data[i * 48 + 16], &scan.points[i].intensity, 4);
+  }
+  nano_gicp::Preprocessor<PointType> pre;
+  pre.setCropSize(1.0f); pre.setLeafSize(0.5f);
+  pcl::PointCloud<PointType> a, b;
+  pre.filter(plain, a);
+  pre.filterMsg(msg, b);
+  if (a.points.size() != b.points.size() || a.points.empty()) return 1;
+  return std::memcmp(a.points.data(), b.points.data(), a.points.size() * sizeof(PointType)) == 0 ? 0 : 1;
+}
+
 int main(int argc, char** argv) {
   if (argc < 2) { std::fprintf(stderr, "usage: %s scans.bin\n", argv[0]); return 2; }
   FILE* f = std::fopen(argv[1], "rb");
@@ -141,7 +171,11 @@ int main(int argc, char** argv) {
     scan->resize((size_t)n);
     if (std::fread(scan->points.data(), sizeof(PointType), (size_t)n, f) != (size_t)n) return 2;
     node.current_scan = scan;
-    if (s == 0) { node.initializeInputTarget(); continue; }
+    if (s == 0) {
+      if (check_pointcloud2_path(*scan) != 0) { std::fprintf(stderr, "PointCloud2 path differs from the plain path\n"); return 4; }
+      node.initializeInputTarget();
+      continue;
+    }
     node.setInputSources();
     node.getNextPose(s);
   }

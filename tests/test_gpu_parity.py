@@ -117,6 +117,42 @@ def test_preprocess_fused_crop_nan_voxel(G, O, scan_pair):
     assert st == 1 and np.array_equal(bits(out), bits(ref))
 
 
+def test_preprocess_pointcloud2_decode_fused(G, O, scan_pair):
+    """ngicp_preprocess_pointcloud2 = pcl::fromROSMsg + preprocessPoints on the message bytes (odom.cc:636-637,
+    443-465): bit-exact against the oracle's decode followed by its three preprocessing steps, for Ouster-like (48 B,
+    organised 64 x W), Velodyne-like (22 B, unaligned, padded rows) and xyz-only messages."""
+    from direct_lidar_odometry_b200 import pointcloud2 as pc2
+    g = G()
+    raw = scan_pair["raw0"] if "raw0" in scan_pair else scan_pair["s0"]
+    n = (raw.shape[0] // 64) * 64
+    dirty = raw[:n].copy()
+    dirty[::13, 1] = np.nan
+    dirty[5::17, 0] = -np.inf
+    dirty[:50, :3] *= 0.01
+    for kind, height, pad in (("ouster", 64, 0), ("ouster", 1, 0), ("velodyne", 64, 6), ("velodyne", 1, 0), ("xyz", 64, 2)):
+        msg = pc2.make_pointcloud2(dirty, kind, height=height, row_pad=pad)
+        decoded = O.from_ros_msg(msg)
+        for crop, leaf in ((1.0, 0.25), (None, 0.5), (1.0, 0.0)):
+            ref = O.preprocess_points(decoded, crop, leaf)
+            out = g.preprocess_pointcloud2(msg, crop, leaf)
+            assert out.shape == ref.shape, (kind, crop, leaf, out.shape, ref.shape)
+            assert np.array_equal(bits(out), bits(ref)), (kind, crop, leaf)
+    # the same through the plain-record entry point must agree as well
+    msg = pc2.make_pointcloud2(dirty, "ouster", height=64)
+    assert np.array_equal(bits(g.preprocess_pointcloud2(msg, 1.0, 0.25)), bits(g.preprocess(dirty, 1.0, 0.25)))
+    # empty message, malformed layouts
+    empty = pc2.make_pointcloud2(dirty[:0], "ouster")
+    assert g.preprocess_pointcloud2(empty, 1.0, 0.25).shape[0] == 0
+    bad = pc2.make_pointcloud2(dirty, "ouster", height=64)
+    bad.fields[0] = pc2.PointField("x", 46, pc2.FLOAT32)      # runs past point_step
+    with pytest.raises(Exception):
+        g.preprocess_pointcloud2(bad, 1.0, 0.25)
+    nox = pc2.make_pointcloud2(dirty, "ouster")
+    nox.fields[0] = pc2.PointField("x", 0, pc2.FLOAT64)       # no FLOAT32 x
+    with pytest.raises(Exception):
+        g.preprocess_pointcloud2(nox, 1.0, 0.25)
+
+
 def test_transform_voxel_filter_fused(G, O, scan_pair):
     """transformPointCloud + vf_submap in one pass (keyframes, odom.cc:484-490) == the two steps of the oracle."""
     g = G()

@@ -249,3 +249,32 @@ def test_preprocess_points_restatement():
     assert (kept[:, :3] == pts[1, :3]).all(axis=1).any() and not (kept[:, :3] == pts[0, :3]).all(axis=1).any()
     v = orc.preprocess_points(pts, 1.0, 0.5)
     assert np.array_equal(v, orc.voxel_filter(pts[finite & ~inside], 0.5))
+
+
+def test_from_ros_msg_restatement_and_field_mapping():
+    """pcl::fromROSMsg for PointXYZI (odom.cc:636-637): members are matched by name + FLOAT32 + count 1; padding,
+    foreign fields, unaligned records and row padding do not matter; a missing intensity stays 0."""
+    from oracle import oracle as orc
+    from direct_lidar_odometry_b200 import pointcloud2 as pc2
+    rng = np.random.default_rng(11)
+    pts = np.zeros((64 * 96, 8), np.float32)
+    pts[:, :3] = rng.normal(0, 20, size=(pts.shape[0], 3))
+    pts[:, 3] = 1.0
+    pts[:, 4] = rng.uniform(0, 1, pts.shape[0])
+    pts[7, 2] = np.nan
+    for kind, height, pad in (("ouster", 64, 0), ("ouster", 1, 0), ("velodyne", 1, 0), ("velodyne", 64, 6), ("xyz", 64, 3)):
+        msg = pc2.make_pointcloud2(pts, kind, height=height, row_pad=pad)
+        got = orc.from_ros_msg(msg)
+        ref = pts.copy()
+        if kind == "xyz":
+            ref[:, 4] = 0.0
+        assert np.array_equal(got.view(np.uint32), ref.view(np.uint32)), kind
+        lay = pc2.xyzi_layout(msg)
+        assert (lay.offset_x, lay.offset_y, lay.offset_z) == (0, 4, 8)
+        assert lay.offset_intensity == {"ouster": 16, "velodyne": 12, "xyz": -1}[kind]
+        assert lay.row_step == msg.width * msg.point_step + pad and lay.width * lay.height == pts.shape[0]
+    # a field with the right name but another datatype is NOT a match (PCL: "Failed to find match for field")
+    msg = pc2.make_pointcloud2(pts, "ouster")
+    msg.fields[3] = pc2.PointField("intensity", 16, pc2.UINT32)
+    assert pc2.xyzi_layout(msg).offset_intensity == -1
+    assert (orc.from_ros_msg(msg)[:, 4] == 0).all()
