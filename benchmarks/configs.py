@@ -123,15 +123,21 @@ def run_c1(args):
 
 
 # ------------------------------------------------------------------------------------------------ C3
-class Replay:
-    """OdomNode's per-scan sequence (reference src/dlo/odom.cc:629-697) with the submap chosen as the `knn` nearest
-    keyframes (hull-based selection is out of scope).  `make()` builds a registration object."""
+SELECTION = "hull"   # "hull": OdomNode::getSubmapKeyframes (kNN + convex hull + concave hull, N3); "knn": nearest keyframes only
 
-    def __init__(self, make, voxel, get_T, thresh_d=5.0, knn=10):
+
+class Replay:
+    """OdomNode's per-scan sequence (reference src/dlo/odom.cc:629-697): S2S, submap selection (getSubmapKeyframes,
+    :1240-1293, through submap_select.SubmapSelector), S2M, updateKeyframes (:1097-1181; shipped thresholds threshD 5 m,
+    threshR 45 deg, adaptive parameters off).  `make()` builds a registration object."""
+
+    def __init__(self, make, voxel, get_T, thresh_d=5.0, knn=10, thresh_r=45.0):
+        from direct_lidar_odometry_b200.submap_select import SubmapSelector
         self.s2s, self.s2m = make(S2S), make(S2M)
         self.voxel, self.get_T = voxel, get_T
-        self.thresh_d, self.knn = thresh_d, knn
-        self.keyframes = []   # (position, cloud, covs)
+        self.thresh_d, self.thresh_r, self.knn = thresh_d, thresh_r, knn
+        self.selector = SubmapSelector(knn, knn, knn, alpha=thresh_d) if SELECTION == "hull" else None
+        self.keyframes = []   # (position, cloud, covs, rotation)
         self.prev_set = None
         self.T = None
 
@@ -144,7 +150,22 @@ class Replay:
     def _add_keyframe(self, scan):
         kf = self.voxel(synth.transform_xyzi(scan, self.T), 0.5)
         self.s2s.setInputSource(kf); self.s2s.calculateSourceCovariances()
-        self.keyframes.append((self.T[:3, 3].copy(), kf, self.s2s.getSourceCovariances()))
+        self.keyframes.append((self.T[:3, 3].copy(), kf, self.s2s.getSourceCovariances(), self.T[:3, :3].copy()))
+
+    def _new_keyframe_wanted(self):
+        """updateKeyframes' decision (odom.cc:1102-1153): farther than threshD from the closest keyframe, or within it but
+        rotated by more than threshR with at most one keyframe within 1.5 threshD."""
+        p = self.T[:3, 3].astype(np.float32)
+        d = np.array([np.float32(np.sqrt(((p - kf[0]).astype(np.float64) ** 2).sum())) for kf in self.keyframes], dtype=np.float32)
+        closest = int(np.argmin(d))
+        num_nearby = int((d <= np.float32(self.thresh_d * 1.5)).sum())
+        dR = self.T[:3, :3].astype(np.float64) @ self.keyframes[closest][3].astype(np.float64).T
+        theta = np.degrees(np.arccos(np.clip((np.trace(dR) - 1.0) / 2.0, -1.0, 1.0)))
+        dd = d[closest]
+        new = dd > self.thresh_d or theta > self.thresh_r
+        if dd <= self.thresh_d:
+            new = theta > self.thresh_r and num_nearby <= 1
+        return bool(new)
 
     def _set_submap(self, sel):
         self.submap = np.ascontiguousarray(np.vstack([self.keyframes[i][1] for i in sel]))
@@ -166,8 +187,11 @@ class Replay:
         T_s2s = self.T_prev @ self.s2s.getFinalTransformation()
         self.s2m.source_covs_ = self.s2s.source_covs_
         self.s2s.swapSourceAndTarget()
-        d = [np.linalg.norm(T_s2s[:3, 3] - kf[0]) for kf in self.keyframes]
-        sel = tuple(sorted(np.argsort(d)[: self.knn].tolist()))
+        if self.selector is not None:
+            sel = tuple(self.selector.select([kf[0] for kf in self.keyframes], T_s2s[:3, 3])[0])
+        else:
+            d = [np.linalg.norm(T_s2s[:3, 3] - kf[0]) for kf in self.keyframes]
+            sel = tuple(sorted(np.argsort(d)[: self.knn].tolist()))
         self.events.append(("s2s", (time.perf_counter() - t_) * 1e3)); t_ = time.perf_counter()
         if sel != self.prev_set:
             npts = self._set_submap(sel)
@@ -180,7 +204,7 @@ class Replay:
             self.T = np.array(force_T, dtype=np.float32)
         self.T_prev = self.T
         self.events.append(("s2m", (time.perf_counter() - t_) * 1e3)); t_ = time.perf_counter()
-        if min(np.linalg.norm(self.T[:3, 3] - kf[0]) for kf in self.keyframes) > self.thresh_d:
+        if self._new_keyframe_wanted():
             self._add_keyframe(scan)
             self.events.append(("new_keyframe", (time.perf_counter() - t_) * 1e3))
         return it_s2s, self.s2m.nr_iterations_
@@ -203,7 +227,7 @@ class DeviceReplay(Replay):
         kf = self.pre.transform_voxel_filter(scan, self.T, 0.5, out=self.kf_buf)
         self.s2s.setInputSource(kf); self.s2s.calculateSourceCovariances()
         self.store.push(self.s2s)
-        self.keyframes.append((self.T[:3, 3].copy(), None, None))
+        self.keyframes.append((self.T[:3, 3].copy(), None, None, self.T[:3, :3].copy()))
 
     def _set_submap(self, sel):
         self.store.set_target(self.s2m, list(sel))
@@ -285,7 +309,9 @@ def run_c3(args):
         errs.append(pose_err(rp.T, T_true))
         traj.append(np.array(rp.T, dtype=np.float32).copy())
     ms = np.array(ms)
-    out = {"config": f"C3: odometry replay, {args.scans} synthetic OS1-64 scans (S2S + S2M + keyframes every 5 m, knn-{rp.knn} submap)"
+    sel_txt = (f"submap = {rp.knn} nearest + {rp.knn} convex-hull + {rp.knn} concave-hull keyframes as OdomNode::getSubmapKeyframes" if SELECTION == "hull"
+               else f"knn-{rp.knn} submap")
+    out = {"config": f"C3: odometry replay, {args.scans} synthetic OS1-64 scans (S2S + S2M + keyframes by OdomNode::updateKeyframes' rule, threshD 5 m / threshR 45 deg; {sel_txt})"
                      + (", device-resident keyframes + fused preprocess (N1/N2)" if args.device_store else ", host keyframes as in OdomNode"),
            "gpu": {"ms_per_scan_mean": float(ms.mean()), "ms_per_scan_p50": float(np.percentile(ms, 50)), "ms_per_scan_p99": float(np.percentile(ms, 99)),
                    "keyframes": len(rp.keyframes), "final_translation_error_m": errs[-1][0], "max_translation_error_m": float(max(e[0] for e in errs)),
@@ -534,9 +560,11 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--check", type=int, default=1)
     ap.add_argument("--scans", type=int, default=300)
+    ap.add_argument("--selection", choices=["hull", "knn"], default="hull", help="c3: submap keyframe selection")
     ap.add_argument("--cpu-scans", type=int, default=40)
     ap.add_argument("--pairs", type=int, default=512)
     ap.add_argument("--pool", type=int, default=16)
     ap.add_argument("--handles", type=int, default=8)
     a = ap.parse_args()
+    SELECTION = a.selection
     {"c1": run_c1, "c3": run_c3, "c4": run_c4, "c5": run_c5}[a.which](a)
