@@ -322,6 +322,7 @@ struct GridSync {
   unsigned* flag;     // bar[1]
   double* totals;     // [2][NRED] in global memory
   unsigned phase;     // phases completed so far
+  unsigned max_blocks;  // stride between the two phase-parity halves of the partials buffer
 };
 
 __device__ __forceinline__ unsigned ld_relaxed_u32(const unsigned* p) {
@@ -394,6 +395,51 @@ template <int NV>
 __device__ __forceinline__ void grid_reduce(double* acc, double (*s_red)[NRED], double* s_tot, double* partials, GridSync& gs,
                                             const PeerComm& pc) {
   __shared__ int s_last;
+  if (pc.world == 1) {
+    // Single GPU: every block waits until all partials of this phase are published, then sums them ITSELF in the same
+    // fixed order (identical totals everywhere, bit-deterministic) — no "last block sums, publishes, the others read
+    // back" relay: two L2 round trips less per barrier.  Partials are double-buffered by phase parity: a fast block may
+    // already be writing phase p+1 while a slow one still reads phase p (it cannot reach p+2 before that one arrives).
+    double* mine = partials + ((size_t)(gs.phase & 1u) * gs.max_blocks + blockIdx.x) * NRED;
+    block_reduce_store<NV>(acc, s_red, mine);
+    if (threadIdx.x == 0) {
+      __threadfence();
+      atomicAdd(gs.arrive, 1u);
+      const unsigned target = (gs.phase + 1u) * gridDim.x;
+      while (ld_relaxed_u32(gs.arrive) < target) __nanosleep(20);
+      __threadfence();
+    }
+    __syncthreads();
+    const double* all = partials + (size_t)(gs.phase & 1u) * gs.max_blocks * NRED;
+    const int v = threadIdx.x & 31, seg = threadIdx.x >> 5;
+    if (v < NV) {
+      double part[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) part[u] = 0.0;
+      const unsigned nb = gridDim.x;
+      for (unsigned b0 = seg; b0 < nb; b0 += AL_WARPS * 8) {
+        double x[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const unsigned bk = b0 + u * AL_WARPS;
+          x[u] = bk < nb ? __ldcg(all + (size_t)bk * NRED + v) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) part[u] += x[u];
+      }
+      s_red[seg][v] = ((part[0] + part[1]) + (part[2] + part[3])) + ((part[4] + part[5]) + (part[6] + part[7]));
+    }
+    __syncthreads();
+    if (threadIdx.x < NV) {
+      double s = 0.0;
+#pragma unroll
+      for (int sg = 0; sg < AL_WARPS; sg++) s += s_red[sg][threadIdx.x];
+      s_tot[threadIdx.x] = s;
+    }
+    gs.phase++;
+    __syncthreads();
+    return;
+  }
   block_reduce_store<NV>(acc, s_red, partials + (size_t)blockIdx.x * NRED);
   if (threadIdx.x == 0) {
     __threadfence();
@@ -476,7 +522,7 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) align_fused_kernel(AlignArgs
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const int gstride = gridDim.x * blockDim.x;
   GridSync gs;
-  gs.arrive = bar; gs.flag = bar + 1; gs.totals = totals; gs.phase = 0;
+  gs.arrive = bar; gs.flag = bar + 1; gs.totals = totals; gs.phase = 0; gs.max_blocks = (unsigned)a.max_blocks;
 
   // scalar LM state, kept by thread 0 of every block (identical everywhere)
   Iso3 x0, xi, delta;

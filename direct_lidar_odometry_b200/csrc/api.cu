@@ -225,7 +225,7 @@ int prepare_align(ngicp_t* h, bool lazy, AlignBuffers& ab) {
   NG_CUDA(h, sc.corr.reserve(sizeof(int) * ns, h->stream));
   NG_CUDA(h, sc.sqd.reserve(sizeof(float) * ns, h->stream));
   NG_CUDA(h, sc.tgt_pt.reserve(sizeof(float4) * ns, h->stream));
-  NG_CUDA(h, sc.partials.reserve(sizeof(double) * NRED * (size_t)h->align_max_blocks, h->stream));
+  NG_CUDA(h, sc.partials.reserve(sizeof(double) * NRED * (size_t)h->align_max_blocks * 2, h->stream));   // two phase-parity halves
   NG_CUDA(h, sc.reduced.reserve(sizeof(double) * 64, h->stream));
   if (!sc.barrier.p) {   // zeroed once; the fused kernel leaves it zeroed (last departing block)
     NG_CUDA(h, sc.barrier.reserve(64, h->stream));

@@ -80,20 +80,33 @@ def concave_hull_vertices(pos: np.ndarray, alpha: float) -> list:
     except (QhullError, ValueError):
         return []
     tets, nbrs = tri.simplices, tri.neighbors
-    good = np.array([_circumsphere_radius(p[t]) <= alpha for t in tets], dtype=bool)
-    used = set()
-    for ti, t in enumerate(tets):
-        for f in range(4):
-            nb = int(nbrs[ti, f])
-            if nb >= 0 and nb < ti:
-                continue                                   # each inner face once
-            face = [int(t[j]) for j in range(4) if j != f]
-            nb_good = nb >= 0 and bool(good[nb])
-            candidate = bool(good[ti]) or nb_good or _circumcircle_radius(pf[face[0]], pf[face[1]], pf[face[2]]) <= alpha
-            boundary = nb < 0 or not good[ti] or not nb_good
-            if candidate and boundary:
-                used.update(face)
-    return sorted(used)
+    # all tetrahedra at once: circumsphere radius = |Voronoi centre - vertex 0| (qh_pointdist(vertex, facet->center))
+    P = p[tets]                                                   # (T, 4, 3)
+    A = 2.0 * (P[:, 1:, :] - P[:, :1, :])
+    b = (P[:, 1:, :] ** 2).sum(axis=2) - (P[:, :1, :] ** 2).sum(axis=2)
+    det = np.linalg.det(A)
+    ok = np.abs(det) > 0
+    centre = np.zeros((tets.shape[0], 3))
+    if ok.any():
+        centre[ok] = np.linalg.solve(A[ok], b[ok][..., None])[..., 0]
+    r_tet = np.where(ok, np.linalg.norm(centre - P[:, 0, :], axis=1), np.inf)
+    good = r_tet <= alpha
+    # all faces at once: face f is opposite vertex f
+    face_idx = np.array([[1, 2, 3], [0, 2, 3], [0, 1, 3], [0, 1, 2]])
+    faces = tets[:, face_idx]                                     # (T, 4, 3) point indices
+    F = pf[faces]                                                 # float coordinates, as pcl::getCircumcircleRadius sees them
+    l1 = np.linalg.norm(F[:, :, 1] - F[:, :, 0], axis=2).astype(np.float64)
+    l2 = np.linalg.norm(F[:, :, 2] - F[:, :, 1], axis=2).astype(np.float64)
+    l3 = np.linalg.norm(F[:, :, 0] - F[:, :, 2], axis=2).astype(np.float64)
+    sp = (l1 + l2 + l3) / 2.0
+    area2 = sp * (sp - l1) * (sp - l2) * (sp - l3)
+    with np.errstate(divide="ignore", invalid="ignore"):
+        r_face = (l1 * l2 * l3) / (4.0 * np.sqrt(np.where(area2 > 0, area2, 0.0)))
+    nb_good = np.where(nbrs >= 0, good[np.clip(nbrs, 0, None)], False)
+    candidate = good[:, None] | nb_good | (r_face <= alpha)
+    boundary = (nbrs < 0) | ~good[:, None] | ~nb_good
+    keep = candidate & boundary
+    return sorted(set(int(v) for v in faces[keep].reshape(-1)))
 
 
 class SubmapSelector:
@@ -102,10 +115,13 @@ class SubmapSelector:
 
     def __init__(self, knn: int = 10, kcv: int = 10, kcc: int = 10, alpha: float = 5.0):
         # defaults: cfg/params.yaml submap.keyframe.{knn,kcv,kcc} = 10, keyframe.threshD = 5.0 (alpha, odom.cc:97)
+        import scipy.spatial  # noqa: F401  (pay the import here, not inside the first scan that needs a hull)
         self.knn, self.kcv, self.kcc, self.alpha = knn, kcv, kcc, float(alpha)
         self.keyframe_convex: list = []
         self.keyframe_concave: list = []
         self.prev: list | None = None
+        self._hulls_of = None     # keyframe positions the hulls were computed for (they only change with a new keyframe;
+                                  # the reference recomputes them every scan, with the same result)
 
     def select(self, keyframe_positions, current_position):
         """-> (sorted unique keyframe indices, submap_hasChanged)"""
@@ -116,11 +132,13 @@ class SubmapSelector:
         ds = np.sqrt((diff ** 2).sum(axis=1)).astype(np.float32)
         out: list = []
         push_submap_indices(ds, self.knn, list(range(pos.shape[0])), out)
-        if pos.shape[0] >= 4:
+        fresh = self._hulls_of is None or self._hulls_of.shape != pos.shape or not np.array_equal(self._hulls_of, pos)
+        if pos.shape[0] >= 4 and fresh:
             self.keyframe_convex = convex_hull_vertices(pos)
         push_submap_indices([ds[c] for c in self.keyframe_convex], self.kcv, self.keyframe_convex, out)
-        if pos.shape[0] >= 5:
+        if pos.shape[0] >= 5 and fresh:
             self.keyframe_concave = concave_hull_vertices(pos, self.alpha)
+        self._hulls_of = pos.copy()
         push_submap_indices([ds[c] for c in self.keyframe_concave], self.kcc, self.keyframe_concave, out)
         cur_idx = sorted(set(out))
         changed = cur_idx != self.prev
