@@ -486,7 +486,9 @@ def run_c5(args):
     # ---- target: this rank's slab, index + k=20 covariances on this GPU, halo grown until exact ----
     sync_all()
     t0 = time.perf_counter()
-    info = be.build_target_shard(target, rank, world, halo=S2M["thr"] + 0.01, k=S2M["k"], cov_halo=args.cov_halo)
+    expected = synth.transform_xyzi(source, np.asarray(guess, dtype=np.float64))[:, :3] if args.balance > 0 else None
+    info = be.build_target_shard(target, rank, world, halo=S2M["thr"] + 0.01, k=S2M["k"], cov_halo=args.cov_halo,
+                                 queries=expected, query_weight=args.balance)
     sync_all()
     t_build = time.perf_counter() - t0
     tm = g.timings()
@@ -530,7 +532,7 @@ def run_c5(args):
                           f"{world} GPU(s): slabs + halo, k=20 covariances per slab, fused LM with the H/b/err exchange in NVLink peer memory",
                 "n_gpus": world, "steps": args.steps, "ms_per_scan": float(ms[0].item()), "align_ms": float(ms[1].item()),
                 "target_build_gpu_ms": float(ms[2].item()), "target_build_wall_s": t_build, "cov_halo_m": info["cov_halo"],
-                "halo_rounds": info["rounds"], "shard_points": [int(x.item()) for x in shard_pts],
+                "halo_rounds": info["rounds"], "shard_points": [int(x.item()) for x in shard_pts], "slab_query_weight": args.balance,
                 "iterations": res["nr_iterations"], "n_linearize": res["n_linearize"], "n_compute_error": res["n_compute_error"],
                 "converged": res["converged"], "ranks_bit_identical": identical, "pose_error_m": dt, "pose_error_rad": dr}
         if args.check and world > 1:
@@ -557,6 +559,7 @@ if __name__ == "__main__":
     ap.add_argument("--device-store", type=int, default=0, help="c3: device-resident keyframes + fused preprocess (N1/N2)")
     ap.add_argument("--target-points", type=int, default=5_000_000)
     ap.add_argument("--cov-halo", type=float, default=2.0)
+    ap.add_argument("--balance", type=float, default=0.8, help="c5: weight of the scan's point distribution when placing the slab cuts (0 = equal target counts)")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--check", type=int, default=1)
     ap.add_argument("--scans", type=int, default=300)

@@ -277,70 +277,14 @@ __device__ __forceinline__ void nn1_scan_range(const GridView& g, int a, int b, 
   }
 }
 
-// Radius-1 cube only.  Returns true when the search is NOT finished (a closer point may exist outside the cube and
-// within the cap): the caller continues with grid_nn1_grow_thread or hands the query to a warp
-// (grid_search_warp with resume_s0 = 1).
-__device__ __forceinline__ bool grid_nn1_cube1(const GridView& g, const GridParams& gp, float qx, float qy, float qz,
-                                               float cap_d2, float& best_d, int& best_p) {
-  best_d = FLT_MAX;
-  best_p = -1;
-  const int cx = cell_coord(qx, gp.ox, gp.inv, gp.dx);
-  const int cy = cell_coord(qy, gp.oy, gp.inv, gp.dy);
-  const int cz = cell_coord(qz, gp.oz, gp.inv, gp.dz);
-  const int rmax = max(max(max(cx, gp.dx - 1 - cx), max(cy, gp.dy - 1 - cy)), max(cz, gp.dz - 1 - cz));
-  // cube of radius 1, cell by cell: the own cell first, then the 26 neighbours, each skipped when even its
-  // nearest face is farther than the best distance so far (exact: margin-shrunk face distances).
-  {
-    // per-row table entries: e0..e3 bound the cells x-1, x, x+1 (empty when outside the grid)
-    const int e0 = max(cx - 1, 0), e1 = cx, e2 = cx + 1, e3 = min(cx + 2, gp.dx);
-    int v[9][4];
-#pragma unroll
-    for (int r = 0; r < 9; ++r) {
-      const int y = cy + (r % 3) - 1, z = cz + (r / 3) - 1;
-      const bool in = (y >= 0 && y < gp.dy && z >= 0 && z < gp.dz);
-      const int* row = g.cell_start + (in ? (z * gp.dy + y) * gp.dx : 0);
-      v[r][0] = in ? __ldg(row + e0) : 0;
-      v[r][1] = in ? __ldg(row + e1) : 0;
-      v[r][2] = in ? __ldg(row + e2) : 0;
-      v[r][3] = in ? __ldg(row + e3) : 0;
-    }
-    // distances from the query to the faces of its own cell (shrunk by the margin, clamped at 0)
-    const float fx0 = fmaxf(qx - (gp.ox + (float)cx * gp.cell) - gp.margin, 0.f);
-    const float fx1 = fmaxf((gp.ox + (float)(cx + 1) * gp.cell) - qx - gp.margin, 0.f);
-    const float fy0 = fmaxf(qy - (gp.oy + (float)cy * gp.cell) - gp.margin, 0.f);
-    const float fy1 = fmaxf((gp.oy + (float)(cy + 1) * gp.cell) - qy - gp.margin, 0.f);
-    const float fz0 = fmaxf(qz - (gp.oz + (float)cz * gp.cell) - gp.margin, 0.f);
-    const float fz1 = fmaxf((gp.oz + (float)(cz + 1) * gp.cell) - qz - gp.margin, 0.f);
-    const float gx[3] = {fx0 * fx0, 0.f, fx1 * fx1};
-    const float gy[3] = {fy0 * fy0, 0.f, fy1 * fy1};
-    const float gz[3] = {fz0 * fz0, 0.f, fz1 * fz1};
-    nn1_scan_range(g, v[4][1], v[4][2], qx, qy, qz, best_d, best_p);   // own cell
-#pragma unroll
-    for (int r = 0; r < 9; ++r) {
-      const float dyz = gy[r % 3] + gz[r / 3];
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        if (r == 4 && c == 1) continue;
-        const float lb = (dyz + gx[c]) * 0.999999f;
-        if (lb < best_d && lb < cap_d2) nn1_scan_range(g, v[r][c], v[r][c + 1], qx, qy, qz, best_d, best_p);
-      }
-    }
-  }
-  if (rmax <= 1) return false;
-  const float m = cube_face_distance(gp, cx, cy, cz, 1, qx, qy, qz);
-  if (m > 0.f) {
-    const float m2 = m * m * 0.999999f;
-    if (cap_d2 <= m2 || best_d <= m2) return false;
-  }
-  return true;
-}
-
 // ---------------------------------------------------------------------------------------------
-// The same radius-1 search by a GROUP of LPP (2 or 4) adjacent lanes per query.  One thread per query leaves the
-// GPU almost empty for a 20k-point scan and every thread walks its candidates as a chain of dependent round trips;
-// a group reads LPP x 8 candidates per round trip.  Visiting order and tie rule are those of grid_nn1_cube1 (own
-// cell, then the rest row by row; strictly closer wins, among equals the lowest slot of the earliest range), so the
-// result is the same.  All lanes of a group must call this together with the same query; results are group-uniform.
+// Radius-1 cube search by a GROUP of LPP (1, 2 or 4) adjacent lanes per query.  Returns true when the search is NOT
+// finished (a closer point may exist outside the cube and within the cap): the caller then hands the query to a warp
+// (grid_search_warp with resume_s0 = 1) or continues with grid_nn1_grow_thread.
+// One thread per query leaves the GPU almost empty for a 20k-point scan and every thread walks its candidates as a
+// chain of dependent round trips; a group reads LPP x 8 candidates per round trip.  Strictly closer wins; among equals
+// the earliest scanned range, inside a range the lowest slot.  All lanes of a group must call this together with the
+// same query; results are group-uniform.
 // ---------------------------------------------------------------------------------------------
 template <int LPP>
 __device__ __forceinline__ void nn1_group_scan(const GridView& g, int a, int b, int sub, unsigned gmask, float qx, float qy, float qz, float& bd, int& bp) {
@@ -399,15 +343,22 @@ __device__ __forceinline__ bool grid_nn1_cube1_group(const GridView& g, const Gr
   const float gx[3] = {fx0 * fx0, 0.f, fx1 * fx1};
   const float gy[3] = {fy0 * fy0, 0.f, fy1 * fy1};
   const float gz[3] = {fz0 * fz0, 0.f, fz1 * fz1};
-  nn1_group_scan<LPP>(g, v[4][1], v[4][2], sub, gmask, qx, qy, qz, best_d, best_p);   // own cell
+  // Row by row, not cell by cell: the three cells of a (y,z) row are one contiguous slot range, and every scan is a
+  // dependent round trip (load -> compare -> prune test of the next one), so 9 steps instead of up to 27.  The own row
+  // first, then the four rows sharing a face with it, then the four diagonal ones; a row is skipped when even its
+  // nearest point is too far, and trimmed to the cells that can still hold a closer point (the middle cell has the
+  // smallest bound, so the kept cells are contiguous).
+  nn1_group_scan<LPP>(g, v[4][0], v[4][3], sub, gmask, qx, qy, qz, best_d, best_p);
+  constexpr int kRowOrder[8] = {1, 3, 5, 7, 0, 2, 6, 8};
 #pragma unroll
-  for (int r = 0; r < 9; ++r) {
+  for (int k = 0; k < 8; ++k) {
+    const int r = kRowOrder[k];
     const float dyz = gy[r % 3] + gz[r / 3];
-#pragma unroll
-    for (int c = 0; c < 3; ++c) {
-      if (r == 4 && c == 1) continue;
-      const float lb = (dyz + gx[c]) * 0.999999f;
-      if (lb < best_d && lb < cap_d2) nn1_group_scan<LPP>(g, v[r][c], v[r][c + 1], sub, gmask, qx, qy, qz, best_d, best_p);
+    const float lim = fminf(best_d, cap_d2);
+    if (dyz * 0.999999f < lim) {
+      const int a = (dyz + gx[0]) * 0.999999f < lim ? v[r][0] : v[r][1];
+      const int b = (dyz + gx[2]) * 0.999999f < lim ? v[r][3] : v[r][2];
+      nn1_group_scan<LPP>(g, a, b, sub, gmask, qx, qy, qz, best_d, best_p);
     }
   }
   if (rmax <= 1) return false;
@@ -417,6 +368,11 @@ __device__ __forceinline__ bool grid_nn1_cube1_group(const GridView& g, const Gr
     if (cap_d2 <= m2 || best_d <= m2) return false;
   }
   return true;
+}
+
+__device__ __forceinline__ bool grid_nn1_cube1(const GridView& g, const GridParams& gp, float qx, float qy, float qz,
+                                               float cap_d2, float& best_d, int& best_p) {
+  return grid_nn1_cube1_group<1>(g, gp, 0, 0u, qx, qy, qz, cap_d2, best_d, best_p);
 }
 
 // further growth by the same thread (only when the cell edge is smaller than the cap, or the cap is unbounded):

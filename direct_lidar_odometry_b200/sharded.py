@@ -28,11 +28,31 @@ def partition_pairs(n_pairs: int, rank: int, world: int) -> range:
     return range(start, start + base + (1 if rank < extra else 0))
 
 
-def slab_bounds(points: np.ndarray, world: int):
-    """Axis with the largest extent and `world+1` boundaries giving equal point counts; outer bounds are +-inf."""
+def slab_bounds(points: np.ndarray, world: int, queries: np.ndarray | None = None, query_weight: float = 0.0):
+    """Axis with the largest extent of the target and `world+1` boundaries; outer bounds are +-inf.
+
+    Without `queries` the cuts give every rank the same number of TARGET points (balances the one-off index +
+    covariance build).  The per-scan work, however, follows the SOURCE points: a scan crowds around the sensor, so the
+    rank that owns the sensor's slab does most of the correspondence search.  With `queries` (where the scan's points
+    are expected to land, e.g. the scan under the initial guess) the cuts are the quantiles of the mixture
+    (1 - query_weight) x target distribution + query_weight x query distribution: query_weight = 1 balances the
+    align alone, values in between trade it against the build and the memory per rank."""
     xyz = np.asarray(points)[:, :3]
     axis = int(np.argmax(xyz.max(0) - xyz.min(0)))
-    q = np.quantile(xyz[:, axis].astype(np.float64), np.linspace(0, 1, world + 1)[1:-1]) if world > 1 else np.array([])
+    if world <= 1:
+        return axis, np.array([-np.inf, np.inf])
+    t = xyz[:, axis].astype(np.float64)
+    levels = np.linspace(0, 1, world + 1)[1:-1]
+    if queries is None or query_weight <= 0.0 or len(queries) == 0:
+        q = np.quantile(t, levels)
+    else:
+        s = np.asarray(queries)[:, axis].astype(np.float64)
+        s = s[np.isfinite(s)]
+        v = np.concatenate([t, s])
+        w = np.concatenate([np.full(t.size, (1.0 - query_weight) / t.size), np.full(s.size, query_weight / max(s.size, 1))])
+        o = np.argsort(v, kind="stable")
+        cw = np.cumsum(w[o])
+        q = v[o][np.minimum(np.searchsorted(cw, levels * cw[-1]), v.size - 1)]
     bounds = np.concatenate([[-np.inf], q.astype(np.float32).astype(np.float64), [np.inf]])
     return axis, bounds
 
@@ -72,14 +92,14 @@ class CudaShardBackend:
             self.g.setSourceCovariances(covs)
 
     def build_target_shard(self, points: np.ndarray, rank: int, world: int, halo: float, k: int, cov_halo: float = 2.0,
-                           chunk: int = 1 << 18) -> dict:
+                           chunk: int = 1 << 18, queries: np.ndarray | None = None, query_weight: float = 0.0) -> dict:
         """This rank's slab of `points` with covariances computed HERE, on the slab widened by a halo that is grown
         until the result is exact: a point the rank can be asked to match (inside the slab widened by `halo`, the
         max-correspondence distance) must have its k-th neighbour closer than the nearest cut plane, otherwise its
         neighbourhood may continue on the other side of the cut.  The check reads back the k-th distances of those
         points through the kNN entry of the C ABI, in chunks."""
         from . import _lib
-        axis, bounds = slab_bounds(points, world)
+        axis, bounds = slab_bounds(points, world, queries, query_weight)
         lo, hi = float(bounds[rank]), float(bounds[rank + 1])
         c = np.asarray(points)[:, axis].astype(np.float64)
         H, rounds = max(float(cov_halo), float(halo)), 0

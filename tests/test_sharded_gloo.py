@@ -145,3 +145,27 @@ def test_partition_pairs_covers_everything():
         assert got == list(range(n))
         sizes = [len(sharded.partition_pairs(n, r, w)) for r in range(w)]
         assert max(sizes) - min(sizes) <= 1
+
+
+def test_slab_bounds_balance_target_or_queries():
+    """Cut planes: equal target counts by default; with the scan's expected positions and weight 1 equal QUERY counts
+    (the per-scan work), a mixture in between."""
+    from direct_lidar_odometry_b200 import sharded
+    rng = np.random.default_rng(2)
+    target = np.zeros((20000, 3), np.float32)
+    target[:, 0] = rng.uniform(-300, 300, 20000); target[:, 1] = rng.uniform(-50, 50, 20000)
+    queries = np.zeros((4000, 3), np.float32)
+    queries[:, 0] = rng.normal(10, 15, 4000)           # crowded around the sensor
+    axis, b0 = sharded.slab_bounds(target, 4)
+    assert axis == 0 and b0[0] == -np.inf and b0[-1] == np.inf
+    cnt = np.histogram(target[:, 0], bins=np.concatenate([[-1e9], b0[1:-1], [1e9]]))[0]
+    assert cnt.max() - cnt.min() <= 2
+    _, b1 = sharded.slab_bounds(target, 4, queries, 1.0)
+    qc = np.histogram(queries[:, 0], bins=np.concatenate([[-1e9], b1[1:-1], [1e9]]))[0]
+    assert qc.max() - qc.min() <= 2
+    _, bh = sharded.slab_bounds(target, 4, queries, 0.5)
+    assert np.all(np.diff(bh[1:-1]) > 0) and abs(bh[2] - b1[2]) < abs(b0[2] - b1[2]) + 1e-9
+    qh = np.histogram(queries[:, 0], bins=np.concatenate([[-1e9], bh[1:-1], [1e9]]))[0]
+    qz = np.histogram(queries[:, 0], bins=np.concatenate([[-1e9], b0[1:-1], [1e9]]))[0]
+    assert qh.max() < qz.max()                          # less crowded than with target-only cuts
+    assert sharded.slab_bounds(target, 1)[1].tolist() == [-np.inf, np.inf]
