@@ -182,7 +182,9 @@ class Replay:
         self.s2m.registerInputSource(scan)
         self.s2m.source_kdtree_ = self.s2s.source_kdtree_
         self.s2m.source_covs_.clear()
-        self.s2s.align()
+        ta = time.perf_counter()
+        self.s2s.align()                      # includes the lazily computed source covariances, as in the reference
+        self.align_ms = [(time.perf_counter() - ta) * 1e3, 0.0]
         it_s2s = self.s2s.nr_iterations_
         T_s2s = self.T_prev @ self.s2s.getFinalTransformation()
         self.s2m.source_covs_ = self.s2s.source_covs_
@@ -197,7 +199,9 @@ class Replay:
             npts = self._set_submap(sel)
             self.prev_set = sel
             self.events.append(("submap_rebuild_%d" % npts, (time.perf_counter() - t_) * 1e3)); t_ = time.perf_counter()
+        ta = time.perf_counter()
         self.s2m.align(T_s2s)
+        self.align_ms[1] = (time.perf_counter() - ta) * 1e3
         self.T = self.s2m.getFinalTransformation()
         self.T_result = self.T
         if force_T is not None:
@@ -290,6 +294,7 @@ def run_c3(args):
     else:
         rp = Replay(make_gpu, lambda p, l: vox.voxel_filter(p, l), None)
     ms, iters, errs, traj = [], [], [], []
+    phase = {}
     for i in idx:
         T_true, raw = scans[i]
         t1 = time.perf_counter()
@@ -297,11 +302,15 @@ def run_c3(args):
             scan = vox.preprocess(raw, 1.0, 0.25, out=scan_buf[i & 1])
         else:
             scan = vox.voxel_filter(raw, 0.25)    # preprocessPoints: vf_scan (crop box applied by the generator)
+        t_pre = (time.perf_counter() - t1) * 1e3
         if i == 0:
             rp.first(scan, T_true)
             continue
         its = rp.step(scan)
         ms.append((time.perf_counter() - t1) * 1e3)
+        for name, v in [("preprocess", t_pre), ("align_s2s_call", rp.align_ms[0]), ("align_s2m_call", rp.align_ms[1])] + \
+                [(n.split("_")[0] if n.startswith("submap") else n, v) for n, v in rp.events]:
+            phase.setdefault(name, []).append(v)
         if ms[-1] > 5.0:
             print(f"slow scan {i}: {ms[-1]:.1f} ms voxel+{[(n, round(v, 2)) for n, v in rp.events]} "
                   f"s2s kernels {({k: round(v, 3) for k, v in rp.s2s.timings().items()})} grid {rp.s2s.grid_info(1)}", file=sys.stderr)
@@ -318,6 +327,9 @@ def run_c3(args):
                    "max_rotation_error_rad": float(max(e[1] for e in errs)), "mean_iterations_s2s": float(np.mean([i[0] for i in iters])),
                    "mean_iterations_s2m": float(np.mean([i[1] for i in iters]))},
            "scan_generation_s": gen_s}
+    # host wall time per phase, summed over the run and divided by the number of scans (rebuilds / keyframes are rare)
+    out["gpu"]["phase_ms_per_scan"] = {k: float(np.sum(v) / len(ms)) for k, v in phase.items()}
+    out["gpu"]["phase_counts"] = {k: len(v) for k, v in phase.items()}
     if args.device_store:
         # the additive path must reproduce the OdomNode-style host path bit for bit
         rh = Replay(make_gpu, lambda p, l: vox.voxel_filter(p, l), None)
@@ -336,7 +348,7 @@ def run_c3(args):
     if n_cpu > 1:
         threads = os.cpu_count()
         rc = Replay(lambda cfg: OracleGicp(O, cfg, threads), lambda p, l: O.voxel_filter(p, l), None)
-        cms, same_iters, dpose, mism = [], 0, [], []
+        cms, same_iters, dpose, mism, cal = [], 0, [], [], []
         rg = Replay(make_gpu, lambda p, l: vox.voxel_filter(p, l), None)
         for i in range(n_cpu):
             T_true, raw = scans[i]
@@ -347,6 +359,7 @@ def run_c3(args):
                 continue
             ic = rc.step(scan)
             cms.append((time.perf_counter() - t1) * 1e3)
+            cal.append(list(rc.align_ms))
             # teacher forcing: the GPU replay continues from the CPU replay's pose, so both see the same scan, the same
             # guess and keyframes placed by the same poses at every step (chained replays drift apart by rounding and
             # are then no longer "identical inputs")
@@ -356,6 +369,7 @@ def run_c3(args):
                 mism.append({"scan": i, "cpu": [int(v) for v in ic], "gpu": [int(v) for v in ig], "dt_m": pose_err(rc.T, rg.T_result)[0]})
             dpose.append(pose_err(rc.T, rg.T_result))
         out["cpu"] = {"scans": n_cpu, "threads": threads, "ms_per_scan_mean": float(np.mean(cms)),
+                      "align_s2s_call_ms": float(np.mean([c[0] for c in cal])), "align_s2m_call_ms": float(np.mean([c[1] for c in cal])),
                       "identical_iteration_counts": f"{same_iters}/{n_cpu - 1}", "iteration_mismatches": mism[:20],
                       "comparison": "per scan on identical inputs (GPU replay teacher-forced onto the CPU trajectory)", "max_gpu_vs_cpu_dt_m": float(max(d[0] for d in dpose)),
                       "max_gpu_vs_cpu_dr_rad": float(max(d[1] for d in dpose))}

@@ -691,6 +691,45 @@ static int sm_count_of(int device) {
   if (device >= 0 && device < 64) cached[device] = sms;
   return sms;
 }
+// The first launch of a kernel variant is expensive: CUDA loads kernels lazily and, worse, a variant with a larger
+// stack frame than anything launched before makes the driver re-size the context's local-memory pool (measured:
+// 165-414 ms in the middle of an odometry stream, when the submap first became large enough for the
+// two-lanes-per-point variant).  Launch every variant once on an empty problem at ngicp_create time instead.
+void align_prime_kernels(int device) {
+  unsigned char* buf = nullptr;
+  if (cudaMalloc(&buf, 8192) != cudaSuccess) { cudaGetLastError(); return; }
+  cudaMemset(buf, 0, 8192);
+  AlignArgs a;
+  memset(&a, 0, sizeof a);
+  a.tgt.desc = reinterpret_cast<GridDesc*>(buf);          // zeroed descriptor: never searched, ns = 0
+  a.partials = reinterpret_cast<double*>(buf + 4096);
+  a.max_blocks = 4;
+  a.slab_axis = -1;
+  LmParams prm;
+  memset(&prm, 0, sizeof prm);                            // max_iterations = 0: the LM loop is not entered
+  Guess16 g;
+  for (int i = 0; i < 16; i++) g.g[i] = (i % 5 == 0) ? 1.0f : 0.0f;
+  ngicp_result* res = reinterpret_cast<ngicp_result*>(buf + 1024);
+  unsigned* bar = reinterpret_cast<unsigned*>(buf + 2048);
+  double* totals = reinterpret_cast<double*>(buf + 3072);
+  PeerComm pc;
+  memset(&pc, 0, sizeof pc);
+  pc.world = 1;
+  void* args[] = {(void*)&a, (void*)&prm, (void*)&g, (void*)&res, (void*)&bar, (void*)&totals, (void*)&pc};
+  for (int lpp = 1; lpp <= 2; ++lpp)
+    for (int minb = (lpp == 2 ? 2 : 1); minb <= 3; ++minb) {
+      fused_blocks_per_sm(device, minb, lpp);
+      cudaLaunchCooperativeKernel(fused_variant(minb, lpp), dim3(1), dim3(AL_THREADS), args, 0, 0);
+    }
+  cudaDeviceSynchronize();
+  cudaFree(buf);
+  cudaFuncAttributes fa;
+  cudaFuncGetAttributes(&fa, linearize_kernel);
+  cudaFuncGetAttributes(&fa, compute_error_kernel);
+  cudaFuncGetAttributes(&fa, reduce_partials_kernel);
+  cudaGetLastError();
+}
+
 int align_fused_max_blocks(int device) { return fused_blocks_per_sm(device, 1) * sm_count_of(device); }
 
 cudaError_t launch_align_fused(const AlignBuffers& ab, const ngicp_params& p, const float* guess16, ngicp_result* res_dev,

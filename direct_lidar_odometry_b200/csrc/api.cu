@@ -404,7 +404,7 @@ int ngicp_create(int device, ngicp_t** out) {
     return NGICP_E_CUDA;
   }
   // Working-set priming, once per device and process: grow the stream-ordered pool to NGICP_POOL_PRIME_MB (default 512)
-  // and park NGICP_TABLE_PRIME (default 3) cell tables in the free list, so that the first scans of a stream do not pay
+  // and park NGICP_TABLE_PRIME (default 5) cell tables in the free list, so that the first scans of a stream do not pay
   // for driver-level allocations (a fresh 128 MiB cudaMalloc costs 0.6-25 ms, pool growth ~10 ms per step; measured
   // with benchmarks/configs.py c3).  Both are one-time costs of ngicp_create.
   {
@@ -419,7 +419,7 @@ int ngicp_create(int device, ngicp_t** out) {
         cudaGetLastError();
       }
       const char* e2 = getenv("NGICP_TABLE_PRIME");
-      const int nt = e2 ? atoi(e2) : 3;
+      const int nt = e2 ? atoi(e2) : 5;
       const size_t tb = sizeof(int) * ((size_t)h->prm.grid_table_cells + 8);
       std::vector<TableBuf*> tmp;
       for (int i = 0; i < nt && i < 8; i++) {
@@ -428,6 +428,8 @@ int ngicp_create(int device, ngicp_t** out) {
         tmp.push_back(t);
       }
       for (TableBuf* t : tmp) delete t;   // release() parks them in the free list
+      align_prime_kernels(device);
+      knn_prime_kernels();
       cudaStreamSynchronize(h->stream->s);
     }
   }
@@ -623,7 +625,8 @@ int ngicp_voxel_filter(ngicp_t* h, const void* in, size_t n, size_t stride, floa
   ph_begin(h, PH_VOXEL);
   size_t mm = 0;
   int overflow = 0;
-  NG_CUDA(h, voxel_filter_device(in, n, stride, leaf, h->sc, h->stream, &mm, &overflow));
+  bool copied = false;
+  NG_CUDA(h, voxel_filter_device(in, n, stride, leaf, h->sc, h->stream, &mm, &overflow, nullptr, false, nullptr, out, cap, &copied));
   int status = NGICP_OK;
   if (overflow) {
     // PCL: "Leaf size is too small for the input dataset. Integer indices would overflow." and output = input
@@ -633,9 +636,9 @@ int ngicp_voxel_filter(ngicp_t* h, const void* in, size_t n, size_t stride, floa
     status = NGICP_W_VOXEL_OVERFLOW;
   }
   if (mm > cap) return fail(h, NGICP_E_INVALID, "voxel filter: output capacity too small");
-  if (mm && out) NG_CUDA(h, cudaMemcpyAsync(out, h->sc.vox_out.p, 32 * mm, cudaMemcpyDefault, h->stream->s));
+  if (mm && out && !copied) NG_CUDA(h, cudaMemcpyAsync(out, h->sc.vox_out.p, 32 * mm, cudaMemcpyDefault, h->stream->s));
   ph_end(h, PH_VOXEL);
-  NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
+  if (!copied) NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
   *m = mm;
   return status;
 }
@@ -649,11 +652,12 @@ int ngicp_transform_voxel_filter(ngicp_t* h, const void* in, size_t n, size_t st
   ph_begin(h, PH_VOXEL);
   size_t mm = 0;
   int overflow = 0;
-  NG_CUDA(h, voxel_filter_device(in, n, stride, leaf, h->sc, h->stream, &mm, &overflow, nullptr, true, T16));
+  bool copied = false;
+  NG_CUDA(h, voxel_filter_device(in, n, stride, leaf, h->sc, h->stream, &mm, &overflow, nullptr, true, T16, out, cap, &copied));
   if (mm > cap) return fail(h, NGICP_E_INVALID, "transform+voxel: output capacity too small");
-  if (mm && out) NG_CUDA(h, cudaMemcpyAsync(out, h->sc.vox_out.p, 32 * mm, cudaMemcpyDefault, h->stream->s));
+  if (mm && out && !copied) NG_CUDA(h, cudaMemcpyAsync(out, h->sc.vox_out.p, 32 * mm, cudaMemcpyDefault, h->stream->s));
   ph_end(h, PH_VOXEL);
-  NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
+  if (!copied) NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
   *m = mm;
   return overflow ? NGICP_W_VOXEL_OVERFLOW : NGICP_OK;
 }
@@ -669,11 +673,12 @@ int ngicp_preprocess(ngicp_t* h, const void* in, size_t n, size_t stride, const 
   ph_begin(h, PH_VOXEL);
   size_t mm = 0;
   int overflow = 0;
-  NG_CUDA(h, voxel_filter_device(in, n, stride, leaf, h->sc, h->stream, &mm, &overflow, crop_min ? crop6 : nullptr, true));
+  bool copied = false;
+  NG_CUDA(h, voxel_filter_device(in, n, stride, leaf, h->sc, h->stream, &mm, &overflow, crop_min ? crop6 : nullptr, true, nullptr, out, cap, &copied));
   if (mm > cap) return fail(h, NGICP_E_INVALID, "preprocess: output capacity too small");
-  if (mm && out) NG_CUDA(h, cudaMemcpyAsync(out, h->sc.vox_out.p, 32 * mm, cudaMemcpyDefault, h->stream->s));
+  if (mm && out && !copied) NG_CUDA(h, cudaMemcpyAsync(out, h->sc.vox_out.p, 32 * mm, cudaMemcpyDefault, h->stream->s));
   ph_end(h, PH_VOXEL);
-  NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
+  if (!copied) NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
   *m = mm;
   return overflow ? NGICP_W_VOXEL_OVERFLOW : NGICP_OK;
 }
@@ -707,11 +712,12 @@ int ngicp_preprocess_pointcloud2(ngicp_t* h, const void* data, const ngicp_pc2_l
   ph_begin(h, PH_VOXEL);
   size_t mm = 0;
   int overflow = 0;
-  NG_CUDA(h, voxel_filter_records(data, (size_t)n64, lay, leaf, h->sc, h->stream, &mm, &overflow, crop_min ? crop6 : nullptr, true));
+  bool copied = false;
+  NG_CUDA(h, voxel_filter_records(data, (size_t)n64, lay, leaf, h->sc, h->stream, &mm, &overflow, crop_min ? crop6 : nullptr, true, nullptr, out, cap, &copied));
   if (mm > cap) return fail(h, NGICP_E_INVALID, "preprocess: output capacity too small");
-  if (mm && out) NG_CUDA(h, cudaMemcpyAsync(out, h->sc.vox_out.p, 32 * mm, cudaMemcpyDefault, h->stream->s));
+  if (mm && out && !copied) NG_CUDA(h, cudaMemcpyAsync(out, h->sc.vox_out.p, 32 * mm, cudaMemcpyDefault, h->stream->s));
   ph_end(h, PH_VOXEL);
-  NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
+  if (!copied) NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
   *m = mm;
   return overflow ? NGICP_W_VOXEL_OVERFLOW : NGICP_OK;
 }

@@ -82,11 +82,19 @@ typedef std::shared_ptr<DevCovs> CovsPtr;
 
 // grow-only scratch owned by a handle
 struct Scratch {
+  Scratch() {}
+  Scratch(const Scratch&) = delete;
+  Scratch& operator=(const Scratch&) = delete;
+  ~Scratch() { if (vox_result) cudaFreeHost(vox_result); }
   DevBuf staging;    // raw bytes of caller records
   DevBuf keys_a, keys_b, vals_a, vals_b;
   DevBuf hist, tile_sums;
   DevBuf flags;      // voxel head flags / scanned slots
   DevBuf vox_desc;   // GridDesc for the voxel filter
+  int vox_bits_hint = 0;        // key bits the last voxel filter needed (0 = unknown): lets the next call queue its radix
+                                // passes without a mid-pipeline read-back of the grid dimensions
+  int* vox_result = nullptr;    // mapped pinned {m, overflow, key bits needed}: written by the pipeline's last kernel
+  int* vox_result_dev = nullptr;
   DevBuf vox_out;    // PointXYZI records
   DevBuf vox_slot;   // int per input point
   DevBuf knn_idx, knn_d2, queries;
@@ -156,6 +164,8 @@ cudaError_t launch_align_fused(const AlignBuffers& ab, const ngicp_params& prm, 
                                unsigned* barrier, int device, cudaStream_t st, unsigned long long* trace = nullptr,
                                const PeerComm* comm = nullptr);
 int align_fused_max_blocks(int device);
+void align_prime_kernels(int device);
+void knn_prime_kernels();
 
 // ---- voxel.cu -------------------------------------------------------------------------------------
 // returns cudaSuccess; *m_out and *overflow are valid after the call (it synchronises once to learn m)
@@ -168,11 +178,15 @@ struct RecordLayout {
   int off[4];
   int aligned;               // every field address is 4-byte aligned (offsets, steps; the staging copy itself is)
 };
+// out/out_cap/copied: when given, the routine may deliver the records to the caller's buffer itself (device buffers:
+// by a kernel that reads the count on the device, so that the whole call needs ONE synchronisation) and says so.
 cudaError_t voxel_filter_records(const void* in, size_t n, RecordLayout lay, float leaf, Scratch& sc, const StreamPtr& st,
                                  size_t* m_out, int* overflow, const float* crop6 = nullptr, bool compact_on_overflow = false,
-                                 const float* T16 = nullptr);
+                                 const float* T16 = nullptr, void* out = nullptr, size_t out_cap = 0, bool* copied = nullptr,
+                                 bool allow_speculation = true);
 cudaError_t voxel_filter_device(const void* in, size_t n, size_t stride_bytes, float leaf, Scratch& sc, const StreamPtr& st,
                                 size_t* m_out, int* overflow, const float* crop6 = nullptr, bool compact_on_overflow = false,
-                                const float* T16_colmajor = nullptr /* transformPointCloud first */);
+                                const float* T16_colmajor = nullptr /* transformPointCloud first */, void* out = nullptr,
+                                size_t out_cap = 0, bool* copied = nullptr);
 
 }  // namespace ngicp

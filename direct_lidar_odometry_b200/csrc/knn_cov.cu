@@ -613,6 +613,16 @@ __global__ void __launch_bounds__(128) cov_from_lists_kernel(GridView g, int n, 
   for (int i = 0; i < 6; i++) dst[i] = out[i];
 }
 
+void knn_prime_kernels() {
+  cudaFuncAttributes fa;
+  cudaFuncGetAttributes(&fa, knn_query_kernel);
+  cudaFuncGetAttributes(&fa, knn_lists_kernel);
+  cudaFuncGetAttributes(&fa, knn_plan_kernel);
+  cudaFuncGetAttributes(&fa, knn_lists_tile_kernel);
+  cudaFuncGetAttributes(&fa, cov_from_lists_kernel);
+  cudaGetLastError();
+}
+
 cudaError_t launch_knn_queries(const DevCloud& c, const float4* queries, int nq, int k, int* idx, float* d2, cudaStream_t st) {
   if (nq <= 0) return cudaSuccess;
   int blocks = (nq + KC_WARPS - 1) / KC_WARPS;

@@ -133,7 +133,9 @@ __global__ void __launch_bounds__(256) vox_keys_kernel(const float4* __restrict_
 }
 
 // flags[i] = 1 at the first element of every run of equal valid keys; flags[n] = 0 (sentinel for the total)
-__global__ void __launch_bounds__(256) vox_heads_kernel(const unsigned* __restrict__ keys, int n, int* __restrict__ flags, unsigned VOX_INVALID) {
+__global__ void __launch_bounds__(256) vox_heads_kernel(const unsigned* __restrict__ keys, int n, int* __restrict__ flags, GridDesc* __restrict__ d) {
+  const unsigned VOX_INVALID = d->voverflow ? 0u : (unsigned)(d->vdiv[0] * d->vdiv[1] * d->vdiv[2]);
+  if (blockIdx.x == 0 && threadIdx.x == 0) d->n = n + 1;   // length of the scan that follows
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i <= n; i += gridDim.x * blockDim.x) {
     int f = 0;
     if (i < n) {
@@ -147,7 +149,8 @@ __global__ void __launch_bounds__(256) vox_heads_kernel(const unsigned* __restri
 // one thread per run head: sequential float accumulation in sorted (= ascending input index) order
 __global__ void __launch_bounds__(128) vox_centroid_kernel(const unsigned* __restrict__ keys, const unsigned* __restrict__ perm, int n,
                                                            const int* __restrict__ slots, const float4* __restrict__ pts,
-                                                           float* __restrict__ out, int* __restrict__ slot_of_point, unsigned VOX_INVALID) {
+                                                           float* __restrict__ out, int* __restrict__ slot_of_point, const GridDesc* __restrict__ d) {
+  const unsigned VOX_INVALID = d->voverflow ? 0u : (unsigned)(d->vdiv[0] * d->vdiv[1] * d->vdiv[2]);
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
     const unsigned k = keys[i];
     if (k == VOX_INVALID) { slot_of_point[perm[i]] = -1; continue; }
@@ -197,8 +200,27 @@ static inline int vgrid(int n, int threads) {
   return g > 148 * 16 ? 148 * 16 : g;
 }
 
+// the pipeline's outcome for the host: {m, overflow, key bits this cloud needs}, stored into mapped pinned memory
+__global__ void vox_result_kernel(const GridDesc* __restrict__ d, const int* __restrict__ total, int* __restrict__ result) {
+  const unsigned long long cells = (unsigned long long)d->vdiv[0] * (unsigned long long)d->vdiv[1] * (unsigned long long)d->vdiv[2];
+  int bits = 1;
+  while (bits < 32 && (1ull << bits) <= cells) bits++;
+  result[0] = *total;
+  result[1] = d->voverflow;
+  result[2] = bits;
+}
+
+// records -> the caller's DEVICE buffer, count read on the device (no host round trip before the copy)
+__global__ void __launch_bounds__(256) vox_copy_out_kernel(const float4* __restrict__ src, const int* __restrict__ total, size_t cap,
+                                                           float4* __restrict__ dst) {
+  const size_t m = (size_t)*total;
+  if (m > cap) return;                                    // reported by the host after the synchronisation
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * m; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+
 cudaError_t voxel_filter_device(const void* in, size_t n, size_t stride_bytes, float leaf, Scratch& sc, const StreamPtr& st,
-                                size_t* m_out, int* overflow, const float* crop6, bool compact_on_overflow, const float* T16) {
+                                size_t* m_out, int* overflow, const float* crop6, bool compact_on_overflow, const float* T16,
+                                void* out, size_t out_cap, bool* copied) {
   RecordLayout lay;
   lay.width = (int)(n < 0x7fffffffu ? n : 0x7fffffffu);
   lay.point_step = stride_bytes;
@@ -206,14 +228,16 @@ cudaError_t voxel_filter_device(const void* in, size_t n, size_t stride_bytes, f
   lay.off[0] = 0; lay.off[1] = 4; lay.off[2] = 8;
   lay.off[3] = stride_bytes >= 20 ? 16 : (stride_bytes >= 16 ? 12 : -1);
   lay.aligned = 1;
-  return voxel_filter_records(in, n, lay, leaf, sc, st, m_out, overflow, crop6, compact_on_overflow, T16);
+  return voxel_filter_records(in, n, lay, leaf, sc, st, m_out, overflow, crop6, compact_on_overflow, T16, out, out_cap, copied);
 }
 
 cudaError_t voxel_filter_records(const void* in, size_t n, RecordLayout lay, float leaf, Scratch& sc, const StreamPtr& st,
-                                 size_t* m_out, int* overflow, const float* crop6, bool compact_on_overflow, const float* T16) {
+                                 size_t* m_out, int* overflow, const float* crop6, bool compact_on_overflow, const float* T16,
+                                 void* out, size_t out_cap, bool* copied, bool allow_speculation) {
   cudaError_t e;
   *m_out = 0;
   *overflow = 0;
+  if (copied) *copied = false;
   if (n == 0) return cudaSuccess;
   const int ni = (int)n;
   const bool use_grid = leaf > 0.f;
@@ -267,6 +291,50 @@ cudaError_t voxel_filter_records(const void* in, size_t n, RecordLayout lay, flo
   if (!use_grid) return compact();
   vox_setup_kernel<<<1, 1, 0, st->s>>>(d, inv);
   vox_keys_kernel<<<vgrid(ni, 256), 256, 0, st->s>>>(pts, ni, d, inv, sc.keys_a.as<unsigned>(), sc.vals_a.as<unsigned>());
+  // ---- speculative path: queue everything behind the key pass with the number of radix passes the PREVIOUS cloud
+  //      needed (consecutive scans have nearly the same extent), let the last kernel report {m, overflow, bits needed}
+  //      through mapped memory and synchronise ONCE.  More passes than needed are harmless; if this cloud needed more,
+  //      or overflowed PCL's index range, the call is redone on the exact path below (rare). ----
+  if (allow_speculation && sc.vox_bits_hint > 0) {
+    if (!sc.vox_result) {
+      if (cudaHostAlloc(&sc.vox_result, 8 * sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+          cudaHostGetDevicePointer(&sc.vox_result_dev, sc.vox_result, 0) != cudaSuccess) { cudaGetLastError(); sc.vox_result = nullptr; }
+    }
+    if (sc.vox_result) {
+      const int bits = sc.vox_bits_hint;
+      const int where = radix_sort_pairs(sc.keys_a.as<unsigned>(), sc.vals_a.as<unsigned>(), sc.keys_b.as<unsigned>(), sc.vals_b.as<unsigned>(),
+                                         ni, bits, sc.hist.as<int>(), st->s);
+      const unsigned* keys = where ? sc.keys_b.as<unsigned>() : sc.keys_a.as<unsigned>();
+      const unsigned* perm = where ? sc.vals_b.as<unsigned>() : sc.vals_a.as<unsigned>();
+      vox_heads_kernel<<<vgrid(ni + 1, 256), 256, 0, st->s>>>(keys, ni, flags, d);
+      exclusive_scan_inplace(flags, &d->n, 0, ni + 1, sc.tile_sums.as<int>(), st->s);
+      vox_centroid_kernel<<<vgrid(ni, 128), 128, 0, st->s>>>(keys, perm, ni, flags, pts, sc.vox_out.as<float>(), sc.vox_slot.as<int>(), d);
+      vox_result_kernel<<<1, 1, 0, st->s>>>(d, flags + ni, sc.vox_result_dev);
+      note_launches(4);
+      bool out_dev = false;
+      if (out && copied) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, out) == cudaSuccess) out_dev = attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+        else cudaGetLastError();
+        out_dev = out_dev && (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+        if (out_dev) {
+          vox_copy_out_kernel<<<vgrid(ni, 256), 256, 0, st->s>>>(sc.vox_out.as<float4>(), flags + ni, out_cap, reinterpret_cast<float4*>(out));
+          note_launches(1);
+        }
+      }
+      if ((e = cudaStreamSynchronize(st->s)) != cudaSuccess) return e;
+      const int r_m = sc.vox_result[0], r_over = sc.vox_result[1], r_bits = sc.vox_result[2];
+      if (!r_over && r_bits <= bits) {
+        sc.vox_bits_hint = r_bits;
+        *m_out = (size_t)r_m;
+        if (out_dev && (size_t)r_m <= out_cap) *copied = true;
+        return cudaGetLastError();
+      }
+      // mis-speculated: redo exactly (the staging copy and the packed points are still in place, but keep it simple)
+      sc.vox_bits_hint = 0;
+      return voxel_filter_records(in, n, lay, leaf, sc, st, m_out, overflow, crop6, compact_on_overflow, T16, out, out_cap, copied, false);
+    }
+  }
   // the voxel grid dimensions decide how many radix passes are needed: one small read-back (the call has to
   // synchronise for the output count anyway) instead of always sorting 32 bits
   int dims[4] = {1, 1, 1, 0};
@@ -286,12 +354,10 @@ cudaError_t voxel_filter_records(const void* in, size_t n, RecordLayout lay, flo
                                      ni, bits, sc.hist.as<int>(), st->s);
   const unsigned* keys = where ? sc.keys_b.as<unsigned>() : sc.keys_a.as<unsigned>();
   const unsigned* perm = where ? sc.vals_b.as<unsigned>() : sc.vals_a.as<unsigned>();
-  vox_heads_kernel<<<vgrid(ni + 1, 256), 256, 0, st->s>>>(keys, ni, flags, invalid_key);
-  // the scan length (n+1) is known on the host; park it in the descriptor so the generic scan can read it
-  int len = ni + 1;
-  if ((e = cudaMemcpyAsync(&d->n, &len, sizeof(int), cudaMemcpyHostToDevice, st->s)) != cudaSuccess) return e;
+  sc.vox_bits_hint = bits;
+  vox_heads_kernel<<<vgrid(ni + 1, 256), 256, 0, st->s>>>(keys, ni, flags, d);   // also parks the scan length n+1 in the descriptor
   exclusive_scan_inplace(flags, &d->n, 0, ni + 1, sc.tile_sums.as<int>(), st->s);
-  vox_centroid_kernel<<<vgrid(ni, 128), 128, 0, st->s>>>(keys, perm, ni, flags, pts, sc.vox_out.as<float>(), sc.vox_slot.as<int>(), invalid_key);
+  vox_centroid_kernel<<<vgrid(ni, 128), 128, 0, st->s>>>(keys, perm, ni, flags, pts, sc.vox_out.as<float>(), sc.vox_slot.as<int>(), d);
   note_launches(4);
   int host_m = 0;
   if ((e = cudaMemcpyAsync(&host_m, flags + ni, sizeof(int), cudaMemcpyDeviceToHost, st->s)) != cudaSuccess) return e;

@@ -21,10 +21,9 @@ def push_submap_indices(dists, k: int, frames, out: list) -> None:
     d = np.asarray(dists, dtype=np.float32)
     if d.size == 0:
         return
-    kth = np.sort(d)[min(k, d.size) - 1] if k > 0 else np.float32(-np.inf)
-    for i in range(d.size):
-        if d[i] <= kth:
-            out.append(int(frames[i]))
+    kk = min(k, d.size)
+    kth = np.partition(d, kk - 1)[kk - 1] if k > 0 else np.float32(-np.inf)
+    out.extend(np.asarray(frames, dtype=np.int64)[d <= kth].tolist())
 
 
 def convex_hull_vertices(pos: np.ndarray) -> list:
@@ -131,15 +130,15 @@ class SubmapSelector:
         diff = (cur[None, :] - pos).astype(np.float64)
         ds = np.sqrt((diff ** 2).sum(axis=1)).astype(np.float32)
         out: list = []
-        push_submap_indices(ds, self.knn, list(range(pos.shape[0])), out)
+        push_submap_indices(ds, self.knn, np.arange(pos.shape[0]), out)
         fresh = self._hulls_of is None or self._hulls_of.shape != pos.shape or not np.array_equal(self._hulls_of, pos)
         if pos.shape[0] >= 4 and fresh:
             self.keyframe_convex = convex_hull_vertices(pos)
-        push_submap_indices([ds[c] for c in self.keyframe_convex], self.kcv, self.keyframe_convex, out)
+        push_submap_indices(ds[self.keyframe_convex], self.kcv, self.keyframe_convex, out)
         if pos.shape[0] >= 5 and fresh:
             self.keyframe_concave = concave_hull_vertices(pos, self.alpha)
         self._hulls_of = pos.copy()
-        push_submap_indices([ds[c] for c in self.keyframe_concave], self.kcc, self.keyframe_concave, out)
+        push_submap_indices(ds[self.keyframe_concave], self.kcc, self.keyframe_concave, out)
         cur_idx = sorted(set(out))
         changed = cur_idx != self.prev
         if changed:
