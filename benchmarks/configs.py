@@ -295,8 +295,13 @@ def run_c3(args):
         rp = Replay(make_gpu, lambda p, l: vox.voxel_filter(p, l), None)
     ms, iters, errs, traj = [], [], [], []
     phase = {}
+    raw_in = {}
+    if args.pinned:      # raw scans in page-locked host memory (what a driver node that owns its message buffers can do)
+        for i in idx:
+            raw_in[i] = torch.from_numpy(scans[i][1]).pin_memory()
     for i in idx:
         T_true, raw = scans[i]
+        raw = raw_in.get(i, raw)
         t1 = time.perf_counter()
         if args.device_store:                     # preprocessPoints fused, output stays on the device
             scan = vox.preprocess(raw, 1.0, 0.25, out=scan_buf[i & 1])
@@ -321,7 +326,8 @@ def run_c3(args):
     sel_txt = (f"submap = {rp.knn} nearest + {rp.knn} convex-hull + {rp.knn} concave-hull keyframes as OdomNode::getSubmapKeyframes" if SELECTION == "hull"
                else f"knn-{rp.knn} submap")
     out = {"config": f"C3: odometry replay, {args.scans} synthetic OS1-64 scans (S2S + S2M + keyframes by OdomNode::updateKeyframes' rule, threshD 5 m / threshR 45 deg; {sel_txt})"
-                     + (", device-resident keyframes + fused preprocess (N1/N2)" if args.device_store else ", host keyframes as in OdomNode"),
+                     + (", device-resident keyframes + fused preprocess (N1/N2)" if args.device_store else ", host keyframes as in OdomNode")
+                     + (", raw scans in pinned host memory" if args.pinned else ", raw scans in pageable host memory"),
            "gpu": {"ms_per_scan_mean": float(ms.mean()), "ms_per_scan_p50": float(np.percentile(ms, 50)), "ms_per_scan_p99": float(np.percentile(ms, 99)),
                    "keyframes": len(rp.keyframes), "final_translation_error_m": errs[-1][0], "max_translation_error_m": float(max(e[0] for e in errs)),
                    "max_rotation_error_rad": float(max(e[1] for e in errs)), "mean_iterations_s2s": float(np.mean([i[0] for i in iters])),
@@ -573,12 +579,13 @@ if __name__ == "__main__":
     ap.add_argument("--device-store", type=int, default=0, help="c3: device-resident keyframes + fused preprocess (N1/N2)")
     ap.add_argument("--target-points", type=int, default=5_000_000)
     ap.add_argument("--cov-halo", type=float, default=2.0)
-    ap.add_argument("--balance", type=float, default=0.8, help="c5: weight of the scan's point distribution when placing the slab cuts (0 = equal target counts)")
+    ap.add_argument("--balance", type=float, default=0.0, help="c5: weight of the scan's point distribution when placing the slab cuts (0 = equal target counts)")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--check", type=int, default=1)
     ap.add_argument("--scans", type=int, default=300)
     ap.add_argument("--selection", choices=["hull", "knn"], default="hull", help="c3: submap keyframe selection")
     ap.add_argument("--cpu-scans", type=int, default=40)
+    ap.add_argument("--pinned", type=int, default=0, help="c3: keep the raw scans in pinned host memory")
     ap.add_argument("--pairs", type=int, default=512)
     ap.add_argument("--pool", type=int, default=16)
     ap.add_argument("--handles", type=int, default=8)
