@@ -117,6 +117,37 @@ def test_preprocess_fused_crop_nan_voxel(G, O, scan_pair):
     assert st == 1 and np.array_equal(bits(out), bits(ref))
 
 
+def test_voxel_filter_speculative_passes_and_fallback(G, O, scan_pair):
+    """The voxel pipeline queues its radix passes with the key width the PREVIOUS call needed and checks afterwards;
+    a cloud that needs more bits (or overflows PCL's index range) must fall back to the exact path, and device
+    output buffers (copied by a kernel that reads the count on the device) must match host ones."""
+    import torch
+    g = G()
+    s0 = scan_pair["s0"]
+    small = s0[:3000].copy()
+    small[:, :3] = small[:, :3] * 0.01                      # a few centimetres across: very few key bits
+    wide = s0.copy()
+    wide[::7, :3] *= 4.0                                     # four times the extent: one more radix pass
+    far = s0[:200].copy()
+    far[0, :3] = 1e6                                         # index overflow at leaf 0.01
+    seq = [(small, 0.5), (wide, 0.25), (small, 0.01), (wide, 0.25), (s0, 0.25), (s0, 0.25), (small, 0.5)]
+    for pts, leaf in seq:
+        ref = O.voxel_filter(pts, leaf)
+        out = g.voxel_filter(pts, leaf)
+        assert out.shape == ref.shape and np.array_equal(bits(out), bits(ref)), (pts.shape, leaf)
+        buf = torch.zeros((pts.shape[0], 8), dtype=torch.float32, device="cuda")
+        outd = g.voxel_filter(pts, leaf, out=buf)
+        assert np.array_equal(bits(outd.cpu().numpy()), bits(ref)), ("device out", pts.shape, leaf)
+    out, st = g.voxel_filter(far, 0.01, return_status=True)   # after a hinted call: overflow must still pass through
+    assert st == 1 and out.shape[0] == far.shape[0]
+    out = g.voxel_filter(s0, 0.25)                           # and the next ordinary call is exact again
+    assert np.array_equal(bits(out), bits(O.voxel_filter(s0, 0.25)))
+    # device output buffer too small: an error, not a silent truncation
+    tiny = torch.zeros((8, 8), dtype=torch.float32, device="cuda")
+    with pytest.raises(Exception):
+        g.voxel_filter(s0, 0.25, out=tiny)
+
+
 def test_preprocess_pointcloud2_decode_fused(G, O, scan_pair):
     """ngicp_preprocess_pointcloud2 = pcl::fromROSMsg + preprocessPoints on the message bytes (odom.cc:636-637,
     443-465): bit-exact against the oracle's decode followed by its three preprocessing steps, for Ouster-like (48 B,
