@@ -329,7 +329,9 @@ def main():
                 "roofline": {"kernel": "K2+K3 over the 500k-pt submap: knn_plan_kernel + knn_lists_tile_kernel (exact kNN, k=20) + cov_from_lists_kernel (plane covariances)", "bound": "hbm",
                              "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                              "algorithmic_bytes_per_launch": alg_bytes, "kernel_ms": kcov_ms, "peak_source": peak_src,
-                             "share_of_step": kcov_ms / (tot_dev_ms / args.steps)},
+                             "share_of_step": kcov_ms / (tot_dev_ms / args.steps),
+                             "limiter": "instruction issue, not bandwidth: the tile kNN kernel runs at 43 % issue slots busy with 12 warps/SM "
+                                        "(ncu: profiles/knn_lists_tile_kernel_r1_v8_ncu_details.txt); the fraction of the HBM roofline is small by construction"},
                 "e2e": {"value": e2e_value, "unit": "pairs/s", "ms_per_step": tot_e2e_ms / args.steps,
                         "h2d_bytes_per_step": int(submap_np.nbytes + scan_np.nbytes), "d2h_bytes_per_step": 496},
                 "gpu_launches": int(launches), "grids": grids, "clocks": clk.summary()}
