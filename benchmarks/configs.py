@@ -518,7 +518,10 @@ def run_c5(args):
     src_d = torch.from_numpy(source).to(dev)
 
     def step():
-        be.set_source(src_d)             # index + k=20 covariances of the dense scan (replicated on every rank)
+        if args.shard_source_covs and world > 1:
+            be.set_source_sharded(src_d, rank, world)   # index replicated, k=20 covariances split over the ranks + all-reduce
+        else:
+            be.set_source(src_d)         # index + k=20 covariances of the dense scan (replicated on every rank)
         return be.align_fused(guess)     # persistent LM kernel, exchange in peer memory
 
     for _ in range(3):
@@ -553,8 +556,10 @@ def run_c5(args):
                 "n_gpus": world, "steps": args.steps, "ms_per_scan": float(ms[0].item()), "align_ms": float(ms[1].item()),
                 "target_build_gpu_ms": float(ms[2].item()), "target_build_wall_s": t_build, "cov_halo_m": info["cov_halo"],
                 "halo_rounds": info["rounds"], "shard_points": [int(x.item()) for x in shard_pts], "slab_query_weight": args.balance,
+                "source_covs": "split over the ranks + NCCL all-reduce" if (args.shard_source_covs and world > 1) else "replicated on every rank",
                 "iterations": res["nr_iterations"], "n_linearize": res["n_linearize"], "n_compute_error": res["n_compute_error"],
-                "converged": res["converged"], "ranks_bit_identical": identical, "pose_error_m": dt, "pose_error_rad": dr}
+                "converged": res["converged"], "ranks_bit_identical": identical, "pose_error_m": dt, "pose_error_rad": dr,
+                "rank0_kernel_ms": {k: round(v, 4) for k, v in g.timings().items()}}
         if args.check and world > 1:
             # the same registration unsharded on this GPU: iteration counts and pose must agree
             u = NanoGICP(local)
@@ -579,6 +584,7 @@ if __name__ == "__main__":
     ap.add_argument("--device-store", type=int, default=0, help="c3: device-resident keyframes + fused preprocess (N1/N2)")
     ap.add_argument("--target-points", type=int, default=5_000_000)
     ap.add_argument("--cov-halo", type=float, default=2.0)
+    ap.add_argument("--shard-source-covs", type=int, default=0, help="c5: split the scan's covariances over the ranks (all-reduce) instead of replicating them")
     ap.add_argument("--balance", type=float, default=0.0, help="c5: weight of the scan's point distribution when placing the slab cuts (0 = equal target counts)")
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--check", type=int, default=1)

@@ -26,7 +26,7 @@ EXPORTS = [
     "ngicp_get_target_covs", "ngicp_align", "ngicp_transform_source", "ngicp_voxel_filter", "ngicp_voxel_assignment",
     "ngicp_knn", "ngicp_linearize", "ngicp_compute_error", "ngicp_linearize_partial", "ngicp_compute_error_partial",
     "ngicp_version", "ngicp_launch_count", "ngicp_grid_info", "ngicp_set_owner_slab", "ngicp_lm_trial",
-    "ngicp_lm_is_converged", "ngicp_comm_export", "ngicp_comm_connect", "ngicp_comm_connect_local", "ngicp_comm_close", "ngicp_preprocess", "ngicp_preprocess_pointcloud2", "ngicp_transform_voxel_filter", "ngicp_kfstore_create", "ngicp_kfstore_destroy", "ngicp_kfstore_size",
+    "ngicp_lm_is_converged", "ngicp_comm_export", "ngicp_comm_connect", "ngicp_comm_connect_local", "ngicp_comm_close", "ngicp_preprocess", "ngicp_preprocess_pointcloud2", "ngicp_calc_source_covs_part", "ngicp_covs_device", "ngicp_transform_voxel_filter", "ngicp_kfstore_create", "ngicp_kfstore_destroy", "ngicp_kfstore_size",
     "ngicp_kfstore_points", "ngicp_kfstore_push", "ngicp_kfstore_set_target",
 ]
 
@@ -100,6 +100,8 @@ def load() -> C.CDLL:
     proto("ngicp_transform_voxel_filter", i32, vp, vp, sz, sz, fp, f32, vp, sz, C.POINTER(sz))
     proto("ngicp_preprocess", i32, vp, vp, sz, sz, fp, fp, f32, vp, sz, C.POINTER(sz))
     proto("ngicp_preprocess_pointcloud2", i32, vp, vp, vp, fp, fp, f32, vp, sz, C.POINTER(sz))
+    proto("ngicp_calc_source_covs_part", i32, vp, i32, i32)
+    proto("ngicp_covs_device", i32, vp, i32, C.POINTER(vp), C.POINTER(sz))
     proto("ngicp_knn", i32, vp, i32, vp, sz, sz, i32, ip, fp)
     proto("ngicp_linearize", i32, vp, dp, dp, dp, dp, ip, fp, dp)
     proto("ngicp_compute_error", i32, vp, dp, dp)

@@ -146,8 +146,9 @@ int ensure_index(ngicp_t* h, CloudPtr& c) {
   return NGICP_OK;
 }
 
-int calc_covs(ngicp_t* h, int which) {
+int calc_covs(ngicp_t* h, int which, int part = 0, int nparts = 1) {
   if (!h) return NGICP_E_INVALID;
+  if (nparts < 1 || part < 0 || part >= nparts) return fail(h, NGICP_E_INVALID, "calculate covariances: bad part / nparts");
   DeviceGuard g(h->device);
   CloudPtr& c = which == NGICP_SOURCE ? h->src : h->tgt;
   if (!c) return fail(h, NGICP_E_STATE, "calculate covariances: cloud not set");
@@ -163,7 +164,8 @@ int calc_covs(ngicp_t* h, int which) {
   const int ph = which == NGICP_SOURCE ? PH_COV_SRC : PH_COV_TGT;
   ph_begin(h, ph);
   NG_CUDA(h, h->sc.nbr.reserve(sizeof(int) * covariance_scratch_ints(c->n, k), h->stream));
-  NG_CUDA(h, launch_covariances(*c, k, h->prm.regularization_method, h->sc.nbr.as<int>(), cv->c.as<double>(), c->table_cap, h->stream->s));
+  NG_CUDA(h, launch_covariances(*c, k, h->prm.regularization_method, h->sc.nbr.as<int>(), cv->c.as<double>(), c->table_cap, h->stream->s,
+                                part, nparts));
   ph_end(h, ph);
   (which == NGICP_SOURCE ? h->src_cov : h->tgt_cov) = cv;
   h->lin_valid = false;
@@ -179,6 +181,7 @@ int set_covs(ngicp_t* h, int which, const double* covs, size_t n) {
   if (n) {
     NG_CUDA(h, h->sc.cov_stage.reserve(sizeof(double) * 16 * n, h->stream));
     NG_CUDA(h, cudaMemcpyAsync(h->sc.cov_stage.p, covs, sizeof(double) * 16 * n, cudaMemcpyDefault, h->stream->s));
+    NG_CUDA(h, host_source_consumed(covs, h->sc, h->stream->s));
     mat4_to_sym6_kernel<<<blocks_for((int)n), 256, 0, h->stream->s>>>(h->sc.cov_stage.as<double>(), (int)n, cv->c.as<double>());
     note_launches(1);
     NG_CUDA(h, cudaGetLastError());
@@ -546,6 +549,14 @@ size_t ngicp_cloud_size(const ngicp_t* h, int which) {
 
 int ngicp_calc_source_covs(ngicp_t* h) { return calc_covs(h, NGICP_SOURCE); }
 int ngicp_calc_target_covs(ngicp_t* h) { return calc_covs(h, NGICP_TARGET); }
+int ngicp_calc_source_covs_part(ngicp_t* h, int part, int nparts) { return calc_covs(h, NGICP_SOURCE, part, nparts); }
+int ngicp_covs_device(ngicp_t* h, int which, double** covs6, size_t* n) {
+  if (!h || !covs6 || !n) return NGICP_E_INVALID;
+  const CovsPtr& cv = which == NGICP_SOURCE ? h->src_cov : h->tgt_cov;
+  *covs6 = cv ? cv->c.as<double>() : nullptr;
+  *n = cv ? (size_t)cv->n : 0;
+  return cv ? NGICP_OK : fail(h, NGICP_E_STATE, "no covariances");
+}
 int ngicp_set_source_covs(ngicp_t* h, const double* covs, size_t n) { return set_covs(h, NGICP_SOURCE, covs, n); }
 int ngicp_set_target_covs(ngicp_t* h, const double* covs, size_t n) { return set_covs(h, NGICP_TARGET, covs, n); }
 int ngicp_clear_covs(ngicp_t* h, int which) {

@@ -287,6 +287,16 @@ static inline int grid_for(int n, int threads = 256, int max_blocks = 148 * 8) {
   return g > max_blocks ? max_blocks : g;
 }
 
+cudaError_t host_source_consumed(const void* src, Scratch& sc, cudaStream_t st) {
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, src) != cudaSuccess) { cudaGetLastError(); return cudaSuccess; }   // plain pageable memory
+  if (attr.type != cudaMemoryTypeHost) return cudaSuccess;
+  cudaError_t e;
+  if (!sc.copy_done && (e = cudaEventCreateWithFlags(&sc.copy_done, cudaEventDisableTiming)) != cudaSuccess) return e;
+  if ((e = cudaEventRecord(sc.copy_done, st)) != cudaSuccess) return e;
+  return cudaEventSynchronize(sc.copy_done);
+}
+
 cudaError_t upload_cloud(DevCloud& c, const void* pts, size_t n, size_t stride_bytes, Scratch& sc, const StreamPtr& st) {
   cudaError_t e;
   c.n = (int)n;
@@ -307,6 +317,7 @@ cudaError_t upload_cloud(DevCloud& c, const void* pts, size_t n, size_t stride_b
     cudaGetLastError();  // clear a possible "invalid value" from probing a plain host pointer
     if ((e = sc.staging.reserve(raw_bytes + 16, st)) != cudaSuccess) return e;
     if ((e = cudaMemcpyAsync(sc.staging.p, pts, raw_bytes, cudaMemcpyDefault, st->s)) != cudaSuccess) return e;
+    if ((e = host_source_consumed(pts, sc, st->s)) != cudaSuccess) return e;
     raw = sc.staging.as<unsigned char>();
   }
   pack_bbox_kernel<<<grid_for((int)n), 256, 0, st->s>>>(raw, stride_bytes, (int)n, c.pts.as<float4>(), c.desc.as<GridDesc>());

@@ -85,7 +85,8 @@ struct Scratch {
   Scratch() {}
   Scratch(const Scratch&) = delete;
   Scratch& operator=(const Scratch&) = delete;
-  ~Scratch() { if (vox_result) cudaFreeHost(vox_result); }
+  ~Scratch() { if (vox_result) cudaFreeHost(vox_result); if (copy_done) cudaEventDestroy(copy_done); }
+  cudaEvent_t copy_done = nullptr;   // see host_source_consumed()
   DevBuf staging;    // raw bytes of caller records
   DevBuf keys_a, keys_b, vals_a, vals_b;
   DevBuf hist, tile_sums;
@@ -130,7 +131,8 @@ cudaError_t build_index(DevCloud& c, float cell_req, int table_cap, Scratch& sc,
 // ---- knn_cov.cu -----------------------------------------------------------------------------------
 cudaError_t launch_knn_queries(const DevCloud& c, const float4* queries, int nq, int k, int* idx, float* d2, cudaStream_t st);
 size_t covariance_scratch_ints(int n, int k);   // neighbour lists + the work lists of the kNN kernels
-cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_scratch /* covariance_scratch_ints() */, double* covs6, int table_cap, cudaStream_t st);
+cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_scratch /* covariance_scratch_ints() */, double* covs6, int table_cap, cudaStream_t st,
+                               int part = 0, int nparts = 1);
 constexpr int KNN_MAX_K = 32;
 
 // ---- align.cu -------------------------------------------------------------------------------------
@@ -171,6 +173,11 @@ void knn_prime_kernels();
 // returns cudaSuccess; *m_out and *overflow are valid after the call (it synchronises once to learn m)
 // crop6 = {min xyz, max xyz} of a negative pcl::CropBox or nullptr; leaf <= 0 skips the voxel grid (compaction only);
 // compact_on_overflow: on PCL's index-overflow pass-through emit the surviving points instead of leaving it to the caller
+// "The caller keeps ownership and may free the buffer on return": a staging copy from PAGEABLE host memory has left the
+// caller's buffer when cudaMemcpyAsync returns, one from PINNED host memory has not — wait for it (the copy only, not
+// the kernels queued behind it).  Device-resident inputs are read in stream order and documented as such.
+cudaError_t host_source_consumed(const void* src, Scratch& sc, cudaStream_t st);
+
 // where record i of a raw cloud lives and where its FLOAT32 fields are (byte offsets; off[3] = intensity, -1 = absent)
 struct RecordLayout {
   int width;                 // records per row (>= n: one row)

@@ -45,12 +45,14 @@ __global__ void __launch_bounds__(KC_THREADS) knn_query_kernel(GridView g, const
 
 // K2: neighbour lists of the cloud's own points, one warp per point, visited in cell order so that
 // concurrently running warps read the same cells.  nbr[q*k + j] = sorted slot of the j-th neighbour.
-__global__ void __launch_bounds__(KC_THREADS, KNN_MIN_BLOCKS) knn_lists_kernel(GridView g, int n, int k, int* __restrict__ nbr) {
+// Only the sorted slots [q_lo, q_hi) are answered (the whole cloud by default; a part of it when the covariances of one
+// cloud are split over several GPUs, ngicp_calc_source_covs_part).
+__global__ void __launch_bounds__(KC_THREADS, KNN_MIN_BLOCKS) knn_lists_kernel(GridView g, int n, int k, int* __restrict__ nbr, int q_lo, int q_hi) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const GridParams gp = load_grid(g.desc);
-  for (int q = warp; q < n; q += nwarps) {
+  for (int q = q_lo + warp; q < q_hi; q += nwarps) {
     const float4 qp = __ldg(g.sorted + q);
     WarpTopK rs;
     rs.init(k, lane);
@@ -304,7 +306,8 @@ __device__ __forceinline__ int collect_pass(TileSmem& S, int c, int cend, float 
 
 __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView g, int n, int k, int* __restrict__ nbr,
                                                                         const int4* __restrict__ items, int* __restrict__ ctrl,
-                                                                        int* __restrict__ fb_list, unsigned long long* __restrict__ stats) {
+                                                                        int* __restrict__ fb_list, unsigned long long* __restrict__ stats,
+                                                                        int q_lo, int q_hi) {
   extern __shared__ __align__(16) unsigned char tq_smem_raw[];
   TileSmem& S = reinterpret_cast<TileSmem*>(tq_smem_raw)[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
@@ -338,12 +341,21 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
       const int Q = __shfl_sync(FULL, qinc, 31);
       const int qexcl = qinc - qlen;
       ncur = min(TQ_ITEM, Q - first);
+      int nkept = 0;                                       // of those, the ones inside the slot range this launch answers
       for (int t0 = 0; t0 < ncur; t0 += 32) {
         const int t = first + t0 + lane;
         const int j = run_of(qinc, t);
         const int ja = __shfl_sync(FULL, qa, j), je = __shfl_sync(FULL, qexcl, j);
-        if (t0 + lane < ncur) { S.cur[t0 + lane] = ja + (t - je); S.cur_t[t0 + lane] = 0.f; S.cur_lo[t0 + lane] = 0.f; S.cur_hi[t0 + lane] = -1.f; }
+        const int slot = ja + (t - je);
+        const bool keep = t0 + lane < ncur && slot >= q_lo && slot < q_hi;
+        const unsigned km = __ballot_sync(FULL, keep);
+        if (keep) {
+          const int pos = nkept + __popc(km & lt);
+          S.cur[pos] = slot; S.cur_t[pos] = 0.f; S.cur_lo[pos] = 0.f; S.cur_hi[pos] = -1.f;
+        }
+        nkept += __popc(km);
       }
+      ncur = nkept;
       __syncwarp();
     }
     for (int s = 1; s <= TQ_SMAX && ncur > 0; s *= 2) {
@@ -584,9 +596,9 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
 
 // K3: one thread per point — mean, covariance / k, regularisation, all fp64 (nano_gicp_impl.hpp:315-353)
 __global__ void __launch_bounds__(128) cov_from_lists_kernel(GridView g, int n, int k, int method, const int* __restrict__ nbr,
-                                                             double* __restrict__ covs6) {
-  const int q = blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= n) return;
+                                                             double* __restrict__ covs6, int q_lo, int q_hi) {
+  const int q = q_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= q_hi || q >= n) return;
   const int* my = nbr + (size_t)q * k;
   const int orig = __float_as_int(__ldg(g.sorted + q).w);
   double mx = 0.0, my_ = 0.0, mz = 0.0;
@@ -636,8 +648,20 @@ cudaError_t launch_knn_queries(const DevCloud& c, const float4* queries, int nq,
 static inline size_t items_offset_ints(int n, int k) { return (((size_t)n * k + CT_N + (size_t)n) + 3) & ~(size_t)3; }
 size_t covariance_scratch_ints(int n, int k) { return items_offset_ints(n, k) + 4 * (size_t)n + 16; }
 
-cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_scratch, double* covs6, int table_cap, cudaStream_t st) {
+cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_scratch, double* covs6, int table_cap, cudaStream_t st,
+                               int part, int nparts) {
   if (c.n <= 0) return cudaSuccess;
+  // the sorted slots this launch answers: everything, or part `part` of `nparts` equal slices (the rest of covs6 is zeroed
+  // so that the slices of all parts add up to the full result)
+  int q_lo = 0, q_hi = c.n;
+  if (nparts > 1) {
+    q_lo = (int)((long long)c.n * part / nparts);
+    q_hi = (int)((long long)c.n * (part + 1) / nparts);
+    cudaError_t ez = cudaMemsetAsync(covs6, 0, sizeof(double) * 6 * (size_t)c.n, st);
+    if (ez != cudaSuccess) return ez;
+  }
+  const int nq = q_hi - q_lo;
+  if (nq <= 0) return cudaSuccess;
   // Two exact paths.  One warp per point (knn_lists_kernel): massively parallel, best for scans.  Cell-major tiles
   // (plan + tile launches): half the instructions per point but a longer serial path per warp, best for
   // submaps — measured on the C2 submap (500k points, k=20) 0.63 ms against 0.82 ms, on a 22k-point scan 0.19 ms against
@@ -648,7 +672,7 @@ cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_sc
   const bool warp_only = tile_env == 0 || (tile_env < 0 && c.n < tile_min);
   static const bool want_stats = getenv("NGICP_KNN_STATS") != nullptr;
   if (warp_only) {
-    knn_lists_kernel<<<(c.n + KC_WARPS - 1) / KC_WARPS, KC_THREADS, 0, st>>>(c.view(), c.n, k, nbr_scratch);
+    knn_lists_kernel<<<(nq + KC_WARPS - 1) / KC_WARPS, KC_THREADS, 0, st>>>(c.view(), c.n, k, nbr_scratch, q_lo, q_hi);
     note_launches(1);
   } else {
     static bool attr_set[64] = {};
@@ -690,7 +714,7 @@ cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_sc
       fprintf(stderr, "[ngicp knn] plan: %s items=%d (n=%d, grid %u blocks)\n", cudaGetErrorString(se), hc[CT_ITEMS], c.n, (unsigned)((plan_warps + 7) / 8));
     }
     // persistent grid: every resident warp pulls work items until the counter runs out
-    knn_lists_tile_kernel<<<sm_count[di] * blocks_per_sm[di], TQ_WARPS * 32, smem, st>>>(c.view(), c.n, k, nbr_scratch, items, ctrl, fb_list, stats);
+    knn_lists_tile_kernel<<<sm_count[di] * blocks_per_sm[di], TQ_WARPS * 32, smem, st>>>(c.view(), c.n, k, nbr_scratch, items, ctrl, fb_list, stats, q_lo, q_hi);
     note_launches(2);
     if (want_stats) {
       unsigned long long h[ST_N] = {};
@@ -702,7 +726,7 @@ cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_sc
               h[ST_PASSES] ? (double)h[ST_LANES] / (double)h[ST_PASSES] : 0.0);
     }
   }
-  cov_from_lists_kernel<<<(c.n + 127) / 128, 128, 0, st>>>(c.view(), c.n, k, method, nbr_scratch, covs6);
+  cov_from_lists_kernel<<<(nq + 127) / 128, 128, 0, st>>>(c.view(), c.n, k, method, nbr_scratch, covs6, q_lo, q_hi);
   note_launches(1);
   return cudaGetLastError();
 }

@@ -237,6 +237,24 @@ class NanoGICP:
         self._check(self._L.ngicp_calc_target_covs(self._h))
         return True
 
+    def calculateSourceCovariancesPart(self, part: int, nparts: int) -> bool:
+        """Covariances of slice `part` of `nparts` of the source cloud, zeros elsewhere (ngicp_calc_source_covs_part);
+        summing the buffers of all parts (covs_device_tensor + all-reduce) gives the complete set."""
+        self._check(self._L.ngicp_calc_source_covs_part(self._h, int(part), int(nparts)))
+        return True
+
+    def covs_device_tensor(self, which: int):
+        """The handle's covariance buffer as a (n, 6) float64 CUDA tensor WITHOUT copying (xx,xy,xz,yy,yz,zz per point);
+        valid until the covariances are replaced.  The kernels that fill it run on the handle's stream: call sync() first,
+        or use the tensor under torch.cuda.stream(ExternalStream(handle stream)) as sharded.set_source_sharded does."""
+        import torch
+        ptr, n = C.c_void_p(0), C.c_size_t(0)
+        self._check(self._L.ngicp_covs_device(self._h, which, C.byref(ptr), C.byref(n)))
+
+        class _View:
+            __cuda_array_interface__ = {"shape": (int(n.value), 6), "typestr": "<f8", "data": (int(ptr.value), False), "version": 2}
+        return torch.as_tensor(_View(), device=torch.device("cuda", self.device))
+
     def _set_covs(self, which: int, covs):
         if isinstance(covs, CovarianceView):
             if which == _lib.SOURCE and covs.which == _lib.SOURCE:

@@ -11,7 +11,9 @@
  *   - plain pointers and sizes only; no CUDA/torch types.  `pts` arguments point at n records of
  *     `stride_bytes` each whose first three floats are x,y,z (stride 32 for pcl::PointXYZI, 16 for
  *     float4, 12 for packed xyz).  They may be HOST or DEVICE pointers (unified addressing decides);
- *     the call snapshots them into HBM, the caller keeps ownership and may free them on return.
+ *     the call snapshots them into HBM, the caller keeps ownership.  HOST buffers (pageable or pinned) may be
+ *     freed or overwritten as soon as the call returns; DEVICE buffers are read in stream order on the handle's
+ *     stream, so the caller must not overwrite them before ngicp_sync() / a later synchronising call (align).
  *   - 4x4 matrices are column-major like Eigen (element (r,c) at [c*4+r]); covariances are
  *     Eigen::Matrix4d records (16 doubles, 128 B) of which only the symmetric upper-left 3x3 is used.
  *   - every function returns an int status: 0 ok, <0 error (ngicp_last_error() has the text),
@@ -133,6 +135,14 @@ size_t ngicp_cloud_size(const ngicp_t* h, int which);
 /* NanoGICP::calculateSourceCovariances / calculateTargetCovariances, nano_gicp_impl.hpp:151-159,298-357 */
 int ngicp_calc_source_covs(ngicp_t* h);
 int ngicp_calc_target_covs(ngicp_t* h);
+/* One cloud's covariances split over several GPUs (dense scans against a sharded submap): every
+ * rank holds the same source cloud (same index, the build is deterministic) and computes the covariances of slice
+ * `part` of `nparts` of it (equal slices of the cell-sorted order, i.e. spatially coherent); the entries of the other
+ * slices are zero, so an element-wise SUM over the ranks (one all-reduce of 48 B/point over NVLink, exact: x + 0) gives
+ * every rank the complete set.  ngicp_covs_device exposes the device buffer (n x 6 doubles: xx,xy,xz,yy,yz,zz in the
+ * cloud's own point order) for that collective; it stays owned by the handle. */
+int ngicp_calc_source_covs_part(ngicp_t* h, int part, int nparts);
+int ngicp_covs_device(ngicp_t* h, int which, double** covs6, size_t* n);
 /* NanoGICP::setSourceCovariances / setTargetCovariances, nano_gicp_impl.hpp:141-149 (n Matrix4d records, host or device) */
 int ngicp_set_source_covs(ngicp_t* h, const double* covs, size_t n);
 int ngicp_set_target_covs(ngicp_t* h, const double* covs, size_t n);
