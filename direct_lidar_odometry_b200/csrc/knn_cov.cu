@@ -47,9 +47,7 @@ __global__ void __launch_bounds__(KC_THREADS) knn_query_kernel(GridView g, const
 // concurrently running warps read the same cells.  nbr[q*k + j] = sorted slot of the j-th neighbour.
 // Only the sorted slots [q_lo, q_hi) are answered (the whole cloud by default; a part of it when the covariances of one
 // cloud are split over several GPUs, ngicp_calc_source_covs_part).
-__global__ void __launch_bounds__(KC_THREADS, KNN_MIN_BLOCKS) knn_lists_kernel(GridView g, int n, int k, int* __restrict__ nbr, int q_lo, int q_hi,
-                                                                               const int* __restrict__ mode_flag) {
-  if (mode_flag != nullptr && *mode_flag != 1) return;   // the tile path was chosen for this cloud
+__global__ void __launch_bounds__(KC_THREADS, KNN_MIN_BLOCKS) knn_lists_kernel(GridView g, int n, int k, int* __restrict__ nbr, int q_lo, int q_hi) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -129,15 +127,7 @@ __device__ __forceinline__ float box_face_distance(const GridParams& gp, int x0,
 #endif
 enum { ST_FALLBACK = 0, ST_TIES, ST_TILES, ST_PASSES, ST_LANES, ST_ITEMS, ST_N };
 // control words shared by the plan and tile launches
-enum { CT_ITEMS = 0, CT_NEXT, CT_REST, CT_REST_NEXT, CT_DONE, CT_OVERFLOW, CT_MODE, CT_N = 8 };
-// CT_OVERFLOW: points sitting in single cells whose radius-1 surroundings alone exceed a tile (they can only be answered
-// by the warp search).  CT_MODE: 0 = tiles, 1 = one warp per query for the whole cloud — decided ON THE DEVICE after the
-// plan (knn_decide_kernel): raw, unfiltered scans have cells far denser than a tile near the sensor; measured on the
-// 213k-point 128-beam scan of C5 21.7 % of the points ended in the warp search anyway and the tile path took 0.85 ms
-// against 0.54 ms for the warp path, while the voxelised 500k-point submap (2.2 %) is the other way round (0.63 / 0.82).
-#ifndef TQ_OVERFLOW_PERCENT
-#define TQ_OVERFLOW_PERCENT 5
-#endif
+enum { CT_ITEMS = 0, CT_NEXT, CT_REST, CT_REST_NEXT, CT_DONE, CT_N = 8 };
 
 // warp-aggregated append of the lanes in `mask` to the warp-search list
 __device__ __forceinline__ void fb_append(unsigned mask, int slot, int lane, int* __restrict__ fb_list, int* __restrict__ fb_count) {
@@ -245,8 +235,6 @@ __global__ void __launch_bounds__(256) knn_plan_kernel(GridView g, int4* __restr
         // 8 single cells of that child; whether their radius-1 tile fits is left to the tile kernel
         const int gx = px + (ch & 1), gy = py + ((ch >> 1) & 1), gz = pz + (ch >> 2);
         const int Qg = box_population(g, gp, gx, gy, gz, 1, 0, sub, 4);
-        const int Cg = box_population(g, gp, gx, gy, gz, 1, 1, sub, 4);
-        if (sub == 0 && Qg > 0 && Cg > TQ_CMAX) atomicAdd(ctrl + CT_OVERFLOW, Qg);
         emit_items(sub == 0 && Qg > 0, gx, gy, gz, 1, Qg, lane, items, ctrl);
       }
     }
@@ -316,10 +304,6 @@ __device__ __forceinline__ int collect_pass(TileSmem& S, int c, int cend, float 
   return (int)((p - a0) >> 8);
 }
 
-__global__ void knn_decide_kernel(int* __restrict__ ctrl, int n, int force_mode) {
-  ctrl[CT_MODE] = force_mode >= 0 ? force_mode : ((long long)ctrl[CT_OVERFLOW] * 100 > (long long)n * TQ_OVERFLOW_PERCENT ? 1 : 0);
-}
-
 __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView g, int n, int k, int* __restrict__ nbr,
                                                                         const int4* __restrict__ items, int* __restrict__ ctrl,
                                                                         int* __restrict__ fb_list, unsigned long long* __restrict__ stats,
@@ -329,7 +313,6 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
   const GridParams gp = load_grid(g.desc);
-  if (ctrl[CT_MODE] != 0) return;                      // this cloud goes through knn_lists_kernel (launched right behind)
   const int nitems = ctrl[CT_ITEMS];
   unsigned st_fb = 0, st_ties = 0, st_tiles = 0, st_passes = 0, st_lanes = 0, st_items = 0;
 
@@ -689,7 +672,7 @@ cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_sc
   const bool warp_only = tile_env == 0 || (tile_env < 0 && c.n < tile_min);
   static const bool want_stats = getenv("NGICP_KNN_STATS") != nullptr;
   if (warp_only) {
-    knn_lists_kernel<<<(nq + KC_WARPS - 1) / KC_WARPS, KC_THREADS, 0, st>>>(c.view(), c.n, k, nbr_scratch, q_lo, q_hi, nullptr);
+    knn_lists_kernel<<<(nq + KC_WARPS - 1) / KC_WARPS, KC_THREADS, 0, st>>>(c.view(), c.n, k, nbr_scratch, q_lo, q_hi);
     note_launches(1);
   } else {
     static bool attr_set[64] = {};
@@ -730,25 +713,14 @@ cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_sc
       cudaMemcpy(hc, ctrl, sizeof(hc), cudaMemcpyDeviceToHost);
       fprintf(stderr, "[ngicp knn] plan: %s items=%d (n=%d, grid %u blocks)\n", cudaGetErrorString(se), hc[CT_ITEMS], c.n, (unsigned)((plan_warps + 7) / 8));
     }
-    // tiles or one warp per query?  decided on the device from what the plan found; both kernels are queued, the one
-    // that was not chosen returns at once (NGICP_KNN_TILE=1 forces the tiles)
-    knn_decide_kernel<<<1, 1, 0, st>>>(ctrl, c.n, tile_env == 1 ? 0 : -1);
     // persistent grid: every resident warp pulls work items until the counter runs out
     knn_lists_tile_kernel<<<sm_count[di] * blocks_per_sm[di], TQ_WARPS * 32, smem, st>>>(c.view(), c.n, k, nbr_scratch, items, ctrl, fb_list, stats, q_lo, q_hi);
-    // (bounded grid + stride loop: when the tiles were chosen this launch is nothing but blocks that return at once)
-    {
-      const int want = (nq + KC_WARPS - 1) / KC_WARPS, cap = sm_count[di] * 2 * KNN_MIN_BLOCKS;
-      knn_lists_kernel<<<want < cap ? want : cap, KC_THREADS, 0, st>>>(c.view(), c.n, k, nbr_scratch, q_lo, q_hi, ctrl + CT_MODE);
-    }
-    note_launches(4);
+    note_launches(2);
     if (want_stats) {
       unsigned long long h[ST_N] = {};
       cudaMemcpyAsync(h, stats, sizeof(h), cudaMemcpyDeviceToHost, st);
       cudaStreamSynchronize(st);
       cudaFree(stats);
-      int hc2[CT_N] = {};
-      cudaMemcpy(hc2, ctrl, sizeof(hc2), cudaMemcpyDeviceToHost);
-      fprintf(stderr, "[ngicp knn] overflow points=%d (%.1f%%) mode=%s\n", hc2[CT_OVERFLOW], 100.0 * hc2[CT_OVERFLOW] / (double)c.n, hc2[CT_MODE] ? "warp" : "tiles");
       fprintf(stderr, "[ngicp knn] n=%d k=%d warp-search=%llu (%.1f%%, ties %llu) items=%llu tiles=%llu passes=%llu lanes/pass=%.1f\n",
               c.n, k, h[ST_FALLBACK], 100.0 * (double)h[ST_FALLBACK] / (double)c.n, h[ST_TIES], h[ST_ITEMS], h[ST_TILES], h[ST_PASSES],
               h[ST_PASSES] ? (double)h[ST_LANES] / (double)h[ST_PASSES] : 0.0);
