@@ -2,16 +2,19 @@
 //
 // K4  linearize        = NanoGICP::update_correspondences + NanoGICP::linearize fused
 //                        (reference include/nano_gicp/impl/nano_gicp_impl.hpp:173-211, :213-270):
-//                        one THREAD per source point:  q = float(T) * p  ->  bounded 1-NN on the target grid  ->
-//                        M = (C_B + R C_A R^T)^-1  ->  J^T M J / J^T M e / e^T M e, reduced with warp
-//                        shuffles and per-block partials into one packed {H(21), b(6), err} per call.
+//                        per source point (one thread, or a pair of lanes against large targets):
+//                        q = float(T) * p  ->  bounded 1-NN on the target grid (3x3x3 cells row by row; searches that
+//                        must go farther are finished warp-cooperatively from a shared-memory queue)  ->
+//                        M = (C_B + R C_A R^T)^-1  ->  J^T M J / J^T M e / e^T M e, reduced with a transposed warp
+//                        butterfly per pass and per-block partials into one packed {H(21), b(6), err} per call.
 // K5  compute_error    = NanoGICP::compute_error (:272-296) with correspondences and M frozen.
 // LM  align_fused      = LsqRegistration::computeTransformation / step_lm / step_gn / is_converged
 //                        (include/nano_gicp/impl/lsq_registration_impl.hpp:89-208) as ONE persistent
 //                        cooperative kernel: K4 and K5 phases separated by a grid barrier, the 6x6
-//                        pivoted LDL^T solve and the accept/reject logic done redundantly by every
-//                        block from the same fixed-order sum of partials (bit-deterministic, no host
-//                        round trip until the final transform is read back).
+//                        LDL^T solve and the accept/reject logic done redundantly by every block from the
+//                        same fixed-order sum of partials (every block sums them itself on one GPU; with a
+//                        sharded submap the last block sums and exchanges with the peers) — bit-deterministic,
+//                        no host round trip: the result is stored straight into mapped host memory.
 //
 // Per source point K4 touches p_A 16 B + C_A 48 B + p_B 16 B + C_B 48 B + corr 4 B = 132 B of
 // compulsory traffic (+48 B M +16 B p_B stored for K5, which then reads 16+48+16+4 = 84 B).
