@@ -133,6 +133,9 @@ size_t ngicp_cloud_size(const ngicp_t* h, int which);
 
 /* ---- covariances ------------------------------------------------------------------------------ */
 /* NanoGICP::calculateSourceCovariances / calculateTargetCovariances, nano_gicp_impl.hpp:151-159,298-357 */
+/* Note (round 1): for clouds of 131 072 points or more the covariance kernels assume that no OTHER handle computes the
+ * covariances of another such cloud on the same GPU at the same time; smaller clouds and the
+ * rest of the API are free of that restriction. */
 int ngicp_calc_source_covs(ngicp_t* h);
 int ngicp_calc_target_covs(ngicp_t* h);
 /* One cloud's covariances split over several GPUs (dense scans against a sharded submap): every
