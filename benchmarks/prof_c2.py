@@ -1,0 +1,23 @@
+"""Profiling helper: N plain C2 steps (bench.py's gpu_step on device-resident inputs, no CPU leg, no timing harness) —
+the short command ncu wraps.  NGICP_KNN_STATS=1 prints the tile path's item / fallback statistics per step."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch  # noqa: E402
+import bench  # noqa: E402
+from direct_lidar_odometry_b200 import NanoGICP  # noqa: E402
+
+steps = int(sys.argv[1]) if len(sys.argv) > 1 else 4
+g = NanoGICP(0)
+g.setCorrespondenceRandomness(bench.S2M["k"]); g.setMaxCorrespondenceDistance(bench.S2M["thr"])
+g.setMaximumIterations(bench.S2M["max_iter"]); g.setTransformationEpsilon(bench.S2M["trans_eps"])
+wl = bench.make_workload(lambda p, leaf: g.voxel_filter(p, leaf))
+submap = torch.from_numpy(wl["submap"]).cuda()
+scan = torch.from_numpy(wl["scan_0"]).cuda()
+for _ in range(steps):
+    res = bench.gpu_step(g, submap, scan, wl["guesses"][0])
+print(res.nr_iterations, {k: round(v, 4) for k, v in g.timings().items()}, g.grid_info(1))

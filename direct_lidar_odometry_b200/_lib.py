@@ -15,6 +15,7 @@ REG_NONE, REG_MIN_EIG, REG_NORMALIZED_MIN_EIG, REG_PLANE, REG_FROBENIUS = range(
 OPT_GAUSS_NEWTON, OPT_LEVENBERG_MARQUARDT = 0, 1
 SOURCE, TARGET = 0, 1
 ALIGN_FUSED, ALIGN_STEPPED = 0, 1
+KNN_AUTO, KNN_WARP, KNN_TILE = 0, 1, 2
 
 # every symbol include/nanogicp_c.h declares (checked by tests/test_abi.py)
 EXPORTS = [
@@ -27,7 +28,7 @@ EXPORTS = [
     "ngicp_knn", "ngicp_linearize", "ngicp_compute_error", "ngicp_linearize_partial", "ngicp_compute_error_partial",
     "ngicp_version", "ngicp_launch_count", "ngicp_grid_info", "ngicp_set_owner_slab", "ngicp_lm_trial",
     "ngicp_lm_is_converged", "ngicp_comm_export", "ngicp_comm_connect", "ngicp_comm_connect_local", "ngicp_comm_close", "ngicp_preprocess", "ngicp_preprocess_pointcloud2", "ngicp_calc_source_covs_part", "ngicp_covs_device", "ngicp_transform_voxel_filter", "ngicp_kfstore_create", "ngicp_kfstore_destroy", "ngicp_kfstore_size",
-    "ngicp_kfstore_points", "ngicp_kfstore_push", "ngicp_kfstore_set_target",
+    "ngicp_kfstore_points", "ngicp_kfstore_push", "ngicp_kfstore_set_target", "ngicp_cov_neighbors",
 ]
 
 
@@ -36,7 +37,7 @@ class Params(C.Structure):
                 ("max_iterations", C.c_int), ("transformation_epsilon", C.c_double), ("rotation_epsilon", C.c_double),
                 ("optimizer", C.c_int), ("lm_max_iterations", C.c_int), ("lm_init_lambda_factor", C.c_double),
                 ("regularization_method", C.c_int), ("grid_cell_size", C.c_float), ("grid_table_cells", C.c_int),
-                ("align_mode", C.c_int)]
+                ("align_mode", C.c_int), ("knn_path", C.c_int), ("knn_tile_min_points", C.c_int)]
 
 
 class Result(C.Structure):
@@ -103,6 +104,7 @@ def load() -> C.CDLL:
     proto("ngicp_calc_source_covs_part", i32, vp, i32, i32)
     proto("ngicp_covs_device", i32, vp, i32, C.POINTER(vp), C.POINTER(sz))
     proto("ngicp_knn", i32, vp, i32, vp, sz, sz, i32, ip, fp)
+    proto("ngicp_cov_neighbors", i32, vp, i32, ip, fp)
     proto("ngicp_linearize", i32, vp, dp, dp, dp, dp, ip, fp, dp)
     proto("ngicp_compute_error", i32, vp, dp, dp)
     proto("ngicp_linearize_partial", i32, vp, dp, vp)

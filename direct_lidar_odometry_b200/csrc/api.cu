@@ -5,6 +5,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <cmath>
+#include <mutex>
 #include <new>
 
 #include "internal.h"
@@ -27,6 +28,8 @@ struct ngicp_handle {
   bool ev_used[6] = {false, false, false, false, false, false};
   ngicp_timings tm;
   bool lin_valid = false;               // correspondences_/mahalanobis_ valid for compute_error
+  std::weak_ptr<DevCloud> nbr_cloud;    // the cloud whose neighbour lists sc.nbr holds (ngicp_cov_neighbors), and their k
+  int nbr_k = 0;
   int align_max_blocks = 2048;
   int slab_axis = -1;
   float slab_lo = 0.f, slab_hi = 0.f;
@@ -164,9 +167,11 @@ int calc_covs(ngicp_t* h, int which, int part = 0, int nparts = 1) {
   const int ph = which == NGICP_SOURCE ? PH_COV_SRC : PH_COV_TGT;
   ph_begin(h, ph);
   NG_CUDA(h, h->sc.nbr.reserve(sizeof(int) * covariance_scratch_ints(c->n, k), h->stream));
+  h->nbr_cloud.reset();
   NG_CUDA(h, launch_covariances(*c, k, h->prm.regularization_method, h->sc.nbr.as<int>(), cv->c.as<double>(), c->table_cap, h->stream->s,
-                                part, nparts));
+                                part, nparts, h->prm.knn_path, h->prm.knn_tile_min_points));
   ph_end(h, ph);
+  if (nparts == 1) { h->nbr_cloud = c; h->nbr_k = k; }
   (which == NGICP_SOURCE ? h->src_cov : h->tgt_cov) = cv;
   h->lin_valid = false;
   return NGICP_OK;
@@ -176,6 +181,7 @@ int set_covs(ngicp_t* h, int which, const double* covs, size_t n) {
   if (!h || (!covs && n)) return NGICP_E_INVALID;
   DeviceGuard g(h->device);
   CovsPtr cv(new (std::nothrow) DevCovs());
+  if (!cv) return fail(h, NGICP_E_INVALID, "out of host memory");
   cv->n = (int)n;
   NG_CUDA(h, cv->c.alloc(sizeof(double) * 6 * (n ? n : 1), h->stream));
   if (n) {
@@ -373,6 +379,8 @@ void ngicp_params_default(ngicp_params* p) {
   p->grid_cell_size = 0.f;
   p->grid_table_cells = 1 << 25;
   p->align_mode = NGICP_ALIGN_FUSED;
+  p->knn_path = NGICP_KNN_AUTO;
+  p->knn_tile_min_points = 131072;
 }
 
 int ngicp_create(int device, ngicp_t** out) {
@@ -411,7 +419,9 @@ int ngicp_create(int device, ngicp_t** out) {
   // for driver-level allocations (a fresh 128 MiB cudaMalloc costs 0.6-25 ms, pool growth ~10 ms per step; measured
   // with benchmarks/configs.py c3).  Both are one-time costs of ngicp_create.
   {
+    static std::mutex prime_mutex;
     static bool primed[64] = {};
+    std::lock_guard<std::mutex> prime_lock(prime_mutex);
     if (device < 64 && !primed[device]) {
       primed[device] = true;
       const char* e1 = getenv("NGICP_POOL_PRIME_MB");
@@ -498,6 +508,9 @@ int ngicp_set_params(ngicp_t* h, const ngicp_params* p) {
   if (p->k_correspondences < 1 || p->k_correspondences > KNN_MAX_K) return fail(h, NGICP_E_UNSUPPORTED, "k_correspondences must be in [1,32]");
   if (p->regularization_method < 0 || p->regularization_method > 4) return fail(h, NGICP_E_INVALID, "unknown regularization method");  // the reference abort()s here (nano_gicp_impl.hpp:336-338)
   if (p->grid_table_cells < 64) return fail(h, NGICP_E_INVALID, "grid_table_cells too small");
+  if (p->knn_path < NGICP_KNN_AUTO || p->knn_path > NGICP_KNN_TILE) return fail(h, NGICP_E_INVALID, "unknown knn_path");
+  if (p->align_mode != NGICP_ALIGN_FUSED && p->align_mode != NGICP_ALIGN_STEPPED) return fail(h, NGICP_E_INVALID, "unknown align_mode");
+  if (p->optimizer != NGICP_OPT_GAUSS_NEWTON && p->optimizer != NGICP_OPT_LEVENBERG_MARQUARDT) return fail(h, NGICP_E_INVALID, "unknown optimizer");
   h->prm = *p;
   return NGICP_OK;
 }
@@ -556,6 +569,20 @@ int ngicp_covs_device(ngicp_t* h, int which, double** covs6, size_t* n) {
   *covs6 = cv ? cv->c.as<double>() : nullptr;
   *n = cv ? (size_t)cv->n : 0;
   return cv ? NGICP_OK : fail(h, NGICP_E_STATE, "no covariances");
+}
+int ngicp_cov_neighbors(ngicp_t* h, int which, int* idx, float* d2) {
+  if (!h || !idx || !d2) return NGICP_E_INVALID;
+  DeviceGuard g(h->device);
+  CloudPtr& c = which == NGICP_SOURCE ? h->src : h->tgt;
+  if (!c || h->nbr_cloud.lock() != c || h->nbr_k < 1) return fail(h, NGICP_E_STATE, "cov_neighbors: the last covariance computation on this handle was not for this cloud");
+  const size_t cnt = (size_t)c->n * h->nbr_k;
+  NG_CUDA(h, h->sc.knn_idx.reserve(sizeof(int) * cnt, h->stream));
+  NG_CUDA(h, h->sc.knn_d2.reserve(sizeof(float) * cnt, h->stream));
+  NG_CUDA(h, launch_export_neighbors(*c, h->nbr_k, h->sc.nbr.as<int>(), h->sc.knn_idx.as<int>(), h->sc.knn_d2.as<float>(), h->stream->s));
+  NG_CUDA(h, cudaMemcpyAsync(idx, h->sc.knn_idx.p, sizeof(int) * cnt, cudaMemcpyDefault, h->stream->s));
+  NG_CUDA(h, cudaMemcpyAsync(d2, h->sc.knn_d2.p, sizeof(float) * cnt, cudaMemcpyDefault, h->stream->s));
+  NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
+  return NGICP_OK;
 }
 int ngicp_set_source_covs(ngicp_t* h, const double* covs, size_t n) { return set_covs(h, NGICP_SOURCE, covs, n); }
 int ngicp_set_target_covs(ngicp_t* h, const double* covs, size_t n) { return set_covs(h, NGICP_TARGET, covs, n); }

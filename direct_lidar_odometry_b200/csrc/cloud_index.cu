@@ -165,7 +165,12 @@ __device__ void grid_setup_device(GridDesc* d, float cell, int cap, int n) {
   for (int a = 0; a < 3; a++) { lo[a] = ord2f(d->bb_min[a]); hi[a] = ord2f(d->bb_max[a]); }
   if (d->nfinite == 0) { for (int a = 0; a < 3; a++) { lo[a] = 0.f; hi[a] = 0.f; } }
   int dim[3];
-  for (int it = 0; it < 64; it++) {
+  // Grow the cell edge until the dense table fits.  The extent can be anything a float holds (DLO only strips NaN/Inf:
+  // one stray 1e20 return is a legal input), so the loop runs until it fits — 1.25^400 spans the whole float range —
+  // and when even that fails (extent overflowing to infinity) the grid degenerates to ONE cell: slow but correct, and
+  // dim[] can never exceed the table the following kernels write into.
+  bool fits = false;
+  for (int it = 0; it < 400 && !fits; it++) {
     double prod = 1.0;
     const float inv = 1.0f / cell;
     for (int a = 0; a < 3; a++) {
@@ -174,8 +179,17 @@ __device__ void grid_setup_device(GridDesc* d, float cell, int cap, int n) {
       dim[a] = (int)floorf(ext) + 1;
       prod *= (double)dim[a];
     }
-    if (prod <= (double)cap) break;
-    cell *= 1.25f;
+    fits = prod <= (double)cap;
+    if (!fits) {
+      // jump most of the way at once (a volume ratio r needs a factor cbrt(r) on compact clouds, at most r on
+      // degenerate ones), then the +25 % steps finish; never past the float range
+      const float jump = (float)fmin(cbrt(prod / (double)cap), 1.0e6);
+      cell = fminf(cell * fmaxf(1.25f, jump), 1.0e37f);
+    }
+  }
+  if (!fits) {
+    cell = 3.0e38f;
+    for (int a = 0; a < 3; a++) dim[a] = 1;
   }
   for (int a = 0; a < 3; a++) { d->origin[a] = lo[a]; d->dim[a] = dim[a]; }
   d->cell = cell;

@@ -132,7 +132,9 @@ cudaError_t build_index(DevCloud& c, float cell_req, int table_cap, Scratch& sc,
 cudaError_t launch_knn_queries(const DevCloud& c, const float4* queries, int nq, int k, int* idx, float* d2, cudaStream_t st);
 size_t covariance_scratch_ints(int n, int k);   // neighbour lists + the work lists of the kNN kernels
 cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_scratch /* covariance_scratch_ints() */, double* covs6, int table_cap, cudaStream_t st,
-                               int part = 0, int nparts = 1);
+                               int part = 0, int nparts = 1, int knn_path = NGICP_KNN_AUTO, int tile_min_points = 131072);
+// test hook: the neighbour lists left in nbr_scratch by launch_covariances, in summation order, as original indices
+cudaError_t launch_export_neighbors(const DevCloud& c, int k, const int* nbr_scratch, int* idx_out, float* d2_out, cudaStream_t st);
 constexpr int KNN_MAX_K = 32;
 
 // ---- align.cu -------------------------------------------------------------------------------------

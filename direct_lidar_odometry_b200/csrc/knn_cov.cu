@@ -9,6 +9,7 @@
 // 48 B covariance write = 64 B/point.
 #include <cstdio>
 #include <cstdlib>
+#include <mutex>
 #include "internal.h"
 #include "grid_search.cuh"
 #include "gicp_math.cuh"
@@ -79,8 +80,10 @@ __global__ void __launch_bounds__(KC_THREADS, KNN_MIN_BLOCKS) knn_lists_kernel(G
 //                          no dependent shuffles.  An exact tie at the k-th distance has no such threshold: those
 //                          (rare) points take the warp search.
 // One distance evaluation therefore costs one instruction slot per 32 queries instead of one per query.  Points that
-// cannot be decided inside a radius-TQ_SMAX tile (isolated points, ties at the k-th distance) are appended to a list;
-// warps that run out of tiles drain it with the growing-cube warp search while the others are still at work.
+// cannot be decided inside a radius-TQ_SMAX tile (isolated points, ties at the k-th distance) are appended to a list
+// that knn_lists_rest_kernel — the next launch on the stream — answers with the growing-cube warp search.  (Round 1
+// drained that list inside this kernel and waited for every warp of the launch to finish producing; two such launches
+// sharing a GPU could then wait for blocks of their own that were not resident.  No kernel here waits on another block.)
 #ifndef TQ_WARPS
 #define TQ_WARPS 2
 #endif
@@ -556,34 +559,6 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
     }
     __syncwarp();
   }
-  // ---- drain: warps that ran out of tiles answer the listed points with the growing-cube warp search while other
-  //      warps are still producing; an entry is -1 until its producer has written it ----
-  __threadfence();
-  if (lane == 0) atomicAdd(ctrl + CT_DONE, 1);
-  {
-    const int total_warps = (int)gridDim.x * TQ_WARPS;
-    for (;;) {
-      int i = 0;
-      if (lane == 0) i = atomicAdd(ctrl + CT_REST_NEXT, 1);
-      i = __shfl_sync(FULL, i, 0);
-      int q = -1;
-      if (lane == 0 && i < n) {
-        for (;;) {
-          q = *(volatile int*)(fb_list + i);
-          if (q >= 0) break;
-          if (*(volatile int*)(ctrl + CT_DONE) == total_warps) { q = *(volatile int*)(fb_list + i); break; }
-          __nanosleep(200);
-        }
-      }
-      q = __shfl_sync(FULL, q, 0);
-      if (q < 0) break;
-      const float4 qp = __ldg(g.sorted + q);
-      WarpTopK rs;
-      rs.init(k, lane);
-      if (isfinite(qp.x) && isfinite(qp.y) && isfinite(qp.z)) grid_search_warp(g, gp, qp.x, qp.y, qp.z, FLT_MAX, rs, k >= 4);
-      if (lane < k) nbr[(size_t)q * k + lane] = rs.p;
-    }
-  }
   if (stats != nullptr && lane == 0) {
     atomicAdd(stats + ST_FALLBACK, (unsigned long long)st_fb);
     atomicAdd(stats + ST_TIES, (unsigned long long)st_ties);
@@ -594,24 +569,104 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
   }
 }
 
-// K3: one thread per point — mean, covariance / k, regularisation, all fp64 (nano_gicp_impl.hpp:315-353)
-__global__ void __launch_bounds__(128) cov_from_lists_kernel(GridView g, int n, int k, int method, const int* __restrict__ nbr,
-                                                             double* __restrict__ covs6, int q_lo, int q_hi) {
+// the points the tile kernel could not decide: one warp per listed point, growing-cube search (same result definition)
+__global__ void __launch_bounds__(KC_THREADS, KNN_MIN_BLOCKS) knn_lists_rest_kernel(GridView g, int k, int* __restrict__ nbr, const int* __restrict__ ctrl,
+                                                                                     const int* __restrict__ fb_list) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const GridParams gp = load_grid(g.desc);
+  const int total = ctrl[CT_REST];
+  for (int i = warp; i < total; i += nwarps) {
+    const int q = fb_list[i];
+    const float4 qp = __ldg(g.sorted + q);
+    WarpTopK rs;
+    rs.init(k, lane);
+    if (isfinite(qp.x) && isfinite(qp.y) && isfinite(qp.z)) grid_search_warp(g, gp, qp.x, qp.y, qp.z, FLT_MAX, rs, k >= 4);
+    if (lane < k) nbr[(size_t)q * k + lane] = rs.p;
+  }
+}
+
+// K3: one thread per point — mean, covariance / k, regularisation, all fp64 (nano_gicp_impl.hpp:315-353).
+// The sums run over the k neighbours in ascending (squared distance, original index) order: nearestKSearch returns them
+// ascending (nanoflann_impl.hpp:184-211) and the reference adds them up in that order (:315-321), so on neighbourhoods
+// without exact distance ties the fp64 mean and covariance reproduce the reference's bits whichever kNN kernel made the
+// list (the tile kernel delivers the SET in slot order; the warp search delivers it sorted, ties in visiting order).
+// KT > 0: k known at compile time (10 and 20, the values DLO uses) — keys in registers, k^2 unrolled rank computation.
+__device__ __forceinline__ bool nb_before(float da, int oa, int ia, float db, int ob, int ib) {
+  return da < db || (da == db && (oa < ob || (oa == ob && ia < ib)));
+}
+template <int KT>
+__global__ void __launch_bounds__(128) cov_from_lists_kernel(GridView g, int n, int k_rt, int method, const int* __restrict__ nbr,
+                                                             double* __restrict__ covs6, int q_lo, int q_hi,
+                                                             int* __restrict__ idx_out, float* __restrict__ d2_out) {
+  constexpr int KA = KT > 0 ? KT : KNN_MAX_K;
+  const int k = KT > 0 ? KT : k_rt;
   const int q = q_lo + blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= q_hi || q >= n) return;
   const int* my = nbr + (size_t)q * k;
-  const int orig = __float_as_int(__ldg(g.sorted + q).w);
+  const float4 qp = __ldg(g.sorted + q);
+  const int orig = __float_as_int(qp.w);
+  int ord[KA];          // neighbour slots in summation order (dynamically indexed: local memory, L1 resident)
+  if (KT > 0) {
+    int p[KA], o[KA];
+    float d[KA];
+    bool in_order = true;
+#pragma unroll
+    for (int j = 0; j < KA; ++j) {
+      p[j] = __ldg(my + j);
+      TQ_CHECK(p[j] < n, "nbr", p[j], q);
+      d[j] = INFINITY; o[j] = 0x7fffffff;
+      if (p[j] >= 0) { const float4 c = __ldg(g.sorted + p[j]); d[j] = sqdist_unfused(qp.x, qp.y, qp.z, c.x, c.y, c.z); o[j] = __float_as_int(c.w); }
+      if (j > 0) in_order = in_order && !nb_before(d[j], o[j], j, d[j - 1], o[j - 1], j - 1);
+    }
+    if (in_order) {
+#pragma unroll
+      for (int j = 0; j < KA; ++j) ord[j] = p[j];
+    } else {
+#pragma unroll
+      for (int j = 0; j < KA; ++j) {
+        int r = 0;
+#pragma unroll
+        for (int i = 0; i < KA; ++i) r += nb_before(d[i], o[i], i, d[j], o[j], j) ? 1 : 0;
+        ord[r] = p[j];
+      }
+    }
+  } else {
+    int o[KA];
+    float d[KA];
+    for (int j = 0; j < k; ++j) {
+      const int p = __ldg(my + j);
+      d[j] = INFINITY; o[j] = 0x7fffffff;
+      if (p >= 0) { const float4 c = __ldg(g.sorted + p); d[j] = sqdist_unfused(qp.x, qp.y, qp.z, c.x, c.y, c.z); o[j] = __float_as_int(c.w); }
+    }
+    for (int j = 0; j < k; ++j) {
+      int r = 0;
+      for (int i = 0; i < k; ++i) r += nb_before(d[i], o[i], i, d[j], o[j], j) ? 1 : 0;
+      ord[r] = __ldg(my + j);
+    }
+  }
+  if (idx_out != nullptr) {   // test hook (ngicp_cov_neighbors): the list as it is summed, original indices, caller's point order
+    for (int r = 0; r < k; ++r) {
+      const int p = ord[r];
+      int oi = -1;
+      float dd = -1.f;
+      if (p >= 0) { const float4 c = __ldg(g.sorted + p); oi = __float_as_int(c.w); dd = sqdist_unfused(qp.x, qp.y, qp.z, c.x, c.y, c.z); }
+      idx_out[(size_t)orig * k + r] = oi;
+      d2_out[(size_t)orig * k + r] = dd;
+    }
+    return;
+  }
   double mx = 0.0, my_ = 0.0, mz = 0.0;
-  for (int j = 0; j < k; ++j) {
-    const int p = __ldg(my + j);
-    TQ_CHECK(p < n, "nbr", p, q);
+  for (int r = 0; r < k; ++r) {
+    const int p = ord[r];
     if (p >= 0) { const float4 c = __ldg(g.sorted + p); mx += (double)c.x; my_ += (double)c.y; mz += (double)c.z; }
   }
   const double kd = (double)k;
   mx /= kd; my_ /= kd; mz /= kd;
   double c[6] = {0, 0, 0, 0, 0, 0};
-  for (int j = 0; j < k; ++j) {
-    const int p = __ldg(my + j);
+  for (int r = 0; r < k; ++r) {
+    const int p = ord[r];
     double x = -mx, y = -my_, z = -mz;   // a missing neighbour is a zero column minus the mean, like the reference's zero-initialised matrix would be
     if (p >= 0) { const float4 v = __ldg(g.sorted + p); x += (double)v.x; y += (double)v.y; z += (double)v.z; }
     c[0] += x * x; c[1] += x * y; c[2] += x * z; c[3] += y * y; c[4] += y * z; c[5] += z * z;
@@ -625,13 +680,32 @@ __global__ void __launch_bounds__(128) cov_from_lists_kernel(GridView g, int n, 
   for (int i = 0; i < 6; i++) dst[i] = out[i];
 }
 
+static void launch_cov_kernel(const DevCloud& c, int k, int method, const int* nbr, double* covs6, int q_lo, int q_hi, int* idx_out, float* d2_out,
+                              cudaStream_t st) {
+  const int nq = q_hi - q_lo;
+  const dim3 grid((nq + 127) / 128), block(128);
+  if (k == 10) cov_from_lists_kernel<10><<<grid, block, 0, st>>>(c.view(), c.n, k, method, nbr, covs6, q_lo, q_hi, idx_out, d2_out);
+  else if (k == 20) cov_from_lists_kernel<20><<<grid, block, 0, st>>>(c.view(), c.n, k, method, nbr, covs6, q_lo, q_hi, idx_out, d2_out);
+  else cov_from_lists_kernel<0><<<grid, block, 0, st>>>(c.view(), c.n, k, method, nbr, covs6, q_lo, q_hi, idx_out, d2_out);
+  note_launches(1);
+}
+
+cudaError_t launch_export_neighbors(const DevCloud& c, int k, const int* nbr_scratch, int* idx_out, float* d2_out, cudaStream_t st) {
+  if (c.n <= 0) return cudaSuccess;
+  launch_cov_kernel(c, k, 0, nbr_scratch, nullptr, 0, c.n, idx_out, d2_out, st);
+  return cudaGetLastError();
+}
+
 void knn_prime_kernels() {
   cudaFuncAttributes fa;
   cudaFuncGetAttributes(&fa, knn_query_kernel);
   cudaFuncGetAttributes(&fa, knn_lists_kernel);
   cudaFuncGetAttributes(&fa, knn_plan_kernel);
   cudaFuncGetAttributes(&fa, knn_lists_tile_kernel);
-  cudaFuncGetAttributes(&fa, cov_from_lists_kernel);
+  cudaFuncGetAttributes(&fa, knn_lists_rest_kernel);
+  cudaFuncGetAttributes(&fa, cov_from_lists_kernel<0>);
+  cudaFuncGetAttributes(&fa, cov_from_lists_kernel<10>);
+  cudaFuncGetAttributes(&fa, cov_from_lists_kernel<20>);
   cudaGetLastError();
 }
 
@@ -649,7 +723,7 @@ static inline size_t items_offset_ints(int n, int k) { return (((size_t)n * k + 
 size_t covariance_scratch_ints(int n, int k) { return items_offset_ints(n, k) + 4 * (size_t)n + 16; }
 
 cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_scratch, double* covs6, int table_cap, cudaStream_t st,
-                               int part, int nparts) {
+                               int part, int nparts, int knn_path, int tile_min_points) {
   if (c.n <= 0) return cudaSuccess;
   // the sorted slots this launch answers: everything, or part `part` of `nparts` equal slices (the rest of covs6 is zeroed
   // so that the slices of all parts add up to the full result)
@@ -662,19 +736,17 @@ cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_sc
   }
   const int nq = q_hi - q_lo;
   if (nq <= 0) return cudaSuccess;
-  // Two exact paths.  One warp per point (knn_lists_kernel): massively parallel, best for scans.  Cell-major tiles
-  // (plan + tile launches): half the instructions per point but a longer serial path per warp, best for
-  // submaps — measured on the C2 submap (500k points, k=20) 0.63 ms against 0.82 ms, on a 22k-point scan 0.19 ms against
-  // 0.10 ms.  NGICP_KNN_TILE=0/1 forces a path; by default clouds of NGICP_KNN_TILE_MIN
-  // (131072) points or more take the tiles.
-  static const int tile_env = getenv("NGICP_KNN_TILE") ? atoi(getenv("NGICP_KNN_TILE")) : -1;
-  static const int tile_min = getenv("NGICP_KNN_TILE_MIN") ? atoi(getenv("NGICP_KNN_TILE_MIN")) : 131072;
-  const bool warp_only = tile_env == 0 || (tile_env < 0 && c.n < tile_min);
+  // Two exact paths (ngicp_params::knn_path).  One warp per point (knn_lists_kernel): massively parallel, best for scans.
+  // Cell-major tiles (plan + tile + rest launches): half the instructions per point but a longer serial path per warp,
+  // best for submaps — measured on the C2 submap (500k points, k=20) 0.63 ms against 0.82 ms, on a 22k-point scan 0.19 ms
+  // against 0.10 ms.  AUTO takes the tiles from knn_tile_min_points (131072) points on.
+  const bool warp_only = knn_path == NGICP_KNN_WARP || (knn_path != NGICP_KNN_TILE && c.n < tile_min_points);
   static const bool want_stats = getenv("NGICP_KNN_STATS") != nullptr;
   if (warp_only) {
     knn_lists_kernel<<<(nq + KC_WARPS - 1) / KC_WARPS, KC_THREADS, 0, st>>>(c.view(), c.n, k, nbr_scratch, q_lo, q_hi);
     note_launches(1);
   } else {
+    static std::mutex attr_mutex;
     static bool attr_set[64] = {};
     static int blocks_per_sm[64] = {};
     static int sm_count[64] = {};
@@ -682,13 +754,16 @@ cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_sc
     int dev = 0;
     cudaGetDevice(&dev);
     const int di = dev & 63;
-    if (!attr_set[di]) {
-      cudaError_t e = cudaFuncSetAttribute(knn_lists_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-      if (e != cudaSuccess) return e;
-      if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[di], knn_lists_tile_kernel, TQ_WARPS * 32, smem)) != cudaSuccess) return e;
-      if ((e = cudaDeviceGetAttribute(&sm_count[di], cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
-      if (blocks_per_sm[di] < 1) blocks_per_sm[di] = 1;
-      attr_set[di] = true;
+    {
+      std::lock_guard<std::mutex> lock(attr_mutex);
+      if (!attr_set[di]) {
+        cudaError_t e = cudaFuncSetAttribute(knn_lists_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[di], knn_lists_tile_kernel, TQ_WARPS * 32, smem)) != cudaSuccess) return e;
+        if ((e = cudaDeviceGetAttribute(&sm_count[di], cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
+        if (blocks_per_sm[di] < 1) blocks_per_sm[di] = 1;
+        attr_set[di] = true;
+      }
     }
     int* ctrl = nbr_scratch + (size_t)c.n * k;
     int* fb_list = ctrl + CT_N;
@@ -696,7 +771,6 @@ cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_sc
     items = reinterpret_cast<int4*>((reinterpret_cast<uintptr_t>(items) + 15) & ~(uintptr_t)15);
     cudaError_t e = cudaMemsetAsync(ctrl, 0, CT_N * sizeof(int), st);
     if (e != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(fb_list, 0xff, (size_t)c.n * sizeof(int), st)) != cudaSuccess) return e;   // -1 = not written yet
     unsigned long long* stats = nullptr;
     if (want_stats) {
       if (cudaMalloc(&stats, ST_N * sizeof(unsigned long long)) != cudaSuccess) return cudaGetLastError();
@@ -713,9 +787,11 @@ cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_sc
       cudaMemcpy(hc, ctrl, sizeof(hc), cudaMemcpyDeviceToHost);
       fprintf(stderr, "[ngicp knn] plan: %s items=%d (n=%d, grid %u blocks)\n", cudaGetErrorString(se), hc[CT_ITEMS], c.n, (unsigned)((plan_warps + 7) / 8));
     }
-    // persistent grid: every resident warp pulls work items until the counter runs out
+    // persistent grid: every resident warp pulls work items until the counter runs out; no block waits for another one,
+    // so it does not matter how many of the blocks are resident at a time (other handles may share the GPU)
     knn_lists_tile_kernel<<<sm_count[di] * blocks_per_sm[di], TQ_WARPS * 32, smem, st>>>(c.view(), c.n, k, nbr_scratch, items, ctrl, fb_list, stats, q_lo, q_hi);
-    note_launches(2);
+    knn_lists_rest_kernel<<<sm_count[di] * 2, KC_THREADS, 0, st>>>(c.view(), k, nbr_scratch, ctrl, fb_list);
+    note_launches(3);
     if (want_stats) {
       unsigned long long h[ST_N] = {};
       cudaMemcpyAsync(h, stats, sizeof(h), cudaMemcpyDeviceToHost, st);
@@ -726,8 +802,7 @@ cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_sc
               h[ST_PASSES] ? (double)h[ST_LANES] / (double)h[ST_PASSES] : 0.0);
     }
   }
-  cov_from_lists_kernel<<<(nq + 127) / 128, 128, 0, st>>>(c.view(), c.n, k, method, nbr_scratch, covs6, q_lo, q_hi);
-  note_launches(1);
+  launch_cov_kernel(c, k, method, nbr_scratch, covs6, q_lo, q_hi, nullptr, nullptr, st);
   return cudaGetLastError();
 }
 

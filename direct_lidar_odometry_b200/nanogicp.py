@@ -174,6 +174,13 @@ class NanoGICP:
         self._p.align_mode = int(mode)
         self._push_params()
 
+    def setKnnPath(self, path: int, tile_min_points: int | None = None):
+        """Which exact kNN kernel family the covariance computation runs: _lib.KNN_AUTO / KNN_WARP / KNN_TILE."""
+        self._p.knn_path = int(path)
+        if tile_min_points is not None:
+            self._p.knn_tile_min_points = int(tile_min_points)
+        self._push_params()
+
     # ------------------------------------------------------------------ clouds
     def setInputSource(self, cloud):
         if self._input is cloud:  # pointer-identity early-out, nano_gicp_impl.hpp:122
@@ -356,6 +363,17 @@ class NanoGICP:
         d2 = np.zeros((nq, k), dtype=np.float32)
         self._check(self._L.ngicp_knn(self._h, which, p, nq, st, k, idx.ctypes.data_as(C.POINTER(C.c_int)),
                                       d2.ctypes.data_as(C.POINTER(C.c_float))))
+        return idx, d2
+
+    def cov_neighbors(self, which: int):
+        """(idx (n,k) original indices, d2 (n,k)) of the neighbours the last calculate*Covariances call on this handle
+        summed over, in summation order (ascending distance, ties by index) — ngicp_cov_neighbors."""
+        n = int(self._L.ngicp_cloud_size(self._h, which))
+        k = int(self._p.k_correspondences)
+        idx = np.zeros((n, k), dtype=np.int32)
+        d2 = np.zeros((n, k), dtype=np.float32)
+        self._check(self._L.ngicp_cov_neighbors(self._h, which, idx.ctypes.data_as(C.POINTER(C.c_int)),
+                                                d2.ctypes.data_as(C.POINTER(C.c_float))))
         return idx, d2
 
     def linearize(self, T, per_point: bool = False):

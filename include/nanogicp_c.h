@@ -54,6 +54,13 @@ enum { NGICP_REG_NONE = 0, NGICP_REG_MIN_EIG = 1, NGICP_REG_NORMALIZED_MIN_EIG =
 enum { NGICP_OPT_GAUSS_NEWTON = 0, NGICP_OPT_LEVENBERG_MARQUARDT = 1 };
 enum { NGICP_SOURCE = 0, NGICP_TARGET = 1 };
 /* how ngicp_align drives the LM loop */
+/* which exact kNN kernel family calculate*Covariances runs (both give the same neighbour sets and, since the
+ * covariance kernel accumulates in ascending (distance, index) order, the same covariance bits) */
+enum {
+  NGICP_KNN_AUTO = 0,   /* tiles for clouds of knn_tile_min_points or more, one warp per query below */
+  NGICP_KNN_WARP = 1,   /* one warp per query: growing-cube search with a warp-distributed sorted top-k list */
+  NGICP_KNN_TILE = 2    /* cell-major tiles staged in shared memory, one thread per query, threshold selection */
+};
 enum {
   NGICP_ALIGN_FUSED = 0,   /* one persistent cooperative kernel runs the whole LM loop, state stays in HBM/registers */
   NGICP_ALIGN_STEPPED = 1  /* one launch per linearize/compute_error, LM decisions on the host (debug + sharded mode) */
@@ -74,6 +81,8 @@ typedef struct {
   float grid_cell_size;                /* uniform-grid cell edge in metres; 0 = choose from the data */
   int grid_table_cells;                /* capacity of the dense cell table (cells); the cell edge grows to fit */
   int align_mode;                      /* NGICP_ALIGN_FUSED / NGICP_ALIGN_STEPPED */
+  int knn_path;                        /* NGICP_KNN_AUTO / _WARP / _TILE */
+  int knn_tile_min_points;             /* NGICP_KNN_AUTO switches to the tile kernels at this cloud size (131072) */
 } ngicp_params;
 
 /* what pcl::Registration / LsqRegistration expose after align() */
@@ -133,9 +142,6 @@ size_t ngicp_cloud_size(const ngicp_t* h, int which);
 
 /* ---- covariances ------------------------------------------------------------------------------ */
 /* NanoGICP::calculateSourceCovariances / calculateTargetCovariances, nano_gicp_impl.hpp:151-159,298-357 */
-/* Note (round 1): for clouds of 131 072 points or more the covariance kernels assume that no OTHER handle computes the
- * covariances of another such cloud on the same GPU at the same time; smaller clouds and the
- * rest of the API are free of that restriction. */
 int ngicp_calc_source_covs(ngicp_t* h);
 int ngicp_calc_target_covs(ngicp_t* h);
 /* One cloud's covariances split over several GPUs (dense scans against a sharded submap): every
@@ -146,6 +152,11 @@ int ngicp_calc_target_covs(ngicp_t* h);
  * cloud's own point order) for that collective; it stays owned by the handle. */
 int ngicp_calc_source_covs_part(ngicp_t* h, int part, int nparts);
 int ngicp_covs_device(ngicp_t* h, int which, double** covs6, size_t* n);
+/* test hook: the k neighbours (nearestKSearch result at nano_gicp_impl.hpp:313) the LAST calculate*Covariances call on
+ * this handle used for every point of that cloud, in the order the covariance sums ran over them — ascending
+ * (squared distance, original index): idx[n*k] original point indices (-1 = none), d2[n*k] squared distances.  Valid
+ * until the next covariance / kNN call on the handle. */
+int ngicp_cov_neighbors(ngicp_t* h, int which, int* idx, float* d2);
 /* NanoGICP::setSourceCovariances / setTargetCovariances, nano_gicp_impl.hpp:141-149 (n Matrix4d records, host or device) */
 int ngicp_set_source_covs(ngicp_t* h, const double* covs, size_t n);
 int ngicp_set_target_covs(ngicp_t* h, const double* covs, size_t n);

@@ -148,41 +148,29 @@ def test_voxel_filter_speculative_passes_and_fallback(G, O, scan_pair):
         g.voxel_filter(s0, 0.25, out=tiny)
 
 
-@pytest.mark.parametrize("tile", [0, 1])
-def test_covariances_in_parts_sum_to_full(G, scan_pair, tile, monkeypatch):
+@pytest.mark.parametrize("path", [1, 2])
+def test_covariances_in_parts_sum_to_full(G, path):
     """ngicp_calc_source_covs_part: the slices of all parts (zeros elsewhere) add up to the full result bit for bit —
-    what the all-reduce over the ranks of a sharded registration relies on; both kNN paths."""
-    import subprocess, sys, os, json
-    # the kNN path is chosen by an environment variable read once per process: run in a fresh interpreter
-    code = (
-        "import numpy as np, json, sys\n"
-        "sys.path.insert(0, %r)\n"
-        "from direct_lidar_odometry_b200 import NanoGICP, synth, _lib\n"
-        "T = synth.trajectory_pose(0)\n"
-        "g = NanoGICP(0); v = g.voxel_filter(synth.crop_box_negative(synth.os1_like(0, T, cols=512)), 0.25)\n"
-        "g.setCorrespondenceRandomness(20); g.setInputSource(v); g.calculateSourceCovariances(); g.sync()\n"
-        "full = g.covs_device_tensor(_lib.SOURCE).cpu().numpy().copy()\n"
-        "acc = np.zeros_like(full); nz = 0\n"
-        "for p in range(3):\n"
-        "    g.calculateSourceCovariancesPart(p, 3); g.sync()   # the view is read on torch's stream, not the handle's\n"
-        "    part = g.covs_device_tensor(_lib.SOURCE).cpu().numpy()\n"
-        "    nz += int((np.abs(part).sum(axis=1) > 0).sum())\n"
-        "    acc += part\n"
-        "print(json.dumps({'n': int(v.shape[0]), 'nz': nz, 'equal': bool(np.array_equal(acc.view(np.uint64), full.view(np.uint64))), "
-        "'maxdiff': float(np.abs(acc - full).max()), 'ndiff': int((np.abs(acc - full).max(axis=1) > 0).sum()), "
-        "'host_equal': bool(np.allclose(g.getSourceCovariances()[:, :3, :3].reshape(-1, 9)[:, [0, 1, 2, 4, 5, 8]], part))}))\n"
-    ) % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, NGICP_KNN_TILE=str(tile))
-    out = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
-    assert out.returncode == 0, out.stderr
-    r = json.loads(out.stdout.strip().splitlines()[-1])
-    assert r["nz"] == r["n"] and r["host_equal"], r
-    if tile == 0:
-        assert r["equal"], r          # one warp per query, neighbours in ascending order: the same bits however the cloud is sliced
-    else:
-        # tile path: a query's neighbour SET is exact, the order its fp64 sums run in follows the tile it was answered from,
-        # which can differ with the batch it shares a tile with: rounding-level differences only
-        assert r["maxdiff"] < 1e-9, r
+    what the all-reduce over the ranks of a sharded registration relies on; both kNN kernel families (ngicp_params
+    knn_path: 1 = one warp per query, 2 = tiles).  The covariance kernel sums every neighbourhood in ascending
+    (distance, index) order, so the bits do not depend on how the cloud is sliced or which kernel found the neighbours."""
+    from direct_lidar_odometry_b200 import _lib
+    T = synth.trajectory_pose(0)
+    g = G()
+    g.setKnnPath(path)
+    v = g.voxel_filter(synth.crop_box_negative(synth.os1_like(0, T, cols=512)), 0.25)
+    g.setCorrespondenceRandomness(20); g.setInputSource(v); g.calculateSourceCovariances(); g.sync()
+    full = g.covs_device_tensor(_lib.SOURCE).cpu().numpy().copy()
+    acc = np.zeros_like(full)
+    nz = 0
+    for p in range(3):
+        g.calculateSourceCovariancesPart(p, 3); g.sync()   # the view is read on torch's stream, not the handle's
+        part = g.covs_device_tensor(_lib.SOURCE).cpu().numpy()
+        nz += int((np.abs(part).sum(axis=1) > 0).sum())
+        acc += part
+    assert nz == v.shape[0]
+    assert np.array_equal(acc.view(np.uint64), full.view(np.uint64)), float(np.abs(acc - full).max())
+    assert np.allclose(g.getSourceCovariances()[:, :3, :3].reshape(-1, 9)[:, [0, 1, 2, 4, 5, 8]], part)
 
 
 def test_preprocess_pointcloud2_decode_fused(G, O, scan_pair):
