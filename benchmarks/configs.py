@@ -384,9 +384,120 @@ def run_c3(args):
 
 
 # ------------------------------------------------------------------------------------------------ C4
+def c4_pair_indices(n_pairs, rank, world):
+    """Pair i registers scan i+1 against scan i of the 10 001-pose trajectory; ranks take contiguous
+    blocks of pairs (direct_lidar_odometry_b200.sharded.partition_pairs)."""
+    from direct_lidar_odometry_b200 import sharded
+    return list(sharded.partition_pairs(n_pairs, rank, world))
+
+
+def c4_make_scans(vox, first, count, device, batch=16):
+    """Voxelised (0.25 m) scans first .. first+count-1 as device tensors, generated on the GPU by the torch ray-caster
+    (synth.os1_like_batch_torch: same scene, same per-scan RNG streams as the numpy generator)."""
+    import torch
+    out = []
+    buf = torch.empty((1 << 17, 8), dtype=torch.float32, device=device)
+    for b0 in range(first, first + count, batch):
+        idx = list(range(b0, min(b0 + batch, first + count)))
+        raws = synth.os1_like_batch_torch(idx, [synth.trajectory_pose(i) for i in idx], device)
+        for raw in raws:
+            v = vox.voxel_filter(raw, 0.25, out=buf)
+            out.append(v.clone())
+    return out
+
+
+def c4_run(handle_sets, scans, pair_offsets, wave, threads=8):
+    """Register pairs (scans[o+1] -> scans[o]) for o in pair_offsets in waves of `wave` pairs.  A wave's clouds are
+    indexed and their covariances computed from `threads` host threads, each pair on its own handle / stream; the wave's
+    LM loops then run as ONE ngicp_align_batch launch.  Two sets of handles alternate, so the host threads prepare wave
+    w+1 while wave w's batch kernel runs.  Returns per pair (nr_iterations, n_compute_error, final_x)."""
+    from direct_lidar_odometry_b200 import align_batch
+    results = []
+
+    def prep(args):
+        h, o = args
+        h.clearSource(); h.clearTarget()
+        h.setInputTarget(scans[o]); h.calculateTargetCovariances()
+        h.setInputSource(scans[o + 1]); h.calculateSourceCovariances()
+    waves = [pair_offsets[w0:w0 + wave] for w0 in range(0, len(pair_offsets), wave)]
+    with ThreadPoolExecutor(threads) as ex:
+        def submit(w):
+            hs = handle_sets[w & 1][:len(waves[w])]
+            return hs, [ex.submit(prep, a) for a in zip(hs, waves[w])]
+        nxt = submit(0) if waves else None
+        for w in range(len(waves)):
+            hs, futs = nxt
+            for f in futs:
+                f.result()
+            nxt = submit(w + 1) if w + 1 < len(waves) else None
+            align_batch(hs)
+            for h in hs:
+                results.append((int(h.result.nr_iterations), int(h.result.n_compute_error), np.array(h.result.final_x)))
+    return results
+
+
+def c4_bench(local, rank, world, pairs=10000, wave=64, threads=8, sample_check=0):
+    """C4 on this rank's GPU (torch.distributed already initialised when world > 1).  Returns the result dict on rank 0,
+    None elsewhere.  Timing: barrier, wall clock around this rank's waves (each wave ends with the host reading the
+    results of its ngicp_align_batch launch), max over ranks."""
+    import torch
+    import torch.distributed as dist
+    from direct_lidar_odometry_b200 import NanoGICP
+    dev = torch.device("cuda", local)
+    mine = c4_pair_indices(pairs, rank, world)
+    vox = NanoGICP(local)
+    t0 = time.perf_counter()
+    scans = c4_make_scans(vox, mine[0], len(mine) + 1, dev)          # this rank's pairs are contiguous: n+1 scans
+    gen_s = time.perf_counter() - t0
+    from direct_lidar_odometry_b200 import _lib
+    handles = [[NanoGICP(local) for _ in range(wave)] for _ in range(2)]
+    for hs in handles:
+        for h in hs:
+            configure(h, S2S)
+            h.setKnnPath(_lib.KNN_TILE)      # throughput, not latency: the tile kernels need half the instructions per point
+    offs = list(range(len(mine)))
+    c4_run(handles, scans, offs[:2 * wave], wave, threads)      # warm-up (both handle sets)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    res = c4_run(handles, scans, offs, wave, threads)
+    torch.cuda.synchronize()
+    el = time.perf_counter() - t0
+    t = torch.tensor([el], dtype=torch.float64, device=dev)
+    cnt = torch.tensor([len(res)], dtype=torch.int64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(cnt)
+    out = None
+    if rank == 0:
+        out = {"config": f"C4: {pairs} DISTINCT independent S2S scan pairs (pair i = scans i+1 -> i of the 10 001-pose trajectory, "
+                         f"~{int(np.mean([s.shape[0] for s in scans[:64]]))} pts each; index + k=10 covariances for both clouds + align per pair), "
+                         f"partitioned over {world} GPU(s); waves of {wave} pairs, one ngicp_align_batch launch per wave",
+               "n_gpus": world, "pairs": int(cnt.item()), "wave": wave, "host_threads_per_gpu": threads, "seconds": float(t.item()),
+               "pairs_per_s": float(cnt.item() / t.item()), "ms_per_pair_per_gpu": float(t.item() * 1e3 * world / cnt.item()),
+               "mean_iterations": float(np.mean([r[0] for r in res])), "scan_generation_s_rank0": gen_s}
+        if sample_check > 0:
+            # a seeded sample of this rank's pairs against the CPU oracle (identical inputs: the device scans copied back)
+            from oracle import oracle as O
+            rng = np.random.default_rng(2026)
+            pick = np.sort(rng.choice(len(offs), size=min(sample_check, len(offs)), replace=False))
+            same, worst = 0, (0.0, 0.0)
+            for o in pick.tolist():
+                a, b = scans[o].cpu().numpy(), scans[o + 1].cpu().numpy()
+                og = O.Gicp(k=S2S["k"], max_corr_dist=S2S["thr"], max_iter=S2S["max_iter"], trans_eps=S2S["trans_eps"], num_threads=os.cpu_count())
+                og.set_target(O.Cloud(a)); og.set_source(O.Cloud(b))
+                r = og.align()
+                it, ne, fx = res[o]
+                dt, dr = pose_err(fx.reshape(4, 4).T, r.Tx())
+                same += int((it, ne) == (int(r.nr_iterations), int(r.n_compute_error)))
+                worst = (max(worst[0], dt), max(worst[1], dr))
+            out["oracle_sample"] = {"pairs_checked": int(len(pick)), "identical_counts": same, "max_dt_m": worst[0], "max_dr_rad": worst[1]}
+    del handles, scans
+    return out
+
+
 def run_c4(args):
     import torch
-    from direct_lidar_odometry_b200 import NanoGICP, sharded
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -394,48 +505,9 @@ def run_c4(args):
         import torch.distributed as dist
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    # a pool of distinct pre-voxelised scans; pair i registers scan (i+1) against scan i of the pool (cyclic)
-    pool_n = args.pool
-    scans = gen_scans(list(range(0, pool_n * 3, 3)))
-    vox = NanoGICP(local)
-    pool = [vox.voxel_filter(scans[i][1], 0.25) for i in sorted(scans)]
-    dev = torch.device("cuda", local)
-    pool_d = [torch.from_numpy(p).to(dev) for p in pool]
-    mine = sharded.partition_pairs(args.pairs, rank, world)
-    handles = [NanoGICP(local) for _ in range(args.handles)]
-    for h in handles:
-        configure(h, S2S)
-
-    def work(hi):
-        h = handles[hi]
-        done = 0
-        for pi in list(mine)[hi::args.handles]:
-            a, b = pool_d[pi % pool_n], pool_d[(pi + 1) % pool_n]
-            h.clearSource(); h.clearTarget()
-            h.setInputTarget(a); h.setInputSource(b)      # index x2; covariances are computed lazily inside align
-            h.align()
-            done += 1
-        return done
-    # warm-up
-    with ThreadPoolExecutor(args.handles) as ex:
-        list(ex.map(lambda hi: [handles[hi].clearTarget(), handles[hi].setInputTarget(pool_d[0]), handles[hi].setInputSource(pool_d[1]), handles[hi].align()], range(args.handles)))
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    t0 = time.perf_counter()
-    with ThreadPoolExecutor(args.handles) as ex:
-        n_done = sum(ex.map(work, range(args.handles)))
-    torch.cuda.synchronize()
-    el = time.perf_counter() - t0
-    t = torch.tensor([el], dtype=torch.float64, device=dev)
-    cnt = torch.tensor([n_done], dtype=torch.int64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX); dist.all_reduce(cnt)
+    out = c4_bench(local, rank, world, args.pairs, args.wave, args.handles, args.check_pairs)
     if rank == 0:
-        print(json.dumps({"config": f"C4: {args.pairs} independent S2S scan pairs (~{int(np.mean([p.shape[0] for p in pool]))} pts each, index + k=10 "
-                                    f"covariances for both clouds + align per pair), partitioned over {world} GPU(s)",
-                          "n_gpus": world, "pairs": int(cnt.item()), "handles_per_gpu": args.handles, "seconds": float(t.item()),
-                          "pairs_per_s": float(cnt.item() / t.item()), "ms_per_pair_per_gpu": float(t.item() * 1e3 * world / cnt.item())}))
+        print(json.dumps(out))
     if world > 1:
         dist.barrier(); dist.destroy_process_group()
 
@@ -474,24 +546,26 @@ def c5_workload(n_target, log):
     return wl
 
 
-def run_c5(args):
+def _sha1(a):
+    import hashlib
+    return hashlib.sha1(np.ascontiguousarray(a).view(np.uint8)).hexdigest()
+
+
+def c5_bench(local, rank, world, target_points=5_000_000, steps=10, cov_halo=2.0, balance=0.0, shard_source_covs=0, check=1):
+    """C5 on `world` GPUs (torch.distributed already initialised when world > 1): every rank holds one slab (+ halo) of the
+    target, the scan's index + covariances and the fused LM kernel with the in-kernel NVLink exchange run per step.
+    Returns the result dict on rank 0.  Compared with the CPU oracle through tests/golden/c5_oracle_<n>.json."""
     import torch
     import torch.distributed as dist
     from direct_lidar_odometry_b200 import NanoGICP, sharded
-    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
-    local = int(os.environ.get("LOCAL_RANK", 0))
-    torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
-        dist.init_process_group("nccl", device_id=dev)
     log = (lambda *a: print(*a, file=sys.stderr)) if rank == 0 else (lambda *a: None)
     if rank == 0:
-        wl = c5_workload(args.target_points, log)
+        wl = c5_workload(target_points, log)
     if world > 1:
         dist.barrier()
     if rank != 0:
-        wl = c5_workload(args.target_points, log)
+        wl = c5_workload(target_points, log)
     target, source, guess, truth = wl["target"], wl["source"], wl["guess"], wl["truth"]
     be = sharded.CudaShardBackend(local, k=S2M["k"], max_corr_dist=S2M["thr"])
     be.set_align_params(S2M["max_iter"], S2M["trans_eps"])
@@ -506,9 +580,9 @@ def run_c5(args):
     # ---- target: this rank's slab, index + k=20 covariances on this GPU, halo grown until exact ----
     sync_all()
     t0 = time.perf_counter()
-    expected = synth.transform_xyzi(source, np.asarray(guess, dtype=np.float64))[:, :3] if args.balance > 0 else None
-    info = be.build_target_shard(target, rank, world, halo=S2M["thr"] + 0.01, k=S2M["k"], cov_halo=args.cov_halo,
-                                 queries=expected, query_weight=args.balance)
+    expected = synth.transform_xyzi(source, np.asarray(guess, dtype=np.float64))[:, :3] if balance > 0 else None
+    info = be.build_target_shard(target, rank, world, halo=S2M["thr"] + 0.01, k=S2M["k"], cov_halo=cov_halo,
+                                 queries=expected, query_weight=balance)
     sync_all()
     t_build = time.perf_counter() - t0
     tm = g.timings()
@@ -518,7 +592,7 @@ def run_c5(args):
     src_d = torch.from_numpy(source).to(dev)
 
     def step():
-        if args.shard_source_covs and world > 1:
+        if shard_source_covs and world > 1:
             be.set_source_sharded(src_d, rank, world)   # index replicated, k=20 covariances split over the ranks + all-reduce
         else:
             be.set_source(src_d)         # index + k=20 covariances of the dense scan (replicated on every rank)
@@ -527,7 +601,7 @@ def run_c5(args):
     for _ in range(3):
         res = step()
     sync_all()
-    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
     al = []
     for a, b in ev:
         sync_all()
@@ -536,7 +610,7 @@ def run_c5(args):
         b.record(stream)
         b.synchronize()
         al.append(g.timings()["align_ms"])
-    ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev) / args.steps, float(np.mean(al)), build_gpu_ms],
+    ms = torch.tensor([sum(a.elapsed_time(b) for a, b in ev) / steps, float(np.mean(al)), build_gpu_ms],
                       dtype=torch.float64, device=dev)
     npts = torch.tensor([info["shard_points"]], dtype=torch.int64, device=dev)
     fx = torch.from_numpy(res["final_x"]).to(dev)
@@ -549,32 +623,59 @@ def run_c5(args):
     else:
         fx_all, shard_pts = [fx], [npts]
     identical = all(bool(torch.equal(fx_all[0], f)) for f in fx_all)
+    line = None
     if rank == 0:
         dt, dr = pose_err(res["final_x"], truth)
         line = {"config": f"C5: dense 128-beam scan ({source.shape[0]} pts, no voxel filter) vs {target.shape[0]}-pt submap sharded over "
                           f"{world} GPU(s): slabs + halo, k=20 covariances per slab, fused LM with the H/b/err exchange in NVLink peer memory",
-                "n_gpus": world, "steps": args.steps, "ms_per_scan": float(ms[0].item()), "align_ms": float(ms[1].item()),
+                "n_gpus": world, "steps": steps, "ms_per_scan": float(ms[0].item()), "align_ms": float(ms[1].item()),
                 "target_build_gpu_ms": float(ms[2].item()), "target_build_wall_s": t_build, "cov_halo_m": info["cov_halo"],
-                "halo_rounds": info["rounds"], "shard_points": [int(x.item()) for x in shard_pts], "slab_query_weight": args.balance,
-                "source_covs": "split over the ranks + NCCL all-reduce" if (args.shard_source_covs and world > 1) else "replicated on every rank",
+                "halo_rounds": info["rounds"], "shard_points": [int(x.item()) for x in shard_pts], "slab_query_weight": balance,
+                "source_covs": "split over the ranks + NCCL all-reduce" if (shard_source_covs and world > 1) else "replicated on every rank",
                 "iterations": res["nr_iterations"], "n_linearize": res["n_linearize"], "n_compute_error": res["n_compute_error"],
                 "converged": res["converged"], "ranks_bit_identical": identical, "pose_error_m": dt, "pose_error_rad": dr,
                 "rank0_kernel_ms": {k: round(v, 4) for k, v in g.timings().items()}}
-        if args.check and world > 1:
+        gold_path = os.path.join(ROOT, "tests", "golden", f"c5_oracle_{target.shape[0]}.json")
+        if os.path.exists(gold_path):
+            gold = json.load(open(gold_path))
+            gdt, gdr = pose_err(res["final_x"], np.array(gold["final_x"]).reshape(4, 4))
+            line["vs_oracle"] = {"fixture": os.path.relpath(gold_path, ROOT),
+                                 "inputs_identical_to_fixture": bool(_sha1(target) == gold["target_sha1"] and _sha1(source) == gold["source_sha1"]),
+                                 "dT_vs_oracle_m": gdt, "dR_vs_oracle_rad": gdr,
+                                 "counts_equal": bool((res["nr_iterations"], res["n_linearize"], res["n_compute_error"]) ==
+                                                      (gold["nr_iterations"], gold["n_linearize"], gold["n_compute_error"])),
+                                 "oracle_counts": [gold["nr_iterations"], gold["n_linearize"], gold["n_compute_error"]]}
+        if check and world > 1:
             # the same registration unsharded on this GPU: iteration counts and pose must agree
             u = NanoGICP(local)
             configure(u, S2M)
             u.setInputTarget(target); u.calculateTargetCovariances()
             u.setInputSource(src_d); u.calculateSourceCovariances()
-            t1 = time.perf_counter()
             u.align(guess)
             line["unsharded_align_ms"] = u.timings()["align_ms"]
             line["unsharded_iterations"] = int(u.result.nr_iterations)
             line["max_abs_dT_vs_unsharded"] = float(np.abs(u.final_state() - res["final_x"]).max())
-        print(json.dumps(line))
+            del u
     if world > 1:
         dist.barrier()
         be.g.comm_close()
+    return line
+
+
+def run_c5(args):
+    import torch
+    import torch.distributed as dist
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    line = c5_bench(local, rank, world, args.target_points, args.steps, args.cov_halo, args.balance, args.shard_source_covs, args.check)
+    if rank == 0:
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
 
 
@@ -592,8 +693,9 @@ if __name__ == "__main__":
     ap.add_argument("--selection", choices=["hull", "knn"], default="hull", help="c3: submap keyframe selection")
     ap.add_argument("--cpu-scans", type=int, default=40)
     ap.add_argument("--pinned", type=int, default=0, help="c3: keep the raw scans in pinned host memory")
-    ap.add_argument("--pairs", type=int, default=512)
-    ap.add_argument("--pool", type=int, default=16)
+    ap.add_argument("--pairs", type=int, default=10000)
+    ap.add_argument("--wave", type=int, default=64, help="c4: pairs per ngicp_align_batch launch")
+    ap.add_argument("--check-pairs", type=int, default=0, help="c4: oracle-check a seeded sample of this many of rank 0's pairs")
     ap.add_argument("--handles", type=int, default=8)
     a = ap.parse_args()
     SELECTION = a.selection

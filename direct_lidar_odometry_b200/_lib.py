@@ -8,7 +8,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libnanogicp_b200.so")
+LIB_PATH = os.environ.get("NGICP_LIB_PATH") or os.path.join(_HERE, "csrc", "libnanogicp_b200.so")   # override: A/B builds of the same library
 
 OK, E_INVALID, E_STATE, E_TOO_FEW_POINTS, E_COV_SIZE, E_CUDA, E_UNSUPPORTED, E_COMM, W_VOXEL_OVERFLOW = 0, -1, -2, -3, -4, -5, -6, -7, 1
 REG_NONE, REG_MIN_EIG, REG_NORMALIZED_MIN_EIG, REG_PLANE, REG_FROBENIUS = range(5)
@@ -28,7 +28,7 @@ EXPORTS = [
     "ngicp_knn", "ngicp_linearize", "ngicp_compute_error", "ngicp_linearize_partial", "ngicp_compute_error_partial",
     "ngicp_version", "ngicp_launch_count", "ngicp_grid_info", "ngicp_set_owner_slab", "ngicp_lm_trial",
     "ngicp_lm_is_converged", "ngicp_comm_export", "ngicp_comm_connect", "ngicp_comm_connect_local", "ngicp_comm_close", "ngicp_preprocess", "ngicp_preprocess_pointcloud2", "ngicp_calc_source_covs_part", "ngicp_covs_device", "ngicp_transform_voxel_filter", "ngicp_kfstore_create", "ngicp_kfstore_destroy", "ngicp_kfstore_size",
-    "ngicp_kfstore_points", "ngicp_kfstore_push", "ngicp_kfstore_set_target", "ngicp_cov_neighbors",
+    "ngicp_kfstore_points", "ngicp_kfstore_push", "ngicp_kfstore_set_target", "ngicp_cov_neighbors", "ngicp_align_batch",
 ]
 
 
@@ -95,6 +95,7 @@ def load() -> C.CDLL:
     for n in ("ngicp_set_source_covs", "ngicp_set_target_covs", "ngicp_get_source_covs", "ngicp_get_target_covs"):
         proto(n, i32, vp, vp, sz)
     proto("ngicp_align", i32, vp, fp, C.POINTER(Result))
+    proto("ngicp_align_batch", i32, C.POINTER(vp), sz, fp, C.POINTER(Result))
     proto("ngicp_transform_source", i32, vp, fp, vp, sz)
     proto("ngicp_voxel_filter", i32, vp, vp, sz, sz, f32, vp, sz, C.POINTER(sz))
     proto("ngicp_voxel_assignment", i32, vp, ip, sz)

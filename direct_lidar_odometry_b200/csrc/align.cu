@@ -20,6 +20,7 @@
 // compulsory traffic (+48 B M +16 B p_B stored for K5, which then reads 16+48+16+4 = 84 B).
 #include <cstdlib>
 #include <cstring>
+#include <cooperative_groups.h>
 #include "internal.h"
 #include "grid_search.cuh"
 #include "gicp_math.cuh"
@@ -28,6 +29,7 @@ namespace ngicp {
 
 constexpr int AL_THREADS = 256;
 constexpr int AL_WARPS = AL_THREADS / 32;
+constexpr int ALIGN_BATCH_CLUSTER = 8;   // blocks per pair in the batched kernel (portable cluster size)
 
 struct XformF { float m[12]; };   // rows: m[r*4+c], c=3 is translation; float cast of the double state
 struct AlignArgs {
@@ -671,6 +673,225 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) align_fused_kernel(AlignArgs
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// batched mode: B independent registrations in ONE launch (ngicp_align_batch; BASELINE config C4).
+// One thread-block CLUSTER per pair: the cluster's CTAs work through the pair's "virtual blocks" — exactly the blocks
+// (same points, same warps, same lanes) a single align_fused launch of that pair would run — and publish one partial per
+// virtual block; a hardware cluster barrier replaces the grid barrier, and every CTA then sums the partials in the
+// single launch's fixed order.  Every sum therefore has the single launch's bits and every LM decision is the same:
+// a batch result is bit-identical to the B single calls.  Clusters never wait for one another, so the launch is an
+// ordinary one with any number of pairs (no co-residency requirement).
+// ------------------------------------------------------------------------------------------
+namespace cg = cooperative_groups;
+
+struct BatchPair {
+  AlignArgs a;
+  LmParams prm;
+  Guess16 guess;
+  ngicp_result* res;
+  int vblocks;      // blocks of the equivalent single launch
+};
+
+// fixed-order sum of nb per-block partials (the single-GPU branch of grid_reduce): totals -> s_tot[0..NV)
+template <int NV>
+__device__ __forceinline__ void sum_partials(const double* __restrict__ all, unsigned nb, double (*s_red)[NRED], double* s_tot) {
+  const int v = threadIdx.x & 31, seg = threadIdx.x >> 5;
+  if (v < NV) {
+    double part[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) part[u] = 0.0;
+    for (unsigned b0 = seg; b0 < nb; b0 += AL_WARPS * 8) {
+      double x[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const unsigned bk = b0 + u * AL_WARPS;
+        x[u] = bk < nb ? __ldcg(all + (size_t)bk * NRED + v) : 0.0;
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) part[u] += x[u];
+    }
+    s_red[seg][v] = ((part[0] + part[1]) + (part[2] + part[3])) + ((part[4] + part[5]) + (part[6] + part[7]));
+  }
+  __syncthreads();
+  if (threadIdx.x < NV) {
+    double s = 0.0;
+#pragma unroll
+    for (int sg = 0; sg < AL_WARPS; sg++) s += s_red[sg][threadIdx.x];
+    s_tot[threadIdx.x] = s;
+  }
+  __syncthreads();
+}
+
+template <int LPP>
+__global__ void __launch_bounds__(AL_THREADS, 2) align_batch_kernel(const BatchPair* __restrict__ pairs) {
+  cg::cluster_group cluster = cg::this_cluster();
+  const unsigned crank = cluster.block_rank(), csize = cluster.num_blocks();
+  __shared__ double s_red[AL_WARPS][NRED];
+  __shared__ double s_tot[NRED];
+  __shared__ TailQueue s_tq;
+  __shared__ Iso3 s_x;
+  __shared__ int s_decision;
+  __shared__ BatchPair s_pair;
+  {
+    const int* src = reinterpret_cast<const int*>(pairs + blockIdx.x / csize);
+    int* dst = reinterpret_cast<int*>(&s_pair);
+    for (int i = threadIdx.x; i < (int)(sizeof(BatchPair) / sizeof(int)); i += blockDim.x) dst[i] = src[i];
+  }
+  __syncthreads();
+  const AlignArgs& a = s_pair.a;
+  const LmParams& prm = s_pair.prm;
+  const int VB = s_pair.vblocks;
+  const int ppb = AL_THREADS / LPP;
+  const GridParams gp = load_grid(a.tgt.desc);
+  unsigned phase = 0;
+
+  Iso3 x0, xi, delta;
+  double H36[36], b6[6], d6[6];
+  double lambda = -1.0, y0 = 0.0, nu = 2.0;
+  double final_H[36];
+  int nr_iterations = 0, n_lin = 0, n_err = 0, lm_failed = 0;
+  bool converged = false;
+  if (threadIdx.x == 0) {
+    double g16[16];
+    for (int i = 0; i < 16; i++) g16[i] = (double)s_pair.guess.g[i];
+    iso_from_colmajor16(g16, x0);
+    iso_identity(delta);
+    for (int i = 0; i < 36; i++) final_H[i] = (i % 7 == 0) ? 1.0 : 0.0;
+    for (int i = 0; i < 6; i++) d6[i] = 0.0;
+    s_x = x0;
+  }
+  __syncthreads();
+
+  for (int it = 0; it < prm.max_iterations; ++it) {
+    // ---------------- linearize at s_x: this CTA's virtual blocks ----------------
+    {
+      const Iso3 T = s_x;
+      XformF Tf;
+      make_xforms(T, Tf);
+      double* mine = a.partials + (size_t)(phase & 1u) * a.max_blocks * NRED;
+      for (int vb = (int)crank; vb < VB; vb += (int)csize) {
+        double acc[1] = {0.0};
+        linearize_block<LPP>(a, gp, Tf, T, prm.cap_d2, prm.thr2, vb * ppb, VB * ppb, s_tq, acc[0]);
+        block_reduce_store<NRED>(acc, s_red, mine + (size_t)vb * NRED);
+      }
+      __threadfence();
+      cluster.sync();
+      sum_partials<NRED>(mine, (unsigned)VB, s_red, s_tot);
+      phase++;
+    }
+    int outcome = 0;
+    if (threadIdx.x == 0) {
+      nr_iterations = it;
+      n_lin++;
+      unpack_H(s_tot, H36);
+      for (int i = 0; i < 6; i++) b6[i] = s_tot[21 + i];
+      y0 = s_tot[27];
+    }
+    if (prm.optimizer == NGICP_OPT_GAUSS_NEWTON) {
+      if (threadIdx.x == 0) {
+        double nb[6];
+        for (int i = 0; i < 6; i++) nb[i] = -b6[i];
+        lm_solve(H36, nb, d6);
+        delta_from_step(d6, delta);
+        iso_mul(delta, x0, xi);
+        x0 = xi;
+        for (int i = 0; i < 36; i++) final_H[i] = H36[i];
+        converged = lm_is_converged(delta, prm.rot_eps, prm.trans_eps);
+        s_x = x0;
+        s_decision = converged ? 2 : 1;
+      }
+      __syncthreads();
+      outcome = 1;
+    } else {
+      if (threadIdx.x == 0) {
+        if (lambda < 0.0) {
+          double mx = 0.0;
+          for (int i = 0; i < 6; i++) mx = fmax(mx, fabs(H36[i * 7]));
+          lambda = prm.lm_init_lambda_factor * mx;
+        }
+        nu = 2.0;
+      }
+      for (int j = 0; j < prm.lm_max_iterations; ++j) {
+        if (threadIdx.x == 0) {
+          double A[36], nb[6];
+          for (int i = 0; i < 36; i++) A[i] = H36[i];
+          for (int i = 0; i < 6; i++) { A[i * 7] += lambda; nb[i] = -b6[i]; }
+          lm_solve(A, nb, d6);
+          delta_from_step(d6, delta);
+          iso_mul(delta, x0, xi);
+          s_x = xi;
+        }
+        __syncthreads();
+        // ---------------- compute_error at xi ----------------
+        {
+          const Iso3 T = s_x;
+          double* mine = a.partials + (size_t)(phase & 1u) * a.max_blocks * NRED;
+          for (int vb = (int)crank; vb < VB; vb += (int)csize) {
+            double acc[1] = {0.0};
+            for (int i = vb * AL_THREADS + threadIdx.x; i < a.ns; i += VB * AL_THREADS) acc[0] += error_point(a, T, i);
+            block_reduce_store<1>(acc, s_red, mine + (size_t)vb * NRED);
+          }
+          __threadfence();
+          cluster.sync();
+          sum_partials<1>(mine, (unsigned)VB, s_red, s_tot);
+          phase++;
+        }
+        if (threadIdx.x == 0) {
+          n_err++;
+          const double yi = s_tot[0];
+          double denom = 0.0;
+          for (int i = 0; i < 6; i++) denom += d6[i] * (lambda * d6[i] - b6[i]);
+          const double rho = (y0 - yi) / denom;
+          int dec;
+          if (rho < 0) {
+            if (lm_is_converged(delta, prm.rot_eps, prm.trans_eps)) dec = 3;
+            else { lambda = nu * lambda; nu = 2 * nu; dec = 0; }
+          } else {
+            x0 = xi;
+            const double w3 = 2.0 * rho - 1.0;
+            const double v = 1.0 - w3 * w3 * w3;
+            lambda = lambda * ((1.0 / 3.0 < v) ? v : 1.0 / 3.0);
+            for (int i = 0; i < 36; i++) final_H[i] = H36[i];
+            dec = 1;
+          }
+          s_decision = dec;
+        }
+        __syncthreads();
+        const int dec = s_decision;
+        __syncthreads();
+        if (dec != 0) { outcome = 1; break; }
+      }
+      if (threadIdx.x == 0) {
+        if (outcome == 0) lm_failed = 1;
+        else converged = lm_is_converged(delta, prm.rot_eps, prm.trans_eps);
+        s_x = x0;
+        s_decision = (outcome == 0) ? 0 : (converged ? 2 : 1);
+      }
+      __syncthreads();
+    }
+    const int dec = s_decision;
+    __syncthreads();
+    if (dec == 0 || dec == 2) break;
+  }
+
+  if (crank == 0 && threadIdx.x == 0) {
+    ngicp_result* res = s_pair.res;
+    double T16[16];
+    iso_to_colmajor16(x0, T16);
+    for (int i = 0; i < 16; i++) { res->final_x[i] = T16[i]; res->final_transformation[i] = (float)T16[i]; }
+    for (int i = 0; i < 36; i++) res->final_hessian[i] = final_H[i];
+    res->lm_lambda = lambda;
+    res->last_error = y0;
+    res->nr_iterations = nr_iterations;
+    res->converged = converged ? 1 : 0;
+    res->n_linearize = n_lin;
+    res->n_compute_error = n_err;
+    res->lm_failed = lm_failed;
+    res->reserved = 0;
+  }
+  cluster.sync();   // no CTA of the cluster exits while another may still read its partials / shared memory
+}
+
 // compiled variants: (resident blocks per SM, lanes per source point)
 static const void* fused_variant(int minb, int lpp) {
   if (lpp == 2) return minb <= 2 ? (const void*)align_fused_kernel<2, 2> : (const void*)align_fused_kernel<3, 2>;
@@ -730,29 +951,31 @@ void align_prime_kernels(int device) {
   cudaFuncGetAttributes(&fa, linearize_kernel);
   cudaFuncGetAttributes(&fa, compute_error_kernel);
   cudaFuncGetAttributes(&fa, reduce_partials_kernel);
+  cudaFuncGetAttributes(&fa, align_batch_kernel<1>);
+  cudaFuncGetAttributes(&fa, align_batch_kernel<2>);
   cudaGetLastError();
 }
 
 int align_fused_max_blocks(int device) { return fused_blocks_per_sm(device, 1) * sm_count_of(device); }
 
-cudaError_t launch_align_fused(const AlignBuffers& ab, const ngicp_params& p, const float* guess16, ngicp_result* res_dev,
-                               unsigned* barrier, int device, cudaStream_t st, unsigned long long* trace, const PeerComm* comm) {
-  // Variant.  Lanes per source point: 2 when the target is much larger than the scan (scan-to-map against a submap of
-  // overlapping keyframes: hundreds of candidates per query, the pair halves the chain of round trips; measured on C2:
-  // align 0.207 -> 0.178 ms) and the grid can still give every point its own pair; 1 otherwise (scan-to-scan: 0.092 vs
-  // 0.096 ms, the 255-register variant wins).  4 lanes per point need the 80-register variant and lose (0.123 ms).
-  // Then the fewest resident blocks per SM (= most registers) that hold the grid.  NGICP_ALIGN_LPP / _MINB override.
+// Launch shape of the fused LM kernel for one registration.  Lanes per source point: 2 when the target is much larger
+// than the scan (scan-to-map against a submap of overlapping keyframes: hundreds of candidates per query, the pair
+// halves the chain of round trips; measured on C2: align 0.207 -> 0.178 ms) and the grid can still give every point its
+// own pair; 1 otherwise (scan-to-scan: 0.092 vs 0.096 ms, the 255-register variant wins).  4 lanes per point need the
+// 80-register variant and lose (0.123 ms).  Then the fewest resident blocks per SM (= most registers) that hold the
+// grid.  NGICP_ALIGN_LPP / _MINB override.  The batched kernel reproduces the same blocks as virtual blocks.
+static void fused_shape(const AlignBuffers& ab, int device, int& lpp, int& minb, int& blocks) {
   static const int minb_env = getenv("NGICP_ALIGN_MINB") ? atoi(getenv("NGICP_ALIGN_MINB")) : 0;
   static const int lpp_env = getenv("NGICP_ALIGN_LPP") ? atoi(getenv("NGICP_ALIGN_LPP")) : 0;
   const int sms = sm_count_of(device);
-  int lpp = 1, minb = 1;
+  lpp = 1; minb = 1;
   if (lpp_env == 1 || lpp_env == 2) lpp = lpp_env;
   else if ((long long)ab.nt >= 4ll * ab.ns) {
     const int need = (ab.ns + AL_THREADS / 2 - 1) / (AL_THREADS / 2);
     if (need <= fused_blocks_per_sm(device, 2, 2) * sms && need <= ab.max_blocks) lpp = 2;
   }
   const int ppb = AL_THREADS / lpp;                      // source points per block and pass
-  int blocks = (ab.ns + ppb - 1) / ppb;
+  blocks = (ab.ns + ppb - 1) / ppb;
   minb = lpp == 2 ? 2 : 1;
   while (minb < 3 && blocks > fused_blocks_per_sm(device, minb, lpp) * sms) ++minb;
   if (minb_env >= 1 && minb_env <= 3) minb = minb_env;
@@ -761,7 +984,9 @@ cudaError_t launch_align_fused(const AlignBuffers& ab, const ngicp_params& p, co
   if (blocks > lim) blocks = lim;
   if (blocks > ab.max_blocks) blocks = ab.max_blocks;
   if (blocks < 1) blocks = 1;
-  AlignArgs a = make_args(ab, blocks);
+}
+
+static LmParams make_lm_params(const ngicp_params& p, unsigned long long* trace) {
   LmParams prm;
   prm.trace = trace;
   prm.max_iterations = p.max_iterations;
@@ -772,6 +997,55 @@ cudaError_t launch_align_fused(const AlignBuffers& ab, const ngicp_params& p, co
   prm.lm_init_lambda_factor = p.lm_init_lambda_factor;
   prm.thr2 = p.max_correspondence_distance * p.max_correspondence_distance;
   prm.cap_d2 = cap_from(p.max_correspondence_distance);
+  return prm;
+}
+
+size_t align_batch_pair_bytes() { return sizeof(BatchPair); }
+
+// fill one BatchPair record (host staging memory) for launch_align_batch; returns the lanes per point it needs
+int align_batch_fill(void* dst, const AlignBuffers& ab, const ngicp_params& p, const float* guess16, ngicp_result* res_dev, int device) {
+  int lpp, minb, blocks;
+  fused_shape(ab, device, lpp, minb, blocks);
+  BatchPair bp;
+  memset(&bp, 0, sizeof bp);
+  bp.a = make_args(ab, blocks);
+  bp.prm = make_lm_params(p, nullptr);
+  for (int i = 0; i < 16; i++) bp.guess.g[i] = guess16 ? guess16[i] : ((i % 5 == 0) ? 1.0f : 0.0f);
+  bp.res = res_dev;
+  bp.vblocks = blocks;
+  memcpy(dst, &bp, sizeof bp);
+  return lpp;
+}
+
+// one cluster of ALIGN_BATCH_CLUSTER blocks per pair; pairs_dev = n_pairs BatchPair records in device memory, all with
+// the same lanes-per-point
+cudaError_t launch_align_batch(const void* pairs_dev, int n_pairs, int lpp, cudaStream_t st) {
+  if (n_pairs <= 0) return cudaSuccess;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof cfg);
+  cfg.gridDim = dim3((unsigned)n_pairs * ALIGN_BATCH_CLUSTER);
+  cfg.blockDim = dim3(AL_THREADS);
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = ALIGN_BATCH_CLUSTER;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const BatchPair* pp = static_cast<const BatchPair*>(pairs_dev);
+  note_launches(1);
+  if (lpp == 2) return cudaLaunchKernelEx(&cfg, align_batch_kernel<2>, pp);
+  return cudaLaunchKernelEx(&cfg, align_batch_kernel<1>, pp);
+}
+
+cudaError_t launch_align_fused(const AlignBuffers& ab, const ngicp_params& p, const float* guess16, ngicp_result* res_dev,
+                               unsigned* barrier, int device, cudaStream_t st, unsigned long long* trace, const PeerComm* comm) {
+  int lpp, minb, blocks;
+  fused_shape(ab, device, lpp, minb, blocks);
+  AlignArgs a = make_args(ab, blocks);
+  LmParams prm = make_lm_params(p, trace);
   Guess16 g;
   for (int i = 0; i < 16; i++) g.g[i] = guess16 ? guess16[i] : ((i % 5 == 0) ? 1.0f : 0.0f);
   double* totals = ab.reduced;  // [2][NRED]

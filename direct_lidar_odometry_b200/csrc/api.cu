@@ -7,6 +7,8 @@
 #include <cmath>
 #include <mutex>
 #include <new>
+#include <string>
+#include <vector>
 
 #include "internal.h"
 #include "gicp_math.cuh"
@@ -168,8 +170,15 @@ int calc_covs(ngicp_t* h, int which, int part = 0, int nparts = 1) {
   ph_begin(h, ph);
   NG_CUDA(h, h->sc.nbr.reserve(sizeof(int) * covariance_scratch_ints(c->n, k), h->stream));
   h->nbr_cloud.reset();
+  if (!h->sc.cov_side.stream) {
+    int lo_pri = 0, hi_pri = 0;
+    cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
+    NG_CUDA(h, cudaStreamCreateWithPriority(&h->sc.cov_side.stream, cudaStreamNonBlocking, hi_pri));
+    NG_CUDA(h, cudaEventCreateWithFlags(&h->sc.cov_side.fork, cudaEventDisableTiming));
+    NG_CUDA(h, cudaEventCreateWithFlags(&h->sc.cov_side.join, cudaEventDisableTiming));
+  }
   NG_CUDA(h, launch_covariances(*c, k, h->prm.regularization_method, h->sc.nbr.as<int>(), cv->c.as<double>(), c->table_cap, h->stream->s,
-                                part, nparts, h->prm.knn_path, h->prm.knn_tile_min_points));
+                                part, nparts, h->prm.knn_path, h->prm.knn_tile_min_points, &h->sc.cov_side));
   ph_end(h, ph);
   if (nparts == 1) { h->nbr_cloud = c; h->nbr_k = k; }
   (which == NGICP_SOURCE ? h->src_cov : h->tgt_cov) = cv;
@@ -638,6 +647,55 @@ int ngicp_align(ngicp_t* h, const float* guess16, ngicp_result* out) {
   ph_end(h, PH_ALIGN);
   h->lin_valid = true;
   if (out->lm_failed) fprintf(stderr, "lm not converged!!\n");  // lsq_registration_impl.hpp:106
+  return NGICP_OK;
+}
+
+// B independent registrations in one launch: every handle is prepared like a single ngicp_align (lazy covariances,
+// per-handle state buffers), the handles' streams are joined into the first one's, and ONE kernel with a thread-block
+// cluster per pair runs all the LM loops (align.cu: align_batch_kernel).  Bit-identical to the single calls.
+int ngicp_align_batch(ngicp_t* const* hs, size_t n, const float* guesses16, ngicp_result* results) {
+  if (!hs || !results || n == 0 || !hs[0]) return NGICP_E_INVALID;
+  ngicp_t* h0 = hs[0];
+  for (size_t i = 0; i < n; ++i) {
+    if (!hs[i]) return fail(h0, NGICP_E_INVALID, "align_batch: null handle");
+    if (hs[i]->device != h0->device) return fail(h0, NGICP_E_INVALID, "align_batch: handles live on different devices");
+    if (hs[i]->comm_on) return fail(h0, NGICP_E_UNSUPPORTED, "align_batch: a handle is in sharded mode");
+    for (size_t j = 0; j < i; ++j)
+      if (hs[j] == hs[i]) return fail(h0, NGICP_E_INVALID, "align_batch: the same handle appears twice");
+  }
+  DeviceGuard g(h0->device);
+  const size_t rec = align_batch_pair_bytes();
+  std::vector<unsigned char> stage(n * rec), ordered(n * rec);
+  std::vector<int> lpp(n);
+  ph_begin(h0, PH_ALIGN);
+  for (size_t i = 0; i < n; ++i) {
+    ngicp_t* h = hs[i];
+    AlignBuffers ab;
+    int rc = prepare_align(h, true, ab);
+    if (rc) { if (h != h0) h0->err = "align_batch: pair " + std::to_string(i) + ": " + h->err; return rc; }
+    lpp[i] = align_batch_fill(stage.data() + i * rec, ab, h->prm, guesses16 ? guesses16 + 16 * i : nullptr, h->res_mapped, h->device);
+    if (h != h0) {   // everything queued on this handle's stream (index, covariances) precedes the batch kernel
+      if (!h->sc.copy_done) NG_CUDA(h0, cudaEventCreateWithFlags(&h->sc.copy_done, cudaEventDisableTiming));
+      NG_CUDA(h0, cudaEventRecord(h->sc.copy_done, h->stream->s));
+      NG_CUDA(h0, cudaStreamWaitEvent(h0->stream->s, h->sc.copy_done, 0));
+    }
+  }
+  // pairs that need two lanes per source point (target >= 4x the scan) go into a launch of their own
+  size_t n1 = 0;
+  for (size_t i = 0; i < n; ++i) if (lpp[i] != 2) memcpy(ordered.data() + (n1++) * rec, stage.data() + i * rec, rec);
+  size_t n2 = 0;
+  for (size_t i = 0; i < n; ++i) if (lpp[i] == 2) memcpy(ordered.data() + (n1 + n2++) * rec, stage.data() + i * rec, rec);
+  NG_CUDA(h0, h0->sc.batch_args.reserve(n * rec, h0->stream));
+  NG_CUDA(h0, cudaMemcpyAsync(h0->sc.batch_args.p, ordered.data(), n * rec, cudaMemcpyHostToDevice, h0->stream->s));
+  NG_CUDA(h0, launch_align_batch(h0->sc.batch_args.p, (int)n1, 1, h0->stream->s));
+  NG_CUDA(h0, launch_align_batch(h0->sc.batch_args.as<unsigned char>() + n1 * rec, (int)n2, 2, h0->stream->s));
+  ph_end(h0, PH_ALIGN);
+  NG_CUDA(h0, cudaStreamSynchronize(h0->stream->s));
+  for (size_t i = 0; i < n; ++i) {
+    results[i] = *hs[i]->res_pinned;
+    hs[i]->lin_valid = true;
+    if (results[i].lm_failed) fprintf(stderr, "lm not converged!!\n");  // lsq_registration_impl.hpp:106
+  }
   return NGICP_OK;
 }
 

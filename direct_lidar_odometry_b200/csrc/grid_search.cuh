@@ -148,7 +148,9 @@ __device__ __forceinline__ void scan_range_warp(const GridView& g, int ra, int r
 // sparse regions do not pay O(r^3) single-cell probes.
 // PRUNE (used by the 1-NN tail of the registration kernels): rows and side runs whose nearest possible point is already
 // farther than min(current bound, cap) are skipped without touching memory — exact, the bounds are margin-shrunk.
-template <class RS, bool PRUNE = false>
+// U = (y,z) row groups of 32 whose table lookups are issued together: the far shells of an isolated point are hundreds of
+// mostly empty rows, each group a dependent round trip to the (uncached) cell table — with U = 4 four of them overlap.
+template <class RS, bool PRUNE = false, int U = 1>
 __device__ __forceinline__ void grid_search_warp(const GridView& g, const GridParams& gp, float qx, float qy, float qz,
                                                  float cap_d2, RS& rs, bool start1 = false, int resume_s0 = -1) {
   const int lane = threadIdx.x & 31;
@@ -176,68 +178,79 @@ __device__ __forceinline__ void grid_search_warp(const GridView& g, const GridPa
       fz0 = fmaxf(qz - (gp.oz + (float)cz * gp.cell) - gp.margin, 0.f);
       fz1 = fmaxf((gp.oz + (float)(cz + 1) * gp.cell) - qz - gp.margin, 0.f);
     }
-    for (int base = 0; base < nrows; base += 32) {
-      const int r = base + lane;
-      int a1 = 0, b1 = 0, a2 = 0, b2 = 0;
-      if (r < nrows) {
-        // first 3x3 step: own row first, then the edge-adjacent rows, then the corners (tighter bound earlier)
-        const int rr = (s0 < 0 && s1 == 1) ? (int)((0x620837154ULL >> (4 * r)) & 15ULL) : r;
-        const int rz = rr / w;
-        const int yy = rr - rz * w - s1, zz = rz - s1;
-        const int y = cy + yy, z = cz + zz;
-        bool keep = (y >= 0 && y < gp.dy && z >= 0 && z < gp.dz);
-        float dyz = 0.f;
-        if (PRUNE) {
-          const float dy = yy == 0 ? 0.f : (yy < 0 ? fy0 + (float)(-yy - 1) * gp.cell : fy1 + (float)(yy - 1) * gp.cell);
-          const float dz = zz == 0 ? 0.f : (zz < 0 ? fz0 + (float)(-zz - 1) * gp.cell : fz1 + (float)(zz - 1) * gp.cell);
-          dyz = (dy * dy + dz * dz) * 0.999999f;
-          keep = keep && dyz < lim;
-        }
-        if (keep) {
-          const int* row = g.cell_start + (z * gp.dy + y) * gp.dx;
-          if (max(abs(yy), abs(zz)) > s0) {
-            a1 = __ldg(row + xlo);
-            b1 = __ldg(row + xhi + 1);
-          } else {
-            const int xl = cx - s0 - 1, xr = cx + s0 + 1;
-            bool kl = xlo <= xl, kr = xr <= xhi;
-            if (PRUNE) {   // nearest x distance to the side runs [.., cx-s0-1] and [cx+s0+1, ..]
-              const float sxl = fx0 + (float)s0 * gp.cell, sxr = fx1 + (float)s0 * gp.cell;
-              kl = kl && dyz + sxl * sxl * 0.999999f < lim;
-              kr = kr && dyz + sxr * sxr * 0.999999f < lim;
+    for (int base0 = 0; base0 < nrows; base0 += 32 * U) {
+      int A1[U], B1[U], A2[U], B2[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int r = base0 + u * 32 + lane;
+        int a1 = 0, b1 = 0, a2 = 0, b2 = 0;
+        if (r < nrows) {
+          // first 3x3 step: own row first, then the edge-adjacent rows, then the corners (tighter bound earlier)
+          const int rr = (s0 < 0 && s1 == 1) ? (int)((0x620837154ULL >> (4 * r)) & 15ULL) : r;
+          const int rz = rr / w;
+          const int yy = rr - rz * w - s1, zz = rz - s1;
+          const int y = cy + yy, z = cz + zz;
+          bool keep = (y >= 0 && y < gp.dy && z >= 0 && z < gp.dz);
+          float dyz = 0.f;
+          if (PRUNE) {
+            const float dy = yy == 0 ? 0.f : (yy < 0 ? fy0 + (float)(-yy - 1) * gp.cell : fy1 + (float)(yy - 1) * gp.cell);
+            const float dz = zz == 0 ? 0.f : (zz < 0 ? fz0 + (float)(-zz - 1) * gp.cell : fz1 + (float)(zz - 1) * gp.cell);
+            dyz = (dy * dy + dz * dz) * 0.999999f;
+            keep = keep && dyz < lim;
+          }
+          if (keep) {
+            const int* row = g.cell_start + (z * gp.dy + y) * gp.dx;
+            if (max(abs(yy), abs(zz)) > s0) {
+              a1 = __ldg(row + xlo);
+              b1 = __ldg(row + xhi + 1);
+            } else {
+              const int xl = cx - s0 - 1, xr = cx + s0 + 1;
+              bool kl = xlo <= xl, kr = xr <= xhi;
+              if (PRUNE) {   // nearest x distance to the side runs [.., cx-s0-1] and [cx+s0+1, ..]
+                const float sxl = fx0 + (float)s0 * gp.cell, sxr = fx1 + (float)s0 * gp.cell;
+                kl = kl && dyz + sxl * sxl * 0.999999f < lim;
+                kr = kr && dyz + sxr * sxr * 0.999999f < lim;
+              }
+              if (kl) { a1 = __ldg(row + xlo); b1 = __ldg(row + xl + 1); }
+              if (kr) { a2 = __ldg(row + xr); b2 = __ldg(row + xhi + 1); }
             }
-            if (kl) { a1 = __ldg(row + xlo); b1 = __ldg(row + xl + 1); }
-            if (kr) { a2 = __ldg(row + xr); b2 = __ldg(row + xhi + 1); }
           }
         }
+        A1[u] = a1; B1[u] = b1; A2[u] = a2; B2[u] = b2;
       }
-      // flatten the (mostly short) runs of the 32 rows into one candidate stream: inclusive scan of the run
-      // lengths, then every lane finds the run its candidate index falls into (5-step search over lanes)
-      const int len1 = b1 - a1;
-      const int len = len1 + (b2 - a2);
-      int inc = len;
 #pragma unroll
-      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
-      const int total = __shfl_sync(FULL, inc, 31);
-      const int excl = inc - len;
-      for (int t0 = 0; t0 < total; t0 += 32) {
-        const int t = t0 + lane;
-        const bool valid = t < total;
-        int j = 0;
+      for (int u = 0; u < U; ++u) {
+        if (U > 1 && base0 + u * 32 >= nrows) break;
+        const int a1 = A1[u], b1 = B1[u], a2 = A2[u], b2 = B2[u];
+        // flatten the (mostly short) runs of the 32 rows into one candidate stream: inclusive scan of the run
+        // lengths, then every lane finds the run its candidate index falls into (5-step search over lanes)
+        const int len1 = b1 - a1;
+        const int len = len1 + (b2 - a2);
+        if (!__any_sync(FULL, len != 0)) continue;            // 32 empty rows: nothing to scan
+        int inc = len;
 #pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {
-          const int v = __shfl_sync(FULL, inc, j + step - 1);
-          if (v <= t) j += step;
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+        const int total = __shfl_sync(FULL, inc, 31);
+        const int excl = inc - len;
+        for (int t0 = 0; t0 < total; t0 += 32) {
+          const int t = t0 + lane;
+          const bool valid = t < total;
+          int j = 0;
+#pragma unroll
+          for (int step = 16; step > 0; step >>= 1) {
+            const int v = __shfl_sync(FULL, inc, j + step - 1);
+            if (v <= t) j += step;
+          }
+          const int off = t - __shfl_sync(FULL, excl, j);
+          const int ja1 = __shfl_sync(FULL, a1, j), jl1 = __shfl_sync(FULL, len1, j), ja2 = __shfl_sync(FULL, a2, j);
+          const int p = off < jl1 ? ja1 + off : ja2 + (off - jl1);
+          float d = FLT_MAX;
+          if (valid) {
+            const float4 c = __ldg(g.sorted + p);
+            d = sqdist_unfused(qx, qy, qz, c.x, c.y, c.z);
+          }
+          rs.offer(valid, d, p);
         }
-        const int off = t - __shfl_sync(FULL, excl, j);
-        const int ja1 = __shfl_sync(FULL, a1, j), jl1 = __shfl_sync(FULL, len1, j), ja2 = __shfl_sync(FULL, a2, j);
-        const int p = off < jl1 ? ja1 + off : ja2 + (off - jl1);
-        float d = FLT_MAX;
-        if (valid) {
-          const float4 c = __ldg(g.sorted + p);
-          d = sqdist_unfused(qx, qy, qz, c.x, c.y, c.z);
-        }
-        rs.offer(valid, d, p);
       }
     }
     if (s1 >= rmax) break;

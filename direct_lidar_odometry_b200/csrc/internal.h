@@ -80,12 +80,23 @@ struct DevCovs {
 };
 typedef std::shared_ptr<DevCovs> CovsPtr;
 
+// side stream (high priority) + fork/join events on which the tile path answers its warp-search rest beside the main
+// covariance launch; nullptr = everything on the one stream
+struct CovSideStream { cudaStream_t stream = nullptr; cudaEvent_t fork = nullptr, join = nullptr; };
+
 // grow-only scratch owned by a handle
 struct Scratch {
   Scratch() {}
   Scratch(const Scratch&) = delete;
   Scratch& operator=(const Scratch&) = delete;
-  ~Scratch() { if (vox_result) cudaFreeHost(vox_result); if (copy_done) cudaEventDestroy(copy_done); }
+  ~Scratch() {
+    if (vox_result) cudaFreeHost(vox_result);
+    if (copy_done) cudaEventDestroy(copy_done);
+    if (cov_side.stream) { cudaStreamSynchronize(cov_side.stream); cudaStreamDestroy(cov_side.stream); }
+    if (cov_side.fork) cudaEventDestroy(cov_side.fork);
+    if (cov_side.join) cudaEventDestroy(cov_side.join);
+  }
+  CovSideStream cov_side;            // created on first use by calc_covs
   cudaEvent_t copy_done = nullptr;   // see host_source_consumed()
   DevBuf staging;    // raw bytes of caller records
   DevBuf keys_a, keys_b, vals_a, vals_b;
@@ -111,6 +122,7 @@ struct Scratch {
   DevBuf lm_state;   // device-resident LM state / result of the fused kernel
   DevBuf barrier;    // unsigned counters for the grid barrier
   DevBuf trace;      // debug: %globaltimer stamps of the fused kernel
+  DevBuf batch_args; // BatchPair records of ngicp_align_batch
 };
 
 // number of kernels launched by this library since load (diagnostics; ngicp_launch_count())
@@ -132,7 +144,8 @@ cudaError_t build_index(DevCloud& c, float cell_req, int table_cap, Scratch& sc,
 cudaError_t launch_knn_queries(const DevCloud& c, const float4* queries, int nq, int k, int* idx, float* d2, cudaStream_t st);
 size_t covariance_scratch_ints(int n, int k);   // neighbour lists + the work lists of the kNN kernels
 cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_scratch /* covariance_scratch_ints() */, double* covs6, int table_cap, cudaStream_t st,
-                               int part = 0, int nparts = 1, int knn_path = NGICP_KNN_AUTO, int tile_min_points = 131072);
+                               int part = 0, int nparts = 1, int knn_path = NGICP_KNN_AUTO, int tile_min_points = 131072,
+                               const CovSideStream* side = nullptr);
 // test hook: the neighbour lists left in nbr_scratch by launch_covariances, in summation order, as original indices
 cudaError_t launch_export_neighbors(const DevCloud& c, int k, const int* nbr_scratch, int* idx_out, float* d2_out, cudaStream_t st);
 constexpr int KNN_MAX_K = 32;
@@ -168,6 +181,10 @@ cudaError_t launch_align_fused(const AlignBuffers& ab, const ngicp_params& prm, 
                                unsigned* barrier, int device, cudaStream_t st, unsigned long long* trace = nullptr,
                                const PeerComm* comm = nullptr);
 int align_fused_max_blocks(int device);
+// batched registration (ngicp_align_batch): one cluster per pair, see align.cu
+size_t align_batch_pair_bytes();
+int align_batch_fill(void* dst, const AlignBuffers& ab, const ngicp_params& p, const float* guess16, ngicp_result* res_dev, int device);
+cudaError_t launch_align_batch(const void* pairs_dev, int n_pairs, int lpp, cudaStream_t st);
 void align_prime_kernels(int device);
 void knn_prime_kernels();
 

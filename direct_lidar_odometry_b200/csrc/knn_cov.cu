@@ -13,6 +13,7 @@
 #include "internal.h"
 #include "grid_search.cuh"
 #include "gicp_math.cuh"
+#include "sort_networks.inc"
 
 namespace ngicp {
 
@@ -88,7 +89,7 @@ __global__ void __launch_bounds__(KC_THREADS, KNN_MIN_BLOCKS) knn_lists_kernel(G
 #define TQ_WARPS 2
 #endif
 #ifndef TQ_CMAX
-#define TQ_CMAX 384      // tile capacity (points)
+#define TQ_CMAX 384      // tile capacity (slots: rows are padded to even lengths)
 #endif
 #ifndef TQ_LCAP
 #define TQ_LCAP 40       // per-query collection capacity
@@ -96,12 +97,27 @@ __global__ void __launch_bounds__(KC_THREADS, KNN_MIN_BLOCKS) knn_lists_kernel(G
 #ifndef TQ_CORE
 #define TQ_CORE 4        // box edge in cells
 #endif
+#ifndef TQ_SELECT_NET
+#define TQ_SELECT_NET 1  // 1: sorting-network selection of the k nearest in registers; 0: secant steps on the count
+#endif
+#ifndef TQ_PACKED
+#define TQ_PACKED 1      // 1: packed f32x2 distance arithmetic (two candidates per instruction); 0: scalar
+#endif
+#ifndef TQ_UNROLL
+#define TQ_UNROLL 1   // measured on C2 (benchmarks/ab_knn.py): 1: 0.752 ms, 2: 0.764, 4: 0.869 for the covariance phase
+#endif
+#define NG_PRAGMA_(x) _Pragma(#x)
+#define NG_UNROLL(n) NG_PRAGMA_(unroll n)
 #ifndef TQ_SMAX
 #define TQ_SMAX 16       // largest tile radius tried before a point goes to the warp search
 #endif
 constexpr int TQ_ITEM = 64;  // points per work item
 struct TileSmem {
-  float4 cand[TQ_CMAX];                  // x, y, z, bits(sorted slot)
+  // staged candidates, structure of arrays: two neighbouring candidates are one 64-bit shared load per coordinate and go
+  // through the packed f32x2 pipe together (FADD2 / FMUL2 / FFMA2, sm_100).  Every (y,z) row of the tile starts at an
+  // even position and is padded to an even length with a point at +infinity (its distance is +inf: never collected).
+  float xs[TQ_CMAX], ys[TQ_CMAX], zs[TQ_CMAX];
+  int slot[TQ_CMAX];                     // sorted slot of the candidate
   uint2 lst[TQ_LCAP + 1][32];            // collected {bits(distance), tile position}, one column per lane; last row = dump
   int cur[TQ_ITEM];                      // sorted slots of the points being answered from the current tile
   float cur_t[TQ_ITEM];                  // their threshold guesses (0 = none yet) ...
@@ -133,8 +149,10 @@ enum { ST_FALLBACK = 0, ST_TIES, ST_TILES, ST_PASSES, ST_LANES, ST_ITEMS, ST_N }
 enum { CT_ITEMS = 0, CT_NEXT, CT_REST, CT_REST_NEXT, CT_DONE, CT_N = 8 };
 
 // warp-aggregated append of the lanes in `mask` to the warp-search list
-__device__ __forceinline__ void fb_append(unsigned mask, int slot, int lane, int* __restrict__ fb_list, int* __restrict__ fb_count) {
+__device__ __forceinline__ void fb_append(unsigned mask, int slot, int lane, int* __restrict__ fb_list, int* __restrict__ fb_count,
+                                          unsigned char* __restrict__ fb_flags) {
   if (!mask) return;
+  if ((mask >> lane) & 1u) fb_flags[slot] = 1;     // the main covariance launch skips it; cov_rest_kernel does it after the warp search
   const int leader = __ffs(mask) - 1;
   int base = 0;
   if (lane == leader) base = atomicAdd(fb_count, __popc(mask));
@@ -266,11 +284,35 @@ __device__ __noinline__ Shrunk shrink_list(uint2* col, float T2, int cnt) {
   r.T2 = T2; r.cnt = cnt;
   return r;
 }
+// packed f32x2 arithmetic (sm_100): one instruction works on two candidates.  Every operation is the IEEE round-to-nearest
+// one of nanoflann's metric, in the same order — d = ((dx*dx) + dy*dy) + dz*dz with every product and sum rounded on its
+// own.  ptxas contracts a packed multiply followed by a packed add into FFMA2 even under -fmad=false, so the sums are
+// written as fma(a, 1, b) with a ONE the compiler cannot see through (a kernel argument): round(a * 1 + b) == round(a + b).
+__device__ __forceinline__ unsigned long long f2_pack(float lo, float hi) { unsigned long long r; asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ void f2_unpack(unsigned long long v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ unsigned long long f2_sub(unsigned long long a, unsigned long long b) { unsigned long long r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ unsigned long long f2_mul(unsigned long long a, unsigned long long b) { unsigned long long r; asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ unsigned long long f2_fma(unsigned long long a, unsigned long long b, unsigned long long c) { unsigned long long r; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c)); return r; }
+struct Query2 { unsigned long long x, y, z, one; };   // the query's coordinates and 1.0f, each duplicated into both halves
+__device__ __forceinline__ unsigned long long sqdist2_unfused(const Query2& q, unsigned long long px, unsigned long long py, unsigned long long pz) {
+#if TQ_PACKED
+  const unsigned long long dx = f2_sub(q.x, px), dy = f2_sub(q.y, py), dz = f2_sub(q.z, pz);
+  return f2_fma(f2_fma(f2_mul(dx, dx), q.one, f2_mul(dy, dy)), q.one, f2_mul(dz, dz));
+#else
+  float qx, qy, qz, t, x0, x1, y0, y1, z0, z1;
+  f2_unpack(q.x, qx, t); f2_unpack(q.y, qy, t); f2_unpack(q.z, qz, t);
+  f2_unpack(px, x0, x1); f2_unpack(py, y0, y1); f2_unpack(pz, z0, z1);
+  return f2_pack(sqdist_unfused(qx, qy, qz, x0, y0, z0), sqdist_unfused(qx, qy, qz, x1, y1, z1));
+#endif
+}
+
 // "write, then advance if it passed": the slot after the last accepted entry is simply overwritten by the next
-// candidate, so an offer is one 64-bit shared store plus one predicated pointer bump (row stride 256 B)
-__device__ __forceinline__ int collect_pass(TileSmem& S, int c, int cend, float qx, float qy, float qz, float& T2_io, int lane, int cnt) {
-  uint2* const col = &S.lst[0][lane];
+// candidate, so an offer is one 64-bit shared store plus one predicated pointer bump (row stride 256 B).
+// c and cend are even (rows are padded to even lengths).
+__device__ __forceinline__ int collect_pass(const TileSmem& S, uint2* const col, int c, int cend, float qx, float qy, float qz, float one, float& T2_io, int cnt) {
   float T2 = T2_io;
+  Query2 q;
+  q.x = f2_pack(qx, qx); q.y = f2_pack(qy, qy); q.z = f2_pack(qz, qz); q.one = f2_pack(one, one);
   // 32-bit shared-window addresses: the bump is one predicated integer add
   const unsigned a0 = (unsigned)__cvta_generic_to_shared(col);
   unsigned p = a0 + (unsigned)cnt * 256u;
@@ -286,32 +328,47 @@ __device__ __forceinline__ int collect_pass(TileSmem& S, int c, int cend, float 
     T2 = r.T2;                                                                  \
     p = a0 + (unsigned)r.cnt * 256u;                                            \
   }
+#define TQ_PAIR(CI)                                                                                                     \
+  {                                                                                                                     \
+    const unsigned long long d01 = sqdist2_unfused(q, *reinterpret_cast<const unsigned long long*>(S.xs + (CI)),        \
+                                                   *reinterpret_cast<const unsigned long long*>(S.ys + (CI)),           \
+                                                   *reinterpret_cast<const unsigned long long*>(S.zs + (CI)));          \
+    float da, db;                                                                                                       \
+    f2_unpack(d01, da, db);                                                                                             \
+    TQ_OFFER(da, (CI)) TQ_OFFER(db, (CI) + 1)                                                                           \
+  }
+  if ((c & 2) && c < cend) { TQ_PAIR(c) TQ_MAYBE_SHRINK() c += 2; }   // up to a multiple of four: 128-bit loads from here on
+NG_UNROLL(TQ_UNROLL)
   for (; c + 4 <= cend; c += 4) {
-    const float4 p0 = S.cand[c], p1 = S.cand[c + 1], p2 = S.cand[c + 2], p3 = S.cand[c + 3];
-    const float d0 = sqdist_unfused(qx, qy, qz, p0.x, p0.y, p0.z);
-    const float d1 = sqdist_unfused(qx, qy, qz, p1.x, p1.y, p1.z);
-    const float d2 = sqdist_unfused(qx, qy, qz, p2.x, p2.y, p2.z);
-    const float d3 = sqdist_unfused(qx, qy, qz, p3.x, p3.y, p3.z);
+    const ulonglong2 X = *reinterpret_cast<const ulonglong2*>(S.xs + c);
+    const ulonglong2 Y = *reinterpret_cast<const ulonglong2*>(S.ys + c);
+    const ulonglong2 Z = *reinterpret_cast<const ulonglong2*>(S.zs + c);
+    const unsigned long long d01 = sqdist2_unfused(q, X.x, Y.x, Z.x), d23 = sqdist2_unfused(q, X.y, Y.y, Z.y);
+    float d0, d1, d2, d3;
+    f2_unpack(d01, d0, d1);
+    f2_unpack(d23, d2, d3);
     TQ_OFFER(d0, c) TQ_OFFER(d1, c + 1) TQ_OFFER(d2, c + 2) TQ_OFFER(d3, c + 3)
     TQ_MAYBE_SHRINK()                                           // room for the next four is guaranteed
   }
-  for (; c < cend; ++c) {
-    const float4 p0 = S.cand[c];
-    const float d0 = sqdist_unfused(qx, qy, qz, p0.x, p0.y, p0.z);
-    TQ_OFFER(d0, c)
-    TQ_MAYBE_SHRINK()
-  }
+  if (c < cend) { TQ_PAIR(c) TQ_MAYBE_SHRINK() }
+#undef TQ_PAIR
 #undef TQ_OFFER
 #undef TQ_MAYBE_SHRINK
   T2_io = T2;
   return (int)((p - a0) >> 8);
 }
 
-__global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView g, int n, int k, int* __restrict__ nbr,
+// v[k-1], v[k] of a register array with a run-time k (forces the array through local memory; generic-k path only)
+__device__ __noinline__ float2 pick_kth(const float* v, int k) { return make_float2(v[k - 1], v[k]); }
+
+template <int KT>
+__global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView g, int n, int k_rt, int* __restrict__ nbr,
                                                                         const int4* __restrict__ items, int* __restrict__ ctrl,
-                                                                        int* __restrict__ fb_list, unsigned long long* __restrict__ stats,
-                                                                        int q_lo, int q_hi) {
+                                                                        int* __restrict__ fb_list, unsigned char* __restrict__ fb_flags,
+                                                                        unsigned long long* __restrict__ stats,
+                                                                        int q_lo, int q_hi, float one /* 1.0f, see sqdist2_unfused */) {
   extern __shared__ __align__(16) unsigned char tq_smem_raw[];
+  const int k = KT > 0 ? KT : k_rt;
   TileSmem& S = reinterpret_cast<TileSmem*>(tq_smem_raw)[threadIdx.x >> 5];
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
@@ -381,20 +438,22 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
           if (s <= 2 && r < nrows) S.rowoff[r] = C;
           continue;
         }
-        const int inc = warp_incl_scan(b - a, lane);
+        const int len = b - a, plen = (len + 1) & ~1;           // rows are padded to even lengths
+        const int inc = warp_incl_scan(plen, lane);
         const int Cr = __shfl_sync(FULL, inc, 31);
         if (C + Cr > TQ_CMAX) { overflow = true; break; }
-        const int excl = inc - (b - a);
+        const int excl = inc - plen;
         if (s <= 2 && r < nrows) S.rowoff[r] = C + excl;
         for (int t0 = 0; t0 < Cr; t0 += 32) {
           const int t = t0 + lane;
           const int j = run_of(inc, t);
-          const int ja = __shfl_sync(FULL, a, j), je = __shfl_sync(FULL, excl, j);
+          const int ja = __shfl_sync(FULL, a, j), je = __shfl_sync(FULL, excl, j), jl = __shfl_sync(FULL, len, j);
           if (t < Cr) {
-            int p = ja + (t - je);
-            float4 c = __ldg(g.sorted + p);
-            c.w = __int_as_float(p);
-            S.cand[C + t] = c;
+            const int off = t - je;
+            float4 c = make_float4(INFINITY, 0.f, 0.f, 0.f);    // the padding slot of an odd row
+            int p = -1;
+            if (off < jl) { p = ja + off; c = __ldg(g.sorted + p); }
+            S.xs[C + t] = c.x; S.ys[C + t] = c.y; S.zs[C + t] = c.z; S.slot[C + t] = p;
           }
         }
         C += Cr;
@@ -450,9 +509,9 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
             float Tc = active ? T2 : -1.f;      // may come back lower: the lane shrank its list on the way
             if (s <= 2) {
               for (int zr = zlo; zr <= zhi && yhi >= ylo; ++zr)
-                c_now = collect_pass(S, S.rowoff[zr * ny + ylo], S.rowoff[zr * ny + yhi + 1], qp.x, qp.y, qp.z, Tc, lane, c_now);
+                c_now = collect_pass(S, &S.lst[0][lane], S.rowoff[zr * ny + ylo], S.rowoff[zr * ny + yhi + 1], qp.x, qp.y, qp.z, one, Tc, c_now);
             } else {
-              c_now = collect_pass(S, 0, C, qp.x, qp.y, qp.z, Tc, lane, 0);
+              c_now = collect_pass(S, &S.lst[0][lane], 0, C, qp.x, qp.y, qp.z, one, Tc, 0);
             }
             if (active) T2 = Tc;
           }
@@ -460,11 +519,54 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
           // too few even at the largest provable radius (or no provable radius at all): needs a larger tile
           const bool grow = me && (!active || (c_now < k && T2 >= m2));
           const bool retry = active && !good && !grow;
+#if TQ_SELECT_NET
+          // ---- exactly k of the collected points: the lane sorts the distances of its list in registers (a fixed
+          //      compare-exchange network: no data-dependent loop, every lane of the warp does the same work) and keeps
+          //      what lies below the (k+1)-th smallest; an exact tie between the k-th and the (k+1)-th has no such
+          //      threshold: those (rare) points take the warp search ----
+          bool decided = good;
+          bool tie = false;
+          float Tk = T2, kth = T2;
+          {
+            const bool searching = good && c_now > k;
+            const bool any_search = __any_sync(FULL, searching);
+            if (any_search) {
+              static_assert(TQ_LCAP == 40 || TQ_LCAP == 32, "the selection networks are generated for 32 and 40 wires");
+              float v[TQ_LCAP];
+#pragma unroll
+              for (int i = 0; i < TQ_LCAP; ++i) v[i] = (searching && i < c_now) ? __uint_as_float(S.lst[i][lane].x) : INFINITY;
+#define NG_FCAS(A, B) { const float lo_ = fminf(v[A], v[B]), hi_ = fmaxf(v[A], v[B]); v[A] = lo_; v[B] = hi_; }
+#if TQ_LCAP == 40
+              NGICP_SORTNET_40(NG_FCAS)
+#else
+              NGICP_SORTNET_32(NG_FCAS)
+#endif
+#undef NG_FCAS
+              // the k-th and (k+1)-th smallest: static register indices when k is a template argument (10 and 20, what
+              // DLO uses); a run-time k goes through a small local array (one copy of the network either way — indexing
+              // the registers with a run-time k made the compiler clone the whole network per value of k)
+              float vk, vk1;
+              if (KT > 0) { vk = v[KT > 0 ? KT - 1 : 0]; vk1 = v[KT > 0 ? KT : 0]; }
+              else { const float2 pk = pick_kth(v, k); vk = pk.x; vk1 = pk.y; }
+              if (searching) {
+                if (vk == vk1) { tie = true; decided = false; st_ties++; }
+                else { Tk = vk1; kth = vk; }
+              }
+              const bool compact = searching && !tie;
+              int pos = 0;
+#pragma unroll
+              for (int i = 0; i < TQ_LCAP; ++i) {
+                const uint2 e = S.lst[i][lane];
+                if (compact && i < c_now && __uint_as_float(e.x) < Tk) { S.lst[pos][lane].y = e.y; ++pos; }
+              }
+            }
+          }
+#else
           // ---- tighten the threshold on the lane's own list until exactly k remain: the distances move into
           //      registers once, the secant steps on the count then run without touching memory (warp-uniform loops) ----
           bool decided = good;
           bool tie = false;
-          float Tk = T2;
+          float Tk = T2, kth = T2;
           {
             bool searching = good && c_now > k;
             const bool any_search = __any_sync(FULL, searching);
@@ -483,7 +585,7 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
 #pragma unroll
               for (int i = 0; i < TQ_LCAP; ++i) c += (dl[i] < T) ? 1 : 0;
               if (searching) {
-                if (c == k) { searching = false; Tk = T; }
+                if (c == k) { searching = false; Tk = T; kth = T; }
                 else if (c < k) { slo = T; clo = c; }
                 else { shi = T; chi = c; }
               }
@@ -499,21 +601,22 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
               }
             }
           }
-          if (decided) prevT = Tk;
+#endif
+          if (decided) prevT = kth;
           const unsigned dmask = __ballot_sync(FULL, decided);
           __syncwarp();
           // ---- coalesced write-out: one query per step, lane j writes the j-th neighbour ----
           for (unsigned mm = dmask; mm; mm &= mm - 1) {
             const int l = __ffs(mm) - 1;
             const int sl = __shfl_sync(FULL, slot, l);
-            TQ_CHECK(lane >= k || S.lst[lane][l].y < (unsigned)C, "tilepos", (int)S.lst[lane][l].y, C);
-            if (lane < k) nbr[(size_t)sl * k + lane] = __float_as_int(S.cand[S.lst[lane][l].y].w);
+            TQ_CHECK(lane >= k || (S.lst[lane][l].y < (unsigned)C && S.slot[S.lst[lane][l].y] >= 0), "tilepos", (int)S.lst[lane][l].y, C);
+            if (lane < k) nbr[(size_t)sl * k + lane] = S.slot[S.lst[lane][l].y];
           }
           __syncwarp();
           // ---- the rest: ties to the warp search, growers to the next radius, retries back into the queue ----
           const unsigned tm = __ballot_sync(FULL, tie);
           st_fb += __popc(tm);
-          fb_append(tm, slot, lane, fb_list, ctrl + CT_REST);
+          fb_append(tm, slot, lane, fb_list, ctrl + CT_REST, fb_flags);
           const unsigned gm = __ballot_sync(FULL, grow);
           if (grow) S.nxt[nnxt + __popc(gm & lt)] = slot;
           nnxt += __popc(gm);
@@ -555,7 +658,7 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
       const int slot = has ? S.cur[t0 + lane] : -1;
       const unsigned m = __ballot_sync(FULL, has);
       st_fb += __popc(m);
-      fb_append(m, slot, lane, fb_list, ctrl + CT_REST);
+      fb_append(m, slot, lane, fb_list, ctrl + CT_REST, fb_flags);
     }
     __syncwarp();
   }
@@ -570,7 +673,7 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
 }
 
 // the points the tile kernel could not decide: one warp per listed point, growing-cube search (same result definition)
-__global__ void __launch_bounds__(KC_THREADS, KNN_MIN_BLOCKS) knn_lists_rest_kernel(GridView g, int k, int* __restrict__ nbr, const int* __restrict__ ctrl,
+__global__ void __launch_bounds__(KC_THREADS, 4) knn_lists_rest_kernel(GridView g, int k, int* __restrict__ nbr, const int* __restrict__ ctrl,
                                                                                      const int* __restrict__ fb_list) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -582,67 +685,63 @@ __global__ void __launch_bounds__(KC_THREADS, KNN_MIN_BLOCKS) knn_lists_rest_ker
     const float4 qp = __ldg(g.sorted + q);
     WarpTopK rs;
     rs.init(k, lane);
-    if (isfinite(qp.x) && isfinite(qp.y) && isfinite(qp.z)) grid_search_warp(g, gp, qp.x, qp.y, qp.z, FLT_MAX, rs, k >= 4);
+    if (isfinite(qp.x) && isfinite(qp.y) && isfinite(qp.z)) grid_search_warp<WarpTopK, false, 4>(g, gp, qp.x, qp.y, qp.z, FLT_MAX, rs, k >= 4);
     if (lane < k) nbr[(size_t)q * k + lane] = rs.p;
   }
 }
 
 // K3: one thread per point — mean, covariance / k, regularisation, all fp64 (nano_gicp_impl.hpp:315-353).
-// The sums run over the k neighbours in ascending (squared distance, original index) order: nearestKSearch returns them
+// The sums run over the k neighbours in ascending (squared distance, sorted slot) order: nearestKSearch returns them
 // ascending (nanoflann_impl.hpp:184-211) and the reference adds them up in that order (:315-321), so on neighbourhoods
 // without exact distance ties the fp64 mean and covariance reproduce the reference's bits whichever kNN kernel made the
 // list (the tile kernel delivers the SET in slot order; the warp search delivers it sorted, ties in visiting order).
 // KT > 0: k known at compile time (10 and 20, the values DLO uses) — keys in registers, k^2 unrolled rank computation.
-__device__ __forceinline__ bool nb_before(float da, int oa, int ia, float db, int ob, int ib) {
-  return da < db || (da == db && (oa < ob || (oa == ob && ia < ib)));
-}
 template <int KT>
-__global__ void __launch_bounds__(128) cov_from_lists_kernel(GridView g, int n, int k_rt, int method, const int* __restrict__ nbr,
-                                                             double* __restrict__ covs6, int q_lo, int q_hi,
-                                                             int* __restrict__ idx_out, float* __restrict__ d2_out) {
+__device__ __forceinline__ void cov_point(const GridView& g, int n, int k_rt, int method, const int* __restrict__ nbr, double* __restrict__ covs6,
+                                          int q, int* __restrict__ idx_out, float* __restrict__ d2_out) {
   constexpr int KA = KT > 0 ? KT : KNN_MAX_K;
   const int k = KT > 0 ? KT : k_rt;
-  const int q = q_lo + blockIdx.x * blockDim.x + threadIdx.x;
-  if (q >= q_hi || q >= n) return;
   const int* my = nbr + (size_t)q * k;
   const float4 qp = __ldg(g.sorted + q);
   const int orig = __float_as_int(qp.w);
   int ord[KA];          // neighbour slots in summation order (dynamically indexed: local memory, L1 resident)
   if (KT > 0) {
-    int p[KA], o[KA];
-    float d[KA];
+    // keys = (bits of the squared distance) << 32 | sorted slot: non-negative floats order like their bit patterns, the
+    // slot breaks exact ties (slots follow (cell, original index), the same for every kNN kernel and every slicing)
+    unsigned long long key[KA];
     bool in_order = true;
 #pragma unroll
     for (int j = 0; j < KA; ++j) {
-      p[j] = __ldg(my + j);
-      TQ_CHECK(p[j] < n, "nbr", p[j], q);
-      d[j] = INFINITY; o[j] = 0x7fffffff;
-      if (p[j] >= 0) { const float4 c = __ldg(g.sorted + p[j]); d[j] = sqdist_unfused(qp.x, qp.y, qp.z, c.x, c.y, c.z); o[j] = __float_as_int(c.w); }
-      if (j > 0) in_order = in_order && !nb_before(d[j], o[j], j, d[j - 1], o[j - 1], j - 1);
-    }
-    if (in_order) {
-#pragma unroll
-      for (int j = 0; j < KA; ++j) ord[j] = p[j];
-    } else {
-#pragma unroll
-      for (int j = 0; j < KA; ++j) {
-        int r = 0;
-#pragma unroll
-        for (int i = 0; i < KA; ++i) r += nb_before(d[i], o[i], i, d[j], o[j], j) ? 1 : 0;
-        ord[r] = p[j];
+      const int p = __ldg(my + j);
+      TQ_CHECK(p < n, "nbr", p, q);
+      key[j] = 0xffffffff00000000ull | (unsigned)j;           // no neighbour: sorts last, decodes to -1
+      if (p >= 0) {
+        const float4 c = __ldg(g.sorted + p);
+        key[j] = ((unsigned long long)__float_as_uint(sqdist_unfused(qp.x, qp.y, qp.z, c.x, c.y, c.z)) << 32) | (unsigned)p;
       }
+      if (j > 0) in_order = in_order && key[j - 1] <= key[j];
     }
+    if (!in_order) {
+#define NG_CAS(A, B) { const unsigned long long ka = key[A], kb = key[B]; const bool sw = kb < ka; key[A] = sw ? kb : ka; key[B] = sw ? ka : kb; }
+      if (KT == 10) { NGICP_SORTNET_10(NG_CAS) }
+      else { NGICP_SORTNET_20(NG_CAS) }
+#undef NG_CAS
+    }
+#pragma unroll
+    for (int j = 0; j < KA; ++j) ord[j] = (key[j] >> 32) == 0xffffffffull ? -1 : (int)(unsigned)key[j];
   } else {
-    int o[KA];
-    float d[KA];
+    unsigned long long key[KA];
     for (int j = 0; j < k; ++j) {
       const int p = __ldg(my + j);
-      d[j] = INFINITY; o[j] = 0x7fffffff;
-      if (p >= 0) { const float4 c = __ldg(g.sorted + p); d[j] = sqdist_unfused(qp.x, qp.y, qp.z, c.x, c.y, c.z); o[j] = __float_as_int(c.w); }
+      key[j] = 0xffffffff00000000ull | (unsigned)j;
+      if (p >= 0) {
+        const float4 c = __ldg(g.sorted + p);
+        key[j] = ((unsigned long long)__float_as_uint(sqdist_unfused(qp.x, qp.y, qp.z, c.x, c.y, c.z)) << 32) | (unsigned)p;
+      }
     }
-    for (int j = 0; j < k; ++j) {
+    for (int j = 0; j < k; ++j) {       // rank by counting (keys are distinct)
       int r = 0;
-      for (int i = 0; i < k; ++i) r += nb_before(d[i], o[i], i, d[j], o[j], j) ? 1 : 0;
+      for (int i = 0; i < k; ++i) r += key[i] < key[j] ? 1 : 0;
       ord[r] = __ldg(my + j);
     }
   }
@@ -680,19 +779,46 @@ __global__ void __launch_bounds__(128) cov_from_lists_kernel(GridView g, int n, 
   for (int i = 0; i < 6; i++) dst[i] = out[i];
 }
 
-static void launch_cov_kernel(const DevCloud& c, int k, int method, const int* nbr, double* covs6, int q_lo, int q_hi, int* idx_out, float* d2_out,
-                              cudaStream_t st) {
+// main launch: one thread per sorted slot of [q_lo, q_hi); points flagged for the warp search are left to cov_rest_kernel
+template <int KT>
+__global__ void __launch_bounds__(128) cov_from_lists_kernel(GridView g, int n, int k_rt, int method, const int* __restrict__ nbr,
+                                                             double* __restrict__ covs6, int q_lo, int q_hi,
+                                                             const unsigned char* __restrict__ skip_flags,
+                                                             int* __restrict__ idx_out, float* __restrict__ d2_out) {
+  const int q = q_lo + blockIdx.x * blockDim.x + threadIdx.x;
+  if (q >= q_hi || q >= n) return;
+  if (skip_flags != nullptr && skip_flags[q]) return;
+  cov_point<KT>(g, n, k_rt, method, nbr, covs6, q, idx_out, d2_out);
+}
+// the listed points only (after knn_lists_rest_kernel has answered them); runs beside the main launch on a side stream
+template <int KT>
+__global__ void __launch_bounds__(128) cov_rest_kernel(GridView g, int n, int k_rt, int method, const int* __restrict__ nbr,
+                                                       double* __restrict__ covs6, const int* __restrict__ ctrl, const int* __restrict__ fb_list) {
+  const int total = ctrl[CT_REST];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
+    cov_point<KT>(g, n, k_rt, method, nbr, covs6, fb_list[i], nullptr, nullptr);
+}
+
+static void launch_cov_kernel(const DevCloud& c, int k, int method, const int* nbr, double* covs6, int q_lo, int q_hi, const unsigned char* skip,
+                              int* idx_out, float* d2_out, cudaStream_t st) {
   const int nq = q_hi - q_lo;
   const dim3 grid((nq + 127) / 128), block(128);
-  if (k == 10) cov_from_lists_kernel<10><<<grid, block, 0, st>>>(c.view(), c.n, k, method, nbr, covs6, q_lo, q_hi, idx_out, d2_out);
-  else if (k == 20) cov_from_lists_kernel<20><<<grid, block, 0, st>>>(c.view(), c.n, k, method, nbr, covs6, q_lo, q_hi, idx_out, d2_out);
-  else cov_from_lists_kernel<0><<<grid, block, 0, st>>>(c.view(), c.n, k, method, nbr, covs6, q_lo, q_hi, idx_out, d2_out);
+  if (k == 10) cov_from_lists_kernel<10><<<grid, block, 0, st>>>(c.view(), c.n, k, method, nbr, covs6, q_lo, q_hi, skip, idx_out, d2_out);
+  else if (k == 20) cov_from_lists_kernel<20><<<grid, block, 0, st>>>(c.view(), c.n, k, method, nbr, covs6, q_lo, q_hi, skip, idx_out, d2_out);
+  else cov_from_lists_kernel<0><<<grid, block, 0, st>>>(c.view(), c.n, k, method, nbr, covs6, q_lo, q_hi, skip, idx_out, d2_out);
+  note_launches(1);
+}
+static void launch_cov_rest_kernel(const DevCloud& c, int k, int method, const int* nbr, double* covs6, const int* ctrl, const int* fb_list, int blocks,
+                                   cudaStream_t st) {
+  if (k == 10) cov_rest_kernel<10><<<blocks, 128, 0, st>>>(c.view(), c.n, k, method, nbr, covs6, ctrl, fb_list);
+  else if (k == 20) cov_rest_kernel<20><<<blocks, 128, 0, st>>>(c.view(), c.n, k, method, nbr, covs6, ctrl, fb_list);
+  else cov_rest_kernel<0><<<blocks, 128, 0, st>>>(c.view(), c.n, k, method, nbr, covs6, ctrl, fb_list);
   note_launches(1);
 }
 
 cudaError_t launch_export_neighbors(const DevCloud& c, int k, const int* nbr_scratch, int* idx_out, float* d2_out, cudaStream_t st) {
   if (c.n <= 0) return cudaSuccess;
-  launch_cov_kernel(c, k, 0, nbr_scratch, nullptr, 0, c.n, idx_out, d2_out, st);
+  launch_cov_kernel(c, k, 0, nbr_scratch, nullptr, 0, c.n, nullptr, idx_out, d2_out, st);
   return cudaGetLastError();
 }
 
@@ -701,11 +827,16 @@ void knn_prime_kernels() {
   cudaFuncGetAttributes(&fa, knn_query_kernel);
   cudaFuncGetAttributes(&fa, knn_lists_kernel);
   cudaFuncGetAttributes(&fa, knn_plan_kernel);
-  cudaFuncGetAttributes(&fa, knn_lists_tile_kernel);
+  cudaFuncGetAttributes(&fa, knn_lists_tile_kernel<0>);
+  cudaFuncGetAttributes(&fa, knn_lists_tile_kernel<10>);
+  cudaFuncGetAttributes(&fa, knn_lists_tile_kernel<20>);
   cudaFuncGetAttributes(&fa, knn_lists_rest_kernel);
   cudaFuncGetAttributes(&fa, cov_from_lists_kernel<0>);
   cudaFuncGetAttributes(&fa, cov_from_lists_kernel<10>);
   cudaFuncGetAttributes(&fa, cov_from_lists_kernel<20>);
+  cudaFuncGetAttributes(&fa, cov_rest_kernel<0>);
+  cudaFuncGetAttributes(&fa, cov_rest_kernel<10>);
+  cudaFuncGetAttributes(&fa, cov_rest_kernel<20>);
   cudaGetLastError();
 }
 
@@ -718,12 +849,13 @@ cudaError_t launch_knn_queries(const DevCloud& c, const float4* queries, int nq,
   return cudaGetLastError();
 }
 
-// scratch layout (ints): nbr[n*k] | control words[8] | warp-search list[n] | (16-byte aligned) work items int4[n]
+// scratch layout (ints): nbr[n*k] | control words[8] | warp-search list[n] | (16-byte aligned) work items int4[n] | warp-search flags (n bytes)
 static inline size_t items_offset_ints(int n, int k) { return (((size_t)n * k + CT_N + (size_t)n) + 3) & ~(size_t)3; }
-size_t covariance_scratch_ints(int n, int k) { return items_offset_ints(n, k) + 4 * (size_t)n + 16; }
+static inline size_t flags_offset_ints(int n, int k) { return items_offset_ints(n, k) + 4 * (size_t)n + 16; }
+size_t covariance_scratch_ints(int n, int k) { return flags_offset_ints(n, k) + ((size_t)n + 3) / 4 + 4; }
 
 cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_scratch, double* covs6, int table_cap, cudaStream_t st,
-                               int part, int nparts, int knn_path, int tile_min_points) {
+                               int part, int nparts, int knn_path, int tile_min_points, const CovSideStream* side) {
   if (c.n <= 0) return cudaSuccess;
   // the sorted slots this launch answers: everything, or part `part` of `nparts` equal slices (the rest of covs6 is zeroed
   // so that the slices of all parts add up to the full result)
@@ -757,9 +889,15 @@ cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_sc
     {
       std::lock_guard<std::mutex> lock(attr_mutex);
       if (!attr_set[di]) {
-        cudaError_t e = cudaFuncSetAttribute(knn_lists_tile_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        cudaError_t e = cudaFuncSetAttribute(knn_lists_tile_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocks_per_sm[di], knn_lists_tile_kernel, TQ_WARPS * 32, smem)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(knn_lists_tile_kernel<10>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        if ((e = cudaFuncSetAttribute(knn_lists_tile_kernel<20>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
+        int occ[3] = {0, 0, 0};
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[0], knn_lists_tile_kernel<0>, TQ_WARPS * 32, smem)) != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[1], knn_lists_tile_kernel<10>, TQ_WARPS * 32, smem)) != cudaSuccess) return e;
+        if ((e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ[2], knn_lists_tile_kernel<20>, TQ_WARPS * 32, smem)) != cudaSuccess) return e;
+        blocks_per_sm[di] = occ[0] < occ[1] ? (occ[0] < occ[2] ? occ[0] : occ[2]) : (occ[1] < occ[2] ? occ[1] : occ[2]);
         if ((e = cudaDeviceGetAttribute(&sm_count[di], cudaDevAttrMultiProcessorCount, dev)) != cudaSuccess) return e;
         if (blocks_per_sm[di] < 1) blocks_per_sm[di] = 1;
         attr_set[di] = true;
@@ -769,8 +907,10 @@ cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_sc
     int* fb_list = ctrl + CT_N;
     int4* items = reinterpret_cast<int4*>(nbr_scratch + items_offset_ints(c.n, k));
     items = reinterpret_cast<int4*>((reinterpret_cast<uintptr_t>(items) + 15) & ~(uintptr_t)15);
+    unsigned char* fb_flags = reinterpret_cast<unsigned char*>(nbr_scratch + flags_offset_ints(c.n, k));
     cudaError_t e = cudaMemsetAsync(ctrl, 0, CT_N * sizeof(int), st);
     if (e != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(fb_flags, 0, (size_t)c.n, st)) != cudaSuccess) return e;
     unsigned long long* stats = nullptr;
     if (want_stats) {
       if (cudaMalloc(&stats, ST_N * sizeof(unsigned long long)) != cudaSuccess) return cudaGetLastError();
@@ -781,17 +921,25 @@ cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_sc
     const long long max_boxes = ((long long)table_cap + 63) / 64;
     long long plan_warps = max_boxes > 32768 ? (max_boxes + 7) / 8 + 1024 : max_boxes + 1024;
     knn_plan_kernel<<<(unsigned)((plan_warps + 7) / 8), 256, 0, st>>>(c.view(), items, ctrl);
-    if (want_stats) {
-      cudaError_t se = cudaStreamSynchronize(st);
-      int hc[CT_N] = {};
-      cudaMemcpy(hc, ctrl, sizeof(hc), cudaMemcpyDeviceToHost);
-      fprintf(stderr, "[ngicp knn] plan: %s items=%d (n=%d, grid %u blocks)\n", cudaGetErrorString(se), hc[CT_ITEMS], c.n, (unsigned)((plan_warps + 7) / 8));
-    }
     // persistent grid: every resident warp pulls work items until the counter runs out; no block waits for another one,
     // so it does not matter how many of the blocks are resident at a time (other handles may share the GPU)
-    knn_lists_tile_kernel<<<sm_count[di] * blocks_per_sm[di], TQ_WARPS * 32, smem, st>>>(c.view(), c.n, k, nbr_scratch, items, ctrl, fb_list, stats, q_lo, q_hi);
-    knn_lists_rest_kernel<<<sm_count[di] * 2, KC_THREADS, 0, st>>>(c.view(), k, nbr_scratch, ctrl, fb_list);
-    note_launches(3);
+    const dim3 tgrid(sm_count[di] * blocks_per_sm[di]), tblock(TQ_WARPS * 32);
+    if (k == 10) knn_lists_tile_kernel<10><<<tgrid, tblock, smem, st>>>(c.view(), c.n, k, nbr_scratch, items, ctrl, fb_list, fb_flags, stats, q_lo, q_hi, 1.0f);
+    else if (k == 20) knn_lists_tile_kernel<20><<<tgrid, tblock, smem, st>>>(c.view(), c.n, k, nbr_scratch, items, ctrl, fb_list, fb_flags, stats, q_lo, q_hi, 1.0f);
+    else knn_lists_tile_kernel<0><<<tgrid, tblock, smem, st>>>(c.view(), c.n, k, nbr_scratch, items, ctrl, fb_list, fb_flags, stats, q_lo, q_hi, 1.0f);
+    note_launches(2);
+    // The points the tiles could not decide (isolated ones: a long tail of deep searches by few warps) and their
+    // covariances run on a high-priority side stream BESIDE the main covariance launch, which skips them.
+    const bool overlap = side != nullptr && side->stream != nullptr && !want_stats;
+    cudaStream_t rs = overlap ? side->stream : st;
+    if (overlap) {
+      if ((e = cudaEventRecord(side->fork, st)) != cudaSuccess) return e;
+      if ((e = cudaStreamWaitEvent(rs, side->fork, 0)) != cudaSuccess) return e;
+    }
+    knn_lists_rest_kernel<<<sm_count[di] * 4, KC_THREADS, 0, rs>>>(c.view(), k, nbr_scratch, ctrl, fb_list);
+    note_launches(1);
+    launch_cov_rest_kernel(c, k, method, nbr_scratch, covs6, ctrl, fb_list, sm_count[di], rs);
+    if (overlap && (e = cudaEventRecord(side->join, rs)) != cudaSuccess) return e;
     if (want_stats) {
       unsigned long long h[ST_N] = {};
       cudaMemcpyAsync(h, stats, sizeof(h), cudaMemcpyDeviceToHost, st);
@@ -801,8 +949,11 @@ cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_sc
               c.n, k, h[ST_FALLBACK], 100.0 * (double)h[ST_FALLBACK] / (double)c.n, h[ST_TIES], h[ST_ITEMS], h[ST_TILES], h[ST_PASSES],
               h[ST_PASSES] ? (double)h[ST_LANES] / (double)h[ST_PASSES] : 0.0);
     }
+    launch_cov_kernel(c, k, method, nbr_scratch, covs6, q_lo, q_hi, fb_flags, nullptr, nullptr, st);
+    if (overlap && (e = cudaStreamWaitEvent(st, side->join, 0)) != cudaSuccess) return e;
+    return cudaGetLastError();
   }
-  launch_cov_kernel(c, k, method, nbr_scratch, covs6, q_lo, q_hi, nullptr, nullptr, st);
+  launch_cov_kernel(c, k, method, nbr_scratch, covs6, q_lo, q_hi, nullptr, nullptr, nullptr, st);
   return cudaGetLastError();
 }
 

@@ -549,6 +549,37 @@ class NanoGICP:
         return {k: getattr(t, k) for k, _ in Timings._fields_ if k != "reserved"}
 
 
+def align_batch(handles, guesses=None):
+    """ngicp_align_batch: register len(handles) independent pairs (each NanoGICP object holds its own source and target)
+    in ONE kernel launch; every object ends up exactly as if its own align(guess) had been called.  guesses: sequence
+    of 4x4 matrices (None entries = identity) or None.  Returns the list of Result structs."""
+    n = len(handles)
+    if n == 0:
+        return []
+    L = handles[0]._L
+    arr = (C.c_void_p * n)(*[h._h for h in handles])
+    g = None
+    if guesses is not None:
+        ga = np.zeros((n, 16), dtype=np.float32)
+        for i, G in enumerate(guesses):
+            ga[i] = _mat_to_abi(np.eye(4) if G is None else G, np.float32)
+        g = ga.ctypes.data_as(C.POINTER(C.c_float))
+    res = (Result * n)()
+    for h in handles:
+        if h._target is None:
+            raise NanoGICPError(_lib.E_STATE, "align_batch: a handle has no target")
+        h._converged = False
+    handles[0]._check(L.ngicp_align_batch(arr, n, g, res))
+    out = []
+    for i, h in enumerate(handles):
+        C.memmove(C.byref(h._res), C.byref(res[i]), C.sizeof(Result))
+        h._final = np.array(h._res.final_transformation, dtype=np.float32).reshape(4, 4).T.copy()
+        h._converged = bool(h._res.converged)
+        h.nr_iterations_ = int(h._res.nr_iterations)
+        out.append(h._res)
+    return out
+
+
 class KeyframeStore:
     """Device-resident keyframes (include/nanogicp_c.h, ngicp_kfstore_*): what OdomNode keeps in `keyframes` /
     `keyframe_normals` on the host, and the submap concatenation of getSubmapKeyframes, without leaving the GPU."""

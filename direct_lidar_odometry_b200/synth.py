@@ -167,11 +167,19 @@ def os1_like_batch_torch(scan_indices, poses, device, beams: int = 64, cols: int
         tf = torch.fmin(torch.fmin(hi_[..., 0], hi_[..., 1]), hi_[..., 2])
         ok = (tf >= tn) & (tn > 0) & (tn < t_hit)
         t_hit = torch.where(ok, tn, t_hit)
+    def _noise(idx):                                               # the numpy generator's stream, drawn on host threads
+        rng = np.random.default_rng(1000 + int(idx))
+        return rng.normal(0.0, sigma, size=N), rng.random(N) >= drop_prob
+    if B > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(min(B, 8)) as ex:
+            draws = list(ex.map(_noise, scan_indices))
+    else:
+        draws = [_noise(scan_indices[0])]
     out = []
     for b, idx in enumerate(scan_indices):
-        rng = np.random.default_rng(1000 + int(idx))
-        noise = torch.from_numpy(rng.normal(0.0, sigma, size=N)).to(device)
-        keep = torch.from_numpy(rng.random(N) >= drop_prob).to(device)
+        noise = torch.from_numpy(draws[b][0]).to(device)
+        keep = torch.from_numpy(draws[b][1]).to(device)
         th = t_hit[b]
         valid = torch.isfinite(th) & (th <= range_max) & (th >= range_min) & keep
         r = (th + noise)[valid]

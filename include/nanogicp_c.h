@@ -154,7 +154,7 @@ int ngicp_calc_source_covs_part(ngicp_t* h, int part, int nparts);
 int ngicp_covs_device(ngicp_t* h, int which, double** covs6, size_t* n);
 /* test hook: the k neighbours (nearestKSearch result at nano_gicp_impl.hpp:313) the LAST calculate*Covariances call on
  * this handle used for every point of that cloud, in the order the covariance sums ran over them — ascending
- * (squared distance, original index): idx[n*k] original point indices (-1 = none), d2[n*k] squared distances.  Valid
+ * squared distance, exact ties in (cell, original index) order: idx[n*k] original point indices (-1 = none), d2[n*k] squared distances.  Valid
  * until the next covariance / kNN call on the handle. */
 int ngicp_cov_neighbors(ngicp_t* h, int which, int* idx, float* d2);
 /* NanoGICP::setSourceCovariances / setTargetCovariances, nano_gicp_impl.hpp:141-149 (n Matrix4d records, host or device) */
@@ -172,6 +172,14 @@ int ngicp_get_target_covs(ngicp_t* h, double* out, size_t n);
  * -> LsqRegistration::computeTransformation (lsq_registration_impl.hpp:89-115).  Lazily computes missing
  * covariances like the reference.  `guess` NULL = identity (align(output)). */
 int ngicp_align(ngicp_t* h, const float* guess16, ngicp_result* out);
+/* Batched registration (BASELINE config "10k independent scan pairs"; no reference counterpart — the reference loops
+ * over align()): n handles, each set up like for ngicp_align (source, target, parameters; covariances are computed
+ * lazily where missing), registered by ONE kernel launch — a thread-block cluster per pair runs that pair's whole LM loop
+ * (nano_gicp_impl.hpp:173-296, lsq_registration_impl.hpp:89-208) with exactly the sums of the single-pair kernel, so
+ * results[i] is bit-identical to what ngicp_align(handles[i], guess_i, ..) returns.  guesses16: n x 16 floats
+ * (column-major 4x4 each) or NULL for identity.  All handles on one device, each at most once; the index / covariance
+ * work of different handles runs concurrently on their own streams. */
+int ngicp_align_batch(ngicp_t* const* handles, size_t n, const float* guesses16, ngicp_result* results);
 /* pcl::transformPointCloud(*input_, output, final) at lsq_registration_impl.hpp:114: writes n packed
  * {x,y,z,1} float4 records (host or device); the facade merges them into the output cloud's records */
 int ngicp_transform_source(ngicp_t* h, const float* T16, float* out_xyz1, size_t n);

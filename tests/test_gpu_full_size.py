@@ -282,3 +282,57 @@ def test_c4_distinct_pairs_sample_vs_oracle(G, O):
         if not ok:
             bad.append((i, res.nr_iterations, r.nr_iterations, dt, dr))
     assert not bad, f"{len(bad)} of {len(pairs)} pairs differ: {bad[:5]}"
+
+
+def test_align_batch_bit_identical_to_single_calls(G, O, scan_pair):
+    """ngicp_align_batch: B pairs in one launch (one thread-block cluster per pair) == B single ngicp_align calls, bit
+    for bit (state, Hessian, counts), for scan-to-scan pairs (one lane per point), a scan-to-map pair (two lanes per
+    point), different parameters per handle, a guess, and a pair without any correspondence."""
+    from direct_lidar_odometry_b200 import align_batch
+    from util import make_small_submap
+    scans = []
+    for i in (0, 1, 40, 41, 500, 501):
+        T = synth.trajectory_pose(i)
+        scans.append(O.voxel_filter(synth.crop_box_negative(synth.os1_like(i, T)), 0.25))
+    submap, scan_m, Tm = make_small_submap(O)
+    far = scans[0].copy(); far[:, :3] += 500.0
+    cases = [  # (source, target, config, guess)
+        (scans[1], scans[0], S2S, None),
+        (scans[3], scans[2], S2S, synth.perturb_pose(np.eye(4), (0.1, 0.05, 0.0), 0.5).astype(np.float32)),
+        (scans[5], scans[4], dict(k=20, thr=float(np.finfo(np.float32).max), max_iter=64, trans_eps=5e-4), None),
+        (scan_m, submap, S2M, synth.perturb_pose(Tm, (0.2, 0.0, 0.0), 1.0).astype(np.float32)),
+        (far, scans[0], S2S, None),
+        (scans[0], scans[1], S2S, None),
+    ]
+
+    def setup(case):
+        src, tgt, cfg, _ = case
+        g = G()
+        configure(g, cfg)
+        g.setInputTarget(tgt); g.setInputSource(src)
+        return g
+    single = [setup(c) for c in cases]
+    for g, c in zip(single, cases):
+        g.align(c[3])
+    batch = [setup(c) for c in cases]
+    res = align_batch(batch, [c[3] for c in cases])
+    assert len(res) == len(cases)
+    for gs, gb in zip(single, batch):
+        a, b = gs.result, gb.result
+        assert (a.nr_iterations, a.converged, a.n_linearize, a.n_compute_error, a.lm_failed) == \
+               (b.nr_iterations, b.converged, b.n_linearize, b.n_compute_error, b.lm_failed)
+        assert np.array_equal(gs.final_state().view(np.uint64), gb.final_state().view(np.uint64))
+        assert np.array_equal(gs.getFinalHessian().view(np.uint64), gb.getFinalHessian().view(np.uint64))
+        assert np.array_equal(gs.getFinalTransformation(), gb.getFinalTransformation()) and gs.hasConverged() == gb.hasConverged()
+    assert single[0].result.nr_iterations >= 1 and single[4].result.nr_iterations == 0
+    # a second batch on the same handles (covariances now present, other guesses) still matches fresh single calls
+    g2 = [synth.perturb_pose(np.eye(4), (0.05, 0.0, 0.0), 0.2).astype(np.float32)] * 2
+    align_batch(batch[:2], g2)
+    for gs, gb, gg in zip(single[:2], batch[:2], g2):
+        gs.align(gg)
+        assert np.array_equal(gs.final_state().view(np.uint64), gb.final_state().view(np.uint64))
+    # error paths: the same handle twice, a handle without target
+    with pytest.raises(Exception):
+        align_batch([batch[0], batch[0]])
+    with pytest.raises(Exception):
+        align_batch([batch[0], G()])
