@@ -406,6 +406,9 @@ def c4_make_scans(vox, first, count, device, batch=16):
     return out
 
 
+C4_SPLIT = [0.0, 0.0]   # seconds the main thread waited for wave preparation / spent in ngicp_align_batch
+
+
 def c4_run(handle_sets, scans, pair_offsets, wave, threads=8):
     """Register pairs (scans[o+1] -> scans[o]) for o in pair_offsets in waves of `wave` pairs.  A wave's clouds are
     indexed and their covariances computed from `threads` host threads, each pair on its own handle / stream; the wave's
@@ -427,10 +430,14 @@ def c4_run(handle_sets, scans, pair_offsets, wave, threads=8):
         nxt = submit(0) if waves else None
         for w in range(len(waves)):
             hs, futs = nxt
+            t0 = time.perf_counter()
             for f in futs:
                 f.result()
+            t1 = time.perf_counter()
             nxt = submit(w + 1) if w + 1 < len(waves) else None
             align_batch(hs)
+            t2 = time.perf_counter()
+            C4_SPLIT[0] += t1 - t0; C4_SPLIT[1] += t2 - t1
             for h in hs:
                 results.append((int(h.result.nr_iterations), int(h.result.n_compute_error), np.array(h.result.final_x)))
     return results
@@ -460,6 +467,7 @@ def c4_bench(local, rank, world, pairs=10000, wave=64, threads=8, sample_check=0
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
+    C4_SPLIT[0] = C4_SPLIT[1] = 0.0
     t0 = time.perf_counter()
     res = c4_run(handles, scans, offs, wave, threads)
     torch.cuda.synchronize()
@@ -475,7 +483,8 @@ def c4_bench(local, rank, world, pairs=10000, wave=64, threads=8, sample_check=0
                          f"partitioned over {world} GPU(s); waves of {wave} pairs, one ngicp_align_batch launch per wave",
                "n_gpus": world, "pairs": int(cnt.item()), "wave": wave, "host_threads_per_gpu": threads, "seconds": float(t.item()),
                "pairs_per_s": float(cnt.item() / t.item()), "ms_per_pair_per_gpu": float(t.item() * 1e3 * world / cnt.item()),
-               "mean_iterations": float(np.mean([r[0] for r in res])), "scan_generation_s_rank0": gen_s}
+               "mean_iterations": float(np.mean([r[0] for r in res])), "scan_generation_s_rank0": gen_s,
+               "main_thread_split_s": {"waiting_for_index_and_covariances": C4_SPLIT[0], "in_align_batch": C4_SPLIT[1]}}
         if sample_check > 0:
             # a seeded sample of this rank's pairs against the CPU oracle (identical inputs: the device scans copied back)
             from oracle import oracle as O

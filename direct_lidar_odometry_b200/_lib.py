@@ -28,7 +28,7 @@ EXPORTS = [
     "ngicp_knn", "ngicp_linearize", "ngicp_compute_error", "ngicp_linearize_partial", "ngicp_compute_error_partial",
     "ngicp_version", "ngicp_launch_count", "ngicp_grid_info", "ngicp_set_owner_slab", "ngicp_lm_trial",
     "ngicp_lm_is_converged", "ngicp_comm_export", "ngicp_comm_connect", "ngicp_comm_connect_local", "ngicp_comm_close", "ngicp_preprocess", "ngicp_preprocess_pointcloud2", "ngicp_calc_source_covs_part", "ngicp_covs_device", "ngicp_transform_voxel_filter", "ngicp_kfstore_create", "ngicp_kfstore_destroy", "ngicp_kfstore_size",
-    "ngicp_kfstore_points", "ngicp_kfstore_push", "ngicp_kfstore_set_target", "ngicp_cov_neighbors", "ngicp_align_batch",
+    "ngicp_kfstore_points", "ngicp_kfstore_push", "ngicp_kfstore_set_target", "ngicp_cov_neighbors", "ngicp_align_batch", "ngicp_imu_prior",
 ]
 
 
@@ -116,6 +116,7 @@ def load() -> C.CDLL:
     proto("ngicp_set_owner_slab", i32, vp, i32, f32, f32)
     proto("ngicp_lm_trial", i32, dp, dp, C.c_double, dp, dp, dp, dp)
     proto("ngicp_lm_is_converged", i32, dp, C.c_double, C.c_double)
+    proto("ngicp_imu_prior", i32, dp, dp, sz, C.c_double, C.c_double, fp)
     proto("ngicp_kfstore_create", i32, i32, C.POINTER(vp))
     proto("ngicp_kfstore_destroy", None, vp)
     proto("ngicp_kfstore_size", sz, vp)

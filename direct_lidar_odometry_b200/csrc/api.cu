@@ -1,6 +1,7 @@
 // api.cu — the C ABI of libnanogicp_b200.so (include/nanogicp_c.h) and the host side of a handle:
 // device-resident clouds / covariances with O(1) sharing and swapping, the stepped LM driver, and
 // the import/export of Eigen::Matrix4d covariance records.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -930,6 +931,41 @@ int ngicp_lm_is_converged(const double* delta16, double rot_eps, double trans_ep
   Iso3 d;
   iso_from_colmajor16(delta16, d);
   return lm_is_converged(d, rot_eps, trans_eps) ? 1 : 0;
+}
+
+// ---- N4: OdomNode::integrateIMU (odom.cc:859-919), host arithmetic -------------------------------------------------------
+int ngicp_imu_prior(const double* stamps, const double* av, size_t n, double prev_stamp, double curr_stamp, float* out_T16) {
+  if (!out_T16 || ((!stamps || !av) && n)) return NGICP_E_INVALID;
+  struct Sample { double t, x, y, z; };
+  std::vector<Sample> frame;
+  for (size_t i = 0; i < n; ++i)
+    if (curr_stamp - stamps[i] >= 0. && prev_stamp - stamps[i] <= 0.) frame.push_back(Sample{stamps[i], av[3 * i], av[3 * i + 1], av[3 * i + 2]});
+  std::sort(frame.begin(), frame.end(), [](const Sample& a, const Sample& b) { return a.t < b.t; });
+  float w = 1.f, x = 0.f, y = 0.f, z = 0.f;
+  double prev_t = 0.;
+  for (const Sample& m : frame) {
+    if (prev_t == 0.) { prev_t = m.t; continue; }   // the first sample (and any sample stamped exactly 0) only sets the clock
+    const double dt = m.t - prev_t;
+    prev_t = m.t;
+    const float qw = w, qx = x, qy = y, qz = z;
+    w -= 0.5 * (qx * m.x + qy * m.y + qz * m.z) * dt;
+    x += 0.5 * (qw * m.x - qz * m.y + qy * m.z) * dt;
+    y += 0.5 * (qz * m.x + qw * m.y - qx * m.z) * dt;
+    z += 0.5 * (qx * m.y - qy * m.x + qw * m.z) * dt;
+  }
+  const double norm = sqrt((double)(w * w + x * x + y * y + z * z));   // float sum of float products, sqrt in double
+  w /= norm; x /= norm; y /= norm; z /= norm;
+  // Eigen::Quaternionf::toRotationMatrix
+  const float tx = 2.f * x, ty = 2.f * y, tz = 2.f * z;
+  const float twx = tx * w, twy = ty * w, twz = tz * w;
+  const float txx = tx * x, txy = ty * x, txz = tz * x;
+  const float tyy = ty * y, tyz = tz * y, tzz = tz * z;
+  float R[3][3] = {{1.f - (tyy + tzz), txy - twz, txz + twy}, {txy + twz, 1.f - (txx + tzz), tyz - twx}, {txz - twy, tyz + twx, 1.f - (txx + tyy)}};
+  for (int i = 0; i < 16; ++i) out_T16[i] = 0.f;
+  for (int r = 0; r < 3; ++r)
+    for (int c = 0; c < 3; ++c) out_T16[c * 4 + r] = R[r][c];
+  out_T16[15] = 1.f;
+  return NGICP_OK;
 }
 
 // ---- sharded-submap exchange (align.cu: peer_exchange_sum) ----------------------------------------------------

@@ -923,7 +923,10 @@ cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_sc
     knn_plan_kernel<<<(unsigned)((plan_warps + 7) / 8), 256, 0, st>>>(c.view(), items, ctrl);
     // persistent grid: every resident warp pulls work items until the counter runs out; no block waits for another one,
     // so it does not matter how many of the blocks are resident at a time (other handles may share the GPU)
-    const dim3 tgrid(sm_count[di] * blocks_per_sm[di]), tblock(TQ_WARPS * 32);
+    int tblocks = sm_count[di] * blocks_per_sm[di];
+    const int tneed = (nq + 16 * TQ_WARPS - 1) / (16 * TQ_WARPS);     // small clouds: a few items per warp are enough
+    if (tblocks > tneed) tblocks = tneed;
+    const dim3 tgrid(tblocks), tblock(TQ_WARPS * 32);
     if (k == 10) knn_lists_tile_kernel<10><<<tgrid, tblock, smem, st>>>(c.view(), c.n, k, nbr_scratch, items, ctrl, fb_list, fb_flags, stats, q_lo, q_hi, 1.0f);
     else if (k == 20) knn_lists_tile_kernel<20><<<tgrid, tblock, smem, st>>>(c.view(), c.n, k, nbr_scratch, items, ctrl, fb_list, fb_flags, stats, q_lo, q_hi, 1.0f);
     else knn_lists_tile_kernel<0><<<tgrid, tblock, smem, st>>>(c.view(), c.n, k, nbr_scratch, items, ctrl, fb_list, fb_flags, stats, q_lo, q_hi, 1.0f);

@@ -549,6 +549,21 @@ class NanoGICP:
         return {k: getattr(t, k) for k, _ in Timings._fields_ if k != "reserved"}
 
 
+def imu_prior(stamps, ang_vel, prev_frame_stamp: float, curr_frame_stamp: float) -> np.ndarray:
+    """OdomNode::integrateIMU (odom.cc:859-919): the 4x4 float `imu_SE3` guess from the gyro samples between two scans
+    (ngicp_imu_prior; host arithmetic, no GPU needed).  stamps (n,) seconds, ang_vel (n,3) rad/s."""
+    L = _lib.load()
+    st = np.ascontiguousarray(stamps, dtype=np.float64)
+    av = np.ascontiguousarray(ang_vel, dtype=np.float64).reshape(-1, 3)
+    out = np.zeros(16, dtype=np.float32)
+    dp = C.POINTER(C.c_double)
+    rc = L.ngicp_imu_prior(st.ctypes.data_as(dp), av.ctypes.data_as(dp), st.shape[0], float(prev_frame_stamp), float(curr_frame_stamp),
+                           out.ctypes.data_as(C.POINTER(C.c_float)))
+    if rc < 0:
+        raise NanoGICPError(rc, "ngicp_imu_prior: bad arguments")
+    return out.reshape(4, 4).T.copy()
+
+
 def align_batch(handles, guesses=None):
     """ngicp_align_batch: register len(handles) independent pairs (each NanoGICP object holds its own source and target)
     in ONE kernel launch; every object ends up exactly as if its own align(guess) had been called.  guesses: sequence

@@ -18,6 +18,8 @@
 #include <cstdio>
 #include <cstring>
 #include <memory>
+#include <stdexcept>
+#include <string>
 #include <vector>
 
 #if defined(__has_include)
@@ -195,13 +197,19 @@ class NanoGICP {
 
   // ---- nano_gicp.hpp:82-84 ----------------------------------------------------------------------
   void setNumThreads(int) {}   // OpenMP knob; nothing to do on the GPU
-  void setCorrespondenceRandomness(int k) { prm_.k_correspondences = k; push(); }
-  void setRegularizationMethod(RegularizationMethod m) { prm_.regularization_method = (int)m; push(); }
+  // Every setter changes ONE field and keeps it only if the library accepts it (a rejected value used to stay in prm_
+  // and make every later setter fail as well).  A value the GPU path cannot honour is a configuration error and is
+  // reported where it is made: the reference accepts any k, this build k in [1, 32] (warp-wide result set).
+  void setCorrespondenceRandomness(int k) {
+    if (!set_field(&ngicp_params::k_correspondences, k))
+      throw std::invalid_argument("NanoGICP-B200: setCorrespondenceRandomness(" + std::to_string(k) + "): this build supports 1 <= k <= 32");
+  }
+  void setRegularizationMethod(RegularizationMethod m) { set_field(&ngicp_params::regularization_method, (int)m); }
 
   // ---- pcl::Registration setters used at odom.cc:100-120 -----------------------------------------
-  void setMaxCorrespondenceDistance(double d) { prm_.max_correspondence_distance = d; push(); }
-  void setMaximumIterations(int n) { prm_.max_iterations = n; push(); }
-  void setTransformationEpsilon(double e) { prm_.transformation_epsilon = e; push(); }
+  void setMaxCorrespondenceDistance(double d) { set_field(&ngicp_params::max_correspondence_distance, d); }
+  void setMaximumIterations(int n) { set_field(&ngicp_params::max_iterations, n); }
+  void setTransformationEpsilon(double e) { set_field(&ngicp_params::transformation_epsilon, e); }
   void setEuclideanFitnessEpsilon(double) {}               // never read by NanoGICP
   void setRANSACIterations(int) {}
   void setRANSACOutlierRejectionThreshold(double) {}
@@ -211,14 +219,15 @@ class NanoGICP {
   int getMaximumIterations() const { return prm_.max_iterations; }
 
   // ---- lsq_registration.hpp:81-85 ---------------------------------------------------------------
-  void setRotationEpsilon(double e) { prm_.rotation_epsilon = e; push(); }
-  void setInitialLambdaFactor(double f) { prm_.lm_init_lambda_factor = f; push(); }
+  void setRotationEpsilon(double e) { set_field(&ngicp_params::rotation_epsilon, e); }
+  void setInitialLambdaFactor(double f) { set_field(&ngicp_params::lm_init_lambda_factor, f); }
   void setDebugPrint(bool) {}
   const Eigen::Matrix<double, 6, 6>& getFinalHessian() const { return final_hessian_; }
 
   // ---- B200-side knobs ---------------------------------------------------------------------------
-  void setGridCellSize(float c) { prm_.grid_cell_size = c; push(); }
-  void setAlignMode(int mode) { prm_.align_mode = mode; push(); }
+  void setGridCellSize(float c) { set_field(&ngicp_params::grid_cell_size, c); }
+  void setAlignMode(int mode) { set_field(&ngicp_params::align_mode, mode); }
+  void setKnnPath(int path) { set_field(&ngicp_params::knn_path, path); }
   void setFillOutputCloud(bool f) { fill_output_ = f; }
   ngicp_t* handle() const { return h(); }
 
@@ -263,15 +272,18 @@ class NanoGICP {
   // ---- covariances (nano_gicp_impl.hpp:141-159) --------------------------------------------------
   virtual void setSourceCovariances(const CovarianceVectorHost& covs) { source_covs_ = covs; }
   virtual void setTargetCovariances(const CovarianceVectorHost& covs) { target_covs_ = covs; }
+  // the reference returns true unconditionally (nano_gicp_impl.hpp:151-159); here false means "no covariances were made"
   virtual bool calculateSourceCovariances() {
-    detail::report(h(), ngicp_calc_source_covs(h()), "calculateSourceCovariances");
+    const int rc = h() ? ngicp_calc_source_covs(h()) : NGICP_E_STATE;
+    detail::report(h(), rc, "calculateSourceCovariances");
     source_covs_.invalidate_host();
-    return true;
+    return rc >= 0;
   }
   virtual bool calculateTargetCovariances() {
-    detail::report(h(), ngicp_calc_target_covs(h()), "calculateTargetCovariances");
+    const int rc = h() ? ngicp_calc_target_covs(h()) : NGICP_E_STATE;
+    detail::report(h(), rc, "calculateTargetCovariances");
     target_covs_.invalidate_host();
-    return true;
+    return rc >= 0;
   }
   const CovarianceVectorHost& getSourceCovariances() const { return source_covs_.host(); }
   const CovarianceVectorHost& getTargetCovariances() const { return target_covs_.host(); }
@@ -286,7 +298,11 @@ class NanoGICP {
     ngicp_result res;
     int rc = ngicp_align(h(), guess.data(), &res);
     detail::report(h(), rc, "align");
-    if (rc < 0) return;
+    // PCL's own early-outs (missing cloud / index) print and return with converged_ = false, like above.  Anything else
+    // (a CUDA failure, fewer points than k, a sharded peer that never arrived) has no counterpart in the reference, and
+    // returning silently would make OdomNode integrate an identity transform: raise instead.
+    if (rc == NGICP_E_STATE) return;
+    if (rc < 0) throw std::runtime_error(std::string("NanoGICP-B200: align failed: ") + (h() ? ngicp_last_error(h()) : "no handle"));
     std::memcpy(final_transformation_.data(), res.final_transformation, sizeof(float) * 16);
     std::memcpy(final_hessian_.data(), res.final_hessian, sizeof(double) * 36);
     converged_ = res.converged != 0;
@@ -316,7 +332,15 @@ class NanoGICP {
 
  protected:
   ngicp_t* h() const { return handle_ ? handle_->h : nullptr; }
-  void push() { if (h()) detail::report(h(), ngicp_set_params(h(), &prm_), "set parameter"); }
+  // change one parameter; the handle is the judge: a rejected value is rolled back and reported
+  template <class F, class V> bool set_field(F ngicp_params::*field, V value) {
+    const F old = prm_.*field;
+    prm_.*field = (F)value;
+    if (!h()) return true;
+    const int rc = ngicp_set_params(h(), &prm_);
+    if (rc < 0) { detail::report(h(), rc, "set parameter"); prm_.*field = old; return false; }
+    return true;
+  }
   template <class CloudPtr> bool check_cloud(const CloudPtr& c, const char* who) const {
     if (!c || c->points.empty()) { std::fprintf(stderr, "[pcl::Registration::%s] Invalid or empty point cloud dataset given!\n", who); return false; }
     return h() != nullptr;

@@ -259,6 +259,16 @@ int ngicp_lm_trial(const double* H36, const double* b6, double lambda, const dou
 /* LsqRegistration::is_converged (lsq_registration_impl.hpp:118-127) */
 int ngicp_lm_is_converged(const double* delta16, double rot_eps, double trans_eps);
 
+/* ---- the guess of the S2S align when an IMU is used (second half) --------------------------------
+ * OdomNode::integrateIMU (odom.cc:859-919): of the n gyro samples (stamps[i] seconds, ang_vel[3*i..] rad/s) those with
+ * prev_frame_stamp <= stamp <= curr_frame_stamp are sorted by time and integrated from the identity with the first-order
+ * quaternion update q += 0.5 * q (x) (0, w) dt (float quaternion, double products, the first sample only sets the clock),
+ * the result is normalised and written as the rotation block of a column-major 4x4 float matrix with zero translation
+ * — the `imu_SE3` that getNextPose hands to gicp_s2s.align (odom.cc:801-803).  Host arithmetic, like in the reference;
+ * needs no handle and no GPU.  Fewer than two usable samples give the identity. */
+int ngicp_imu_prior(const double* stamps, const double* ang_vel_xyz, size_t n, double prev_frame_stamp, double curr_frame_stamp,
+                    float* out_T16);
+
 /* ---- device-resident keyframes (additive) ------------------------------------------------------
  * OdomNode keeps every keyframe's voxelised world-frame cloud and covariances on the host (keyframes / keyframe_normals,
  * include/dlo/odom.h:80-82), concatenates the selected ones into submap_cloud / submap_normals (odom.cc:1315-1328) and

@@ -137,6 +137,41 @@ def from_ros_msg(msg) -> np.ndarray:
     return out
 
 
+def integrate_imu(stamps, ang_vel, prev_frame_stamp, curr_frame_stamp) -> np.ndarray:
+    """Restatement of OdomNode::integrateIMU (reference src/dlo/odom.cc:859-919) with numpy scalars of the reference's
+    types: Eigen::Quaternionf state (float32), double gyro samples and time steps, first-order update, normalisation by a
+    double norm, Quaternionf::toRotationMatrix in float32.  Returns imu_SE3 (4x4 float32)."""
+    f32, f64 = np.float32, np.float64
+    stamps = np.asarray(stamps, dtype=f64)
+    ang_vel = np.asarray(ang_vel, dtype=f64).reshape(-1, 3)
+    sel = [i for i in range(stamps.shape[0]) if curr_frame_stamp - stamps[i] >= 0.0 and prev_frame_stamp - stamps[i] <= 0.0]
+    sel.sort(key=lambda i: stamps[i])
+    q = [f32(1), f32(0), f32(0), f32(0)]   # w x y z
+    prev = f64(0.0)
+    for i in sel:
+        if prev == 0.0:
+            prev = stamps[i]
+            continue
+        dt = stamps[i] - prev
+        prev = stamps[i]
+        w, x, y, z = q
+        ax, ay, az = ang_vel[i]
+        q[0] = f32(f64(w) - f64(0.5) * (f64(x) * ax + f64(y) * ay + f64(z) * az) * dt)
+        q[1] = f32(f64(x) + f64(0.5) * (f64(w) * ax - f64(z) * ay + f64(y) * az) * dt)
+        q[2] = f32(f64(y) + f64(0.5) * (f64(z) * ax + f64(w) * ay - f64(x) * az) * dt)
+        q[3] = f32(f64(z) + f64(0.5) * (f64(x) * ay - f64(y) * ax + f64(w) * az) * dt)
+    w, x, y, z = q
+    norm = np.sqrt(f64(f32(f32(f32(w * w) + f32(x * x)) + f32(y * y)) + f32(z * z)))
+    w, x, y, z = [f32(f64(v) / norm) for v in (w, x, y, z)]
+    tx, ty, tz = f32(2) * x, f32(2) * y, f32(2) * z
+    twx, twy, twz = tx * w, ty * w, tz * w
+    txx, txy, txz = tx * x, ty * x, tz * x
+    tyy, tyz, tzz = ty * y, tz * y, tz * z
+    T = np.eye(4, dtype=f32)
+    T[:3, :3] = [[f32(1) - (tyy + tzz), txy - twz, txz + twy], [txy + twz, f32(1) - (txx + tzz), tyz - twx], [txz - twy, tyz + twx, f32(1) - (txx + tyy)]]
+    return T
+
+
 def preprocess_points(pts: np.ndarray, crop_size, leaf: float, lib=None):
     """OdomNode::preprocessPoints restated (reference src/dlo/odom.cc:443-465): removeNaNFromPointCloud (:451), the
     negative pcl::CropBox of +-crop_size (:122-124,454-457; PCL keeps a point as "inside" when min <= p <= max on all

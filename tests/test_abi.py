@@ -60,3 +60,32 @@ def test_product_never_imports_oracle():
                 txt = open(os.path.join(dirpath, f), errors="ignore").read()
                 for pat in (r"import\s+oracle", r"from\s+oracle", r"liboracle", r"\borc_[a-z]", r"oracle/", r"oracle\."):
                     assert not re.search(pat, txt), f"{f} references the oracle ({pat})"
+
+
+def test_imu_prior_matches_oracle_restatement():
+    """ngicp_imu_prior (OdomNode::integrateIMU, odom.cc:859-919; host arithmetic, no GPU) against the oracle's numpy
+    restatement: bit-identical float matrices, samples outside the frame interval ignored, unsorted input sorted,
+    degenerate inputs give the identity; and the result is the rotation the gyro actually describes."""
+    import numpy as np
+    from direct_lidar_odometry_b200 import imu_prior
+    from oracle import oracle as O
+    rng = np.random.default_rng(3)
+    t0, t1 = 100.0, 100.1
+    stamps = np.sort(rng.uniform(99.95, 100.15, size=60))
+    av = rng.normal(0.0, 0.4, size=(60, 3)) + np.array([0.0, 0.0, 0.8])
+    perm = rng.permutation(60)
+    for s, a in ((stamps, av), (stamps[perm], av[perm])):
+        got = imu_prior(s, a, t0, t1)
+        ref = O.integrate_imu(s, a, t0, t1)
+        assert got.dtype == np.float32 and np.array_equal(got.view(np.uint32), ref.view(np.uint32))
+        assert np.array_equal(got[3], [0, 0, 0, 1]) and np.array_equal(got[:3, 3], [0, 0, 0])
+        assert np.allclose(got[:3, :3] @ got[:3, :3].T, np.eye(3), atol=1e-6)
+    # constant yaw rate: rotation about z by rate * (span of the samples inside the frame)
+    s = np.linspace(t0, t1, 41)
+    a = np.tile([0.0, 0.0, 0.5], (41, 1))
+    T = imu_prior(s, a, t0, t1)
+    assert abs(np.arctan2(T[1, 0], T[0, 0]) - 0.5 * 0.1) < 1e-5
+    # nothing usable: identity
+    assert np.array_equal(imu_prior(np.zeros(0), np.zeros((0, 3)), t0, t1), np.eye(4, dtype=np.float32))
+    assert np.array_equal(imu_prior(np.array([100.05]), np.ones((1, 3)), t0, t1), np.eye(4, dtype=np.float32))
+    assert np.array_equal(imu_prior(stamps, av, 200.0, 200.1), np.eye(4, dtype=np.float32))
