@@ -18,12 +18,20 @@ using namespace ngicp;
 
 struct ngicp_handle {
   int device = 0;
-  StreamPtr stream;
+  // Two streams per handle.  `stream` carries the target side (setInputTarget, target covariances), the registration
+  // itself and everything else; `stream_src` carries the SOURCE side (setInputSource / registerInputSource, source
+  // covariances) with its own scratch, so that the scan's index + covariances run beside the submap's instead of behind
+  // them (C2: 0.18 ms of small, latency-bound kernels).  Every entry point that needs the source on the main stream joins
+  // first (join_source).  A caller-supplied stream (ngicp_set_stream) serves both sides: no concurrency, plain stream order.
+  StreamPtr stream, stream_src;
   ngicp_params prm;
   std::string err;
   CloudPtr src, tgt;
   CovsPtr src_cov, tgt_cov;
-  Scratch sc;
+  Scratch sc, sc_src;
+  cudaEvent_t ev_join = nullptr, ev_retire = nullptr;
+  bool src_pending = false;             // work queued on stream_src that the main stream has not waited for yet
+  int nbr_side = NGICP_TARGET;          // which scratch holds the neighbour lists of nbr_cloud
   ngicp_result* res_pinned = nullptr;   // pinned + mapped host memory the fused kernel writes its result to
   ngicp_result* res_mapped = nullptr;   // device-side address of res_pinned
   double* red_pinned = nullptr;         // pinned host mirror of reduced[]
@@ -86,8 +94,44 @@ struct DeviceGuard {
 };
 
 enum Phase { PH_SET_SRC = 0, PH_SET_TGT, PH_COV_SRC, PH_COV_TGT, PH_ALIGN, PH_VOXEL, PH_COUNT };
-inline void ph_begin(ngicp_t* h, int ph) { cudaEventRecord(h->ev[ph][0], h->stream->s); }
-inline void ph_end(ngicp_t* h, int ph) { cudaEventRecord(h->ev[ph][1], h->stream->s); h->ev_used[ph] = true; }
+inline StreamPtr& side_stream(ngicp_t* h, int which) { return which == NGICP_SOURCE ? h->stream_src : h->stream; }
+inline Scratch& side_scratch(ngicp_t* h, int which) { return which == NGICP_SOURCE ? h->sc_src : h->sc; }
+inline cudaStream_t ph_stream(ngicp_t* h, int ph);
+inline void ph_begin(ngicp_t* h, int ph) { cudaEventRecord(h->ev[ph][0], ph_stream(h, ph)); }
+inline void ph_end(ngicp_t* h, int ph) { cudaEventRecord(h->ev[ph][1], ph_stream(h, ph)); h->ev_used[ph] = true; }
+
+// the main stream waits for everything queued on the source-side stream so far
+inline void join_source(ngicp_t* h) {
+  if (h->src_pending && h->stream_src->s != h->stream->s) {
+    cudaEventRecord(h->ev_join, h->stream_src->s);
+    cudaStreamWaitEvent(h->stream->s, h->ev_join, 0);
+  }
+  h->src_pending = false;
+}
+inline void sync_both(ngicp_t* h) {
+  if (h->stream_src && h->stream_src->s && h->stream_src->s != h->stream->s) cudaStreamSynchronize(h->stream_src->s);
+  if (h->stream && h->stream->s) cudaStreamSynchronize(h->stream->s);
+  h->src_pending = false;
+}
+// Device buffers are freed in the order of the stream that allocated them.  A buffer that leaves role `which` (source /
+// target) after a swap may have been allocated on the OTHER side's stream while this side's stream still reads it:
+// make the allocating stream wait for this side before the release is queued.
+inline void order_free_after(ngicp_t* h, const StreamPtr& alloc_st, int which) {
+  const StreamPtr& role = side_stream(h, which);
+  if (!alloc_st || !alloc_st->s || !role || alloc_st->s == role->s) return;
+  cudaEventRecord(h->ev_retire, role->s);
+  cudaStreamWaitEvent(alloc_st->s, h->ev_retire, 0);
+}
+inline void drop_cloud(ngicp_t* h, int which) {
+  CloudPtr& c = which == NGICP_SOURCE ? h->src : h->tgt;
+  if (c && c.use_count() == 1) order_free_after(h, c->pts.st, which);
+  c.reset();
+}
+inline void drop_covs(ngicp_t* h, int which) {
+  CovsPtr& c = which == NGICP_SOURCE ? h->src_cov : h->tgt_cov;
+  if (c && c.use_count() == 1) order_free_after(h, c->c.st, which);
+  c.reset();
+}
 
 __global__ void mat4_to_sym6_kernel(const double* __restrict__ m, int n, double* __restrict__ c) {
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
@@ -127,6 +171,8 @@ __global__ void vox_passthrough_kernel(const float4* __restrict__ pts, int n, fl
   }
 }
 
+inline cudaStream_t ph_stream(ngicp_t* h, int ph) { return (ph == PH_SET_SRC || ph == PH_COV_SRC) ? h->stream_src->s : h->stream->s; }
+
 inline int blocks_for(int n) { int g = (n + 255) / 256; return g < 1 ? 1 : (g > 148 * 8 ? 148 * 8 : g); }
 
 int set_cloud(ngicp_t* h, int which, const void* pts, size_t n, size_t stride, bool index) {
@@ -136,19 +182,22 @@ int set_cloud(ngicp_t* h, int which, const void* pts, size_t n, size_t stride, b
   CloudPtr c(new (std::nothrow) DevCloud());
   if (!c) return fail(h, NGICP_E_INVALID, "out of host memory");
   const int ph = which == NGICP_SOURCE ? PH_SET_SRC : PH_SET_TGT;
+  StreamPtr& st = side_stream(h, which);
+  Scratch& sc = side_scratch(h, which);
   ph_begin(h, ph);
-  NG_CUDA(h, upload_cloud(*c, pts, n, stride, h->sc, h->stream));
-  if (index) NG_CUDA(h, build_index(*c, h->prm.grid_cell_size, h->prm.grid_table_cells, h->sc, h->stream, h->device));
+  NG_CUDA(h, upload_cloud(*c, pts, n, stride, sc, st));
+  if (index) NG_CUDA(h, build_index(*c, h->prm.grid_cell_size, h->prm.grid_table_cells, sc, st, h->device));
   ph_end(h, ph);
-  if (which == NGICP_SOURCE) { h->src = c; if (index) h->src_cov.reset(); }
-  else { h->tgt = c; h->tgt_cov.reset(); }
+  drop_cloud(h, which);
+  if (which == NGICP_SOURCE) { h->src = c; if (index) drop_covs(h, NGICP_SOURCE); h->src_pending = true; }
+  else { h->tgt = c; drop_covs(h, NGICP_TARGET); }
   h->lin_valid = false;
   return NGICP_OK;
 }
 
-int ensure_index(ngicp_t* h, CloudPtr& c) {
+int ensure_index(ngicp_t* h, CloudPtr& c, int which) {
   if (c->indexed) return NGICP_OK;
-  NG_CUDA(h, build_index(*c, h->prm.grid_cell_size, h->prm.grid_table_cells, h->sc, h->stream, h->device));
+  NG_CUDA(h, build_index(*c, h->prm.grid_cell_size, h->prm.grid_table_cells, side_scratch(h, which), side_stream(h, which), h->device));
   return NGICP_OK;
 }
 
@@ -161,28 +210,32 @@ int calc_covs(ngicp_t* h, int which, int part = 0, int nparts = 1) {
   const int k = h->prm.k_correspondences;
   if (k < 1 || k > KNN_MAX_K) return fail(h, NGICP_E_UNSUPPORTED, "k_correspondences must be in [1,32]");
   if (c->n < k) return fail(h, NGICP_E_TOO_FEW_POINTS, "cloud has fewer points than k_correspondences");
-  int rc = ensure_index(h, c);  // calculate_covariances re-targets the kd-tree when needed (nano_gicp_impl.hpp:304-306)
+  StreamPtr& st = side_stream(h, which);
+  Scratch& sc = side_scratch(h, which);
+  int rc = ensure_index(h, c, which);  // calculate_covariances re-targets the kd-tree when needed (nano_gicp_impl.hpp:304-306)
   if (rc) return rc;
   CovsPtr cv(new (std::nothrow) DevCovs());
   if (!cv) return fail(h, NGICP_E_INVALID, "out of host memory");
   cv->n = c->n;
-  NG_CUDA(h, cv->c.alloc(sizeof(double) * 6 * (size_t)c->n, h->stream));
+  NG_CUDA(h, cv->c.alloc(sizeof(double) * 6 * (size_t)c->n, st));
   const int ph = which == NGICP_SOURCE ? PH_COV_SRC : PH_COV_TGT;
   ph_begin(h, ph);
-  NG_CUDA(h, h->sc.nbr.reserve(sizeof(int) * covariance_scratch_ints(c->n, k), h->stream));
+  NG_CUDA(h, sc.nbr.reserve(sizeof(int) * covariance_scratch_ints(c->n, k), st));
   h->nbr_cloud.reset();
-  if (!h->sc.cov_side.stream) {
+  if (!sc.cov_side.stream) {
     int lo_pri = 0, hi_pri = 0;
     cudaDeviceGetStreamPriorityRange(&lo_pri, &hi_pri);
-    NG_CUDA(h, cudaStreamCreateWithPriority(&h->sc.cov_side.stream, cudaStreamNonBlocking, hi_pri));
-    NG_CUDA(h, cudaEventCreateWithFlags(&h->sc.cov_side.fork, cudaEventDisableTiming));
-    NG_CUDA(h, cudaEventCreateWithFlags(&h->sc.cov_side.join, cudaEventDisableTiming));
+    NG_CUDA(h, cudaStreamCreateWithPriority(&sc.cov_side.stream, cudaStreamNonBlocking, hi_pri));
+    NG_CUDA(h, cudaEventCreateWithFlags(&sc.cov_side.fork, cudaEventDisableTiming));
+    NG_CUDA(h, cudaEventCreateWithFlags(&sc.cov_side.join, cudaEventDisableTiming));
   }
-  NG_CUDA(h, launch_covariances(*c, k, h->prm.regularization_method, h->sc.nbr.as<int>(), cv->c.as<double>(), c->table_cap, h->stream->s,
-                                part, nparts, h->prm.knn_path, h->prm.knn_tile_min_points, &h->sc.cov_side));
+  NG_CUDA(h, launch_covariances(*c, k, h->prm.regularization_method, sc.nbr.as<int>(), cv->c.as<double>(), c->table_cap, st->s,
+                                part, nparts, h->prm.knn_path, h->prm.knn_tile_min_points, &sc.cov_side));
   ph_end(h, ph);
-  if (nparts == 1) { h->nbr_cloud = c; h->nbr_k = k; }
+  if (nparts == 1) { h->nbr_cloud = c; h->nbr_k = k; h->nbr_side = which; }
+  drop_covs(h, which);
   (which == NGICP_SOURCE ? h->src_cov : h->tgt_cov) = cv;
+  if (which == NGICP_SOURCE) h->src_pending = true;
   h->lin_valid = false;
   return NGICP_OK;
 }
@@ -193,16 +246,20 @@ int set_covs(ngicp_t* h, int which, const double* covs, size_t n) {
   CovsPtr cv(new (std::nothrow) DevCovs());
   if (!cv) return fail(h, NGICP_E_INVALID, "out of host memory");
   cv->n = (int)n;
-  NG_CUDA(h, cv->c.alloc(sizeof(double) * 6 * (n ? n : 1), h->stream));
+  StreamPtr& st = side_stream(h, which);
+  Scratch& sc = side_scratch(h, which);
+  NG_CUDA(h, cv->c.alloc(sizeof(double) * 6 * (n ? n : 1), st));
   if (n) {
-    NG_CUDA(h, h->sc.cov_stage.reserve(sizeof(double) * 16 * n, h->stream));
-    NG_CUDA(h, cudaMemcpyAsync(h->sc.cov_stage.p, covs, sizeof(double) * 16 * n, cudaMemcpyDefault, h->stream->s));
-    NG_CUDA(h, host_source_consumed(covs, h->sc, h->stream->s));
-    mat4_to_sym6_kernel<<<blocks_for((int)n), 256, 0, h->stream->s>>>(h->sc.cov_stage.as<double>(), (int)n, cv->c.as<double>());
+    NG_CUDA(h, sc.cov_stage.reserve(sizeof(double) * 16 * n, st));
+    NG_CUDA(h, cudaMemcpyAsync(sc.cov_stage.p, covs, sizeof(double) * 16 * n, cudaMemcpyDefault, st->s));
+    NG_CUDA(h, host_source_consumed(covs, sc, st->s));
+    mat4_to_sym6_kernel<<<blocks_for((int)n), 256, 0, st->s>>>(sc.cov_stage.as<double>(), (int)n, cv->c.as<double>());
     note_launches(1);
     NG_CUDA(h, cudaGetLastError());
   }
+  drop_covs(h, which);
   (which == NGICP_SOURCE ? h->src_cov : h->tgt_cov) = cv;
+  if (which == NGICP_SOURCE) h->src_pending = true;
   h->lin_valid = false;
   return NGICP_OK;
 }
@@ -213,6 +270,7 @@ int get_covs(ngicp_t* h, int which, double* out, size_t n) {
   CovsPtr& cv = which == NGICP_SOURCE ? h->src_cov : h->tgt_cov;
   if (!cv || (size_t)cv->n != n) return fail(h, NGICP_E_COV_SIZE, "get covariances: size mismatch");
   if (n == 0) return NGICP_OK;
+  join_source(h);
   NG_CUDA(h, h->sc.cov_stage.reserve(sizeof(double) * 16 * n, h->stream));
   sym6_to_mat4_kernel<<<blocks_for((int)n), 256, 0, h->stream->s>>>(cv->c.as<double>(), (int)n, h->sc.cov_stage.as<double>());
   note_launches(1);
@@ -238,6 +296,7 @@ int prepare_align(ngicp_t* h, bool lazy, AlignBuffers& ab) {
     int rc = calc_covs(h, NGICP_TARGET);
     if (rc) return rc;
   }
+  join_source(h);   // the source's index and covariances are queued on the source-side stream
   const size_t ns = (size_t)h->src->n;
   Scratch& sc = h->sc;
   NG_CUDA(h, sc.mahal.reserve(sizeof(double) * 6 * ns, h->stream));
@@ -362,6 +421,7 @@ int ngicp_grid_info(ngicp_t* h, int which, float* cell, int* dims3, int* ncells)
   DeviceGuard g(h->device);
   CloudPtr& c = which == NGICP_SOURCE ? h->src : h->tgt;
   if (!c || !c->indexed) return fail(h, NGICP_E_STATE, "grid info: no search index");
+  join_source(h);
   GridDesc d;
   NG_CUDA(h, cudaMemcpyAsync(&d, c->desc.p, sizeof d, cudaMemcpyDeviceToHost, h->stream->s));
   NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
@@ -408,6 +468,9 @@ int ngicp_create(int device, ngicp_t** out) {
   h->stream.reset(new StreamRef());
   if (cudaStreamCreateWithFlags(&h->stream->s, cudaStreamNonBlocking) != cudaSuccess) { delete h; return NGICP_E_CUDA; }
   h->stream->owned = true;
+  h->stream_src.reset(new StreamRef());
+  if (cudaStreamCreateWithFlags(&h->stream_src->s, cudaStreamNonBlocking) != cudaSuccess) { h->stream_src.reset(); delete h; return NGICP_E_CUDA; }
+  h->stream_src->owned = true;
   // keep freed blocks in the stream-ordered pool instead of returning them to the driver
   cudaMemPool_t pool;
   if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
@@ -420,6 +483,8 @@ int ngicp_create(int device, ngicp_t** out) {
             cudaMallocHost(&h->red_pinned, sizeof(double) * 64) == cudaSuccess;
   for (int i = 0; ok && i < PH_COUNT; i++)
     ok = cudaEventCreate(&h->ev[i][0]) == cudaSuccess && cudaEventCreate(&h->ev[i][1]) == cudaSuccess;
+  ok = ok && cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) == cudaSuccess &&
+       cudaEventCreateWithFlags(&h->ev_retire, cudaEventDisableTiming) == cudaSuccess;
   if (!ok) {
     ngicp_destroy(h);
     return NGICP_E_CUDA;
@@ -466,9 +531,12 @@ int ngicp_create(int device, ngicp_t** out) {
 void ngicp_destroy(ngicp_t* h) {
   if (!h) return;
   DeviceGuard g(h->device);
-  if (h->stream && h->stream->s) cudaStreamSynchronize(h->stream->s);
+  if (h->stream && h->stream_src) sync_both(h);
+  else if (h->stream && h->stream->s) cudaStreamSynchronize(h->stream->s);
   h->src.reset(); h->tgt.reset(); h->src_cov.reset(); h->tgt_cov.reset();
   ngicp_comm_close(h);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  if (h->ev_retire) cudaEventDestroy(h->ev_retire);
   if (h->comm_buf) cudaFree(h->comm_buf);
   if (h->res_pinned) cudaFreeHost(h->res_pinned);
   if (h->red_pinned) cudaFreeHost(h->red_pinned);
@@ -483,14 +551,18 @@ const char* ngicp_last_error(const ngicp_t* h) { return h ? h->err.c_str() : "nu
 int ngicp_set_stream(ngicp_t* h, void* cuda_stream) {
   if (!h) return NGICP_E_INVALID;
   DeviceGuard g(h->device);
-  cudaStreamSynchronize(h->stream->s);
-  StreamPtr s(new StreamRef());
-  if (cuda_stream) { s->s = (cudaStream_t)cuda_stream; s->owned = false; }
+  sync_both(h);
+  StreamPtr s(new StreamRef()), s2;
+  if (cuda_stream) { s->s = (cudaStream_t)cuda_stream; s->owned = false; s2 = s; }   // the caller's stream serves both sides
   else {
     if (cudaStreamCreateWithFlags(&s->s, cudaStreamNonBlocking) != cudaSuccess) return fail(h, NGICP_E_CUDA, "cudaStreamCreate");
     s->owned = true;
+    s2.reset(new StreamRef());
+    if (cudaStreamCreateWithFlags(&s2->s, cudaStreamNonBlocking) != cudaSuccess) return fail(h, NGICP_E_CUDA, "cudaStreamCreate");
+    s2->owned = true;
   }
   h->stream = s;
+  h->stream_src = s2;
   return NGICP_OK;
 }
 void* ngicp_get_stream(const ngicp_t* h) { return h ? (void*)h->stream->s : nullptr; }
@@ -498,14 +570,18 @@ void* ngicp_get_stream(const ngicp_t* h) { return h ? (void*)h->stream->s : null
 int ngicp_sync(ngicp_t* h) {
   if (!h) return NGICP_E_INVALID;
   DeviceGuard g(h->device);
+  if (h->stream_src->s != h->stream->s) NG_CUDA(h, cudaStreamSynchronize(h->stream_src->s));
   NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
+  h->src_pending = false;
   return NGICP_OK;
 }
 
 int ngicp_get_timings(ngicp_t* h, ngicp_timings* out) {
   if (!h || !out) return NGICP_E_INVALID;
   DeviceGuard g(h->device);
+  if (h->stream_src->s != h->stream->s) NG_CUDA(h, cudaStreamSynchronize(h->stream_src->s));
   NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
+  h->src_pending = false;
   float* slots[PH_COUNT] = {&h->tm.set_source_ms, &h->tm.set_target_ms, &h->tm.source_covs_ms, &h->tm.target_covs_ms, &h->tm.align_ms, &h->tm.voxel_ms};
   for (int i = 0; i < PH_COUNT; i++)
     if (h->ev_used[i]) cudaEventElapsedTime(slots[i], h->ev[i][0], h->ev[i][1]);
@@ -539,7 +615,8 @@ int ngicp_share_source(ngicp_t* dst, const ngicp_t* src) {
   if (dst->device != src->device) return fail(dst, NGICP_E_INVALID, "handles live on different devices");
   if (!src->src) return fail(dst, NGICP_E_STATE, "share: source not set");
   DeviceGuard g(dst->device);             // dropping the previous cloud frees stream-ordered memory of that device
-  cudaStreamSynchronize(src->stream->s);  // the index must be complete before another stream reads it
+  sync_both(const_cast<ngicp_t*>(src));   // the index must be complete before another handle's streams read it
+  drop_cloud(dst, NGICP_SOURCE);
   dst->src = src->src;
   dst->lin_valid = false;
   return NGICP_OK;
@@ -548,7 +625,8 @@ int ngicp_share_source_covs(ngicp_t* dst, const ngicp_t* src) {
   if (!dst || !src) return NGICP_E_INVALID;
   if (dst->device != src->device) return fail(dst, NGICP_E_INVALID, "handles live on different devices");
   DeviceGuard g(dst->device);
-  cudaStreamSynchronize(src->stream->s);
+  sync_both(const_cast<ngicp_t*>(src));
+  drop_covs(dst, NGICP_SOURCE);
   dst->src_cov = src->src_cov;
   dst->lin_valid = false;
   return NGICP_OK;
@@ -556,14 +634,20 @@ int ngicp_share_source_covs(ngicp_t* dst, const ngicp_t* src) {
 
 int ngicp_swap(ngicp_t* h) {
   if (!h) return NGICP_E_INVALID;
+  {
+    // the clouds change sides, i.e. streams: nothing may be in flight on either (in OdomNode this follows an align(),
+    // which has just synchronised anyway — odom.cc:818)
+    DeviceGuard g(h->device);
+    sync_both(h);
+  }
   h->src.swap(h->tgt);
   h->src_cov.swap(h->tgt_cov);
   h->lin_valid = false;
   return NGICP_OK;
 }
 // (releasing a cloud frees stream-ordered memory and records events: the handle's device must be current)
-int ngicp_clear_source(ngicp_t* h) { if (!h) return NGICP_E_INVALID; DeviceGuard g(h->device); h->src.reset(); h->src_cov.reset(); h->lin_valid = false; return NGICP_OK; }
-int ngicp_clear_target(ngicp_t* h) { if (!h) return NGICP_E_INVALID; DeviceGuard g(h->device); h->tgt.reset(); h->tgt_cov.reset(); h->lin_valid = false; return NGICP_OK; }
+int ngicp_clear_source(ngicp_t* h) { if (!h) return NGICP_E_INVALID; DeviceGuard g(h->device); drop_cloud(h, NGICP_SOURCE); drop_covs(h, NGICP_SOURCE); h->lin_valid = false; return NGICP_OK; }
+int ngicp_clear_target(ngicp_t* h) { if (!h) return NGICP_E_INVALID; DeviceGuard g(h->device); drop_cloud(h, NGICP_TARGET); drop_covs(h, NGICP_TARGET); h->lin_valid = false; return NGICP_OK; }
 size_t ngicp_cloud_size(const ngicp_t* h, int which) {
   if (!h) return 0;
   const CloudPtr& c = which == NGICP_SOURCE ? h->src : h->tgt;
@@ -576,6 +660,7 @@ int ngicp_calc_source_covs_part(ngicp_t* h, int part, int nparts) { return calc_
 int ngicp_covs_device(ngicp_t* h, int which, double** covs6, size_t* n) {
   if (!h || !covs6 || !n) return NGICP_E_INVALID;
   const CovsPtr& cv = which == NGICP_SOURCE ? h->src_cov : h->tgt_cov;
+  { DeviceGuard g(h->device); join_source(h); }   // callers continue on the main stream (ngicp_get_stream)
   *covs6 = cv ? cv->c.as<double>() : nullptr;
   *n = cv ? (size_t)cv->n : 0;
   return cv ? NGICP_OK : fail(h, NGICP_E_STATE, "no covariances");
@@ -586,9 +671,10 @@ int ngicp_cov_neighbors(ngicp_t* h, int which, int* idx, float* d2) {
   CloudPtr& c = which == NGICP_SOURCE ? h->src : h->tgt;
   if (!c || h->nbr_cloud.lock() != c || h->nbr_k < 1) return fail(h, NGICP_E_STATE, "cov_neighbors: the last covariance computation on this handle was not for this cloud");
   const size_t cnt = (size_t)c->n * h->nbr_k;
+  join_source(h);
   NG_CUDA(h, h->sc.knn_idx.reserve(sizeof(int) * cnt, h->stream));
   NG_CUDA(h, h->sc.knn_d2.reserve(sizeof(float) * cnt, h->stream));
-  NG_CUDA(h, launch_export_neighbors(*c, h->nbr_k, h->sc.nbr.as<int>(), h->sc.knn_idx.as<int>(), h->sc.knn_d2.as<float>(), h->stream->s));
+  NG_CUDA(h, launch_export_neighbors(*c, h->nbr_k, side_scratch(h, h->nbr_side).nbr.as<int>(), h->sc.knn_idx.as<int>(), h->sc.knn_d2.as<float>(), h->stream->s));
   NG_CUDA(h, cudaMemcpyAsync(idx, h->sc.knn_idx.p, sizeof(int) * cnt, cudaMemcpyDefault, h->stream->s));
   NG_CUDA(h, cudaMemcpyAsync(d2, h->sc.knn_d2.p, sizeof(float) * cnt, cudaMemcpyDefault, h->stream->s));
   NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
@@ -599,7 +685,7 @@ int ngicp_set_target_covs(ngicp_t* h, const double* covs, size_t n) { return set
 int ngicp_clear_covs(ngicp_t* h, int which) {
   if (!h) return NGICP_E_INVALID;
   DeviceGuard g(h->device);
-  (which == NGICP_SOURCE ? h->src_cov : h->tgt_cov).reset();
+  drop_covs(h, which);
   h->lin_valid = false;
   return NGICP_OK;
 }
@@ -705,6 +791,7 @@ int ngicp_transform_source(ngicp_t* h, const float* T16, float* out_xyz1, size_t
   if (!h->src || (size_t)h->src->n != n) return fail(h, NGICP_E_STATE, "transform: source size mismatch");
   if (n == 0) return NGICP_OK;
   DeviceGuard g(h->device);
+  join_source(h);
   NG_CUDA(h, h->sc.queries.reserve(sizeof(float4) * n, h->stream));
   Mat16f T;
   memcpy(T.m, T16, sizeof T.m);
@@ -836,6 +923,7 @@ int ngicp_knn(ngicp_t* h, int which, const float* queries, size_t nq, size_t q_s
   if (!c) return fail(h, NGICP_E_STATE, "knn: cloud not set");
   if (!c->indexed) return fail(h, NGICP_E_STATE, "knn: no search index (nanoflann throws here, nanoflann_impl.hpp:1235-1237)");
   if (nq == 0) return NGICP_OK;
+  join_source(h);
   DevCloud qc;
   NG_CUDA(h, upload_cloud(qc, queries, nq, q_stride, h->sc, h->stream));
   NG_CUDA(h, h->sc.knn_idx.reserve(sizeof(int) * nq * k, h->stream));
@@ -1010,7 +1098,7 @@ int ngicp_comm_export(ngicp_t* h, void* handle64) {
 int ngicp_comm_close(ngicp_t* h) {
   if (!h) return NGICP_E_INVALID;
   DeviceGuard g(h->device);
-  if (h->stream) cudaStreamSynchronize(h->stream->s);
+  if (h->stream && h->stream_src) sync_both(h);
   for (int p = 0; p < NGICP_MAX_RANKS; ++p) {
     if (h->comm_peer[p] && h->comm_peer_ipc[p]) cudaIpcCloseMemHandle(h->comm_peer[p]);
     h->comm_peer[p] = nullptr;
@@ -1091,6 +1179,7 @@ int ngicp_kfstore_push(ngicp_kfstore_t* s, ngicp_t* from, size_t* index_out) {
   if (!from->src || !from->src_cov || from->src_cov->n != from->src->n)
     return fail(from, NGICP_E_STATE, "keyframe push: source cloud and its covariances must be set (setInputSource + calculateSourceCovariances)");
   DeviceGuard g(s->device);
+  join_source(from);
   ngicp_kfstore::Keyframe k;
   k.n = from->src->n;
   k.pts.reset(new (std::nothrow) DevBuf());
@@ -1139,6 +1228,8 @@ int ngicp_kfstore_set_target(ngicp_kfstore_t* s, ngicp_t* to, const int* indices
   NG_CUDA(to, upload_cloud(*c, to->sc.staging.p, total, sizeof(float4), to->sc, to->stream));
   NG_CUDA(to, build_index(*c, to->prm.grid_cell_size, to->prm.grid_table_cells, to->sc, to->stream, to->device));
   ph_end(to, PH_SET_TGT);
+  drop_cloud(to, NGICP_TARGET);
+  drop_covs(to, NGICP_TARGET);
   to->tgt = c;
   to->tgt_cov = cv;            // gicp.setTargetCovariances(submap_normals) (:833)
   to->lin_valid = false;
