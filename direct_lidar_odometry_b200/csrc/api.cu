@@ -220,7 +220,7 @@ int calc_covs(ngicp_t* h, int which, int part = 0, int nparts = 1) {
   NG_CUDA(h, cv->c.alloc(sizeof(double) * 6 * (size_t)c->n, st));
   const int ph = which == NGICP_SOURCE ? PH_COV_SRC : PH_COV_TGT;
   ph_begin(h, ph);
-  NG_CUDA(h, sc.nbr.reserve(sizeof(int) * covariance_scratch_ints(c->n, k), st));
+  NG_CUDA(h, sc.nbr.reserve(sizeof(int) * covariance_scratch_ints(c->n, k, c->table_cap), st));
   h->nbr_cloud.reset();
   if (!sc.cov_side.stream) {
     int lo_pri = 0, hi_pri = 0;

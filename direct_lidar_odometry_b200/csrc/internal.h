@@ -142,7 +142,7 @@ cudaError_t build_index(DevCloud& c, float cell_req, int table_cap, Scratch& sc,
 
 // ---- knn_cov.cu -----------------------------------------------------------------------------------
 cudaError_t launch_knn_queries(const DevCloud& c, const float4* queries, int nq, int k, int* idx, float* d2, cudaStream_t st);
-size_t covariance_scratch_ints(int n, int k);   // neighbour lists + the work lists of the kNN kernels
+size_t covariance_scratch_ints(int n, int k, int table_cap);   // neighbour lists + the work lists / flags of the kNN kernels
 cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_scratch /* covariance_scratch_ints() */, double* covs6, int table_cap, cudaStream_t st,
                                int part = 0, int nparts = 1, int knn_path = NGICP_KNN_AUTO, int tile_min_points = 131072,
                                const CovSideStream* side = nullptr);

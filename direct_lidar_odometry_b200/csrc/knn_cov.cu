@@ -88,17 +88,16 @@ __global__ void __launch_bounds__(KC_THREADS, KNN_MIN_BLOCKS) knn_lists_kernel(G
 #ifndef TQ_WARPS
 #define TQ_WARPS 2
 #endif
+#define TQ_POS_BITS 9
+#define TQ_POS_MASK 0x1ffu
 #ifndef TQ_CMAX
-#define TQ_CMAX 384      // tile capacity (slots: rows are padded to even lengths)
+#define TQ_CMAX 448      // tile capacity (slots: rows are padded to even lengths); measured on C2: 320 0.69, 384 0.72, 448 0.67 ms for the covariance phase
 #endif
 #ifndef TQ_LCAP
 #define TQ_LCAP 40       // per-query collection capacity
 #endif
 #ifndef TQ_CORE
 #define TQ_CORE 4        // box edge in cells
-#endif
-#ifndef TQ_SELECT_NET
-#define TQ_SELECT_NET 1  // 1: sorting-network selection of the k nearest in registers; 0: secant steps on the count
 #endif
 #ifndef TQ_PACKED
 #define TQ_PACKED 1      // 1: packed f32x2 distance arithmetic (two candidates per instruction); 0: scalar
@@ -118,7 +117,11 @@ struct TileSmem {
   // even position and is padded to an even length with a point at +infinity (its distance is +inf: never collected).
   float xs[TQ_CMAX], ys[TQ_CMAX], zs[TQ_CMAX];
   int slot[TQ_CMAX];                     // sorted slot of the candidate
-  uint2 lst[TQ_LCAP + 1][32];            // collected {bits(distance), tile position}, one column per lane; last row = dump
+  // collected candidates, one column per lane, last row = dump: ONE 32-bit word per entry = the squared distance with
+  // its 9 low mantissa bits replaced by the tile position (TQ_CMAX <= 512).  All thresholds live on the same lattice
+  // (low 9 bits zero), so "d < T" and "entry < bits(T)" are the same test; two entries closer than 2^-14 relative cannot be
+  // told apart — when that happens exactly at the k-th place the point takes the warp search, like an exact tie.
+  unsigned lst[TQ_LCAP + 1][32];
   int cur[TQ_ITEM];                      // sorted slots of the points being answered from the current tile
   float cur_t[TQ_ITEM];                  // their threshold guesses (0 = none yet) ...
   float cur_lo[TQ_ITEM], cur_hi[TQ_ITEM];  // ... inside this bracket (hi < 0 = open)
@@ -208,7 +211,32 @@ __device__ __forceinline__ void emit_items(bool emit, int x0, int y0, int z0, in
 // one warp per run of x-adjacent boxes (8 on big grids, 1 on small ones): emits the work items of knn_lists_tile_kernel.
 // A box whose radius-1 tile would not fit is split into its 8 children (evaluated 4 lanes each, in parallel), and a
 // child that still does not fit into its 8 single cells.
-__global__ void __launch_bounds__(256) knn_plan_kernel(GridView g, int4* __restrict__ items, int* __restrict__ ctrl) {
+// Brick occupancy flags (one byte per box of TQ_CORE^3 cells), so that the plan does not have to walk the dense cell
+// table to find out that most of space is empty: 64 MB of table reads for the 16 M-cell grid of the 500k-point C2 submap
+// became 0.25 MB of flag reads.  brick_clear zeroes the flags of this grid's boxes, brick_mark sets the flag of every
+// point's box (plain stores of the same value: no atomics needed).
+__global__ void __launch_bounds__(256) brick_clear_kernel(GridView g, unsigned char* __restrict__ flags, long long flag_cap) {
+  const GridParams gp = load_grid(g.desc);
+  const long long nb = (long long)((gp.dx + TQ_CORE - 1) / TQ_CORE) * ((gp.dy + TQ_CORE - 1) / TQ_CORE) * ((gp.dz + TQ_CORE - 1) / TQ_CORE);
+  if (nb > flag_cap) return;                           // the plan then falls back to table lookups
+  const long long nw = (nb + 3) / 4;
+  unsigned* f4 = reinterpret_cast<unsigned*>(flags);
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += (long long)gridDim.x * blockDim.x) f4[i] = 0u;
+}
+__global__ void __launch_bounds__(256) brick_mark_kernel(GridView g, int n, unsigned char* __restrict__ flags, long long flag_cap) {
+  const GridParams gp = load_grid(g.desc);
+  const int nbx = (gp.dx + TQ_CORE - 1) / TQ_CORE, nby = (gp.dy + TQ_CORE - 1) / TQ_CORE, nbz = (gp.dz + TQ_CORE - 1) / TQ_CORE;
+  if ((long long)nbx * nby * nbz > flag_cap) return;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const float4 p = __ldg(g.sorted + i);
+    const int bx = cell_coord(p.x, gp.ox, gp.inv, gp.dx) / TQ_CORE, by = cell_coord(p.y, gp.oy, gp.inv, gp.dy) / TQ_CORE,
+              bz = cell_coord(p.z, gp.oz, gp.inv, gp.dz) / TQ_CORE;
+    flags[((long long)bz * nby + by) * nbx + bx] = 1;
+  }
+}
+
+__global__ void __launch_bounds__(256) knn_plan_kernel(GridView g, int4* __restrict__ items, int* __restrict__ ctrl,
+                                                       const unsigned char* __restrict__ flags, long long flag_cap) {
   const int lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const GridParams gp = load_grid(g.desc);
@@ -219,8 +247,15 @@ __global__ void __launch_bounds__(256) knn_plan_kernel(GridView g, int4* __restr
   // the launch covers the usual run count; the stride loop covers flat grids, whose per-axis rounding makes more boxes
   for (int w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < nruns; w += nwarps) {
     const int rbx = (w % nrx) * run, rby = (w / nrx) % nby, rbz = w / (nrx * nby);
-    if (run > 1) {
-      // whole run empty?  (16 core rows, one lane each)
+    unsigned occ = FULL;                                   // boxes of the run that hold points
+    if (run > 1 && (long long)nbx * nby * nbz <= flag_cap) {
+      // whole run empty?  (one flag byte per box, the run's boxes are consecutive)
+      int e = 0;
+      if (lane < run && rbx + lane < nbx) e = flags[((long long)rbz * nby + rby) * nbx + rbx + lane];
+      occ = __ballot_sync(FULL, e != 0);
+      if (occ == 0u) continue;
+    } else if (run > 1) {
+      // (grids with more boxes than flag bytes) whole run empty?  (16 core rows, one lane each)
       int e = 0;
       if (lane < TQ_CORE * TQ_CORE) {
         const int y = rby * TQ_CORE + (lane % TQ_CORE), z = rbz * TQ_CORE + (lane / TQ_CORE);
@@ -234,6 +269,7 @@ __global__ void __launch_bounds__(256) knn_plan_kernel(GridView g, int4* __restr
     for (int bi = 0; bi < run; ++bi) {
       const int bx = rbx + bi;
       if (bx >= nbx) break;
+      if (!((occ >> bi) & 1u)) continue;
       const int x0 = bx * TQ_CORE, y0 = rby * TQ_CORE, z0 = rbz * TQ_CORE;
       const int Q = box_population(g, gp, x0, y0, z0, TQ_CORE, 0, lane, 32);
       if (Q == 0) continue;
@@ -269,14 +305,17 @@ __global__ void __launch_bounds__(256) knn_plan_kernel(GridView g, int4* __restr
 #ifndef TQ_TARGET_EXTRA
 #define TQ_TARGET_EXTRA 12     // first guesses aim at k + this many collected points
 #endif
+// thresholds are kept on the lattice of the list entries: 9 low mantissa bits zero (rounded towards zero)
+__device__ __forceinline__ float lattice_floor(float t) { return __uint_as_float(__float_as_uint(t) & ~TQ_POS_MASK); }
 struct Shrunk { float T2; int cnt; };
-__device__ __noinline__ Shrunk shrink_list(uint2* col, float T2, int cnt) {
+__device__ __noinline__ Shrunk shrink_list(unsigned* col, float T2, int cnt) {
   do {
-    T2 *= 0.75f;                              // counts grow ~linearly in T^2 on surfaces: about 3/4 survive
+    T2 = lattice_floor(T2 * 0.75f);           // counts grow ~linearly in T^2 on surfaces: about 3/4 survive
+    const unsigned tb = __float_as_uint(T2);
     int pos = 0;
     for (int i = 0; i < cnt; ++i) {
-      const uint2 e = col[i * 32];
-      if (__uint_as_float(e.x) < T2) { col[pos * 32] = e; ++pos; }
+      const unsigned e = col[i * 32];
+      if (e < tb) { col[pos * 32] = e; ++pos; }
     }
     cnt = pos;
   } while (cnt > TQ_LCAP - 4);
@@ -307,26 +346,26 @@ __device__ __forceinline__ unsigned long long sqdist2_unfused(const Query2& q, u
 }
 
 // "write, then advance if it passed": the slot after the last accepted entry is simply overwritten by the next
-// candidate, so an offer is one 64-bit shared store plus one predicated pointer bump (row stride 256 B).
+// candidate, so an offer is one 32-bit shared store plus one predicated pointer bump (row stride 128 B).
 // c and cend are even (rows are padded to even lengths).
-__device__ __forceinline__ int collect_pass(const TileSmem& S, uint2* const col, int c, int cend, float qx, float qy, float qz, float one, float& T2_io, int cnt) {
+__device__ __forceinline__ int collect_pass(const TileSmem& S, unsigned* const col, int c, int cend, float qx, float qy, float qz, float one, float& T2_io, int cnt) {
   float T2 = T2_io;
   Query2 q;
   q.x = f2_pack(qx, qx); q.y = f2_pack(qy, qy); q.z = f2_pack(qz, qz); q.one = f2_pack(one, one);
   // 32-bit shared-window addresses: the bump is one predicated integer add
   const unsigned a0 = (unsigned)__cvta_generic_to_shared(col);
-  unsigned p = a0 + (unsigned)cnt * 256u;
-  const unsigned plim = a0 + (unsigned)(TQ_LCAP - 4) * 256u;
+  unsigned p = a0 + (unsigned)cnt * 128u;
+  const unsigned plim = a0 + (unsigned)(TQ_LCAP - 4) * 128u;
 #define TQ_OFFER(D, CI)                                                                                      \
   {                                                                                                          \
-    asm volatile("st.shared.v2.u32 [%0], {%1, %2};" ::"r"(p), "r"(__float_as_uint(D)), "r"((unsigned)(CI)) : "memory"); \
-    if ((D) < T2) p += 256u;                                                                                 \
+    asm volatile("st.shared.u32 [%0], %1;" ::"r"(p), "r"((__float_as_uint(D) & ~TQ_POS_MASK) | (unsigned)(CI)) : "memory"); \
+    if ((D) < T2) p += 128u;                                                                                 \
   }
 #define TQ_MAYBE_SHRINK()                                                       \
   if (p > plim) {                                                               \
-    const Shrunk r = shrink_list(col, T2, (int)((p - a0) >> 8));                \
+    const Shrunk r = shrink_list(col, T2, (int)((p - a0) >> 7));                \
     T2 = r.T2;                                                                  \
-    p = a0 + (unsigned)r.cnt * 256u;                                            \
+    p = a0 + (unsigned)r.cnt * 128u;                                            \
   }
 #define TQ_PAIR(CI)                                                                                                     \
   {                                                                                                                     \
@@ -355,11 +394,11 @@ NG_UNROLL(TQ_UNROLL)
 #undef TQ_OFFER
 #undef TQ_MAYBE_SHRINK
   T2_io = T2;
-  return (int)((p - a0) >> 8);
+  return (int)((p - a0) >> 7);
 }
 
 // v[k-1], v[k] of a register array with a run-time k (forces the array through local memory; generic-k path only)
-__device__ __noinline__ float2 pick_kth(const float* v, int k) { return make_float2(v[k - 1], v[k]); }
+__device__ __noinline__ uint2 pick_kth(const unsigned* v, int k) { return make_uint2(v[k - 1], v[k]); }
 
 template <int KT>
 __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView g, int n, int k_rt, int* __restrict__ nbr,
@@ -495,12 +534,13 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
           {
             const float m = box_face_distance(gp, x0 - s, x0 + sz - 1 + s, y0 - s + ylo, y0 - s + yhi, z0 - s + zlo, z0 - s + zhi, qp.x, qp.y, qp.z);
             if (m != FLT_MAX) m2 = m > 0.f ? m * m * 0.999999f : 0.f;
+            m2 = lattice_floor(m2);
           }
           // first guess: 1.4 x the k-th distance this lane found last in this tile, else the radius holding k+8
           // points at the tile's surface density (a planar cut through the tile covers ~ny*ny cells)
           if (!(T2 > 0.f)) T2 = prevT > 0.f ? prevT * (float)(k + TQ_TARGET_EXTRA) / (float)k : guess0;
-          T2 = fminf(T2, m2);
-          const bool active = me && m2 > 0.f;
+          T2 = lattice_floor(fminf(T2, m2));
+          const bool active = me && m2 > 0.f && T2 > 0.f;
           st_passes++;
           st_lanes += __popc(__ballot_sync(FULL, active));
           int c_now = 0;
@@ -519,89 +559,49 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
           // too few even at the largest provable radius (or no provable radius at all): needs a larger tile
           const bool grow = me && (!active || (c_now < k && T2 >= m2));
           const bool retry = active && !good && !grow;
-#if TQ_SELECT_NET
-          // ---- exactly k of the collected points: the lane sorts the distances of its list in registers (a fixed
+          // ---- exactly k of the collected points: the lane sorts its list entries in registers (a fixed
           //      compare-exchange network: no data-dependent loop, every lane of the warp does the same work) and keeps
-          //      what lies below the (k+1)-th smallest; an exact tie between the k-th and the (k+1)-th has no such
-          //      threshold: those (rare) points take the warp search ----
+          //      those up to the k-th.  Entries compare by distance down to the lattice; when the k-th and the (k+1)-th
+          //      fall on the same lattice value (an exact tie, or two points closer than 2^-14 relative) the set cannot
+          //      be decided here: those (rare) points take the warp search ----
           bool decided = good;
           bool tie = false;
-          float Tk = T2, kth = T2;
+          float kth = T2;
           {
             const bool searching = good && c_now > k;
             const bool any_search = __any_sync(FULL, searching);
             if (any_search) {
               static_assert(TQ_LCAP == 40 || TQ_LCAP == 32, "the selection networks are generated for 32 and 40 wires");
-              float v[TQ_LCAP];
+              unsigned v[TQ_LCAP];
 #pragma unroll
-              for (int i = 0; i < TQ_LCAP; ++i) v[i] = (searching && i < c_now) ? __uint_as_float(S.lst[i][lane].x) : INFINITY;
-#define NG_FCAS(A, B) { const float lo_ = fminf(v[A], v[B]), hi_ = fmaxf(v[A], v[B]); v[A] = lo_; v[B] = hi_; }
+              for (int i = 0; i < TQ_LCAP; ++i) v[i] = (searching && i < c_now) ? S.lst[i][lane] : 0xffffffffu;
+#define NG_UCAS(A, B) { const unsigned lo_ = min(v[A], v[B]), hi_ = max(v[A], v[B]); v[A] = lo_; v[B] = hi_; }
 #if TQ_LCAP == 40
-              NGICP_SORTNET_40(NG_FCAS)
+              NGICP_SORTNET_40(NG_UCAS)
 #else
-              NGICP_SORTNET_32(NG_FCAS)
+              NGICP_SORTNET_32(NG_UCAS)
 #endif
-#undef NG_FCAS
+#undef NG_UCAS
               // the k-th and (k+1)-th smallest: static register indices when k is a template argument (10 and 20, what
               // DLO uses); a run-time k goes through a small local array (one copy of the network either way — indexing
               // the registers with a run-time k made the compiler clone the whole network per value of k)
-              float vk, vk1;
+              unsigned vk, vk1;
               if (KT > 0) { vk = v[KT > 0 ? KT - 1 : 0]; vk1 = v[KT > 0 ? KT : 0]; }
-              else { const float2 pk = pick_kth(v, k); vk = pk.x; vk1 = pk.y; }
+              else { const uint2 pk = pick_kth(v, k); vk = pk.x; vk1 = pk.y; }
+              unsigned bound = 0u;
               if (searching) {
-                if (vk == vk1) { tie = true; decided = false; st_ties++; }
-                else { Tk = vk1; kth = vk; }
+                if ((vk >> TQ_POS_BITS) == (vk1 >> TQ_POS_BITS)) { tie = true; decided = false; st_ties++; }
+                else { bound = ((vk >> TQ_POS_BITS) + 1u) << TQ_POS_BITS; kth = __uint_as_float(vk & ~TQ_POS_MASK); }
               }
               const bool compact = searching && !tie;
               int pos = 0;
 #pragma unroll
               for (int i = 0; i < TQ_LCAP; ++i) {
-                const uint2 e = S.lst[i][lane];
-                if (compact && i < c_now && __uint_as_float(e.x) < Tk) { S.lst[pos][lane].y = e.y; ++pos; }
+                const unsigned e = S.lst[i][lane];
+                if (compact && i < c_now && e < bound) { S.lst[pos][lane] = e; ++pos; }
               }
             }
           }
-#else
-          // ---- tighten the threshold on the lane's own list until exactly k remain: the distances move into
-          //      registers once, the secant steps on the count then run without touching memory (warp-uniform loops) ----
-          bool decided = good;
-          bool tie = false;
-          float Tk = T2, kth = T2;
-          {
-            bool searching = good && c_now > k;
-            const bool any_search = __any_sync(FULL, searching);
-            float dl[TQ_LCAP];
-            if (any_search) {
-#pragma unroll
-              for (int i = 0; i < TQ_LCAP; ++i) dl[i] = (searching && i < c_now) ? __uint_as_float(S.lst[i][lane].x) : INFINITY;
-            }
-            float slo = 0.f, shi = T2;
-            int clo = 0, chi = c_now;
-            for (int it = 0; it < 16 && __any_sync(FULL, searching); ++it) {
-              float T = slo + (shi - slo) * (((float)(k - clo) + 0.5f) / (float)max(chi - clo, 1));
-              if (!(T > slo && T < shi)) T = 0.5f * (slo + shi);
-              if (searching && !(T > slo && T < shi)) { searching = false; tie = true; }   // adjacent floats: tie at the k-th distance
-              int c = 0;
-#pragma unroll
-              for (int i = 0; i < TQ_LCAP; ++i) c += (dl[i] < T) ? 1 : 0;
-              if (searching) {
-                if (c == k) { searching = false; Tk = T; kth = T; }
-                else if (c < k) { slo = T; clo = c; }
-                else { shi = T; chi = c; }
-              }
-            }
-            if (searching) tie = true;
-            if (tie) { decided = false; st_ties++; }
-            const bool compact = good && c_now > k && !tie;
-            if (any_search) {
-              int pos = 0;
-#pragma unroll
-              for (int i = 0; i < TQ_LCAP; ++i) {
-                if (compact && dl[i] < Tk) { S.lst[pos][lane].y = S.lst[i][lane].y; ++pos; }
-              }
-            }
-          }
-#endif
           if (decided) prevT = kth;
           const unsigned dmask = __ballot_sync(FULL, decided);
           __syncwarp();
@@ -609,8 +609,8 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
           for (unsigned mm = dmask; mm; mm &= mm - 1) {
             const int l = __ffs(mm) - 1;
             const int sl = __shfl_sync(FULL, slot, l);
-            TQ_CHECK(lane >= k || (S.lst[lane][l].y < (unsigned)C && S.slot[S.lst[lane][l].y] >= 0), "tilepos", (int)S.lst[lane][l].y, C);
-            if (lane < k) nbr[(size_t)sl * k + lane] = S.slot[S.lst[lane][l].y];
+            TQ_CHECK(lane >= k || ((S.lst[lane][l] & TQ_POS_MASK) < (unsigned)C && S.slot[S.lst[lane][l] & TQ_POS_MASK] >= 0), "tilepos", (int)(S.lst[lane][l] & TQ_POS_MASK), C);
+            if (lane < k) nbr[(size_t)sl * k + lane] = S.slot[S.lst[lane][l] & TQ_POS_MASK];
           }
           __syncwarp();
           // ---- the rest: ties to the warp search, growers to the next radius, retries back into the queue ----
@@ -627,7 +627,7 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
             if (c_now < k) { lo = T2; if (T2 < T2_asked) hi = hi > 0.f ? fminf(hi, T2_asked) : T2_asked; } else hi = T2;
             float Tn = T2 * (float)(k + TQ_TARGET_EXTRA) / (float)max(c_now, 2);
             if (Tn <= lo || (hi > 0.f && Tn >= hi)) Tn = hi > 0.f ? 0.5f * (lo + hi) : T2 * 2.f;
-            Tn = fminf(Tn, m2);
+            Tn = lattice_floor(fminf(Tn, m2));
             const int pos = nre + __popc(rm & lt);          // nre <= t0: never overtakes the reads
             S.cur[pos] = slot;
             S.cur_t[pos] = Tn;
@@ -673,7 +673,7 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
 }
 
 // the points the tile kernel could not decide: one warp per listed point, growing-cube search (same result definition)
-__global__ void __launch_bounds__(KC_THREADS, 4) knn_lists_rest_kernel(GridView g, int k, int* __restrict__ nbr, const int* __restrict__ ctrl,
+__global__ void __launch_bounds__(64) knn_lists_rest_kernel(GridView g, int k, int* __restrict__ nbr, const int* __restrict__ ctrl,
                                                                                      const int* __restrict__ fb_list) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -780,8 +780,11 @@ __device__ __forceinline__ void cov_point(const GridView& g, int n, int k_rt, in
 }
 
 // main launch: one thread per sorted slot of [q_lo, q_hi); points flagged for the warp search are left to cov_rest_kernel
+#ifndef K3_MINB
+#define K3_MINB 4      // resident blocks per SM the covariance kernel is compiled for (registers: 4 -> 128, 5 -> 96, 6 -> 80)
+#endif
 template <int KT>
-__global__ void __launch_bounds__(128) cov_from_lists_kernel(GridView g, int n, int k_rt, int method, const int* __restrict__ nbr,
+__global__ void __launch_bounds__(128, K3_MINB) cov_from_lists_kernel(GridView g, int n, int k_rt, int method, const int* __restrict__ nbr,
                                                              double* __restrict__ covs6, int q_lo, int q_hi,
                                                              const unsigned char* __restrict__ skip_flags,
                                                              int* __restrict__ idx_out, float* __restrict__ d2_out) {
@@ -827,6 +830,8 @@ void knn_prime_kernels() {
   cudaFuncGetAttributes(&fa, knn_query_kernel);
   cudaFuncGetAttributes(&fa, knn_lists_kernel);
   cudaFuncGetAttributes(&fa, knn_plan_kernel);
+  cudaFuncGetAttributes(&fa, brick_clear_kernel);
+  cudaFuncGetAttributes(&fa, brick_mark_kernel);
   cudaFuncGetAttributes(&fa, knn_lists_tile_kernel<0>);
   cudaFuncGetAttributes(&fa, knn_lists_tile_kernel<10>);
   cudaFuncGetAttributes(&fa, knn_lists_tile_kernel<20>);
@@ -852,7 +857,9 @@ cudaError_t launch_knn_queries(const DevCloud& c, const float4* queries, int nq,
 // scratch layout (ints): nbr[n*k] | control words[8] | warp-search list[n] | (16-byte aligned) work items int4[n] | warp-search flags (n bytes)
 static inline size_t items_offset_ints(int n, int k) { return (((size_t)n * k + CT_N + (size_t)n) + 3) & ~(size_t)3; }
 static inline size_t flags_offset_ints(int n, int k) { return items_offset_ints(n, k) + 4 * (size_t)n + 16; }
-size_t covariance_scratch_ints(int n, int k) { return flags_offset_ints(n, k) + ((size_t)n + 3) / 4 + 4; }
+static inline size_t brick_offset_ints(int n, int k) { return flags_offset_ints(n, k) + ((size_t)n + 3) / 4 + 4; }
+static inline long long brick_flag_bytes(int table_cap) { return ((long long)table_cap / 16 + 4096) & ~3ll; }   // 4x the boxes of a cubic grid
+size_t covariance_scratch_ints(int n, int k, int table_cap) { return brick_offset_ints(n, k) + (size_t)(brick_flag_bytes(table_cap) / 4) + 4; }
 
 cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_scratch, double* covs6, int table_cap, cudaStream_t st,
                                int part, int nparts, int knn_path, int tile_min_points, const CovSideStream* side) {
@@ -920,7 +927,12 @@ cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_sc
     // (runs of 8 boxes above 32768 boxes, single boxes below)
     const long long max_boxes = ((long long)table_cap + 63) / 64;
     long long plan_warps = max_boxes > 32768 ? (max_boxes + 7) / 8 + 1024 : max_boxes + 1024;
-    knn_plan_kernel<<<(unsigned)((plan_warps + 7) / 8), 256, 0, st>>>(c.view(), items, ctrl);
+    unsigned char* bricks = reinterpret_cast<unsigned char*>(nbr_scratch + brick_offset_ints(c.n, k));
+    const long long brick_cap = brick_flag_bytes(table_cap);
+    brick_clear_kernel<<<148 * 2, 256, 0, st>>>(c.view(), bricks, brick_cap);
+    brick_mark_kernel<<<(c.n + 1023) / 1024, 256, 0, st>>>(c.view(), c.n, bricks, brick_cap);
+    knn_plan_kernel<<<(unsigned)((plan_warps + 7) / 8), 256, 0, st>>>(c.view(), items, ctrl, bricks, brick_cap);
+    note_launches(2);
     // persistent grid: every resident warp pulls work items until the counter runs out; no block waits for another one,
     // so it does not matter how many of the blocks are resident at a time (other handles may share the GPU)
     int tblocks = sm_count[di] * blocks_per_sm[di];
@@ -939,7 +951,8 @@ cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_sc
       if ((e = cudaEventRecord(side->fork, st)) != cudaSuccess) return e;
       if ((e = cudaStreamWaitEvent(rs, side->fork, 0)) != cudaSuccess) return e;
     }
-    knn_lists_rest_kernel<<<sm_count[di] * 4, KC_THREADS, 0, rs>>>(c.view(), k, nbr_scratch, ctrl, fb_list);
+    knn_lists_rest_kernel<<<sm_count[di] * 16, 64, 0, rs>>>   // small blocks: the few long searches must not hold the SMs the main covariance launch needs
+       (c.view(), k, nbr_scratch, ctrl, fb_list);
     note_launches(1);
     launch_cov_rest_kernel(c, k, method, nbr_scratch, covs6, ctrl, fb_list, sm_count[di], rs);
     if (overlap && (e = cudaEventRecord(side->join, rs)) != cudaSuccess) return e;
