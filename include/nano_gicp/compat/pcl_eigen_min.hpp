@@ -16,8 +16,20 @@ struct Matrix {
   Matrix() { for (int i = 0; i < R * C; i++) v[i] = T(0); }
   T& operator()(int r, int c) { return v[c * R + r]; }
   const T& operator()(int r, int c) const { return v[c * R + r]; }
+  T& operator[](int i) { return v[i]; }                 // vectors
+  const T& operator[](int i) const { return v[i]; }
   T* data() { return v; }
   const T* data() const { return v; }
+  // m.block(r0, c0, nr, nc) as an rvalue (what OdomNode does: `Eigen::Vector3f p = T.block(0,3,3,1)`)
+  struct ConstBlock {
+    const Matrix& m; int r0, c0;
+    template <int RR, int CC> operator Matrix<T, RR, CC>() const {
+      Matrix<T, RR, CC> o;
+      for (int c = 0; c < CC; c++) for (int r = 0; r < RR; r++) o(r, c) = m(r0 + r, c0 + c);
+      return o;
+    }
+  };
+  ConstBlock block(int r0, int c0, int, int) const { return ConstBlock{*this, r0, c0}; }
   static Matrix Identity() { Matrix m; for (int i = 0; i < (R < C ? R : C); i++) m(i, i) = T(1); return m; }
   static Matrix Zero() { return Matrix(); }
   void setIdentity() { *this = Identity(); }
@@ -31,6 +43,7 @@ struct Matrix {
 };
 typedef Matrix<float, 4, 4> Matrix4f;
 typedef Matrix<double, 4, 4> Matrix4d;
+typedef Matrix<float, 3, 1> Vector3f;
 
 template <class T>
 struct aligned_allocator : public std::allocator<T> {

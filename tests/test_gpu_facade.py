@@ -98,3 +98,59 @@ def test_facade_runs_odom_sequence(tmp_path):
         assert dt < 5e-4 and dr < 5e-5
         dt, dr = pose_delta(got, poses[i])
         assert dt < 0.1 and dr < 5e-3
+
+
+def test_reference_text_compiles_and_runs_against_facade(tmp_path):
+    """tests/cpp/odom_extract = the reference's OWN bodies of initializeInputTarget / setInputSources / getNextPose /
+    updateKeyframes / pushSubmapIndices / getSubmapKeyframes (cut out of src/dlo/odom.cc at build time, never committed)
+    compiled verbatim against include/nano_gicp/nano_gicp.hpp.  It must run OdomNode's loop — including new keyframes
+    (updateKeyframes: setInputSource(keyframe) + calculateSourceCovariances + getSourceCovariances) and the
+    submap_cloud / submap_normals concatenation handed to setInputTarget / setTargetCovariances — and land on the poses
+    the oracle gets with the same sequence."""
+    exe = os.path.join(ROOT, "tests", "cpp", "odom_extract")
+    if not os.path.exists(exe):
+        pytest.skip("odom_extract is built only where the reference tree exists (make -C tests/cpp)")
+    from direct_lidar_odometry_b200 import NanoGICP
+    from oracle import oracle as O
+    vox = NanoGICP(0)
+    idx = [0, 12, 24, 36, 48, 60, 72, 84, 96]          # 1.8 m apart: threshD = 5 m gives new keyframes on the way
+    scans, poses = [], []
+    for i in idx:
+        T = synth.trajectory_pose(i)
+        scans.append(vox.voxel_filter(synth.crop_box_negative(synth.os1_like(i, T)), 0.25))
+        poses.append(T)
+    T0 = poses[0].astype(np.float32)
+    path = tmp_path / "scans.bin"
+    with open(path, "wb") as f:
+        f.write(struct.pack("i", len(scans)))
+        f.write(np.ascontiguousarray(T0.T).tobytes())
+        for s in scans:
+            f.write(struct.pack("i", s.shape[0]))
+            f.write(np.ascontiguousarray(s).tobytes())
+    out = subprocess.run([exe, str(path)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stderr[-2000:]
+    rows = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
+    assert len(rows) == len(scans) - 1
+    assert rows[-1]["keyframes"] >= 3                          # updateKeyframes added keyframes through the facade
+    assert rows[-1]["submap_keyframes"] == rows[-1]["keyframes"]   # every keyframe is in the submap (<= 10 of them)
+    assert all(r["submap_points"] == r["submap_normals"] > 0 for r in rows)
+    # the oracle through the same sequence (same keyframe rule, every keyframe in the submap)
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "benchmarks"))
+    import configs as bc
+    bc.SELECTION = "knn"
+    rc = bc.Replay(lambda cfg: bc.OracleGicp(O, cfg, os.cpu_count()), lambda p, l: O.voxel_filter(p, l), None, knn=10)
+    bc.SELECTION = "hull"
+    for i, s in enumerate(scans):
+        if i == 0:
+            rc.first(s, poses[0])
+            continue
+        its = rc.step(s)
+        row = rows[i - 1]
+        got = np.array(row["T"], dtype=np.float32).reshape(4, 4).T
+        assert (row["s2s_iterations"], row["s2m_iterations"]) == tuple(int(v) for v in its)
+        dt, dr = pose_delta(got, rc.T)
+        assert dt < 5e-4 and dr < 5e-5, (i, dt, dr)
+        assert row["keyframes"] == len(rc.keyframes)
+        dt, dr = pose_delta(got, poses[i])
+        assert dt < 0.1 and dr < 5e-3
