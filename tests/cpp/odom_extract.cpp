@@ -20,7 +20,7 @@ static void print_T(const char* name, const Eigen::Matrix4f& T) {
 }
 
 int main(int argc, char** argv) {
-  if (argc < 2) { std::fprintf(stderr, "usage: %s scans.bin\n", argv[0]); return 2; }
+  if (argc < 2) { std::fprintf(stderr, "usage: %s scans.bin [keyframe_thresh_dist]\n", argv[0]); return 2; }
   FILE* f = std::fopen(argv[1], "rb");
   if (!f) { std::perror("open"); return 2; }
   int nscans = 0;
@@ -28,6 +28,7 @@ int main(int argc, char** argv) {
   if (std::fread(&nscans, 4, 1, f) != 1 || std::fread(T0, 4, 16, f) != 16) return 2;
   dlo::OdomNode node;
   if (!node.gicp.handle() || !node.gicp_s2s.handle()) return 3;   // no GPU: fail loudly
+  if (argc > 2) node.keyframe_thresh_dist_ = std::atof(argv[2]);   // cfg/params.yaml:39 (shipped 5 m)
   for (int i = 0; i < 16; i++) node.T.data()[i] = T0[i];
   node.T_s2s = node.T_s2s_prev = node.T;
   node.propagateS2M();

@@ -113,7 +113,7 @@ def test_reference_text_compiles_and_runs_against_facade(tmp_path):
     from direct_lidar_odometry_b200 import NanoGICP
     from oracle import oracle as O
     vox = NanoGICP(0)
-    idx = [0, 12, 24, 36, 48, 60, 72, 84, 96]          # 1.8 m apart: threshD = 5 m gives new keyframes on the way
+    idx = [0, 3, 6, 9, 12, 15, 18, 21, 24]             # 0.45 m apart (inside the S2S correspondence distance); threshD = 1 m below
     scans, poses = [], []
     for i in idx:
         T = synth.trajectory_pose(i)
@@ -127,11 +127,12 @@ def test_reference_text_compiles_and_runs_against_facade(tmp_path):
         for s in scans:
             f.write(struct.pack("i", s.shape[0]))
             f.write(np.ascontiguousarray(s).tobytes())
-    out = subprocess.run([exe, str(path)], capture_output=True, text=True, timeout=300)
+    out = subprocess.run([exe, str(path), "1.0"], capture_output=True, text=True, timeout=300)   # keyframe_thresh_dist_ = 1 m
     assert out.returncode == 0, out.stderr[-2000:]
     rows = [json.loads(l) for l in out.stdout.splitlines() if l.startswith("{")]
     assert len(rows) == len(scans) - 1
-    assert rows[-1]["keyframes"] >= 3                          # updateKeyframes added keyframes through the facade
+    summary = [(r["scan"], r["keyframes"], r["s2s_iterations"], r["s2m_iterations"], [round(v, 3) for v in r["T"][12:15]]) for r in rows]
+    assert rows[-1]["keyframes"] >= 3, summary                 # updateKeyframes added keyframes through the facade
     assert rows[-1]["submap_keyframes"] == rows[-1]["keyframes"]   # every keyframe is in the submap (<= 10 of them)
     assert all(r["submap_points"] == r["submap_normals"] > 0 for r in rows)
     # the oracle through the same sequence (same keyframe rule, every keyframe in the submap)
@@ -139,7 +140,7 @@ def test_reference_text_compiles_and_runs_against_facade(tmp_path):
     sys.path.insert(0, os.path.join(ROOT, "benchmarks"))
     import configs as bc
     bc.SELECTION = "knn"
-    rc = bc.Replay(lambda cfg: bc.OracleGicp(O, cfg, os.cpu_count()), lambda p, l: O.voxel_filter(p, l), None, knn=10)
+    rc = bc.Replay(lambda cfg: bc.OracleGicp(O, cfg, os.cpu_count()), lambda p, l: O.voxel_filter(p, l), None, thresh_d=1.0, knn=10)
     bc.SELECTION = "hull"
     for i, s in enumerate(scans):
         if i == 0:
