@@ -15,9 +15,17 @@ steps = int(sys.argv[1]) if len(sys.argv) > 1 else 4
 g = NanoGICP(0)
 g.setCorrespondenceRandomness(bench.S2M["k"]); g.setMaxCorrespondenceDistance(bench.S2M["thr"])
 g.setMaximumIterations(bench.S2M["max_iter"]); g.setTransformationEpsilon(bench.S2M["trans_eps"])
+if os.environ.get("NGICP_CELL"):
+    g.setGridCellSize(float(os.environ["NGICP_CELL"]))   # experiments: fixed cell edge instead of the density-driven one
 wl = bench.make_workload(lambda p, leaf: g.voxel_filter(p, leaf))
 submap = torch.from_numpy(wl["submap"]).cuda()
 scan = torch.from_numpy(wl["scan_0"]).cuda()
+flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+T = []
 for _ in range(steps):
+    flush.zero_(); torch.cuda.synchronize()
     res = bench.gpu_step(g, submap, scan, wl["guesses"][0])
+    T.append(g.timings())
+if steps >= 8:
+    print("median of last", steps - 4, {k: round(float(np.median([t[k] for t in T[4:]])), 4) for k in T[0]})
 print(res.nr_iterations, {k: round(v, 4) for k, v in g.timings().items()}, g.grid_info(1))

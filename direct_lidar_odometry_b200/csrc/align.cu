@@ -117,19 +117,29 @@ __device__ __forceinline__ double error_point(const AlignArgs& a, const Iso3& Td
 // One block's share of a linearize pass.  LPP = lanes per source point: 1 = one thread per point; 2 / 4 = a group of
 // adjacent lanes shares the point's candidate scans (a 20k-point scan cannot fill the GPU with one thread per point,
 // and the search is a chain of dependent round trips — a group reads LPP x 8 candidates per round trip) and lane 0
-// of the group does the fp64 part.  The block handles points base + threadIdx.x / LPP for base = first,
-// first + stride, ... (block-uniform trip count: the loop contains barriers).
+// of the group does the fp64 part.
+// Which points a block gets: the cloud is cut into chunks of 32 / LPP consecutive points (one warp's worth) and the
+// chunks are dealt out round-robin — warp w of block blk takes chunks (pass * AL_WARPS + w) * nblk + blk.  A warp's
+// points stay neighbours in space (voxel-filter output is in voxel order: its lanes scan the same target cells), but
+// a block's eight warps sit in eight different places of the scan, so no block ends up with only far-field points
+// whose searches are all long: with contiguous blocks of 256 points the slowest block took twice as long as the
+// fastest (C2: 12 vs 27 us per linearisation) and the grid barrier waits for the slowest.  The trip count is the same
+// for every block (the loop contains barriers).
 template <int LPP>
 __device__ __forceinline__ void linearize_block(const AlignArgs& a, const GridParams& gp, const XformF& Tf, const Iso3& Td,
-                                                float cap_d2, double thr2, int first, int stride, TailQueue& tq, double& wtot) {
-  const int lane = threadIdx.x & 31;
+                                                float cap_d2, double thr2, int blk, int nblk, TailQueue& tq, double& wtot) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int sub = threadIdx.x & (LPP - 1), gi = threadIdx.x / LPP;
   const unsigned gmask = (LPP == 1) ? 0u : (((1u << LPP) - 1u) << (lane & ~(LPP - 1)));
-  for (int base = first; base < a.ns; base += stride) {
+  constexpr int PPW = 32 / LPP;                                   // points per warp and pass
+  const int nchunks = (a.ns + PPW - 1) / PPW;
+  const int npass = (nchunks + AL_WARPS * nblk - 1) / (AL_WARPS * nblk);
+  for (int pass = 0; pass < npass; ++pass) {
     if (threadIdx.x == 0) { tq.n = 0; tq.next = 0; }
     __syncthreads();
-    const int i = base + gi;
-    const bool active = i < a.ns;
+    const int chunk = (pass * AL_WARPS + warp) * nblk + blk;
+    const int i = chunk * PPW + lane / LPP;
+    const bool active = chunk < nchunks && i < a.ns;
     float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
     float my_d = FLT_MAX;
     int my_p = -1;
@@ -216,7 +226,7 @@ __global__ void __launch_bounds__(AL_THREADS) linearize_kernel(AlignArgs a, IsoA
   XformF Tf;
   make_xforms(T.x, Tf);
   double acc[1] = {0.0};
-  linearize_block<1>(a, gp, Tf, T.x, cap_d2, thr2, blockIdx.x * blockDim.x, gridDim.x * blockDim.x, s_tq, acc[0]);
+  linearize_block<1>(a, gp, Tf, T.x, cap_d2, thr2, blockIdx.x, gridDim.x, s_tq, acc[0]);
   block_reduce_store<NRED>(acc, s_red, a.partials + (size_t)blockIdx.x * NRED);
 }
 
@@ -530,10 +540,17 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) align_fused_kernel(AlignArgs
   gs.arrive = bar; gs.flag = bar + 1; gs.totals = totals; gs.phase = 0; gs.max_blocks = (unsigned)a.max_blocks;
 
   // scalar LM state, kept by thread 0 of every block (identical everywhere)
-  Iso3 x0, xi, delta;
-  double H36[36], b6[6], d6[6];
+  // thread 0's matrices and transforms live in shared memory: in registers they cost the 128-register variants 2 KB of
+  // spills (local-memory round trips on the serial solve path between two grid barriers)
+  __shared__ double s_lm[3 * 36 + 12];
+  __shared__ Iso3 s_iso[3];
+  Iso3 &x0 = s_iso[0], &xi = s_iso[1], &delta = s_iso[2];
+  double* const H36 = s_lm;
+  double* const final_H = s_lm + 36;
+  double* const A = s_lm + 72;
+  double* const b6 = s_lm + 108;
+  double* const d6 = s_lm + 114;
   double lambda = -1.0, y0 = 0.0, nu = 2.0;
-  double final_H[36];
   int nr_iterations = 0, n_lin = 0, n_err = 0, lm_failed = 0;
   bool converged = false;
   if (threadIdx.x == 0) {
@@ -554,7 +571,7 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) align_fused_kernel(AlignArgs
       XformF Tf;
       make_xforms(T, Tf);
       double acc[1] = {0.0};
-      linearize_block<LPP>(a, gp, Tf, T, prm.cap_d2, prm.thr2, blockIdx.x * (AL_THREADS / LPP), gridDim.x * (AL_THREADS / LPP), s_tq, acc[0]);
+      linearize_block<LPP>(a, gp, Tf, T, prm.cap_d2, prm.thr2, blockIdx.x, gridDim.x, s_tq, acc[0]);
       trace_stamp(prm, tslot);
       if (prm.trace && it == 1 && threadIdx.x == 0 && blockIdx.x < 1024) prm.trace[256 + blockIdx.x] = global_timer_ns();
       grid_reduce<NRED>(acc, s_red, s_tot, a.partials, gs, pc);
@@ -594,7 +611,7 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) align_fused_kernel(AlignArgs
       }
       for (int j = 0; j < prm.lm_max_iterations; ++j) {
         if (threadIdx.x == 0) {
-          double A[36], nb[6];
+          double nb[6];
           for (int i = 0; i < 36; i++) A[i] = H36[i];
           for (int i = 0; i < 6; i++) { A[i * 7] += lambda; nb[i] = -b6[i]; }
           lm_solve(A, nb, d6);
@@ -741,14 +758,20 @@ __global__ void __launch_bounds__(AL_THREADS, 2) align_batch_kernel(const BatchP
   const AlignArgs& a = s_pair.a;
   const LmParams& prm = s_pair.prm;
   const int VB = s_pair.vblocks;
-  const int ppb = AL_THREADS / LPP;
   const GridParams gp = load_grid(a.tgt.desc);
   unsigned phase = 0;
 
-  Iso3 x0, xi, delta;
-  double H36[36], b6[6], d6[6];
+  // thread 0's matrices and transforms live in shared memory: in registers they cost the 128-register variants 2 KB of
+  // spills (local-memory round trips on the serial solve path between two grid barriers)
+  __shared__ double s_lm[3 * 36 + 12];
+  __shared__ Iso3 s_iso[3];
+  Iso3 &x0 = s_iso[0], &xi = s_iso[1], &delta = s_iso[2];
+  double* const H36 = s_lm;
+  double* const final_H = s_lm + 36;
+  double* const A = s_lm + 72;
+  double* const b6 = s_lm + 108;
+  double* const d6 = s_lm + 114;
   double lambda = -1.0, y0 = 0.0, nu = 2.0;
-  double final_H[36];
   int nr_iterations = 0, n_lin = 0, n_err = 0, lm_failed = 0;
   bool converged = false;
   if (threadIdx.x == 0) {
@@ -771,7 +794,7 @@ __global__ void __launch_bounds__(AL_THREADS, 2) align_batch_kernel(const BatchP
       double* mine = a.partials + (size_t)(phase & 1u) * a.max_blocks * NRED;
       for (int vb = (int)crank; vb < VB; vb += (int)csize) {
         double acc[1] = {0.0};
-        linearize_block<LPP>(a, gp, Tf, T, prm.cap_d2, prm.thr2, vb * ppb, VB * ppb, s_tq, acc[0]);
+        linearize_block<LPP>(a, gp, Tf, T, prm.cap_d2, prm.thr2, vb, VB, s_tq, acc[0]);
         block_reduce_store<NRED>(acc, s_red, mine + (size_t)vb * NRED);
       }
       __threadfence();
@@ -813,7 +836,7 @@ __global__ void __launch_bounds__(AL_THREADS, 2) align_batch_kernel(const BatchP
       }
       for (int j = 0; j < prm.lm_max_iterations; ++j) {
         if (threadIdx.x == 0) {
-          double A[36], nb[6];
+          double nb[6];
           for (int i = 0; i < 36; i++) A[i] = H36[i];
           for (int i = 0; i < 6; i++) { A[i * 7] += lambda; nb[i] = -b6[i]; }
           lm_solve(A, nb, d6);

@@ -343,8 +343,8 @@ static float auto_target_occupancy() {
   static float v = -1.f;
   if (v < 0.f) {
     const char* e = getenv("NGICP_TARGET_OCC");
-    v = e ? (float)atof(e) : 8.0f;
-    if (!(v > 0.f)) v = 8.0f;
+    v = e ? (float)atof(e) : 10.0f;
+    if (!(v > 0.f)) v = 10.0f;
   }
   return v;
 }

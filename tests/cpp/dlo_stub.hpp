@@ -10,6 +10,8 @@
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
+#include <math.h>     // the C++ wrappers put std::abs(float) into the global namespace: OdomNode writes abs(dd) on floats (odom.cc:1145-1153),
+#include <stdlib.h>   // which would otherwise bind to int abs(int) here and truncate (any ROS header brings these in for the real build)
 #include <limits>
 #include <memory>
 #include <queue>
