@@ -128,11 +128,14 @@ SELECTION = "hull"   # "hull": OdomNode::getSubmapKeyframes (kNN + convex hull +
 
 class Replay:
     """OdomNode's per-scan sequence (reference src/dlo/odom.cc:629-697): S2S, submap selection (getSubmapKeyframes,
-    :1240-1293, through submap_select.SubmapSelector), S2M, updateKeyframes (:1097-1181; shipped thresholds threshD 5 m,
+    :1240-1293, through ngicp_submap_select), S2M, updateKeyframes (:1097-1181; shipped thresholds threshD 5 m,
     threshR 45 deg, adaptive parameters off).  `make()` builds a registration object."""
 
     def __init__(self, make, voxel, get_T, thresh_d=5.0, knn=10, thresh_r=45.0):
-        from direct_lidar_odometry_b200.submap_select import SubmapSelector
+        # the C++ implementation behind the C ABI (csrc/submap_select.cpp); NGICP_SUBMAP_SELECT=qhull takes the
+        # scipy/qhull checker instead
+        from direct_lidar_odometry_b200 import submap_select as _ss
+        SubmapSelector = _ss.SubmapSelector if os.environ.get("NGICP_SUBMAP_SELECT") == "qhull" else _ss.NativeSubmapSelector
         self.s2s, self.s2m = make(S2S), make(S2M)
         self.voxel, self.get_T = voxel, get_T
         self.thresh_d, self.thresh_r, self.knn = thresh_d, thresh_r, knn

@@ -29,6 +29,8 @@ EXPORTS = [
     "ngicp_version", "ngicp_launch_count", "ngicp_grid_info", "ngicp_set_owner_slab", "ngicp_lm_trial",
     "ngicp_lm_is_converged", "ngicp_comm_export", "ngicp_comm_connect", "ngicp_comm_connect_local", "ngicp_comm_close", "ngicp_preprocess", "ngicp_preprocess_pointcloud2", "ngicp_calc_source_covs_part", "ngicp_covs_device", "ngicp_transform_voxel_filter", "ngicp_kfstore_create", "ngicp_kfstore_destroy", "ngicp_kfstore_size",
     "ngicp_kfstore_points", "ngicp_kfstore_push", "ngicp_kfstore_set_target", "ngicp_cov_neighbors", "ngicp_align_batch", "ngicp_imu_prior",
+    "ngicp_submap_push_indices", "ngicp_submap_convex_hull", "ngicp_submap_concave_hull", "ngicp_submap_selector_create",
+    "ngicp_submap_selector_destroy", "ngicp_submap_select", "ngicp_submap_selector_hulls", "ngicp_keyframe_wanted",
 ]
 
 
@@ -117,6 +119,14 @@ def load() -> C.CDLL:
     proto("ngicp_lm_trial", i32, dp, dp, C.c_double, dp, dp, dp, dp)
     proto("ngicp_lm_is_converged", i32, dp, C.c_double, C.c_double)
     proto("ngicp_imu_prior", i32, dp, dp, sz, C.c_double, C.c_double, fp)
+    proto("ngicp_submap_push_indices", i32, fp, ip, i32, i32, ip, i32)
+    proto("ngicp_submap_convex_hull", i32, fp, i32, ip, i32)
+    proto("ngicp_submap_concave_hull", i32, fp, i32, C.c_double, ip, i32)
+    proto("ngicp_submap_selector_create", i32, i32, i32, i32, C.c_double, C.POINTER(vp))
+    proto("ngicp_submap_selector_destroy", None, vp)
+    proto("ngicp_submap_select", i32, vp, fp, i32, fp, ip, i32, ip)
+    proto("ngicp_submap_selector_hulls", i32, vp, i32, ip, i32)
+    proto("ngicp_keyframe_wanted", i32, fp, fp, i32, fp, fp, C.c_double, C.c_double)
     proto("ngicp_kfstore_create", i32, i32, C.POINTER(vp))
     proto("ngicp_kfstore_destroy", None, vp)
     proto("ngicp_kfstore_size", sz, vp)

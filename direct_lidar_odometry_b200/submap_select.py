@@ -6,8 +6,11 @@ the vertices of the 3-D convex hull of all keyframe positions, and the `kcc` nea
 alpha shape ("concave hull", alpha = keyframe threshD at construction, odom.cc:95-98).  A few dozen points per call:
 host work in the reference and here.  The reference gets both hulls from PCL, which calls qhull; this mirror calls
 the same library through scipy.spatial (convex hull: qhull's default options as pcl::ConvexHull's 3-D path; Delaunay
-tetrahedra with "QJ" as pcl::ConcaveHull's "qhull d QJ") and restates PCL's alpha filter on top of it.  It is used by
-the replay benchmark and the tests; a DLO build keeps OdomNode's own code for this step (only NanoGICP is replaced).
+tetrahedra with "QJ" as pcl::ConcaveHull's "qhull d QJ") and restates PCL's alpha filter on top of it.
+
+The functions in this file are the qhull-based CHECKER of the product implementation, which is C++ behind the C ABI
+(csrc/submap_select.cpp: ngicp_submap_*, own incremental hull and Bowyer-Watson Delaunay, no qhull); NativeSubmapSelector
+below is its ctypes wrapper — what the replay benchmark uses — and tests/test_submap_select.py compares the two.
 """
 from __future__ import annotations
 
@@ -144,3 +147,106 @@ class SubmapSelector:
         if changed:
             self.prev = cur_idx
         return cur_idx, changed
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the product implementation: C++ behind the C ABI (csrc/submap_select.cpp)
+# ---------------------------------------------------------------------------------------------------------------------
+def _f32(a, cols):
+    import ctypes as C
+    a = np.ascontiguousarray(np.asarray(a, dtype=np.float32).reshape(-1, cols))
+    return a, a.ctypes.data_as(C.POINTER(C.c_float))
+
+
+def native_push_submap_indices(dists, k: int, frames) -> list:
+    import ctypes as C
+    from . import _lib
+    L = _lib.load()
+    d = np.ascontiguousarray(np.asarray(dists, dtype=np.float32))
+    f = np.ascontiguousarray(np.asarray(frames, dtype=np.int32))
+    out = np.zeros(max(d.size, 1), dtype=np.int32)
+    m = L.ngicp_submap_push_indices(d.ctypes.data_as(C.POINTER(C.c_float)), f.ctypes.data_as(C.POINTER(C.c_int)), d.size, int(k),
+                                    out.ctypes.data_as(C.POINTER(C.c_int)), out.size)
+    if m < 0:
+        raise RuntimeError(f"ngicp_submap_push_indices: {m}")
+    return out[:m].tolist()
+
+
+def native_convex_hull_vertices(pos) -> list:
+    import ctypes as C
+    from . import _lib
+    L = _lib.load()
+    a, ap = _f32(pos, 3)
+    out = np.zeros(max(a.shape[0], 1), dtype=np.int32)
+    m = L.ngicp_submap_convex_hull(ap, a.shape[0], out.ctypes.data_as(C.POINTER(C.c_int)), out.size)
+    if m < 0:
+        raise RuntimeError(f"ngicp_submap_convex_hull: {m}")
+    return out[:m].tolist()
+
+
+def native_concave_hull_vertices(pos, alpha: float) -> list:
+    import ctypes as C
+    from . import _lib
+    L = _lib.load()
+    a, ap = _f32(pos, 3)
+    out = np.zeros(max(a.shape[0], 1), dtype=np.int32)
+    m = L.ngicp_submap_concave_hull(ap, a.shape[0], float(alpha), out.ctypes.data_as(C.POINTER(C.c_int)), out.size)
+    if m < 0:
+        raise RuntimeError(f"ngicp_submap_concave_hull: {m}")
+    return out[:m].tolist()
+
+
+def native_keyframe_wanted(kf_pos, kf_quat_wxyz, cur_pos, cur_quat_wxyz, thresh_dist: float, thresh_rot_deg: float) -> bool:
+    from . import _lib
+    L = _lib.load()
+    a, ap = _f32(kf_pos, 3)
+    q, qp = _f32(kf_quat_wxyz, 4)
+    c, cp = _f32(cur_pos, 3)
+    cq, cqp = _f32(cur_quat_wxyz, 4)
+    r = L.ngicp_keyframe_wanted(ap, qp, a.shape[0], cp, cqp, float(thresh_dist), float(thresh_rot_deg))
+    if r < 0:
+        raise RuntimeError(f"ngicp_keyframe_wanted: {r}")
+    return bool(r)
+
+
+class NativeSubmapSelector:
+    """ngicp_submap_select: same interface and state as SubmapSelector, computed by the C++ library."""
+
+    def __init__(self, knn: int = 10, kcv: int = 10, kcc: int = 10, alpha: float = 5.0):
+        import ctypes as C
+        from . import _lib
+        self._L = _lib.load()
+        self._h = C.c_void_p()
+        rc = self._L.ngicp_submap_selector_create(int(knn), int(kcv), int(kcc), float(alpha), C.byref(self._h))
+        if rc != 0:
+            raise RuntimeError(f"ngicp_submap_selector_create: {rc}")
+
+    def __del__(self):
+        if getattr(self, "_h", None):
+            self._L.ngicp_submap_selector_destroy(self._h)
+            self._h = None
+
+    def _hull(self, which):
+        import ctypes as C
+        out = np.zeros(1 << 16, dtype=np.int32)
+        m = self._L.ngicp_submap_selector_hulls(self._h, which, out.ctypes.data_as(C.POINTER(C.c_int)), out.size)
+        return out[:max(m, 0)].tolist()
+
+    @property
+    def keyframe_convex(self):
+        return self._hull(0)
+
+    @property
+    def keyframe_concave(self):
+        return self._hull(1)
+
+    def select(self, keyframe_positions, current_position):
+        import ctypes as C
+        a, ap = _f32(keyframe_positions, 3)
+        c, cp = _f32(current_position, 3)
+        out = np.zeros(max(a.shape[0], 1), dtype=np.int32)
+        changed = C.c_int(0)
+        m = self._L.ngicp_submap_select(self._h, ap, a.shape[0], cp, out.ctypes.data_as(C.POINTER(C.c_int)), out.size, C.byref(changed))
+        if m < 0:
+            raise RuntimeError(f"ngicp_submap_select: {m}")
+        return out[:m].tolist(), bool(changed.value)

@@ -286,6 +286,33 @@ size_t ngicp_kfstore_points(const ngicp_kfstore_t* s, size_t index);
 int ngicp_kfstore_push(ngicp_kfstore_t* s, ngicp_t* from, size_t* index_out);
 int ngicp_kfstore_set_target(ngicp_kfstore_t* s, ngicp_t* to, const int* indices, size_t n_indices);
 
+/* ---- submap keyframe selection (host arithmetic in the host language, no GPU, no handle) ------------
+ * OdomNode::getSubmapKeyframes (odom.cc:1240-1293) picks the keyframes of the scan-to-map target: the knn keyframes
+ * nearest to the current pose, the kcv nearest among the vertices of the 3-D convex hull of all keyframe positions
+ * (computeConvexHull, :1017-1050, pcl::ConvexHull -> qhull) and the kcc nearest among the vertices of their 3-D alpha
+ * shape (computeConcaveHull, :1057-1090, pcl::ConcaveHull with alpha = keyframe threshD, :95-98).  PCL and qhull do not
+ * exist here: csrc/submap_select.cpp builds both hulls from their definitions (incremental hull; Bowyer-Watson Delaunay
+ * + PCL's alpha filter).  Positions are n x 3 floats.  Functions returning a count return NGICP_E_INVALID when out_cap
+ * is too small.
+ *   ngicp_submap_push_indices   pushSubmapIndices (:1210-1233): frames[i] with dists[i] <= the k-th smallest distance
+ *   ngicp_submap_convex_hull    indices of the input points that are convex-hull vertices (ascending); none for flat input
+ *   ngicp_submap_concave_hull   indices of the input points on the alpha shape (ascending)
+ *   ngicp_submap_select         the whole selection with OdomNode's state between scans (hulls kept while there are too
+ *                               few keyframes, *changed = submap_hasChanged); out = sorted unique keyframe indices
+ *   ngicp_submap_selector_hulls keyframe_convex (which = 0) / keyframe_concave (which = 1) after the last select
+ *   ngicp_keyframe_wanted       updateKeyframes' decision (:1102-1153): 1 = add a keyframe at the current pose; quaternions
+ *                               are (w, x, y, z) floats */
+typedef struct ngicp_submap_selector ngicp_submap_selector_t;
+int ngicp_submap_push_indices(const float* dists, const int* frames, int n, int k, int* out, int out_cap);
+int ngicp_submap_convex_hull(const float* xyz, int n, int* out, int out_cap);
+int ngicp_submap_concave_hull(const float* xyz, int n, double alpha, int* out, int out_cap);
+int ngicp_submap_selector_create(int knn, int kcv, int kcc, double alpha, ngicp_submap_selector_t** out);
+void ngicp_submap_selector_destroy(ngicp_submap_selector_t* s);
+int ngicp_submap_select(ngicp_submap_selector_t* s, const float* kf_xyz, int n, const float* cur_xyz, int* out, int out_cap, int* changed);
+int ngicp_submap_selector_hulls(ngicp_submap_selector_t* s, int which, int* out, int out_cap);
+int ngicp_keyframe_wanted(const float* kf_xyz, const float* kf_quat_wxyz, int n, const float* cur_xyz, const float* cur_quat_wxyz,
+                          double thresh_dist, double thresh_rot_deg);
+
 /* diagnostics: the uniform grid chosen for a cloud's search index (cell edge in metres, dims[3], cell count) */
 int ngicp_grid_info(ngicp_t* h, int which, float* cell, int* dims3, int* ncells);
 

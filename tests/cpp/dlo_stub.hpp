@@ -119,10 +119,28 @@ class OdomNode {
     current_scan_t.reset(new pcl::PointCloud<PointType>);
     pcl::transformPointCloud(*current_scan, *current_scan_t, T);
   }
-  // hull membership decides WHICH keyframes enter the submap, not how they are registered: every keyframe counts as a
-  // hull vertex here (the hull code itself is N3: direct_lidar_odometry_b200/submap_select.py)
-  void computeConvexHull() { keyframe_convex.clear(); for (int i = 0; i < (int)keyframes.size(); ++i) keyframe_convex.push_back(i); }
-  void computeConcaveHull() { keyframe_concave.clear(); for (int i = 0; i < (int)keyframes.size(); ++i) keyframe_concave.push_back(i); }
+  // computeConvexHull / computeConcaveHull (odom.cc:1017-1090): the reference asks pcl::ConvexHull / pcl::ConcaveHull
+  // (alpha = keyframe_thresh_dist_, odom.cc:95-98) for the hull point indices of the keyframe positions; here the
+  // library's own hulls (csrc/submap_select.cpp) answer through the C ABI
+  std::vector<float> keyframe_positions() const {
+    std::vector<float> xyz;
+    for (const auto& k : keyframes) { xyz.push_back(k.first.first[0]); xyz.push_back(k.first.first[1]); xyz.push_back(k.first.first[2]); }
+    return xyz;
+  }
+  void computeConvexHull() {
+    if (num_keyframes < 4) return;
+    const std::vector<float> xyz = keyframe_positions();
+    std::vector<int> out(keyframes.size() + 1);
+    const int m = ngicp_submap_convex_hull(xyz.data(), (int)keyframes.size(), out.data(), (int)out.size());
+    keyframe_convex.assign(out.begin(), out.begin() + (m > 0 ? m : 0));
+  }
+  void computeConcaveHull() {
+    if (num_keyframes < 5) return;
+    const std::vector<float> xyz = keyframe_positions();
+    std::vector<int> out(keyframes.size() + 1);
+    const int m = ngicp_submap_concave_hull(xyz.data(), (int)keyframes.size(), keyframe_thresh_dist_, out.data(), (int)out.size());
+    keyframe_concave.assign(out.begin(), out.begin() + (m > 0 ? m : 0));
+  }
 };
 
 }  // namespace dlo

@@ -84,3 +84,67 @@ def test_selector_sequence_matches_reference_rules():
     assert len(hull) >= 4
     near_hull = sorted(hull, key=lambda i: d[i])[:2]
     assert set(near_hull) <= set(idx)
+
+
+# ---- the product implementation (C++ behind the C ABI, csrc/submap_select.cpp) against the qhull-based checker above ----
+def test_native_push_indices_matches():
+    rng = np.random.default_rng(1)
+    for n, k in [(5, 3), (5, 2), (2, 10), (0, 10), (40, 10), (40, 1)]:
+        d = np.round(rng.uniform(0, 5, size=n), 1).astype(np.float32)      # rounded: ties at the k-th distance occur
+        frames = rng.permutation(100)[:n]
+        ref = []
+        ss.push_submap_indices(d, k, frames, ref)
+        assert ss.native_push_submap_indices(d, k, frames) == ref
+
+
+def test_native_convex_hull_equals_qhull():
+    rng = np.random.default_rng(11)
+    for n in (4, 5, 8, 30, 100, 400):
+        for trial in range(4):
+            pts = (rng.normal(size=(n, 3)) * rng.uniform(1, 50)).astype(np.float32)
+            assert ss.native_convex_hull_vertices(pts) == ss.convex_hull_vertices(pts), (n, trial)
+    corners = np.array(list(itertools.product([-10.0, 10.0], repeat=3)), dtype=np.float32)
+    inner = rng.uniform(-9, 9, size=(40, 3)).astype(np.float32)
+    assert ss.native_convex_hull_vertices(np.vstack([inner[:20], corners, inner[20:]])) == list(range(20, 28))
+    flat = np.zeros((10, 3), np.float32); flat[:, :2] = rng.normal(size=(10, 2))
+    assert ss.native_convex_hull_vertices(flat) == []                       # qhull refuses flat input; PCL returns nothing
+    assert ss.native_convex_hull_vertices(flat[:3]) == []
+
+
+def test_native_concave_hull_equals_qhull_alpha_filter():
+    rng = np.random.default_rng(13)
+    for n in (5, 12, 40, 120, 300):
+        pts = (rng.normal(size=(n, 3)) * 4.0).astype(np.float32)
+        for alpha in (0.5, 1.5, 3.0, 8.0, 1e6):
+            assert ss.native_concave_hull_vertices(pts, alpha) == ss.concave_hull_vertices(pts, alpha), (n, alpha)
+    assert ss.native_concave_hull_vertices(pts, 1e-4) == []
+    a = rng.normal(size=(40, 3)).astype(np.float32)
+    two = np.vstack([a, a + np.float32(100.0)])
+    assert ss.native_concave_hull_vertices(two, 3.0) == ss.concave_hull_vertices(two, 3.0)
+    assert ss.native_concave_hull_vertices(pts[:4], 3.0) == []
+
+
+def test_native_selector_equals_python_selector_on_a_replay_like_loop():
+    # keyframes as the C3 replay produces them: a loop with a small z ripple plus pose noise (general position)
+    rng = np.random.default_rng(17)
+    t = np.linspace(0, 2 * np.pi, 61)[:-1]
+    pos = np.stack([60 * np.cos(t), 40 * np.sin(t), 0.05 * np.sin(7 * t)], axis=1) + rng.normal(0, 0.02, size=(60, 3))
+    pos = pos.astype(np.float32)
+    a, b = ss.SubmapSelector(10, 10, 10, 5.0), ss.NativeSubmapSelector(10, 10, 10, 5.0)
+    for nkf in range(1, 61):
+        for cur in (pos[nkf - 1], pos[nkf - 1] + np.float32(2.0), pos[max(nkf - 3, 0)]):
+            ra, rb = a.select(pos[:nkf], cur), b.select(pos[:nkf], cur)
+            assert ra == rb, nkf
+        assert a.keyframe_convex == b.keyframe_convex and a.keyframe_concave == b.keyframe_concave, nkf
+
+
+def test_native_keyframe_decision():
+    ident = np.array([[1, 0, 0, 0]], np.float32)
+    kf = np.array([[0, 0, 0]], np.float32)
+    assert not ss.native_keyframe_wanted(kf, ident, [4.9, 0, 0], ident[0], 5.0, 45.0)
+    assert ss.native_keyframe_wanted(kf, ident, [5.1, 0, 0], ident[0], 5.0, 45.0)
+    h = np.deg2rad(50.0) / 2
+    turned = np.array([np.cos(h), 0, 0, np.sin(h)], np.float32)
+    assert ss.native_keyframe_wanted(kf, ident, [1.0, 0, 0], turned, 5.0, 45.0)        # rotated, only one keyframe nearby
+    kf2 = np.array([[0, 0, 0], [2, 0, 0]], np.float32)
+    assert not ss.native_keyframe_wanted(kf2, np.vstack([ident, ident]), [1.0, 0, 0], turned, 5.0, 45.0)   # two nearby
