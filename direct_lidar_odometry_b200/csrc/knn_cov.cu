@@ -149,7 +149,7 @@ __device__ __forceinline__ float box_face_distance(const GridParams& gp, int x0,
 #endif
 enum { ST_FALLBACK = 0, ST_TIES, ST_TILES, ST_PASSES, ST_LANES, ST_ITEMS, ST_N };
 // control words shared by the plan and tile launches
-enum { CT_ITEMS = 0, CT_NEXT, CT_REST, CT_REST_NEXT, CT_DONE, CT_N = 8 };
+enum { CT_ITEMS = 0, CT_NEXT, CT_REST, CT_REST_NEXT, CT_DONE, CT_FIX, CT_N = 8 };
 
 // warp-aggregated append of the lanes in `mask` to the warp-search list
 __device__ __forceinline__ void fb_append(unsigned mask, int slot, int lane, int* __restrict__ fb_list, int* __restrict__ fb_count,
@@ -161,6 +161,21 @@ __device__ __forceinline__ void fb_append(unsigned mask, int slot, int lane, int
   if (lane == leader) base = atomicAdd(fb_count, __popc(mask));
   base = __shfl_sync(FULL, base, leader);
   if ((mask >> lane) & 1u) fb_list[base + __popc(mask & ((1u << lane) - 1u))] = slot;
+}
+
+// Points whose list the tile kernel delivered but could not ORDER exactly (two of the k kept entries share a lattice
+// value): flagged like the warp-search ones so that the main covariance launch (which trusts the order) skips them, and
+// listed from the BACK of the same array (the two lists are disjoint and hold at most n points together); cov_rest_kernel
+// re-derives their order from exact distances.
+__device__ __forceinline__ void fix_append(unsigned mask, int slot, int lane, int n, int* __restrict__ fb_list, int* __restrict__ fix_count,
+                                           unsigned char* __restrict__ fb_flags) {
+  if (!mask) return;
+  if ((mask >> lane) & 1u) fb_flags[slot] = 1;
+  const int leader = __ffs(mask) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(fix_count, __popc(mask));
+  base = __shfl_sync(FULL, base, leader);
+  if ((mask >> lane) & 1u) fb_list[n - 1 - (base + __popc(mask & ((1u << lane) - 1u)))] = slot;
 }
 
 __device__ __forceinline__ int warp_incl_scan(int v, int lane) {
@@ -566,9 +581,12 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
           //      be decided here: those (rare) points take the warp search ----
           bool decided = good;
           bool tie = false;
+          bool needs_fix = false;
           float kth = T2;
           {
-            const bool searching = good && c_now > k;
+            // generic k keeps the old rule (select only when more than k were collected, deliver in list order; the
+            // covariance kernel orders them); k = 10 / 20 always go through the network and deliver SORTED lists
+            const bool searching = good && (KT > 0 || c_now > k);
             const bool any_search = __any_sync(FULL, searching);
             if (any_search) {
               static_assert(TQ_LCAP == 40 || TQ_LCAP == 32, "the selection networks are generated for 32 and 40 wires");
@@ -593,12 +611,25 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
                 if ((vk >> TQ_POS_BITS) == (vk1 >> TQ_POS_BITS)) { tie = true; decided = false; st_ties++; }
                 else { bound = ((vk >> TQ_POS_BITS) + 1u) << TQ_POS_BITS; kth = __uint_as_float(vk & ~TQ_POS_MASK); }
               }
-              const bool compact = searching && !tie;
-              int pos = 0;
+              if (KT > 0) {
+                // the k nearest back into the lane's column in ascending lattice order = ascending exact distance, unless
+                // two neighbours share a lattice value (an exact tie or closer than 2^-14 relative): those points are
+                // delivered too but flagged, and the covariance fix-up orders them by exact (distance, slot)
+                bool near = false;
 #pragma unroll
-              for (int i = 0; i < TQ_LCAP; ++i) {
-                const unsigned e = S.lst[i][lane];
-                if (compact && i < c_now && e < bound) { S.lst[pos][lane] = e; ++pos; }
+                for (int i = 0; i < (KT > 0 ? KT : 1); ++i) {
+                  S.lst[i][lane] = v[i];
+                  if (i > 0) near = near || ((v[i - 1] >> TQ_POS_BITS) == (v[i] >> TQ_POS_BITS));
+                }
+                needs_fix = searching && !tie && near;
+              } else {
+                const bool compact = searching && !tie;
+                int pos = 0;
+#pragma unroll
+                for (int i = 0; i < TQ_LCAP; ++i) {
+                  const unsigned e = S.lst[i][lane];
+                  if (compact && i < c_now && e < bound) { S.lst[pos][lane] = e; ++pos; }
+                }
               }
             }
           }
@@ -613,6 +644,7 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
             if (lane < k) nbr[(size_t)sl * k + lane] = S.slot[S.lst[lane][l] & TQ_POS_MASK];
           }
           __syncwarp();
+          fix_append(__ballot_sync(FULL, needs_fix), slot, lane, n, fb_list, ctrl + CT_FIX, fb_flags);
           // ---- the rest: ties to the warp search, growers to the next radius, retries back into the queue ----
           const unsigned tm = __ballot_sync(FULL, tie);
           st_fb += __popc(tm);
@@ -696,7 +728,9 @@ __global__ void __launch_bounds__(64) knn_lists_rest_kernel(GridView g, int k, i
 // without exact distance ties the fp64 mean and covariance reproduce the reference's bits whichever kNN kernel made the
 // list (the tile kernel delivers the SET in slot order; the warp search delivers it sorted, ties in visiting order).
 // KT > 0: k known at compile time (10 and 20, the values DLO uses) — keys in registers, k^2 unrolled rank computation.
-template <int KT>
+// SORTED: the list is already in summation order (the tile kernel's k = 10 / 20 lists; points it could not order exactly
+// are flagged and left to cov_rest_kernel) — no distances, no keys, no sorting network.
+template <int KT, bool SORTED>
 __device__ __forceinline__ void cov_point(const GridView& g, int n, int k_rt, int method, const int* __restrict__ nbr, double* __restrict__ covs6,
                                           int q, int* __restrict__ idx_out, float* __restrict__ d2_out) {
   constexpr int KA = KT > 0 ? KT : KNN_MAX_K;
@@ -705,7 +739,10 @@ __device__ __forceinline__ void cov_point(const GridView& g, int n, int k_rt, in
   const float4 qp = __ldg(g.sorted + q);
   const int orig = __float_as_int(qp.w);
   int ord[KA];          // neighbour slots in summation order (dynamically indexed: local memory, L1 resident)
-  if (KT > 0) {
+  if (KT > 0 && SORTED) {
+#pragma unroll
+    for (int j = 0; j < KA; ++j) ord[j] = __ldg(my + j);
+  } else if (KT > 0) {
     // keys = (bits of the squared distance) << 32 | sorted slot: non-negative floats order like their bit patterns, the
     // slot breaks exact ties (slots follow (cell, original index), the same for every kNN kernel and every slicing)
     unsigned long long key[KA];
@@ -783,7 +820,7 @@ __device__ __forceinline__ void cov_point(const GridView& g, int n, int k_rt, in
 #ifndef K3_MINB
 #define K3_MINB 4      // resident blocks per SM the covariance kernel is compiled for (registers: 4 -> 128, 5 -> 96, 6 -> 80)
 #endif
-template <int KT>
+template <int KT, bool SORTED>
 __global__ void __launch_bounds__(128, K3_MINB) cov_from_lists_kernel(GridView g, int n, int k_rt, int method, const int* __restrict__ nbr,
                                                              double* __restrict__ covs6, int q_lo, int q_hi,
                                                              const unsigned char* __restrict__ skip_flags,
@@ -791,24 +828,26 @@ __global__ void __launch_bounds__(128, K3_MINB) cov_from_lists_kernel(GridView g
   const int q = q_lo + blockIdx.x * blockDim.x + threadIdx.x;
   if (q >= q_hi || q >= n) return;
   if (skip_flags != nullptr && skip_flags[q]) return;
-  cov_point<KT>(g, n, k_rt, method, nbr, covs6, q, idx_out, d2_out);
+  cov_point<KT, SORTED>(g, n, k_rt, method, nbr, covs6, q, idx_out, d2_out);
 }
 // the listed points only (after knn_lists_rest_kernel has answered them); runs beside the main launch on a side stream
 template <int KT>
 __global__ void __launch_bounds__(128) cov_rest_kernel(GridView g, int n, int k_rt, int method, const int* __restrict__ nbr,
                                                        double* __restrict__ covs6, const int* __restrict__ ctrl, const int* __restrict__ fb_list) {
-  const int total = ctrl[CT_REST];
+  const int nrest = ctrl[CT_REST], total = nrest + ctrl[CT_FIX];     // warp-search list from the front, order fix-ups from the back
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x)
-    cov_point<KT>(g, n, k_rt, method, nbr, covs6, fb_list[i], nullptr, nullptr);
+    cov_point<KT, false>(g, n, k_rt, method, nbr, covs6, i < nrest ? fb_list[i] : fb_list[n - 1 - (i - nrest)], nullptr, nullptr);
 }
 
 static void launch_cov_kernel(const DevCloud& c, int k, int method, const int* nbr, double* covs6, int q_lo, int q_hi, const unsigned char* skip,
-                              int* idx_out, float* d2_out, cudaStream_t st) {
+                              int* idx_out, float* d2_out, cudaStream_t st, bool sorted = false) {
   const int nq = q_hi - q_lo;
   const dim3 grid((nq + 127) / 128), block(128);
-  if (k == 10) cov_from_lists_kernel<10><<<grid, block, 0, st>>>(c.view(), c.n, k, method, nbr, covs6, q_lo, q_hi, skip, idx_out, d2_out);
-  else if (k == 20) cov_from_lists_kernel<20><<<grid, block, 0, st>>>(c.view(), c.n, k, method, nbr, covs6, q_lo, q_hi, skip, idx_out, d2_out);
-  else cov_from_lists_kernel<0><<<grid, block, 0, st>>>(c.view(), c.n, k, method, nbr, covs6, q_lo, q_hi, skip, idx_out, d2_out);
+  if (k == 10 && sorted) cov_from_lists_kernel<10, true><<<grid, block, 0, st>>>(c.view(), c.n, k, method, nbr, covs6, q_lo, q_hi, skip, idx_out, d2_out);
+  else if (k == 20 && sorted) cov_from_lists_kernel<20, true><<<grid, block, 0, st>>>(c.view(), c.n, k, method, nbr, covs6, q_lo, q_hi, skip, idx_out, d2_out);
+  else if (k == 10) cov_from_lists_kernel<10, false><<<grid, block, 0, st>>>(c.view(), c.n, k, method, nbr, covs6, q_lo, q_hi, skip, idx_out, d2_out);
+  else if (k == 20) cov_from_lists_kernel<20, false><<<grid, block, 0, st>>>(c.view(), c.n, k, method, nbr, covs6, q_lo, q_hi, skip, idx_out, d2_out);
+  else cov_from_lists_kernel<0, false><<<grid, block, 0, st>>>(c.view(), c.n, k, method, nbr, covs6, q_lo, q_hi, skip, idx_out, d2_out);
   note_launches(1);
 }
 static void launch_cov_rest_kernel(const DevCloud& c, int k, int method, const int* nbr, double* covs6, const int* ctrl, const int* fb_list, int blocks,
@@ -836,9 +875,11 @@ void knn_prime_kernels() {
   cudaFuncGetAttributes(&fa, knn_lists_tile_kernel<10>);
   cudaFuncGetAttributes(&fa, knn_lists_tile_kernel<20>);
   cudaFuncGetAttributes(&fa, knn_lists_rest_kernel);
-  cudaFuncGetAttributes(&fa, cov_from_lists_kernel<0>);
-  cudaFuncGetAttributes(&fa, cov_from_lists_kernel<10>);
-  cudaFuncGetAttributes(&fa, cov_from_lists_kernel<20>);
+  cudaFuncGetAttributes(&fa, cov_from_lists_kernel<0, false>);
+  cudaFuncGetAttributes(&fa, cov_from_lists_kernel<10, false>);
+  cudaFuncGetAttributes(&fa, cov_from_lists_kernel<20, false>);
+  cudaFuncGetAttributes(&fa, cov_from_lists_kernel<10, true>);
+  cudaFuncGetAttributes(&fa, cov_from_lists_kernel<20, true>);
   cudaFuncGetAttributes(&fa, cov_rest_kernel<0>);
   cudaFuncGetAttributes(&fa, cov_rest_kernel<10>);
   cudaFuncGetAttributes(&fa, cov_rest_kernel<20>);
@@ -965,7 +1006,7 @@ cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_sc
               c.n, k, h[ST_FALLBACK], 100.0 * (double)h[ST_FALLBACK] / (double)c.n, h[ST_TIES], h[ST_ITEMS], h[ST_TILES], h[ST_PASSES],
               h[ST_PASSES] ? (double)h[ST_LANES] / (double)h[ST_PASSES] : 0.0);
     }
-    launch_cov_kernel(c, k, method, nbr_scratch, covs6, q_lo, q_hi, fb_flags, nullptr, nullptr, st);
+    launch_cov_kernel(c, k, method, nbr_scratch, covs6, q_lo, q_hi, fb_flags, nullptr, nullptr, st, k == 10 || k == 20);
     if (overlap && (e = cudaStreamWaitEvent(st, side->join, 0)) != cudaSuccess) return e;
     return cudaGetLastError();
   }
