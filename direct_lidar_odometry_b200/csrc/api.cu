@@ -451,6 +451,7 @@ void ngicp_params_default(ngicp_params* p) {
   p->align_mode = NGICP_ALIGN_FUSED;
   p->knn_path = NGICP_KNN_AUTO;
   p->knn_tile_min_points = 131072;
+  p->voxel_path = 0;
 }
 
 int ngicp_create(int device, ngicp_t** out) {
@@ -518,6 +519,7 @@ int ngicp_create(int device, ngicp_t** out) {
       for (TableBuf* t : tmp) delete t;   // release() parks them in the free list
       align_prime_kernels(device);
       knn_prime_kernels();
+      voxel_prime_kernels();
       cudaStreamSynchronize(h->stream->s);
     }
   }
@@ -595,9 +597,11 @@ int ngicp_set_params(ngicp_t* h, const ngicp_params* p) {
   if (p->regularization_method < 0 || p->regularization_method > 4) return fail(h, NGICP_E_INVALID, "unknown regularization method");  // the reference abort()s here (nano_gicp_impl.hpp:336-338)
   if (p->grid_table_cells < 64) return fail(h, NGICP_E_INVALID, "grid_table_cells too small");
   if (p->knn_path < NGICP_KNN_AUTO || p->knn_path > NGICP_KNN_TILE) return fail(h, NGICP_E_INVALID, "unknown knn_path");
+  if (p->voxel_path < 0 || p->voxel_path > 2) return fail(h, NGICP_E_INVALID, "unknown voxel_path");
   if (p->align_mode != NGICP_ALIGN_FUSED && p->align_mode != NGICP_ALIGN_STEPPED) return fail(h, NGICP_E_INVALID, "unknown align_mode");
   if (p->optimizer != NGICP_OPT_GAUSS_NEWTON && p->optimizer != NGICP_OPT_LEVENBERG_MARQUARDT) return fail(h, NGICP_E_INVALID, "unknown optimizer");
   h->prm = *p;
+  h->sc.vox_path = p->voxel_path;
   return NGICP_OK;
 }
 int ngicp_get_params(const ngicp_t* h, ngicp_params* p) {

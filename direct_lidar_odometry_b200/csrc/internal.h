@@ -103,6 +103,8 @@ struct Scratch {
   DevBuf hist, tile_sums;
   DevBuf flags;      // voxel head flags / scanned slots
   DevBuf vox_desc;   // GridDesc for the voxel filter
+  DevBuf vox_bar;    // grid barrier words of the fused voxel kernel (zero between launches)
+  int vox_path = 0;             // ngicp_params::voxel_path of the owning handle (1 = multi-kernel pipeline only)
   int vox_bits_hint = 0;        // key bits the last voxel filter needed (0 = unknown): lets the next call queue its radix
                                 // passes without a mid-pipeline read-back of the grid dimensions
   int* vox_result = nullptr;    // mapped pinned {m, overflow, key bits needed}: written by the pipeline's last kernel
@@ -187,6 +189,7 @@ int align_batch_fill(void* dst, const AlignBuffers& ab, const ngicp_params& p, c
 cudaError_t launch_align_batch(const void* pairs_dev, int n_pairs, int lpp, cudaStream_t st);
 void align_prime_kernels(int device);
 void knn_prime_kernels();
+void voxel_prime_kernels();
 
 // ---- voxel.cu -------------------------------------------------------------------------------------
 // returns cudaSuccess; *m_out and *overflow are valid after the call (it synchronises once to learn m)

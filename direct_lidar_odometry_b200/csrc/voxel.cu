@@ -6,6 +6,8 @@
 // The within-voxel accumulation order is ascending input index (the sort is stable), float32 running
 // sums of x,y,z,intensity divided by the float count — the order the CPU oracle fixes as well.
 // Algorithmic bytes: 16 N read + 16 M written (records are 32 B at the boundary).
+#include <mutex>
+#include <cooperative_groups.h>
 #include "internal.h"
 
 namespace ngicp {
@@ -218,6 +220,410 @@ __global__ void __launch_bounds__(256) vox_copy_out_kernel(const float4* __restr
   for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < 2 * m; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// K0 in ONE persistent cooperative launch (clouds up to VF_CH points per block x one block per SM = 606k points on a
+// B200): pack / transform / crop + bounding box -> voxel keys -> stable LSD radix sort (9-bit digits, as many passes as
+// THIS cloud's voxel-index range needs: decided on the device, nothing speculated) -> run heads -> centroids, separated
+// by grid barriers instead of kernel boundaries.  The multi-kernel pipeline below needs ~20 dependent launches for the
+// same work (6 us each at 53k points: launch latency, not bandwidth); here a 53k-point scan is 8 barriers.
+// Every block owns one contiguous chunk of the cloud; a radix pass ranks the chunk's items in order warp by warp
+// (match_any, as rs_scatter), publishes its digit histogram, and after the barrier every block derives ITS offsets
+// itself from the whole (digit-major) histogram table — one digit per thread, no single-block scan kernel in between.
+// Same arithmetic and the same stable order as the multi-kernel path: outputs are bit-identical (tests compare both).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int VF_THREADS = 512;
+constexpr int VF_WARPS = VF_THREADS / 32;
+constexpr int VF_CH = 4096;                 // points per block
+constexpr int VF_BITS = 9;
+constexpr int VF_BINS = 1 << VF_BITS;       // == VF_THREADS: one digit per thread in the offset step
+static_assert(VF_BINS == VF_THREADS, "one digit per thread");
+
+struct VoxFusedArgs {
+  const unsigned char* raw; RecordLayout lay; int n; float inv;
+  CropBox crop; RigidXf xf;
+  float4* pts;
+  unsigned *keys_a, *vals_a, *keys_b, *vals_b;
+  unsigned short* hist;       // [G][VF_BINS] block-major: a block's digit counts (<= VF_CH) are one 1 KB row
+  unsigned* bar;              // grid barrier words {arrivals, -, departures}; zero between launches
+  float* part;                // [G][8]: per-block bbox min[3], max[3], finite count (as int bits)
+  int* blk_heads;             // [G]
+  float* out; int* slot_of_point; GridDesc* d;
+  int* result;                // mapped pinned {m, overflow, key bits}
+  float4* user_out; size_t user_cap;   // optional device destination of the records (nullptr = none)
+};
+
+struct VoxFusedSmem {
+  unsigned key[VF_CH];
+  unsigned val[VF_CH];
+  unsigned short rank[VF_CH];
+  int wcnt[VF_WARPS][VF_BINS];
+  int base[VF_BINS];
+  int tot8[8][VF_BINS], bef8[8][VF_BINS];   // partial column sums of the histogram table (offset step)
+  int scan[VF_WARPS + 1];
+  float red[VF_WARPS][8];
+  int minb[3], div[3], overflow, nfinite, bits;
+  unsigned invalid;
+};
+
+__device__ __forceinline__ int vf_block_exclusive_scan(int v, int* scan /* VF_WARPS + 1 */, int& total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+  if (lane == 31) scan[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    const int ws = lane < VF_WARPS ? scan[lane] : 0;
+    int wi = ws;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, wi, o); if (lane >= o) wi += t; }
+    if (lane < VF_WARPS) scan[lane] = wi - ws;
+    if (lane == 31) scan[VF_WARPS] = wi;
+  }
+  __syncthreads();
+  const int r = scan[w] + inc - v;
+  total = scan[VF_WARPS];
+  __syncthreads();
+  return r;
+}
+
+// Grid barrier for the cooperative launch (all blocks co-resident): one arrival counter that only grows within a launch;
+// thread 0 of every block arrives and polls with relaxed loads, the block waits on it.  ~half the cost of
+// cooperative_groups' grid.sync() at 50-150 blocks.
+__device__ __forceinline__ void vf_grid_barrier(unsigned* bar, unsigned& phase) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    const unsigned target = (phase + 1u) * gridDim.x;
+    unsigned v;
+    do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while (v < target);
+    __threadfence();
+  }
+  phase++;
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(VF_THREADS, 1) vox_fused_kernel(VoxFusedArgs a) {
+  extern __shared__ __align__(16) unsigned char vf_smem_raw[];
+  VoxFusedSmem& S = *reinterpret_cast<VoxFusedSmem*>(vf_smem_raw);
+  unsigned phase = 0;
+  const int G = gridDim.x, blk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int n = a.n;
+  const int chunk = (n + G - 1) / G;                       // <= VF_CH (host guarantees)
+  const int lo = min(blk * chunk, n), hi = min(lo + chunk, n), cnt = hi - lo;
+
+  // ---- pack (+ transform, crop), bounding box of the finite points ----
+  {
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    int finite = 0;
+    const bool al = a.lay.aligned != 0;
+    for (int i = lo + tid; i < hi; i += VF_THREADS) {
+      const int row = a.lay.width >= n ? 0 : i / a.lay.width;
+      const unsigned char* r = a.raw + (size_t)row * a.lay.row_step + (size_t)(i - row * a.lay.width) * a.lay.point_step;
+      float x = load_f32(r + a.lay.off[0], al), y = load_f32(r + a.lay.off[1], al), z = load_f32(r + a.lay.off[2], al);
+      const float it = a.lay.off[3] >= 0 ? load_f32(r + a.lay.off[3], al) : 0.f;
+      if (a.xf.on) {
+        const float* m = a.xf.m;
+        const float tx = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[0], x), __fmul_rn(m[1], y)), __fmul_rn(m[2], z)), m[3]);
+        const float ty = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[4], x), __fmul_rn(m[5], y)), __fmul_rn(m[6], z)), m[7]);
+        const float tz = __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(m[8], x), __fmul_rn(m[9], y)), __fmul_rn(m[10], z)), m[11]);
+        x = tx; y = ty; z = tz;
+      }
+      if (a.crop.on && x >= a.crop.lo[0] && x <= a.crop.hi[0] && y >= a.crop.lo[1] && y <= a.crop.hi[1] && z >= a.crop.lo[2] && z <= a.crop.hi[2])
+        x = __int_as_float(0x7fc00000);   // cropped away
+      a.pts[i] = make_float4(x, y, z, it);
+      if (isfinite(x) && isfinite(y) && isfinite(z)) {
+        finite++;
+        mn[0] = fminf(mn[0], x); mn[1] = fminf(mn[1], y); mn[2] = fminf(mn[2], z);
+        mx[0] = fmaxf(mx[0], x); mx[1] = fmaxf(mx[1], y); mx[2] = fmaxf(mx[2], z);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mn[c] = fminf(mn[c], __shfl_xor_sync(FULL, mn[c], o));
+        mx[c] = fmaxf(mx[c], __shfl_xor_sync(FULL, mx[c], o));
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) finite += __shfl_xor_sync(FULL, finite, o);
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) { S.red[w][c] = mn[c]; S.red[w][3 + c] = mx[c]; }
+      S.red[w][6] = __int_as_float(finite);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int ww = 1; ww < VF_WARPS; ww++) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) { mn[c] = fminf(mn[c], S.red[ww][c]); mx[c] = fmaxf(mx[c], S.red[ww][3 + c]); }
+        finite += __float_as_int(S.red[ww][6]);
+      }
+      float* p = a.part + (size_t)blk * 8;
+#pragma unroll
+      for (int c = 0; c < 3; c++) { p[c] = mn[c]; p[3 + c] = mx[c]; }
+      p[6] = __int_as_float(finite);
+    }
+  }
+  vf_grid_barrier(a.bar, phase);
+
+  // ---- every block: bbox of all blocks -> PCL's min_b / div_b / overflow (vox_setup_kernel's arithmetic) ----
+  if (w == 0) {
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    int finite = 0;
+    for (int b = lane; b < G; b += 32) {
+      const float* p = a.part + (size_t)b * 8;
+#pragma unroll
+      for (int c = 0; c < 3; c++) { mn[c] = fminf(mn[c], __ldcg(p + c)); mx[c] = fmaxf(mx[c], __ldcg(p + 3 + c)); }
+      finite += __float_as_int(__ldcg(p + 6));
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mn[c] = fminf(mn[c], __shfl_xor_sync(FULL, mn[c], o));
+        mx[c] = fmaxf(mx[c], __shfl_xor_sync(FULL, mx[c], o));
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) finite += __shfl_xor_sync(FULL, finite, o);
+    if (lane == 0) {
+      S.nfinite = finite;
+      int over = 0;
+      unsigned long long cells = 1ull;
+      if (finite > 0) {
+        const long long dx = (long long)(__fmul_rn(__fsub_rn(mx[0], mn[0]), a.inv)) + 1;
+        const long long dy = (long long)(__fmul_rn(__fsub_rn(mx[1], mn[1]), a.inv)) + 1;
+        const long long dz = (long long)(__fmul_rn(__fsub_rn(mx[2], mn[2]), a.inv)) + 1;
+        over = (dx * dy * dz > 2147483647ll) ? 1 : 0;
+        for (int c = 0; c < 3; c++) {
+          const int mnb = (int)floorf(__fmul_rn(mn[c], a.inv));
+          const int mxb = (int)floorf(__fmul_rn(mx[c], a.inv));
+          S.minb[c] = mnb;
+          S.div[c] = mxb - mnb + 1;
+        }
+        cells = (unsigned long long)S.div[0] * (unsigned long long)S.div[1] * (unsigned long long)S.div[2];
+      } else {
+        for (int c = 0; c < 3; c++) { S.minb[c] = 0; S.div[c] = 1; }
+      }
+      S.overflow = over;
+      S.invalid = over ? 0u : (unsigned)cells;
+      int bits = 1;
+      while (bits < 32 && (1ull << bits) <= cells) bits++;
+      S.bits = bits;
+      if (blk == 0) {
+        GridDesc* d = a.d;
+        for (int c = 0; c < 3; c++) { d->bb_min[c] = f2ord(mn[c]); d->bb_max[c] = f2ord(mx[c]); d->vmin_b[c] = S.minb[c]; d->vdiv[c] = S.div[c]; }
+        d->nfinite = finite; d->voverflow = over; d->vcount = 0;
+      }
+    }
+  }
+  __syncthreads();
+  if (S.overflow || S.nfinite == 0) {                      // uniform over the grid: PCL passes the input through / nothing to do
+    if (blk == 0 && tid == 0) { a.result[0] = 0; a.result[1] = S.overflow; a.result[2] = S.bits; }
+    if (S.nfinite == 0 && !S.overflow)
+      for (int i = lo + tid; i < hi; i += VF_THREADS) a.slot_of_point[i] = -1;
+    if (tid == 0 && atomicAdd(a.bar + 2, 1u) == gridDim.x - 1u) { a.bar[0] = 0u; a.bar[2] = 0u; }
+    return;
+  }
+
+  // ---- voxel keys of the own chunk (vox_keys_kernel's arithmetic) ----
+  {
+    const int m0 = S.minb[0], m1 = S.minb[1], m2 = S.minb[2];
+    const int mul1 = S.div[0], mul2 = S.div[0] * S.div[1];
+    for (int j = tid; j < cnt; j += VF_THREADS) {
+      const float4 p = a.pts[lo + j];
+      unsigned key = S.invalid;
+      if (isfinite(p.x) && isfinite(p.y) && isfinite(p.z)) {
+        const int i0 = (int)(__fsub_rn(floorf(__fmul_rn(p.x, a.inv)), (float)m0));
+        const int i1 = (int)(__fsub_rn(floorf(__fmul_rn(p.y, a.inv)), (float)m1));
+        const int i2 = (int)(__fsub_rn(floorf(__fmul_rn(p.z, a.inv)), (float)m2));
+        key = (unsigned)(i0 + i1 * mul1 + i2 * mul2);
+      }
+      S.key[j] = key;
+      S.val[j] = (unsigned)(lo + j);
+    }
+  }
+  __syncthreads();
+
+  // ---- stable LSD radix sort ----
+  const int passes = (S.bits + VF_BITS - 1) / VF_BITS;
+  const int seg = ((cnt + VF_WARPS - 1) / VF_WARPS + 31) & ~31;     // items per warp, whole groups of 32
+  const unsigned lt = (1u << lane) - 1u;
+  unsigned *kin = a.keys_a, *vin = a.vals_a, *kout = a.keys_b, *vout = a.vals_b;
+  for (int p = 0; p < passes; ++p) {
+    const int shift = p * VF_BITS;
+    if (p > 0) {
+      for (int j = tid; j < cnt; j += VF_THREADS) { S.key[j] = __ldcg(kin + lo + j); S.val[j] = __ldcg(vin + lo + j); }
+    }
+    for (int i = tid; i < VF_WARPS * VF_BINS; i += VF_THREADS) (&S.wcnt[0][0])[i] = 0;
+    __syncthreads();
+    // rank the warp's items in order (rank among equal digits of this warp)
+    for (int j0 = w * seg; j0 < min((w + 1) * seg, cnt); j0 += 32) {
+      const int j = j0 + lane;
+      const bool valid = j < cnt;
+      const unsigned dgt = valid ? ((S.key[j] >> shift) & (VF_BINS - 1)) : (unsigned)VF_BINS;
+      const unsigned peers = __match_any_sync(FULL, dgt);
+      const int leader = __ffs(peers) - 1;
+      int before = 0;
+      if (valid && lane == leader) { before = S.wcnt[w][dgt]; S.wcnt[w][dgt] = before + __popc(peers); }
+      before = __shfl_sync(FULL, before, leader);
+      if (valid) S.rank[j] = (unsigned short)(before + __popc(peers & lt));
+      __syncwarp();
+    }
+    __syncthreads();
+    {
+      // digit `tid`: block total -> table; per-warp counts -> exclusive over the warps
+      int run = 0;
+#pragma unroll
+      for (int ww = 0; ww < VF_WARPS; ww++) { const int t = S.wcnt[ww][tid]; S.wcnt[ww][tid] = run; run += t; }
+      a.hist[(size_t)blk * VF_BINS + tid] = (unsigned short)run;
+    }
+    vf_grid_barrier(a.bar, phase);
+    {
+      // column sums of the table (all blocks / the blocks before this one) for every digit: thread = (8 consecutive digits,
+      // every 8th block row), one 16-byte load per row — all loads independent, one round of latency
+      const int dg = tid & 63, bsub = tid >> 6;
+      int tot[8], bef[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) { tot[u] = 0; bef[u] = 0; }
+      for (int b = bsub; b < G; b += 8) {
+        const uint4 q = __ldcg(reinterpret_cast<const uint4*>(a.hist + (size_t)b * VF_BINS) + dg);
+        const unsigned wv[4] = {q.x, q.y, q.z, q.w};
+        const bool mine = b < blk;
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          const int c0 = (int)(wv[u] & 0xffffu), c1 = (int)(wv[u] >> 16);
+          tot[2 * u] += c0; tot[2 * u + 1] += c1;
+          if (mine) { bef[2 * u] += c0; bef[2 * u + 1] += c1; }
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; u++) { S.tot8[bsub][dg * 8 + u] = tot[u]; S.bef8[bsub][dg * 8 + u] = bef[u]; }
+      __syncthreads();
+      int total = 0, before = 0;
+#pragma unroll
+      for (int r = 0; r < 8; r++) { total += S.tot8[r][tid]; before += S.bef8[r][tid]; }
+      int all;
+      const int excl = vf_block_exclusive_scan(total, S.scan, all);
+      S.base[tid] = excl + before;
+    }
+    __syncthreads();
+    for (int j = tid; j < cnt; j += VF_THREADS) {
+      const unsigned key = S.key[j];
+      const unsigned dgt = (key >> shift) & (VF_BINS - 1);
+      const int pos = S.base[dgt] + S.wcnt[j / seg][dgt] + (int)S.rank[j];
+      kout[pos] = key;
+      vout[pos] = S.val[j];
+    }
+    vf_grid_barrier(a.bar, phase);
+    unsigned* t = kin; kin = kout; kout = t;
+    t = vin; vin = vout; vout = t;
+  }
+  if (passes == 0) {       // cannot happen (bits >= 1); keeps kin/vin meaningful for the reader
+    for (int j = tid; j < cnt; j += VF_THREADS) { kin[lo + j] = S.key[j]; vin[lo + j] = S.val[j]; }
+    vf_grid_barrier(a.bar, phase);
+  }
+  const unsigned* keys = kin;       // sorted keys, permutation
+  const unsigned* perm = vin;
+
+  // ---- run heads of the own chunk, their local ranks ----
+  {
+    constexpr int IPT = VF_CH / VF_THREADS;                // 8 consecutive items per thread
+    int flags = 0, c = 0;
+#pragma unroll
+    for (int u = 0; u < IPT; u++) {
+      const int j = tid * IPT + u;
+      if (j < cnt) {
+        const int i = lo + j;
+        const unsigned k = __ldcg(keys + i);
+        S.key[j] = k;
+        const bool head = k != S.invalid && (i == 0 || __ldcg(keys + i - 1) != k);
+        if (head) { flags |= 1 << u; c++; }
+      }
+    }
+    int total;
+    int r = vf_block_exclusive_scan(c, S.scan, total);
+#pragma unroll
+    for (int u = 0; u < IPT; u++) {
+      const int j = tid * IPT + u;
+      if (j < cnt) {
+        S.rank[j] = (unsigned short)r;
+        S.val[j] = (flags >> u) & 1;
+        r += (flags >> u) & 1;
+      }
+    }
+    if (tid == 0) a.blk_heads[blk] = total;
+  }
+  vf_grid_barrier(a.bar, phase);
+  int slot_base = 0, m_total = 0;
+  {
+    int before = 0, all = 0;
+    for (int b = tid; b < G; b += VF_THREADS) { const int v = __ldcg(a.blk_heads + b); all += v; before += b < blk ? v : 0; }
+    // G <= VF_THREADS: one value per thread, block sums through the scan helper
+    int t1, t2;
+    vf_block_exclusive_scan(before, S.scan, t1);
+    vf_block_exclusive_scan(all, S.scan, t2);
+    slot_base = t1; m_total = t2;
+  }
+  // ---- centroids: one thread per run head, sequential float accumulation in sorted (= ascending input index) order ----
+  for (int j = tid; j < cnt; j += VF_THREADS) {
+    const int i = lo + j;
+    const unsigned k = S.key[j];
+    if (k == S.invalid) { a.slot_of_point[__ldcg(perm + i)] = -1; continue; }
+    if (!S.val[j]) continue;
+    const int slot = slot_base + (int)S.rank[j];
+    float sx = 0.f, sy = 0.f, sz = 0.f, si = 0.f;
+    int e = i;
+    for (; e < n && __ldcg(keys + e) == k; ++e) {
+      const unsigned o = __ldcg(perm + e);
+      const float4 p = a.pts[o];
+      sx = __fadd_rn(sx, p.x); sy = __fadd_rn(sy, p.y); sz = __fadd_rn(sz, p.z); si = __fadd_rn(si, p.w);
+      a.slot_of_point[o] = slot;
+    }
+    const float c = (float)(e - i);
+    const float4 r0 = make_float4(__fdiv_rn(sx, c), __fdiv_rn(sy, c), __fdiv_rn(sz, c), 1.0f);
+    const float4 r1 = make_float4(__fdiv_rn(si, c), 0.f, 0.f, 0.f);
+    float4* o4 = reinterpret_cast<float4*>(a.out + (size_t)slot * 8);
+    o4[0] = r0; o4[1] = r1;
+    if (a.user_out != nullptr && (size_t)slot < a.user_cap) { a.user_out[2 * (size_t)slot] = r0; a.user_out[2 * (size_t)slot + 1] = r1; }
+  }
+  if (blk == 0 && tid == 0) { a.result[0] = m_total; a.result[1] = 0; a.result[2] = S.bits; a.d->vcount = m_total; }
+  // leave the barrier words zeroed for the next launch: the last block to depart does it (nobody polls any more)
+  if (tid == 0 && atomicAdd(a.bar + 2, 1u) == gridDim.x - 1u) { a.bar[0] = 0u; a.bar[2] = 0u; }
+}
+
+static int vox_fused_grid(int device, int n) {
+  static std::mutex mu;
+  static int sms[64] = {};
+  static bool ok[64] = {};
+  const int di = device & 63;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!sms[di]) {
+      int v = 0, coop = 0;
+      cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, device);
+      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+      sms[di] = v > 0 ? v : 1;
+      ok[di] = coop != 0 && cudaFuncSetAttribute(vox_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(VoxFusedSmem)) == cudaSuccess;
+      cudaGetLastError();
+    }
+  }
+  if (!ok[di]) return 0;
+  int g = (n + 1023) / 1024;               // small clouds: fewer blocks, cheaper barriers
+  if (g > sms[di]) g = sms[di];
+  if (g < 1) g = 1;
+  if ((long long)g * VF_CH < (long long)n) return 0;      // too large for one chunk per block: multi-kernel pipeline
+  return g;
+}
+
+void voxel_prime_kernels() {
+  cudaFuncAttributes fa;
+  cudaFuncGetAttributes(&fa, vox_fused_kernel);
+  cudaGetLastError();
+}
+
 cudaError_t voxel_filter_device(const void* in, size_t n, size_t stride_bytes, float leaf, Scratch& sc, const StreamPtr& st,
                                 size_t* m_out, int* overflow, const float* crop6, bool compact_on_overflow, const float* T16,
                                 void* out, size_t out_cap, bool* copied) {
@@ -270,6 +676,56 @@ cudaError_t voxel_filter_records(const void* in, size_t n, RecordLayout lay, flo
   if ((e = cudaMemcpyAsync(sc.staging.p, in, raw_bytes, cudaMemcpyDefault, st->s)) != cudaSuccess) return e;
   GridDesc* d = sc.vox_desc.as<GridDesc>();
   float4* pts = sc.queries.as<float4>();
+  // ---- one persistent cooperative launch for everything behind the staging copy (NGICP_VOXEL_FUSED=0: the
+  //      multi-kernel pipeline below, kept for clouds beyond 4096 points per SM and as the A/B twin in the tests) ----
+  static const bool fused_on = !(getenv("NGICP_VOXEL_FUSED") && atoi(getenv("NGICP_VOXEL_FUSED")) == 0);
+  int dev_id = 0;
+  cudaGetDevice(&dev_id);
+  const int fg = (use_grid && fused_on && allow_speculation && sc.vox_path != 1) ? vox_fused_grid(dev_id, ni) : 0;
+  if (fg > 0) {
+    if (!sc.vox_result) {
+      if (cudaHostAlloc(&sc.vox_result, 8 * sizeof(int), cudaHostAllocMapped) != cudaSuccess ||
+          cudaHostGetDevicePointer(&sc.vox_result_dev, sc.vox_result, 0) != cudaSuccess) { cudaGetLastError(); sc.vox_result = nullptr; }
+    }
+    if (sc.vox_result) {
+      if ((e = sc.hist.reserve(sizeof(int) * ((size_t)VF_BINS * fg + 9 * (size_t)fg + 64), st)) != cudaSuccess) return e;
+      if (!sc.vox_bar.p) {
+        if ((e = sc.vox_bar.reserve(64, st)) != cudaSuccess) return e;
+        if ((e = cudaMemsetAsync(sc.vox_bar.p, 0, 64, st->s)) != cudaSuccess) return e;
+      }
+      bool out_dev = false;
+      if (out && copied) {
+        cudaPointerAttributes attr;
+        if (cudaPointerGetAttributes(&attr, out) == cudaSuccess) out_dev = attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged;
+        else cudaGetLastError();
+        out_dev = out_dev && (reinterpret_cast<uintptr_t>(out) & 15u) == 0;
+      }
+      VoxFusedArgs fa;
+      fa.raw = sc.staging.as<unsigned char>(); fa.lay = lay; fa.n = ni; fa.inv = inv; fa.crop = crop; fa.xf = xf;
+      fa.pts = pts;
+      fa.keys_a = sc.keys_a.as<unsigned>(); fa.vals_a = sc.vals_a.as<unsigned>();
+      fa.keys_b = sc.keys_b.as<unsigned>(); fa.vals_b = sc.vals_b.as<unsigned>();
+      fa.hist = reinterpret_cast<unsigned short*>(sc.hist.as<int>());
+      fa.bar = sc.vox_bar.as<unsigned>();
+      fa.part = reinterpret_cast<float*>(sc.hist.as<int>() + (size_t)VF_BINS * fg);
+      fa.blk_heads = sc.hist.as<int>() + (size_t)VF_BINS * fg + 8 * (size_t)fg;
+      fa.out = sc.vox_out.as<float>(); fa.slot_of_point = sc.vox_slot.as<int>(); fa.d = d;
+      fa.result = sc.vox_result_dev;
+      fa.user_out = out_dev ? reinterpret_cast<float4*>(out) : nullptr; fa.user_cap = out_cap;
+      void* kargs[] = {(void*)&fa};
+      if ((e = cudaLaunchCooperativeKernel((const void*)vox_fused_kernel, dim3(fg), dim3(VF_THREADS), kargs, sizeof(VoxFusedSmem), st->s)) != cudaSuccess) return e;
+      note_launches(1);
+      if ((e = cudaStreamSynchronize(st->s)) != cudaSuccess) return e;
+      const int r_m = sc.vox_result[0], r_over = sc.vox_result[1];
+      if (!r_over) {
+        sc.vox_bits_hint = sc.vox_result[2];
+        *m_out = (size_t)r_m;
+        if (out_dev && (size_t)r_m <= out_cap) *copied = true;
+        return cudaGetLastError();
+      }
+      // PCL's index-range overflow (leaf far too small for the cloud's extent): handled by the exact path below
+    }
+  }
   vox_desc_init_kernel<<<1, 1, 0, st->s>>>(d);
   vox_pack_kernel<<<vgrid(ni, 256), 256, 0, st->s>>>(sc.staging.as<unsigned char>(), lay, ni, pts, d, crop, xf);
   note_launches(2);

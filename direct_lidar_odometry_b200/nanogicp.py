@@ -181,6 +181,11 @@ class NanoGICP:
             self._p.knn_tile_min_points = int(tile_min_points)
         self._push_params()
 
+    def setVoxelPath(self, path: int):
+        """voxel filter / preprocess: 0 = one persistent cooperative launch when the cloud fits, 1 = multi-kernel pipeline."""
+        self._p.voxel_path = int(path)
+        self._push_params()
+
     # ------------------------------------------------------------------ clouds
     def setInputSource(self, cloud):
         if self._input is cloud:  # pointer-identity early-out, nano_gicp_impl.hpp:122

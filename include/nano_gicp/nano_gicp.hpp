@@ -228,6 +228,7 @@ class NanoGICP {
   void setGridCellSize(float c) { set_field(&ngicp_params::grid_cell_size, c); }
   void setAlignMode(int mode) { set_field(&ngicp_params::align_mode, mode); }
   void setKnnPath(int path) { set_field(&ngicp_params::knn_path, path); }
+  void setVoxelPath(int path) { set_field(&ngicp_params::voxel_path, path); }
   void setFillOutputCloud(bool f) { fill_output_ = f; }
   ngicp_t* handle() const { return h(); }
 

@@ -83,6 +83,8 @@ typedef struct {
   int align_mode;                      /* NGICP_ALIGN_FUSED / NGICP_ALIGN_STEPPED */
   int knn_path;                        /* NGICP_KNN_AUTO / _WARP / _TILE */
   int knn_tile_min_points;             /* NGICP_KNN_AUTO switches to the tile kernels at this cloud size (131072) */
+  int voxel_path;                      /* voxel filter / preprocess: 0 = one persistent cooperative launch when the cloud fits
+                                          (4096 points per SM), 1 = always the multi-kernel pipeline, 2 = as 0 */
 } ngicp_params;
 
 /* what pcl::Registration / LsqRegistration expose after align() */

@@ -91,6 +91,50 @@ def test_voxel_filter_edge_cases(G, O, scan_pair):
     assert np.array_equal(bits(out[:, :4]), bits(ref[:, :4]))
 
 
+
+@pytest.mark.parametrize("path", [0, 1])
+def test_voxel_filter_fused_and_multi_kernel_paths(G, O, scan_pair, path):
+    """ngicp_params::voxel_path: 0 = one persistent cooperative launch (pack -> keys -> radix passes -> heads -> centroids
+    between grid barriers) when the cloud fits 4096 points per SM, 1 = the multi-kernel pipeline.  Both must reproduce
+    the oracle's bits and voxel assignment: raw scan, NaN / Inf, tiny and wide extents (1..4 radix passes), crop box,
+    a cloud larger than the fused path holds (falls back by itself), PCL's overflow pass-through."""
+    g = G()
+    g.setVoxelPath(path)
+    s0 = scan_pair["s0"]
+    small = s0[:3000].copy(); small[:, :3] *= 0.01
+    wide = s0.copy(); wide[::7, :3] *= 4.0
+    dirty = s0[:20000].copy(); dirty[::7, 0] = np.nan; dirty[3::11, 2] = np.inf
+    tiny = s0[:37].copy()
+    for pts, leaf in [(s0, 0.25), (s0, 0.5), (small, 0.5), (small, 0.01), (wide, 0.25), (dirty, 0.5), (tiny, 0.25), (s0[:513], 1.0), (s0[:1], 0.25)]:
+        ref, ref_assign, rc = O.voxel_filter(pts, leaf, return_assignment=True)
+        out, st = g.voxel_filter(pts, leaf, return_status=True)
+        assert st == rc and out.shape == ref.shape and np.array_equal(bits(out), bits(ref)), (path, pts.shape, leaf)
+        if rc == 0:                                          # (PCL's overflow pass-through has no voxel assignment)
+            assert np.array_equal(g.voxel_assignment(pts.shape[0]), ref_assign), (path, pts.shape, leaf)
+    # the fused preprocess (NaN removal + negative crop box + voxel grid) through both paths
+    ref = O.preprocess_points(dirty, 1.0, 0.25)
+    out = g.preprocess(dirty, 1.0, 0.25)
+    assert out.shape == ref.shape and np.array_equal(bits(out), bits(ref))
+    # 700k points: more than 4096 per SM -> the multi-kernel pipeline whatever was asked for
+    rng = np.random.default_rng(3)
+    big = np.zeros((700_000, 8), np.float32)
+    big[:, :3] = rng.uniform(-40, 40, size=(700_000, 3)).astype(np.float32)
+    big[:, 2] *= 0.1
+    big[:, 3] = 1.0
+    big[:, 4] = rng.uniform(0, 1, size=700_000).astype(np.float32)
+    ref = O.voxel_filter(big, 0.4)
+    out = g.voxel_filter(big, 0.4)
+    assert out.shape == ref.shape and np.array_equal(bits(out), bits(ref))
+    half = big[:500_000]                                     # fits the fused path: 3379 points per block
+    ref = O.voxel_filter(half, 0.4)
+    out = g.voxel_filter(half, 0.4)
+    assert out.shape == ref.shape and np.array_equal(bits(out), bits(ref))
+    far = s0[:100].copy(); far[0, :3] = 1e6
+    out, st = g.voxel_filter(far, 0.01, return_status=True)
+    assert st == 1 and out.shape[0] == 100 and np.array_equal(out[:, :3], far[:, :3])
+    assert np.array_equal(bits(g.voxel_filter(s0, 0.25)), bits(O.voxel_filter(s0, 0.25)))
+
+
 def test_preprocess_fused_crop_nan_voxel(G, O, scan_pair):
     """ngicp_preprocess = removeNaN + negative CropBox + voxel grid in one pass (odom.cc:443-465), bit-exact against
     the three steps done one after the other by the oracle."""
