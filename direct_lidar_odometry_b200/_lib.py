@@ -40,7 +40,7 @@ class Params(C.Structure):
                 ("optimizer", C.c_int), ("lm_max_iterations", C.c_int), ("lm_init_lambda_factor", C.c_double),
                 ("regularization_method", C.c_int), ("grid_cell_size", C.c_float), ("grid_table_cells", C.c_int),
                 ("align_mode", C.c_int), ("knn_path", C.c_int), ("knn_tile_min_points", C.c_int),
-                ("voxel_path", C.c_int)]
+                ("voxel_path", C.c_int), ("index_path", C.c_int)]
 
 
 class Result(C.Structure):

@@ -185,8 +185,12 @@ int set_cloud(ngicp_t* h, int which, const void* pts, size_t n, size_t stride, b
   StreamPtr& st = side_stream(h, which);
   Scratch& sc = side_scratch(h, which);
   ph_begin(h, ph);
-  NG_CUDA(h, upload_cloud(*c, pts, n, stride, sc, st));
-  if (index) NG_CUDA(h, build_index(*c, h->prm.grid_cell_size, h->prm.grid_table_cells, sc, st, h->device));
+  bool fused = false;
+  if (index) NG_CUDA(h, upload_and_index_fused(*c, pts, n, stride, h->prm.grid_cell_size, h->prm.grid_table_cells, sc, st, h->device, &fused));
+  if (!fused) {
+    NG_CUDA(h, upload_cloud(*c, pts, n, stride, sc, st));
+    if (index) NG_CUDA(h, build_index(*c, h->prm.grid_cell_size, h->prm.grid_table_cells, sc, st, h->device));
+  }
   ph_end(h, ph);
   drop_cloud(h, which);
   if (which == NGICP_SOURCE) { h->src = c; if (index) drop_covs(h, NGICP_SOURCE); h->src_pending = true; }
@@ -452,6 +456,7 @@ void ngicp_params_default(ngicp_params* p) {
   p->knn_path = NGICP_KNN_AUTO;
   p->knn_tile_min_points = 131072;
   p->voxel_path = 0;
+  p->index_path = 0;
 }
 
 int ngicp_create(int device, ngicp_t** out) {
@@ -520,6 +525,7 @@ int ngicp_create(int device, ngicp_t** out) {
       align_prime_kernels(device);
       knn_prime_kernels();
       voxel_prime_kernels();
+      index_prime_kernels();
       cudaStreamSynchronize(h->stream->s);
     }
   }
@@ -598,10 +604,14 @@ int ngicp_set_params(ngicp_t* h, const ngicp_params* p) {
   if (p->grid_table_cells < 64) return fail(h, NGICP_E_INVALID, "grid_table_cells too small");
   if (p->knn_path < NGICP_KNN_AUTO || p->knn_path > NGICP_KNN_TILE) return fail(h, NGICP_E_INVALID, "unknown knn_path");
   if (p->voxel_path < 0 || p->voxel_path > 2) return fail(h, NGICP_E_INVALID, "unknown voxel_path");
+  if (p->index_path < 0 || p->index_path > 2) return fail(h, NGICP_E_INVALID, "unknown index_path");
   if (p->align_mode != NGICP_ALIGN_FUSED && p->align_mode != NGICP_ALIGN_STEPPED) return fail(h, NGICP_E_INVALID, "unknown align_mode");
   if (p->optimizer != NGICP_OPT_GAUSS_NEWTON && p->optimizer != NGICP_OPT_LEVENBERG_MARQUARDT) return fail(h, NGICP_E_INVALID, "unknown optimizer");
   h->prm = *p;
   h->sc.vox_path = p->voxel_path;
+  h->sc.index_path = p->index_path;
+  h->sc_src.index_path = p->index_path;
+  h->sc_src.vox_path = p->voxel_path;
   return NGICP_OK;
 }
 int ngicp_get_params(const ngicp_t* h, ngicp_params* p) {
@@ -1229,8 +1239,12 @@ int ngicp_kfstore_set_target(ngicp_kfstore_t* s, ngicp_t* to, const int* indices
     off += n;
   }
   // gicp.setInputTarget(submap_cloud) (:830): snapshot + bounding box + search index
-  NG_CUDA(to, upload_cloud(*c, to->sc.staging.p, total, sizeof(float4), to->sc, to->stream));
-  NG_CUDA(to, build_index(*c, to->prm.grid_cell_size, to->prm.grid_table_cells, to->sc, to->stream, to->device));
+  bool fused = false;
+  NG_CUDA(to, upload_and_index_fused(*c, to->sc.staging.p, total, sizeof(float4), to->prm.grid_cell_size, to->prm.grid_table_cells, to->sc, to->stream, to->device, &fused));
+  if (!fused) {
+    NG_CUDA(to, upload_cloud(*c, to->sc.staging.p, total, sizeof(float4), to->sc, to->stream));
+    NG_CUDA(to, build_index(*c, to->prm.grid_cell_size, to->prm.grid_table_cells, to->sc, to->stream, to->device));
+  }
   ph_end(to, PH_SET_TGT);
   drop_cloud(to, NGICP_TARGET);
   drop_covs(to, NGICP_TARGET);

@@ -160,10 +160,26 @@ __global__ void __launch_bounds__(256) pack_bbox_kernel(const unsigned char* __r
 }
 
 // derive the grid from the bounding box; grow the cell until the dense table fits
+struct GridShape { float origin[3]; float cell, inv_cell, margin; int dim[3]; int ncells, max_dim; };
+__device__ void grid_shape_compute(const float* lo_in, const float* hi_in, int nfinite, float cell, int cap, GridShape& gs);
 __device__ void grid_setup_device(GridDesc* d, float cell, int cap, int n) {
   float lo[3], hi[3];
   for (int a = 0; a < 3; a++) { lo[a] = ord2f(d->bb_min[a]); hi[a] = ord2f(d->bb_max[a]); }
-  if (d->nfinite == 0) { for (int a = 0; a < 3; a++) { lo[a] = 0.f; hi[a] = 0.f; } }
+  GridShape gs;
+  grid_shape_compute(lo, hi, d->nfinite, cell, cap, gs);
+  for (int a = 0; a < 3; a++) { d->origin[a] = gs.origin[a]; d->dim[a] = gs.dim[a]; }
+  d->cell = gs.cell;
+  d->inv_cell = gs.inv_cell;
+  d->ncells = gs.ncells;
+  d->n = n;
+  d->max_dim = gs.max_dim;
+  d->margin = gs.margin;
+  d->occ_sq = 0ull;
+}
+__device__ void grid_shape_compute(const float* lo_in, const float* hi_in, int nfinite, float cell, int cap, GridShape& gs) {
+  float lo[3], hi[3];
+  for (int a = 0; a < 3; a++) { lo[a] = lo_in[a]; hi[a] = hi_in[a]; }
+  if (nfinite == 0) { for (int a = 0; a < 3; a++) { lo[a] = 0.f; hi[a] = 0.f; } }
   int dim[3];
   // Grow the cell edge until the dense table fits.  The extent can be anything a float holds (DLO only strips NaN/Inf:
   // one stray 1e20 return is a legal input), so the loop runs until it fits — 1.25^400 spans the whole float range —
@@ -191,14 +207,12 @@ __device__ void grid_setup_device(GridDesc* d, float cell, int cap, int n) {
     cell = 3.0e38f;
     for (int a = 0; a < 3; a++) dim[a] = 1;
   }
-  for (int a = 0; a < 3; a++) { d->origin[a] = lo[a]; d->dim[a] = dim[a]; }
-  d->cell = cell;
-  d->inv_cell = 1.0f / cell;
-  d->ncells = dim[0] * dim[1] * dim[2];
-  d->n = n;
-  d->max_dim = max(dim[0], max(dim[1], dim[2]));
-  d->margin = cell * (0.01f + 1e-6f * (float)d->max_dim);
-  d->occ_sq = 0ull;
+  for (int a = 0; a < 3; a++) { gs.origin[a] = lo[a]; gs.dim[a] = dim[a]; }
+  gs.cell = cell;
+  gs.inv_cell = 1.0f / cell;
+  gs.ncells = dim[0] * dim[1] * dim[2];
+  gs.max_dim = max(dim[0], max(dim[1], dim[2]));
+  gs.margin = cell * (0.01f + 1e-6f * (float)gs.max_dim);
 }
 
 __global__ void grid_setup_kernel(GridDesc* d, float cell, int cap, int n) { grid_setup_device(d, cell, cap, n); }
@@ -339,6 +353,307 @@ cudaError_t upload_cloud(DevCloud& c, const void* pts, size_t n, size_t stride_b
   return cudaGetLastError();
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// K1 in ONE persistent cooperative launch: snapshot + bounding box -> (trial histogram -> occupancy -> cell edge) ->
+// zero the table -> histogram -> exclusive scan -> counting-sort scatter -> deterministic in-cell order + gather, separated by
+// grid barriers instead of the 14 kernel boundaries of upload_cloud + build_index below (a 22k-point scan spends 80 us
+// there on launch latency alone; its actual work is a few microseconds).  Every block derives the grid shape itself from
+// the per-block bounding boxes (same arithmetic as grid_setup_device), block 0 writes the descriptor.  The table scan is
+// slice-per-block: sums, barrier, every block adds up the slices before its own and scans its slice.
+// Same results as the multi-kernel path (the in-cell order is made deterministic by the same last pass).
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int IF_THREADS = 512;
+constexpr int IF_WARPS = IF_THREADS / 32;
+struct IndexFusedArgs {
+  const unsigned char* raw; size_t stride; int n;
+  float4* pts; float4* sorted; int* table; GridDesc* d;
+  unsigned* keys; unsigned* slot_orig;
+  float* part;               // [G][8]: per-block bbox + finite count
+  unsigned long long* occ;   // [G]: per-block occupancy sums
+  int* slice_sum;            // [G]
+  unsigned* bar;             // grid barrier words, zero between launches
+  float cell_req, target_occ; int table_cap, trial_cap;
+};
+
+__device__ __forceinline__ void if_grid_barrier(unsigned* bar, unsigned& phase) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(bar, 1u);
+    const unsigned target = (phase + 1u) * gridDim.x;
+    unsigned v;
+    do { asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar) : "memory"); } while (v < target);
+    __threadfence();
+  }
+  phase++;
+  __syncthreads();
+}
+
+// block-wide exclusive scan of one int per thread; returns the exclusive prefix, `total` = block sum
+__device__ __forceinline__ int if_block_exclusive_scan(int v, int* scan /* IF_WARPS + 1 */, int& total) {
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  int inc = v;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, inc, o); if (lane >= o) inc += t; }
+  if (lane == 31) scan[w] = inc;
+  __syncthreads();
+  if (w == 0) {
+    const int ws = lane < IF_WARPS ? scan[lane] : 0;
+    int wi = ws;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(FULL, wi, o); if (lane >= o) wi += t; }
+    if (lane < IF_WARPS) scan[lane] = wi - ws;
+    if (lane == 31) scan[IF_WARPS] = wi;
+  }
+  __syncthreads();
+  const int r = scan[w] + inc - v;
+  total = scan[IF_WARPS];
+  __syncthreads();
+  return r;
+}
+
+__global__ void __launch_bounds__(IF_THREADS, 2) index_fused_kernel(IndexFusedArgs a) {
+  __shared__ float s_red[IF_WARPS][8];
+  __shared__ int s_scan[IF_WARPS + 1];
+  __shared__ GridShape s_gs;
+  __shared__ float s_lo[3], s_hi[3];
+  __shared__ int s_nfinite, s_carry;
+  __shared__ unsigned long long s_occ[IF_WARPS];
+  unsigned phase = 0;
+  const int G = gridDim.x, blk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int gtid = blk * IF_THREADS + tid, gstride = G * IF_THREADS;
+  const int n = a.n;
+
+  // ---- snapshot + bounding box of the finite points (pack_bbox_kernel) ----
+  {
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    int finite = 0;
+    for (int i = gtid; i < n; i += gstride) {
+      const float* r = reinterpret_cast<const float*>(a.raw + (size_t)i * a.stride);
+      float x, y, z;
+      if ((a.stride & 15) == 0) { const float4 v = *reinterpret_cast<const float4*>(r); x = v.x; y = v.y; z = v.z; }
+      else { x = r[0]; y = r[1]; z = r[2]; }
+      a.pts[i] = make_float4(x, y, z, 1.0f);
+      if (isfinite(x) && isfinite(y) && isfinite(z)) {
+        finite++;
+        mn[0] = fminf(mn[0], x); mn[1] = fminf(mn[1], y); mn[2] = fminf(mn[2], z);
+        mx[0] = fmaxf(mx[0], x); mx[1] = fmaxf(mx[1], y); mx[2] = fmaxf(mx[2], z);
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mn[c] = fminf(mn[c], __shfl_xor_sync(FULL, mn[c], o));
+        mx[c] = fmaxf(mx[c], __shfl_xor_sync(FULL, mx[c], o));
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) finite += __shfl_xor_sync(FULL, finite, o);
+    if (lane == 0) {
+#pragma unroll
+      for (int c = 0; c < 3; c++) { s_red[w][c] = mn[c]; s_red[w][3 + c] = mx[c]; }
+      s_red[w][6] = __int_as_float(finite);
+    }
+    __syncthreads();
+    if (tid == 0) {
+      for (int ww = 1; ww < IF_WARPS; ww++) {
+#pragma unroll
+        for (int c = 0; c < 3; c++) { mn[c] = fminf(mn[c], s_red[ww][c]); mx[c] = fmaxf(mx[c], s_red[ww][3 + c]); }
+        finite += __float_as_int(s_red[ww][6]);
+      }
+      float* p = a.part + (size_t)blk * 8;
+#pragma unroll
+      for (int c = 0; c < 3; c++) { p[c] = mn[c]; p[3 + c] = mx[c]; }
+      p[6] = __int_as_float(finite);
+    }
+  }
+  if_grid_barrier(a.bar, phase);
+
+  // ---- every block: the cloud's bounding box ----
+  if (w == 0) {
+    float mn[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, mx[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    int finite = 0;
+    for (int b = lane; b < G; b += 32) {
+      const float* p = a.part + (size_t)b * 8;
+#pragma unroll
+      for (int c = 0; c < 3; c++) { mn[c] = fminf(mn[c], __ldcg(p + c)); mx[c] = fmaxf(mx[c], __ldcg(p + 3 + c)); }
+      finite += __float_as_int(__ldcg(p + 6));
+    }
+#pragma unroll
+    for (int c = 0; c < 3; c++)
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        mn[c] = fminf(mn[c], __shfl_xor_sync(FULL, mn[c], o));
+        mx[c] = fmaxf(mx[c], __shfl_xor_sync(FULL, mx[c], o));
+      }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) finite += __shfl_xor_sync(FULL, finite, o);
+    if (lane == 0) {
+      // (bb_min / bb_max go through the order-preserving encoding in the multi-kernel path; decode(encode(x)) == x)
+      for (int c = 0; c < 3; c++) { s_lo[c] = mn[c]; s_hi[c] = mx[c]; }
+      s_nfinite = finite;
+      GridShape gs;
+      grid_shape_compute(s_lo, s_hi, finite, a.cell_req > 0.f ? a.cell_req : 1.0f, a.cell_req > 0.f ? a.table_cap : a.trial_cap, gs);
+      s_gs = gs;
+    }
+  }
+  __syncthreads();
+
+  if (!(a.cell_req > 0.f)) {
+    // ---- automatic cell edge: histogram of a 1 m trial grid, point-weighted occupancy (count_points / occupancy /
+    //      grid_autocell kernels) ----
+    {
+      const int total = s_gs.ncells + 2;
+      for (int i = gtid; i < total; i += gstride) a.table[i] = 0;
+    }
+    if_grid_barrier(a.bar, phase);
+    const float ox = s_gs.origin[0], oy = s_gs.origin[1], oz = s_gs.origin[2], inv = s_gs.inv_cell;
+    const int dx = s_gs.dim[0], dy = s_gs.dim[1], dz = s_gs.dim[2];
+    for (int i = gtid; i < n; i += gstride) {
+      const float4 p = a.pts[i];
+      const int cx = cell_coord(p.x, ox, inv, dx), cy = cell_coord(p.y, oy, inv, dy), cz = cell_coord(p.z, oz, inv, dz);
+      atomicAdd(&a.table[(cz * dy + cy) * dx + cx], 1);
+    }
+    if_grid_barrier(a.bar, phase);
+    unsigned long long so = 0ull;
+    for (int i = gtid; i < n; i += gstride) {
+      const float4 p = a.pts[i];
+      const int cx = cell_coord(p.x, ox, inv, dx), cy = cell_coord(p.y, oy, inv, dy), cz = cell_coord(p.z, oz, inv, dz);
+      so += (unsigned long long)__ldcg(&a.table[(cz * dy + cy) * dx + cx]);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) so += __shfl_xor_sync(FULL, so, o);
+    if (lane == 0) s_occ[w] = so;
+    __syncthreads();
+    if (tid == 0) {
+      for (int ww = 1; ww < IF_WARPS; ww++) so += s_occ[ww];
+      a.occ[blk] = so;
+    }
+    if_grid_barrier(a.bar, phase);
+    if (w == 0) {
+      unsigned long long t = 0ull;
+      for (int b = lane; b < G; b += 32) t += __ldcg(a.occ + b);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) t += __shfl_xor_sync(FULL, t, o);
+      if (lane == 0) {
+        float cell = 1.0f;
+        if (n > 0 && t > 0ull) {
+          const float occ = (float)((double)t / (double)n);
+          float f = sqrtf(a.target_occ / occ);
+          f = fminf(fmaxf(f, 0.125f), 2.0f);
+          cell = 1.0f * f;
+        }
+        GridShape gs;
+        grid_shape_compute(s_lo, s_hi, s_nfinite, cell, a.table_cap, gs);
+        s_gs = gs;
+      }
+    }
+    __syncthreads();
+  }
+  if (blk == 0 && tid == 0) {
+    GridDesc* d = a.d;
+    for (int c = 0; c < 3; c++) {
+      d->bb_min[c] = f2ord(s_lo[c]); d->bb_max[c] = f2ord(s_hi[c]);
+      d->origin[c] = s_gs.origin[c]; d->dim[c] = s_gs.dim[c];
+    }
+    d->cell = s_gs.cell; d->inv_cell = s_gs.inv_cell; d->ncells = s_gs.ncells; d->n = n;
+    d->max_dim = s_gs.max_dim; d->margin = s_gs.margin; d->occ_sq = 0ull;
+    d->nfinite = s_nfinite; d->vcount = 0; d->voverflow = 0;
+  }
+  const int ncells = s_gs.ncells;
+
+  // ---- zero the table, histogram of the cell keys (counts of cell c at table[c + 1]) ----
+  {
+    const int total = ncells + 2;
+    int4* t4 = reinterpret_cast<int4*>(a.table + 1);              // &table[1] is 16-byte aligned
+    const int n4 = (total - 1) >> 2;
+    for (int i = gtid; i < n4; i += gstride) t4[i] = make_int4(0, 0, 0, 0);
+    for (int i = 1 + (n4 << 2) + gtid; i < total; i += gstride) a.table[i] = 0;
+    if (gtid == 0) a.table[0] = 0;
+  }
+  if_grid_barrier(a.bar, phase);
+  {
+    const float ox = s_gs.origin[0], oy = s_gs.origin[1], oz = s_gs.origin[2], inv = s_gs.inv_cell;
+    const int dx = s_gs.dim[0], dy = s_gs.dim[1], dz = s_gs.dim[2];
+    for (int i = gtid; i < n; i += gstride) {
+      const float4 p = a.pts[i];
+      const int cx = cell_coord(p.x, ox, inv, dx), cy = cell_coord(p.y, oy, inv, dy), cz = cell_coord(p.z, oz, inv, dz);
+      const unsigned key = (unsigned)((cz * dy + cy) * dx + cx);
+      a.keys[i] = key;
+      atomicAdd(&a.table[key + 1], 1);
+    }
+  }
+  if_grid_barrier(a.bar, phase);
+
+  // ---- exclusive scan of table[1 .. ncells] (data = table + 1, length ncells): slice per block ----
+  int* data = a.table + 1;
+  const int slice = (((ncells + G - 1) / G) + 3) & ~3;             // multiple of four: aligned int4 access
+  const int s_lo_i = min(blk * slice, ncells), s_hi_i = min(s_lo_i + slice, ncells);
+  {
+    int sum = 0;
+    const int n4 = (s_hi_i - s_lo_i) >> 2;
+    const int4* d4 = reinterpret_cast<const int4*>(data + s_lo_i);
+    for (int i = tid; i < n4; i += IF_THREADS) { const int4 v = __ldcg(d4 + i); sum += (v.x + v.y) + (v.z + v.w); }
+    for (int i = s_lo_i + (n4 << 2) + tid; i < s_hi_i; i += IF_THREADS) sum += __ldcg(data + i);
+    int total;
+    if_block_exclusive_scan(sum, s_scan, total);
+    if (tid == 0) a.slice_sum[blk] = total;
+  }
+  if_grid_barrier(a.bar, phase);
+  {
+    int before = 0;
+    for (int b = tid; b < blk; b += IF_THREADS) before += __ldcg(a.slice_sum + b);
+    int carry;
+    if_block_exclusive_scan(before, s_scan, carry);
+    // the slice, 4 consecutive entries per thread and step, running carry across the steps
+    for (int base = s_lo_i; base < s_hi_i; base += IF_THREADS * 4) {
+      const int i = base + tid * 4;
+      int4 v = make_int4(0, 0, 0, 0);
+      if (i + 4 <= s_hi_i) v = __ldcg(reinterpret_cast<const int4*>(data + i));
+      else {
+        if (i < s_hi_i) v.x = __ldcg(data + i);
+        if (i + 1 < s_hi_i) v.y = __ldcg(data + i + 1);
+        if (i + 2 < s_hi_i) v.z = __ldcg(data + i + 2);
+      }
+      const int sum = (v.x + v.y) + (v.z + v.w);
+      int total;
+      const int off = carry + if_block_exclusive_scan(sum, s_scan, total);
+      const int4 o = make_int4(off, off + v.x, off + v.x + v.y, off + v.x + v.y + v.z);
+      if (i + 4 <= s_hi_i) *reinterpret_cast<int4*>(data + i) = o;
+      else {
+        if (i < s_hi_i) data[i] = o.x;
+        if (i + 1 < s_hi_i) data[i + 1] = o.y;
+        if (i + 2 < s_hi_i) data[i + 2] = o.z;
+      }
+      carry += total;
+    }
+  }
+  if_grid_barrier(a.bar, phase);
+
+  // ---- counting-sort scatter (table[c + 1]: start(c) -> start(c + 1)), then deterministic in-cell order + gather ----
+  for (int i = gtid; i < n; i += gstride) {
+    const int pos = atomicAdd(&a.table[__ldcg(a.keys + i) + 1], 1);
+    a.slot_orig[pos] = (unsigned)i;
+  }
+  if_grid_barrier(a.bar, phase);
+  for (int p = gtid; p < n; p += gstride) {
+    const unsigned o = __ldcg(a.slot_orig + p);
+    const unsigned key = __ldcg(a.keys + o);
+    const int ca = __ldcg(a.table + key), cb = __ldcg(a.table + key + 1);
+    int dst = p;
+    if (cb - ca <= ORDER_FIX_MAX) {
+      int rank = 0;
+      for (int j = ca; j < cb; ++j) rank += (__ldcg(a.slot_orig + j) < o) ? 1 : 0;
+      dst = ca + rank;
+    }
+    const float4 v = a.pts[o];
+    a.sorted[dst] = make_float4(v.x, v.y, v.z, __uint_as_float(o));
+  }
+  // leave the barrier words zeroed for the next launch: the last block to depart does it (nobody polls any more)
+  if (tid == 0 && atomicAdd(a.bar + 2, 1u) == gridDim.x - 1u) { a.bar[0] = 0u; a.bar[2] = 0u; }
+}
+
 static float auto_target_occupancy() {
   static float v = -1.f;
   if (v < 0.f) {
@@ -396,6 +711,86 @@ cudaError_t build_index(DevCloud& c, float cell_req, int table_cap, Scratch& sc,
   }
   c.indexed = true;
   return cudaGetLastError();
+}
+
+// upload_cloud + build_index in one cooperative launch (see index_fused_kernel); *done = false when the path does not
+// apply (empty cloud, no cooperative launch, NGICP_INDEX_FUSED=0) and the caller must take the two functions above
+cudaError_t upload_and_index_fused(DevCloud& c, const void* pts, size_t n, size_t stride_bytes, float cell_req, int table_cap, Scratch& sc,
+                                   const StreamPtr& st, int device, bool* done) {
+  *done = false;
+  static const bool fused_on = !(getenv("NGICP_INDEX_FUSED") && atoi(getenv("NGICP_INDEX_FUSED")) == 0);
+  if (!fused_on || n == 0 || sc.index_path == 1) return cudaSuccess;
+  static std::mutex mu;
+  static int max_blocks[64] = {};
+  const int di = device & 63;
+  {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!max_blocks[di]) {
+      int sms = 0, coop = 0, per_sm = 0;
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device);
+      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, index_fused_kernel, IF_THREADS, 0);
+      max_blocks[di] = (coop && sms > 0 && per_sm > 0) ? sms * (per_sm > 2 ? 2 : per_sm) : -1;
+      cudaGetLastError();
+    }
+  }
+  if (max_blocks[di] <= 0) return cudaSuccess;
+  cudaError_t e;
+  if (table_cap < 64) table_cap = 64;
+  c.n = (int)n;
+  c.indexed = false;
+  c.table_cap = table_cap;
+  if ((e = c.pts.alloc(sizeof(float4) * n, st)) != cudaSuccess) return e;
+  if ((e = c.desc.alloc(sizeof(GridDesc), st)) != cudaSuccess) return e;
+  if ((e = c.cell_start.acquire(sizeof(int) * ((size_t)table_cap + 8), device, st)) != cudaSuccess) return e;
+  if ((e = c.sorted.alloc(sizeof(float4) * n, st)) != cudaSuccess) return e;
+  const size_t raw_bytes = (n - 1) * stride_bytes + 12;
+  const unsigned char* raw = nullptr;
+  cudaPointerAttributes attr;
+  if (cudaPointerGetAttributes(&attr, pts) == cudaSuccess && (attr.type == cudaMemoryTypeDevice || attr.type == cudaMemoryTypeManaged) &&
+      (reinterpret_cast<uintptr_t>(pts) & 15) == 0 && (stride_bytes & 15) == 0 && stride_bytes >= 16) {
+    raw = static_cast<const unsigned char*>(pts);
+  } else {
+    cudaGetLastError();
+    if ((e = sc.staging.reserve(raw_bytes + 16, st)) != cudaSuccess) return e;
+    if ((e = cudaMemcpyAsync(sc.staging.p, pts, raw_bytes, cudaMemcpyDefault, st->s)) != cudaSuccess) return e;
+    if ((e = host_source_consumed(pts, sc, st->s)) != cudaSuccess) return e;
+    raw = sc.staging.as<unsigned char>();
+  }
+  int blocks = (int)((n + IF_THREADS - 1) / IF_THREADS);
+  if (blocks < 4) blocks = 4;
+  if (blocks > max_blocks[di]) blocks = max_blocks[di];
+  const size_t nb = sizeof(unsigned) * n;
+  if ((e = sc.keys_a.reserve(nb, st)) != cudaSuccess) return e;
+  if ((e = sc.vals_a.reserve(nb, st)) != cudaSuccess) return e;
+  if ((e = sc.tile_sums.reserve(sizeof(int) * (size_t)(blocks * 12 + 64), st)) != cudaSuccess) return e;
+  if (!sc.index_bar.p) {
+    if ((e = sc.index_bar.reserve(64, st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(sc.index_bar.p, 0, 64, st->s)) != cudaSuccess) return e;
+  }
+  IndexFusedArgs a;
+  a.raw = raw; a.stride = stride_bytes; a.n = (int)n;
+  a.pts = c.pts.as<float4>(); a.sorted = c.sorted.as<float4>(); a.table = c.cell_start.as<int>() + 3; a.d = c.desc.as<GridDesc>();
+  a.keys = sc.keys_a.as<unsigned>(); a.slot_orig = sc.vals_a.as<unsigned>();
+  int* ws = sc.tile_sums.as<int>();
+  a.part = reinterpret_cast<float*>(ws);                                    // [blocks][8]
+  a.occ = reinterpret_cast<unsigned long long*>(ws + (size_t)blocks * 8);   // [blocks] (8-byte aligned: blocks * 8 ints)
+  a.slice_sum = ws + (size_t)blocks * 10;                                   // [blocks]
+  a.bar = sc.index_bar.as<unsigned>();
+  a.cell_req = cell_req; a.target_occ = auto_target_occupancy(); a.table_cap = table_cap;
+  a.trial_cap = table_cap < (1 << 22) ? table_cap : (1 << 22);
+  void* kargs[] = {(void*)&a};
+  if ((e = cudaLaunchCooperativeKernel((const void*)index_fused_kernel, dim3(blocks), dim3(IF_THREADS), kargs, 0, st->s)) != cudaSuccess) return e;
+  note_launches(1);
+  c.indexed = true;
+  *done = true;
+  return cudaGetLastError();
+}
+
+void index_prime_kernels() {
+  cudaFuncAttributes fa;
+  cudaFuncGetAttributes(&fa, index_fused_kernel);
+  cudaGetLastError();
 }
 
 }  // namespace ngicp

@@ -104,6 +104,8 @@ struct Scratch {
   DevBuf flags;      // voxel head flags / scanned slots
   DevBuf vox_desc;   // GridDesc for the voxel filter
   DevBuf vox_bar;    // grid barrier words of the fused voxel kernel (zero between launches)
+  DevBuf index_bar;  // ... of the fused index kernel
+  int index_path = 0;  // ngicp_params::index_path of the owning handle (1 = multi-kernel upload + index build only)
   int vox_path = 0;             // ngicp_params::voxel_path of the owning handle (1 = multi-kernel pipeline only)
   int vox_bits_hint = 0;        // key bits the last voxel filter needed (0 = unknown): lets the next call queue its radix
                                 // passes without a mid-pipeline read-back of the grid dimensions
@@ -141,6 +143,9 @@ int radix_sort_pairs(unsigned* keys_a, unsigned* vals_a, unsigned* keys_b, unsig
 cudaError_t upload_cloud(DevCloud& c, const void* pts, size_t n, size_t stride_bytes, Scratch& sc, const StreamPtr& st);
 // build the uniform grid index of an uploaded cloud
 cudaError_t build_index(DevCloud& c, float cell_req, int table_cap, Scratch& sc, const StreamPtr& st, int device);
+// both of the above in one persistent cooperative launch; *done = false: not applicable, take the two calls
+cudaError_t upload_and_index_fused(DevCloud& c, const void* pts, size_t n, size_t stride_bytes, float cell_req, int table_cap, Scratch& sc,
+                                   const StreamPtr& st, int device, bool* done);
 
 // ---- knn_cov.cu -----------------------------------------------------------------------------------
 cudaError_t launch_knn_queries(const DevCloud& c, const float4* queries, int nq, int k, int* idx, float* d2, cudaStream_t st);
@@ -190,6 +195,7 @@ cudaError_t launch_align_batch(const void* pairs_dev, int n_pairs, int lpp, cuda
 void align_prime_kernels(int device);
 void knn_prime_kernels();
 void voxel_prime_kernels();
+void index_prime_kernels();
 
 // ---- voxel.cu -------------------------------------------------------------------------------------
 // returns cudaSuccess; *m_out and *overflow are valid after the call (it synchronises once to learn m)

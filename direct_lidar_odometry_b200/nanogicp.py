@@ -186,6 +186,11 @@ class NanoGICP:
         self._p.voxel_path = int(path)
         self._push_params()
 
+    def setIndexPath(self, path: int):
+        """setInputSource / setInputTarget: 0 = snapshot + index in one persistent cooperative launch, 1 = multi-kernel pipeline."""
+        self._p.index_path = int(path)
+        self._push_params()
+
     # ------------------------------------------------------------------ clouds
     def setInputSource(self, cloud):
         if self._input is cloud:  # pointer-identity early-out, nano_gicp_impl.hpp:122

@@ -229,6 +229,7 @@ class NanoGICP {
   void setAlignMode(int mode) { set_field(&ngicp_params::align_mode, mode); }
   void setKnnPath(int path) { set_field(&ngicp_params::knn_path, path); }
   void setVoxelPath(int path) { set_field(&ngicp_params::voxel_path, path); }
+  void setIndexPath(int path) { set_field(&ngicp_params::index_path, path); }
   void setFillOutputCloud(bool f) { fill_output_ = f; }
   ngicp_t* handle() const { return h(); }
 

@@ -85,6 +85,8 @@ typedef struct {
   int knn_tile_min_points;             /* NGICP_KNN_AUTO switches to the tile kernels at this cloud size (131072) */
   int voxel_path;                      /* voxel filter / preprocess: 0 = one persistent cooperative launch when the cloud fits
                                           (4096 points per SM), 1 = always the multi-kernel pipeline, 2 = as 0 */
+  int index_path;                      /* setInputSource / setInputTarget: 0 = snapshot + search index in one persistent cooperative
+                                          launch, 1 = the multi-kernel pipeline, 2 = as 0 */
 } ngicp_params;
 
 /* what pcl::Registration / LsqRegistration expose after align() */
