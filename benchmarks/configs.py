@@ -464,7 +464,13 @@ def c4_bench(local, rank, world, pairs=10000, wave=64, threads=8, sample_check=0
     for hs in handles:
         for h in hs:
             configure(h, S2S)
-            h.setKnnPath(_lib.KNN_TILE)      # throughput, not latency: the tile kernels need half the instructions per point
+            # Many handles share the GPU here, so what counts is launches per pair and how well the streams interleave, not
+            # the latency of one call.  Measured on one B200 (2000 pairs, 8 host threads, pairs/s): multi-kernel index +
+            # warp kNN 7436, fused index + warp kNN 6304, multi-kernel index + tile kNN 5462, fused + tile 2855 — a
+            # cooperative launch (the fused index) has to wait until all its blocks fit at once and holds up the other
+            # streams meanwhile, and the tile path needs ten small launches per cloud.  NGICP_C4_KNN / NGICP_C4_INDEX: A/B.
+            h.setKnnPath(_lib.KNN_TILE if os.environ.get("NGICP_C4_KNN") == "tile" else _lib.KNN_WARP)
+            h.setIndexPath(0 if os.environ.get("NGICP_C4_INDEX") == "fused" else 1)
     offs = list(range(len(mine)))
     c4_run(handles, scans, offs[:2 * wave], wave, threads)      # warm-up (both handle sets)
     torch.cuda.synchronize()

@@ -427,13 +427,22 @@ class NanoGICP:
         return out1
 
     # ------------------------------------------------------------------ pcl::VoxelGrid
+    def _host_records(self, n: int) -> np.ndarray:
+        """Reusable host landing buffer for (n, 8) float32 records: a fresh np.zeros per call costs more than the whole
+        device pipeline (1.7 MB of page faults for a 53k-point scan); callers get a copy of the m rows that were written."""
+        buf = getattr(self, "_rec_buf", None)
+        if buf is None or buf.shape[0] < max(n, 1):
+            buf = np.empty((max(n + n // 4, 1024), 8), dtype=np.float32)
+            self._rec_buf = buf
+        return buf
+
     def voxel_filter(self, cloud, leaf: float, out=None, return_status: bool = False):
         """pcl::VoxelGrid<PointXYZI> with leaf (l,l,l): returns (m,8) float32 records (numpy unless `out`
         is a preallocated CUDA tensor of shape (>=n,8), in which case a view of it is returned)."""
         p, n, st, keep = _ptr_n_stride(cloud)
         m = C.c_size_t(0)
         if out is None:
-            buf = np.zeros((max(n, 1), 8), dtype=np.float32)
+            buf = self._host_records(n)
             optr, cap = buf.ctypes.data, buf.shape[0]
         else:
             buf = out
@@ -450,7 +459,7 @@ class NanoGICP:
         p, n, st, keep = _ptr_n_stride(cloud)
         m = C.c_size_t(0)
         if out is None:
-            buf = np.zeros((max(n, 1), 8), dtype=np.float32)
+            buf = self._host_records(n)
             optr, cap = buf.ctypes.data, buf.shape[0]
         else:
             buf = out
@@ -479,7 +488,7 @@ class NanoGICP:
             data_ptr = keep.ctypes.data if keep.size else None
         m = C.c_size_t(0)
         if out is None:
-            buf = np.zeros((max(n, 1), 8), dtype=np.float32)
+            buf = self._host_records(n)
             optr, cap = buf.ctypes.data, buf.shape[0]
         else:
             buf = out
@@ -499,7 +508,7 @@ class NanoGICP:
         p, n, st, keep = _ptr_n_stride(cloud)
         m = C.c_size_t(0)
         if out is None:
-            buf = np.zeros((max(n, 1), 8), dtype=np.float32)
+            buf = self._host_records(n)
             optr, cap = buf.ctypes.data, buf.shape[0]
         else:
             buf = out
