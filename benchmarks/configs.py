@@ -470,7 +470,7 @@ def c4_bench(local, rank, world, pairs=10000, wave=64, threads=8, sample_check=0
             # cooperative launch (the fused index) has to wait until all its blocks fit at once and holds up the other
             # streams meanwhile, and the tile path needs ten small launches per cloud.  NGICP_C4_KNN / NGICP_C4_INDEX: A/B.
             h.setKnnPath(_lib.KNN_TILE if os.environ.get("NGICP_C4_KNN") == "tile" else _lib.KNN_WARP)
-            h.setIndexPath(0 if os.environ.get("NGICP_C4_INDEX") == "fused" else 1)
+            h.setIndexPath({"fused": 0, "multi": 1, "cluster": 3}[os.environ.get("NGICP_C4_INDEX", "cluster")])
     offs = list(range(len(mine)))
     c4_run(handles, scans, offs[:2 * wave], wave, threads)      # warm-up (both handle sets)
     torch.cuda.synchronize()

@@ -604,7 +604,7 @@ int ngicp_set_params(ngicp_t* h, const ngicp_params* p) {
   if (p->grid_table_cells < 64) return fail(h, NGICP_E_INVALID, "grid_table_cells too small");
   if (p->knn_path < NGICP_KNN_AUTO || p->knn_path > NGICP_KNN_TILE) return fail(h, NGICP_E_INVALID, "unknown knn_path");
   if (p->voxel_path < 0 || p->voxel_path > 2) return fail(h, NGICP_E_INVALID, "unknown voxel_path");
-  if (p->index_path < 0 || p->index_path > 2) return fail(h, NGICP_E_INVALID, "unknown index_path");
+  if (p->index_path < 0 || p->index_path > 3) return fail(h, NGICP_E_INVALID, "unknown index_path");
   if (p->align_mode != NGICP_ALIGN_FUSED && p->align_mode != NGICP_ALIGN_STEPPED) return fail(h, NGICP_E_INVALID, "unknown align_mode");
   if (p->optimizer != NGICP_OPT_GAUSS_NEWTON && p->optimizer != NGICP_OPT_LEVENBERG_MARQUARDT) return fail(h, NGICP_E_INVALID, "unknown optimizer");
   h->prm = *p;

@@ -15,6 +15,8 @@
 #include <cstdio>
 #include <ctime>
 #include <cstdint>
+#include <cstring>
+#include <cooperative_groups.h>
 #include "internal.h"
 
 namespace ngicp {
@@ -413,15 +415,25 @@ __device__ __forceinline__ int if_block_exclusive_scan(int v, int* scan /* IF_WA
   return r;
 }
 
-__global__ void __launch_bounds__(IF_THREADS, 2) index_fused_kernel(IndexFusedArgs a) {
+// BAR: grid barrier of the cooperative launch (GridBar) or hardware barrier of a thread-block cluster (ClusterBar: one
+// cluster of IF_CLUSTER blocks builds one small cloud — an ordinary launch, which many streams can interleave)
+struct GridBar {
+  unsigned* bar; unsigned phase;
+  __device__ __forceinline__ void sync() { if_grid_barrier(bar, phase); }
+};
+struct ClusterBar {
+  __device__ __forceinline__ void sync() { __threadfence(); cooperative_groups::this_cluster().sync(); }
+};
+constexpr int IF_CLUSTER = 8;
+template <class BAR>
+__device__ __forceinline__ void index_fused_body(const IndexFusedArgs& a, const int G, const int blk, BAR& bar) {
   __shared__ float s_red[IF_WARPS][8];
   __shared__ int s_scan[IF_WARPS + 1];
   __shared__ GridShape s_gs;
   __shared__ float s_lo[3], s_hi[3];
   __shared__ int s_nfinite, s_carry;
   __shared__ unsigned long long s_occ[IF_WARPS];
-  unsigned phase = 0;
-  const int G = gridDim.x, blk = blockIdx.x, tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+  const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int gtid = blk * IF_THREADS + tid, gstride = G * IF_THREADS;
   const int n = a.n;
 
@@ -468,7 +480,7 @@ __global__ void __launch_bounds__(IF_THREADS, 2) index_fused_kernel(IndexFusedAr
       p[6] = __int_as_float(finite);
     }
   }
-  if_grid_barrier(a.bar, phase);
+  bar.sync();
 
   // ---- every block: the cloud's bounding box ----
   if (w == 0) {
@@ -507,7 +519,7 @@ __global__ void __launch_bounds__(IF_THREADS, 2) index_fused_kernel(IndexFusedAr
       const int total = s_gs.ncells + 2;
       for (int i = gtid; i < total; i += gstride) a.table[i] = 0;
     }
-    if_grid_barrier(a.bar, phase);
+    bar.sync();
     const float ox = s_gs.origin[0], oy = s_gs.origin[1], oz = s_gs.origin[2], inv = s_gs.inv_cell;
     const int dx = s_gs.dim[0], dy = s_gs.dim[1], dz = s_gs.dim[2];
     for (int i = gtid; i < n; i += gstride) {
@@ -515,7 +527,7 @@ __global__ void __launch_bounds__(IF_THREADS, 2) index_fused_kernel(IndexFusedAr
       const int cx = cell_coord(p.x, ox, inv, dx), cy = cell_coord(p.y, oy, inv, dy), cz = cell_coord(p.z, oz, inv, dz);
       atomicAdd(&a.table[(cz * dy + cy) * dx + cx], 1);
     }
-    if_grid_barrier(a.bar, phase);
+    bar.sync();
     unsigned long long so = 0ull;
     for (int i = gtid; i < n; i += gstride) {
       const float4 p = a.pts[i];
@@ -530,7 +542,7 @@ __global__ void __launch_bounds__(IF_THREADS, 2) index_fused_kernel(IndexFusedAr
       for (int ww = 1; ww < IF_WARPS; ww++) so += s_occ[ww];
       a.occ[blk] = so;
     }
-    if_grid_barrier(a.bar, phase);
+    bar.sync();
     if (w == 0) {
       unsigned long long t = 0ull;
       for (int b = lane; b < G; b += 32) t += __ldcg(a.occ + b);
@@ -572,7 +584,7 @@ __global__ void __launch_bounds__(IF_THREADS, 2) index_fused_kernel(IndexFusedAr
     for (int i = 1 + (n4 << 2) + gtid; i < total; i += gstride) a.table[i] = 0;
     if (gtid == 0) a.table[0] = 0;
   }
-  if_grid_barrier(a.bar, phase);
+  bar.sync();
   {
     const float ox = s_gs.origin[0], oy = s_gs.origin[1], oz = s_gs.origin[2], inv = s_gs.inv_cell;
     const int dx = s_gs.dim[0], dy = s_gs.dim[1], dz = s_gs.dim[2];
@@ -584,7 +596,7 @@ __global__ void __launch_bounds__(IF_THREADS, 2) index_fused_kernel(IndexFusedAr
       atomicAdd(&a.table[key + 1], 1);
     }
   }
-  if_grid_barrier(a.bar, phase);
+  bar.sync();
 
   // ---- exclusive scan of table[1 .. ncells] (data = table + 1, length ncells): slice per block ----
   int* data = a.table + 1;
@@ -600,7 +612,7 @@ __global__ void __launch_bounds__(IF_THREADS, 2) index_fused_kernel(IndexFusedAr
     if_block_exclusive_scan(sum, s_scan, total);
     if (tid == 0) a.slice_sum[blk] = total;
   }
-  if_grid_barrier(a.bar, phase);
+  bar.sync();
   {
     int before = 0;
     for (int b = tid; b < blk; b += IF_THREADS) before += __ldcg(a.slice_sum + b);
@@ -629,14 +641,14 @@ __global__ void __launch_bounds__(IF_THREADS, 2) index_fused_kernel(IndexFusedAr
       carry += total;
     }
   }
-  if_grid_barrier(a.bar, phase);
+  bar.sync();
 
   // ---- counting-sort scatter (table[c + 1]: start(c) -> start(c + 1)), then deterministic in-cell order + gather ----
   for (int i = gtid; i < n; i += gstride) {
     const int pos = atomicAdd(&a.table[__ldcg(a.keys + i) + 1], 1);
     a.slot_orig[pos] = (unsigned)i;
   }
-  if_grid_barrier(a.bar, phase);
+  bar.sync();
   for (int p = gtid; p < n; p += gstride) {
     const unsigned o = __ldcg(a.slot_orig + p);
     const unsigned key = __ldcg(a.keys + o);
@@ -650,8 +662,20 @@ __global__ void __launch_bounds__(IF_THREADS, 2) index_fused_kernel(IndexFusedAr
     const float4 v = a.pts[o];
     a.sorted[dst] = make_float4(v.x, v.y, v.z, __uint_as_float(o));
   }
+}
+
+__global__ void __launch_bounds__(IF_THREADS, 2) index_fused_kernel(IndexFusedArgs a) {
+  GridBar bar;
+  bar.bar = a.bar; bar.phase = 0;
+  index_fused_body(a, (int)gridDim.x, (int)blockIdx.x, bar);
   // leave the barrier words zeroed for the next launch: the last block to depart does it (nobody polls any more)
-  if (tid == 0 && atomicAdd(a.bar + 2, 1u) == gridDim.x - 1u) { a.bar[0] = 0u; a.bar[2] = 0u; }
+  if (threadIdx.x == 0 && atomicAdd(a.bar + 2, 1u) == gridDim.x - 1u) { a.bar[0] = 0u; a.bar[2] = 0u; }
+}
+// one cluster = one cloud (grid = IF_CLUSTER blocks)
+__global__ void __launch_bounds__(IF_THREADS, 2) index_cluster_kernel(IndexFusedArgs a) {
+  ClusterBar bar;
+  index_fused_body(a, IF_CLUSTER, (int)cooperative_groups::this_cluster().block_rank(), bar);
+  cooperative_groups::this_cluster().sync();     // no block of the cluster exits while another may still need it resident
 }
 
 static float auto_target_occupancy() {
@@ -757,9 +781,13 @@ cudaError_t upload_and_index_fused(DevCloud& c, const void* pts, size_t n, size_
     if ((e = host_source_consumed(pts, sc, st->s)) != cudaSuccess) return e;
     raw = sc.staging.as<unsigned char>();
   }
+  // index_path 3: one thread-block cluster per cloud (ordinary launch: many handles / streams interleave; a cooperative
+  // launch must wait until all its blocks fit at once and holds the other streams up meanwhile); clouds up to 128k points
+  const bool cluster = sc.index_path == 3 && n <= 131072;
   int blocks = (int)((n + IF_THREADS - 1) / IF_THREADS);
   if (blocks < 4) blocks = 4;
   if (blocks > max_blocks[di]) blocks = max_blocks[di];
+  if (cluster) blocks = IF_CLUSTER;
   const size_t nb = sizeof(unsigned) * n;
   if ((e = sc.keys_a.reserve(nb, st)) != cudaSuccess) return e;
   if ((e = sc.vals_a.reserve(nb, st)) != cudaSuccess) return e;
@@ -780,7 +808,21 @@ cudaError_t upload_and_index_fused(DevCloud& c, const void* pts, size_t n, size_
   a.cell_req = cell_req; a.target_occ = auto_target_occupancy(); a.table_cap = table_cap;
   a.trial_cap = table_cap < (1 << 22) ? table_cap : (1 << 22);
   void* kargs[] = {(void*)&a};
-  if ((e = cudaLaunchCooperativeKernel((const void*)index_fused_kernel, dim3(blocks), dim3(IF_THREADS), kargs, 0, st->s)) != cudaSuccess) return e;
+  if (cluster) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof cfg);
+    cfg.gridDim = dim3(IF_CLUSTER);
+    cfg.blockDim = dim3(IF_THREADS);
+    cfg.stream = st->s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = IF_CLUSTER; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    if ((e = cudaLaunchKernelEx(&cfg, index_cluster_kernel, a)) != cudaSuccess) return e;
+  } else {
+    if ((e = cudaLaunchCooperativeKernel((const void*)index_fused_kernel, dim3(blocks), dim3(IF_THREADS), kargs, 0, st->s)) != cudaSuccess) return e;
+  }
   note_launches(1);
   c.indexed = true;
   *done = true;
@@ -790,6 +832,7 @@ cudaError_t upload_and_index_fused(DevCloud& c, const void* pts, size_t n, size_
 void index_prime_kernels() {
   cudaFuncAttributes fa;
   cudaFuncGetAttributes(&fa, index_fused_kernel);
+  cudaFuncGetAttributes(&fa, index_cluster_kernel);
   cudaGetLastError();
 }
 

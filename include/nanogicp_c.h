@@ -86,7 +86,9 @@ typedef struct {
   int voxel_path;                      /* voxel filter / preprocess: 0 = one persistent cooperative launch when the cloud fits
                                           (4096 points per SM), 1 = always the multi-kernel pipeline, 2 = as 0 */
   int index_path;                      /* setInputSource / setInputTarget: 0 = snapshot + search index in one persistent cooperative
-                                          launch, 1 = the multi-kernel pipeline, 2 = as 0 */
+                                          launch (lowest latency for one stream), 1 = the multi-kernel pipeline, 2 = as 0,
+                                          3 = one thread-block cluster per cloud (ordinary launch: best when many handles share
+                                          the GPU; clouds above 128k points take 0) */
 } ngicp_params;
 
 /* what pcl::Registration / LsqRegistration expose after align() */

@@ -139,13 +139,13 @@ def test_voxel_filter_fused_and_multi_kernel_paths(G, O, scan_pair, path):
 @pytest.mark.parametrize("cell", [0.0, 0.7])
 def test_index_fused_and_multi_kernel_paths_identical(G, O, scan_pair, vox_pair, cell):
     """ngicp_params::index_path: 0 = snapshot + search index in one persistent cooperative launch, 1 = the multi-kernel
-    pipeline.  Same grid (automatic or given cell edge), same sorted order, hence bit-identical kNN answers, covariances
+    pipeline, 3 = one thread-block cluster per cloud.  Same grid (automatic or given cell edge), same sorted order, hence bit-identical kNN answers, covariances
     and registration — on a voxelised scan, on the raw scan (53k points), with NaNs, one point and an empty cloud."""
     v0, v1 = vox_pair
     s0 = scan_pair["s0"]
     dirty = s0[:6000].copy(); dirty[::13, 1] = np.nan
     res = []
-    for path in (1, 0):
+    for path in (1, 0, 3):
         g = G()
         g.setIndexPath(path)
         if cell > 0:
@@ -165,16 +165,17 @@ def test_index_fused_and_multi_kernel_paths_identical(G, O, scan_pair, vox_pair,
         out["iters"] = g.result.nr_iterations
         g.setInputTarget(s0[:1]); g.setInputSource(np.zeros((0, 8), np.float32))
         res.append(out)
-    a, b = res
-    for key in a:
-        if key.endswith("_grid"):
-            assert a[key] == b[key], key
-        elif key.endswith("_knn"):
-            assert np.array_equal(a[key][0], b[key][0]) and np.array_equal(bits(a[key][1]), bits(b[key][1])), key
-        elif key == "iters":
-            assert a[key] == b[key]
-        else:
-            assert np.array_equal(np.ascontiguousarray(a[key]).view(np.uint64), np.ascontiguousarray(b[key]).view(np.uint64)), key
+    a = res[0]
+    for b in res[1:]:
+      for key in a:
+          if key.endswith("_grid"):
+              assert a[key] == b[key], key
+          elif key.endswith("_knn"):
+              assert np.array_equal(a[key][0], b[key][0]) and np.array_equal(bits(a[key][1]), bits(b[key][1])), key
+          elif key == "iters":
+              assert a[key] == b[key]
+          else:
+              assert np.array_equal(np.ascontiguousarray(a[key]).view(np.uint64), np.ascontiguousarray(b[key]).view(np.uint64)), key
 
 
 def test_preprocess_fused_crop_nan_voxel(G, O, scan_pair):
