@@ -237,6 +237,68 @@ __global__ void __launch_bounds__(AL_THREADS) compute_error_kernel(AlignArgs a, 
   block_reduce_store<1>(acc, s_red, a.partials + (size_t)blockIdx.x * NRED);
 }
 
+// ------------------------------------------------------------------------------------------
+// sharded submap with an UNBOUNDED correspondence distance (the library default corr_dist_threshold_ = FLT_MAX,
+// nano_gicp_impl.hpp:59): slabs + halo are only exact for a finite distance, so the ranks exchange the nearest
+// neighbours themselves — every rank finds the nearest point of ITS part of the target for every source point and
+// packs (bits of the squared distance) << 32 | rank; a min-all-reduce over the ranks names the rank that holds the global
+// nearest neighbour (non-negative floats order like their bit patterns; equal distances go to the lowest rank), and
+// that rank alone adds the point's H / b / error terms (fallback row).
+// ------------------------------------------------------------------------------------------
+constexpr unsigned long long NN1_NONE = 0x7f800000ffffffffull;   // +inf distance: loses against every real neighbour
+
+__global__ void __launch_bounds__(AL_THREADS) nn1_packed_kernel(AlignArgs a, IsoArg T, float cap_d2, double thr2, unsigned rank,
+                                                                 unsigned long long* __restrict__ out) {
+  const GridParams gp = load_grid(a.tgt.desc);
+  XformF Tf;
+  make_xforms(T.x, Tf);
+  // one WARP per source point: the growing-cube search of the registration tail, from scratch (a source point may lie
+  // far outside this rank's part of the target: the search has to be able to cross empty space)
+  const int lane = threadIdx.x & 31;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const bool any_target = a.tgt.desc->n > 0;
+  for (int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5; i < a.ns; i += nwarps) {
+    const float4 p = __ldg(a.src_pts + i);
+    const float qx = xform_row(Tf.m + 0, p.x, p.y, p.z), qy = xform_row(Tf.m + 4, p.x, p.y, p.z), qz = xform_row(Tf.m + 8, p.x, p.y, p.z);
+    WarpBest1 rs;
+    rs.init();
+    if (isfinite(qx) && isfinite(qy) && isfinite(qz) && any_target) {
+      grid_search_warp<WarpBest1, true, 4>(a.tgt, gp, qx, qy, qz, cap_d2, rs, true);
+      rs.finalize();
+    }
+    if (lane == 0) {
+      const bool hit = rs.p >= 0 && (double)rs.d < thr2;
+      a.corr[i] = hit ? rs.p : -1;          // parked for linearize_won_kernel: the SORTED SLOT, not yet the original index
+      a.sqd[i] = rs.d;
+      out[i] = hit ? (((unsigned long long)__float_as_uint(rs.d) << 32) | (unsigned long long)rank) : NN1_NONE;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(AL_THREADS) linearize_won_kernel(AlignArgs a, IsoArg T, double thr2, unsigned rank,
+                                                                    const unsigned long long* __restrict__ won) {
+  __shared__ double s_red[AL_WARPS][NRED];
+  double wtot = 0.0;
+  const int npass = (a.ns + gridDim.x * blockDim.x - 1) / (gridDim.x * blockDim.x);      // block-uniform trip count
+  for (int pass = 0; pass < npass; ++pass) {
+    const int i = (pass * gridDim.x + blockIdx.x) * blockDim.x + threadIdx.x;
+    double contrib[NRED];
+#pragma unroll
+    for (int j = 0; j < NRED; j++) contrib[j] = 0.0;
+    if (i < a.ns) {
+      const int slot = a.corr[i];
+      const float d = a.sqd[i];
+      const unsigned long long w = won[i];
+      const bool mine = slot >= 0 && (unsigned)(w & 0xffffffffull) == rank && (unsigned)(w >> 32) == __float_as_uint(d);
+      if (mine) finish_point(a, T.x, thr2, i, __ldg(a.src_pts + i), d, slot, contrib);
+      else a.corr[i] = -1;
+    }
+    wtot += warp_sum_transposed<NRED>(contrib);
+  }
+  double acc[1] = {wtot};
+  block_reduce_store<NRED>(acc, s_red, a.partials + (size_t)blockIdx.x * NRED);
+}
+
 __global__ void reduce_partials_kernel(const double* __restrict__ partials, int nblocks, int nv, double* __restrict__ out) {
   const int t = threadIdx.x;
   if (t < nv) {
@@ -275,6 +337,30 @@ cudaError_t launch_linearize(const AlignBuffers& ab, const double* T16, double m
   IsoArg T;
   iso_from_colmajor16(T16, T.x);
   linearize_kernel<<<blocks, AL_THREADS, 0, st>>>(a, T, cap_from(max_corr_dist), max_corr_dist * max_corr_dist);
+  reduce_partials_kernel<<<1, 32, 0, st>>>(a.partials, blocks, NRED, ab.reduced);
+  note_launches(2);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_nn1_packed(const AlignBuffers& ab, const double* T16, double max_corr_dist, unsigned rank, unsigned long long* out, cudaStream_t st) {
+  int blocks = (ab.ns + AL_WARPS - 1) / AL_WARPS;       // one warp per source point
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  AlignArgs a = make_args(ab, blocks);
+  IsoArg T;
+  iso_from_colmajor16(T16, T.x);
+  nn1_packed_kernel<<<blocks, AL_THREADS, 0, st>>>(a, T, cap_from(max_corr_dist), max_corr_dist * max_corr_dist, rank, out);
+  note_launches(1);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_linearize_won(const AlignBuffers& ab, const double* T16, double max_corr_dist, unsigned rank, const unsigned long long* won,
+                                 cudaStream_t st) {
+  const int blocks = stepped_blocks(ab);
+  AlignArgs a = make_args(ab, blocks);
+  IsoArg T;
+  iso_from_colmajor16(T16, T.x);
+  linearize_won_kernel<<<blocks, AL_THREADS, 0, st>>>(a, T, max_corr_dist * max_corr_dist, rank, won);
   reduce_partials_kernel<<<1, 32, 0, st>>>(a.partials, blocks, NRED, ab.reduced);
   note_launches(2);
   return cudaGetLastError();

@@ -967,6 +967,42 @@ int ngicp_linearize_partial(ngicp_t* h, const double* T16, double* out43) {
   return NGICP_OK;
 }
 
+int ngicp_nn1_packed(ngicp_t* h, const double* T16, unsigned rank, unsigned long long* packed_out) {
+  if (!h || !T16 || !packed_out) return NGICP_E_INVALID;
+  DeviceGuard g(h->device);
+  AlignBuffers ab;
+  int rc = prepare_align(h, false, ab);
+  if (rc) return rc;
+  const size_t ns = (size_t)ab.ns;
+  NG_CUDA(h, h->sc.nn1_packed.reserve(sizeof(unsigned long long) * (ns ? ns : 1), h->stream));
+  NG_CUDA(h, launch_nn1_packed(ab, T16, h->prm.max_correspondence_distance, rank, h->sc.nn1_packed.as<unsigned long long>(), h->stream->s));
+  NG_CUDA(h, cudaMemcpyAsync(packed_out, h->sc.nn1_packed.p, sizeof(unsigned long long) * ns, cudaMemcpyDefault, h->stream->s));
+  NG_CUDA(h, cudaStreamSynchronize(h->stream->s));
+  h->lin_valid = false;
+  return NGICP_OK;
+}
+
+int ngicp_linearize_won(ngicp_t* h, const double* T16, unsigned rank, const unsigned long long* packed_min, double* out43) {
+  if (!h || !T16 || !packed_min || !out43) return NGICP_E_INVALID;
+  DeviceGuard g(h->device);
+  AlignBuffers ab;
+  int rc = prepare_align(h, false, ab);
+  if (rc) return rc;
+  const size_t ns = (size_t)ab.ns;
+  NG_CUDA(h, h->sc.nn1_won.reserve(sizeof(unsigned long long) * (ns ? ns : 1), h->stream));
+  NG_CUDA(h, cudaMemcpyAsync(h->sc.nn1_won.p, packed_min, sizeof(unsigned long long) * ns, cudaMemcpyDefault, h->stream->s));
+  NG_CUDA(h, launch_linearize_won(ab, T16, h->prm.max_correspondence_distance, rank, h->sc.nn1_won.as<unsigned long long>(), h->stream->s));
+  rc = fetch_reduced(h, NRED);
+  if (rc) return rc;
+  double tmp[43];
+  unpack_H(h->red_pinned, tmp);
+  for (int i = 0; i < 6; i++) tmp[36 + i] = h->red_pinned[21 + i];
+  tmp[42] = h->red_pinned[27];
+  NG_CUDA(h, cudaMemcpy(out43, tmp, sizeof tmp, cudaMemcpyDefault));
+  h->lin_valid = true;
+  return NGICP_OK;
+}
+
 int ngicp_linearize(ngicp_t* h, const double* T16, double* H36, double* b6, double* err, int* corr, float* sqd, double* mahal) {
   if (!h || !T16) return NGICP_E_INVALID;
   double tmp[43];

@@ -111,6 +111,7 @@ struct Scratch {
                                 // passes without a mid-pipeline read-back of the grid dimensions
   int* vox_result = nullptr;    // mapped pinned {m, overflow, key bits needed}: written by the pipeline's last kernel
   int* vox_result_dev = nullptr;
+  DevBuf nn1_packed, nn1_won;   // min-exchange mode of the sharded submap (ngicp_nn1_packed / ngicp_linearize_won)
   DevBuf vox_out;    // PointXYZI records
   DevBuf vox_slot;   // int per input point
   DevBuf knn_idx, knn_d2, queries;
@@ -167,6 +168,9 @@ struct AlignBuffers {
 };
 // one linearisation at T (row-major R + t as Iso3 passed by value inside); reduced[0..NRED) <- packed H,b,err
 cudaError_t launch_linearize(const AlignBuffers& ab, const double* T16_colmajor, double max_corr_dist, cudaStream_t st);
+cudaError_t launch_nn1_packed(const AlignBuffers& ab, const double* T16, double max_corr_dist, unsigned rank, unsigned long long* out, cudaStream_t st);
+cudaError_t launch_linearize_won(const AlignBuffers& ab, const double* T16, double max_corr_dist, unsigned rank, const unsigned long long* won,
+                                 cudaStream_t st);
 cudaError_t launch_compute_error(const AlignBuffers& ab, const double* T16_colmajor, cudaStream_t st);
 cudaError_t launch_export_mahal(const AlignBuffers& ab, double* out16, cudaStream_t st);
 // sharded-submap mode: where every rank's exchange buffer is mapped in this process (see align.cu, peer_exchange_sum)

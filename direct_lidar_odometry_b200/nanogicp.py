@@ -418,6 +418,24 @@ class NanoGICP:
         self._check(self._L.ngicp_linearize_partial(self._h, Tc.ctypes.data_as(C.POINTER(C.c_double)), ptr))
         return out43
 
+    def nn1_packed(self, T, rank: int) -> np.ndarray:
+        """Every source point's nearest neighbour in THIS handle's target under T as (float bits of d^2) << 32 | rank
+        (uint64; 0x7f800000ffffffff = none within the max-correspondence distance) — ngicp_nn1_packed."""
+        Tc = _mat_to_abi(T, np.float64)
+        n = int(self._L.ngicp_cloud_size(self._h, _lib.SOURCE))
+        out = np.zeros(max(n, 1), dtype=np.uint64)
+        self._check(self._L.ngicp_nn1_packed(self._h, Tc.ctypes.data_as(C.POINTER(C.c_double)), int(rank), out.ctypes.data))
+        return out[:n]
+
+    def linearize_won(self, T, rank: int, packed_min: np.ndarray) -> np.ndarray:
+        """{H(36, col-major), b(6), err} over the source points whose global nearest neighbour this rank holds
+        (packed_min = element-wise minimum of all ranks' nn1_packed arrays) — ngicp_linearize_won."""
+        Tc = _mat_to_abi(T, np.float64)
+        pm = np.ascontiguousarray(packed_min, dtype=np.uint64)
+        out43 = np.zeros(43)
+        self._check(self._L.ngicp_linearize_won(self._h, Tc.ctypes.data_as(C.POINTER(C.c_double)), int(rank), pm.ctypes.data, out43.ctypes.data))
+        return out43
+
     def compute_error_partial(self, T, out1=None):
         Tc = _mat_to_abi(T, np.float64)
         if out1 is None:

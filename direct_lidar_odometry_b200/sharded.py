@@ -155,6 +155,20 @@ class CudaShardBackend:
     def linearize_partial(self, T) -> np.ndarray:
         return self.g.linearize_partial(T)
 
+    # -- min-exchange mode (unbounded correspondence distance): the ranks exchange nearest neighbours -------------
+    def set_target_part(self, pts, covs):
+        """This rank's PART of the target (any partition: no halo, no ownership by position)."""
+        self.g.clearTarget()
+        self.g.setInputTarget(pts)
+        self.g.setTargetCovariances(covs)
+        self.g.set_owner_slab(-1)
+
+    def nn1_packed(self, T, rank: int) -> np.ndarray:
+        return self.g.nn1_packed(T, rank)
+
+    def linearize_won(self, T, rank: int, packed_min: np.ndarray) -> np.ndarray:
+        return self.g.linearize_won(T, rank, packed_min)
+
     # -- exchange fused into the persistent LM kernel (NVLink peer memory; include/nanogicp_c.h ngicp_comm_*) -----
     def connect_fused(self, rank: int, world: int, group=None):
         """One process per GPU: swap CUDA IPC handles of the exchange buffers over the process group, map them."""
@@ -187,8 +201,17 @@ class ShardedSubmapAligner:
     """Host-stepped LM over a target sharded across the ranks of a torch.distributed process group."""
 
     def __init__(self, backend, max_corr_dist: float, max_iter: int = 64, trans_eps: float = 5e-4, rot_eps: float = 2e-3,
-                 lm_max_iter: int = 10, lm_init_lambda_factor: float = 1e-9, group=None, device=None):
+                 lm_max_iter: int = 10, lm_init_lambda_factor: float = 1e-9, group=None, device=None, exchange: str = "auto",
+                 rank: int = 0):
+        """exchange: "slab" — ownership by slab + halo of the max-correspondence distance, one sum-all-reduce of 43 doubles per
+        linearisation (exact for a FINITE distance); "min" — the ranks hold any partition of the target and exchange the
+        nearest neighbours themselves: one min-all-reduce of n_source packed (distance, rank) words, then the sum (exact for
+        any distance, the only exact way for the library default FLT_MAX, reference nano_gicp_impl.hpp:59); "auto" takes
+        "min" when the distance is unbounded."""
         self.be = backend
+        if exchange == "auto":
+            exchange = "min" if not np.isfinite(max_corr_dist) or max_corr_dist >= 1e18 else "slab"
+        self.exchange, self.rank = exchange, int(rank)
         self.max_corr_dist = max_corr_dist
         self.max_iter, self.trans_eps, self.rot_eps = max_iter, trans_eps, rot_eps
         self.lm_max_iter, self.lm_init_lambda_factor = lm_max_iter, lm_init_lambda_factor
@@ -222,7 +245,23 @@ class ShardedSubmapAligner:
         return bool(self._L.ngicp_lm_is_converged(dc.ctypes.data_as(C.POINTER(C.c_double)), C.c_double(self.rot_eps),
                                                    C.c_double(self.trans_eps)))
 
+    def _allreduce_min_u64(self, v: np.ndarray) -> np.ndarray:
+        import torch
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(self.group) == 1:
+            return v
+        # every packed word is below 2^63 (the distance is a non-negative float): int64 orders them like uint64
+        t = torch.from_numpy(np.ascontiguousarray(v, dtype=np.uint64).view(np.int64).copy())
+        if self.device is not None:
+            t = t.to(self.device)
+        dist.all_reduce(t, op=dist.ReduceOp.MIN, group=self.group)
+        return t.cpu().numpy().view(np.uint64)
+
     def linearize(self, T):
+        if self.exchange == "min":
+            won = self._allreduce_min_u64(self.be.nn1_packed(T, self.rank))
+            tot = self._allreduce(np.asarray(self.be.linearize_won(T, self.rank, won), dtype=np.float64))
+            return tot[:36].reshape(6, 6).T.copy(), tot[36:42].copy(), float(tot[42])
         tot = self._allreduce(np.asarray(self.be.linearize_partial(T), dtype=np.float64))
         return tot[:36].reshape(6, 6).T.copy(), tot[36:42].copy(), float(tot[42])
 

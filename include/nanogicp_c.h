@@ -236,6 +236,17 @@ int ngicp_compute_error(ngicp_t* h, const double* T16, double* err);
 /* sharded-submap building block: like ngicp_linearize but returns the raw partial sums
  * out43 = {H (36, col-major), b (6), err (1)} so that ranks can all-reduce them; out43 may be device memory */
 int ngicp_linearize_partial(ngicp_t* h, const double* T16, double* out43);
+/* sharded submap with an UNBOUNDED correspondence distance (the library default corr_dist_threshold_ = FLT_MAX,
+ * nano_gicp_impl.hpp:59; slabs + halo are only exact for a finite one): the ranks exchange nearest neighbours.
+ *   ngicp_nn1_packed     every source point's nearest neighbour in THIS handle's target under T, as
+ *                        (bits of the squared distance) << 32 | rank, 0x7f800000ffffffff = none within the
+ *                        max-correspondence distance; packed_out: n_source entries, host or device
+ *   (min-all-reduce the arrays over the ranks as int64: the lowest value names the rank holding the global nearest
+ *    neighbour; equal distances go to the lowest rank)
+ *   ngicp_linearize_won  the partial sums {H, b, err} (layout of ngicp_linearize_partial) over the source points this
+ *                        rank won; ngicp_compute_error_partial then works on the same points */
+int ngicp_nn1_packed(ngicp_t* h, const double* T16, unsigned rank, unsigned long long* packed_out);
+int ngicp_linearize_won(ngicp_t* h, const double* T16, unsigned rank, const unsigned long long* packed_min, double* out43);
 int ngicp_compute_error_partial(ngicp_t* h, const double* T16, double* out1);
 
 /* sharded-submap mode (one handle per GPU holds one spatial slab of the target plus a halo of the max-correspondence

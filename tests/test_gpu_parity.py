@@ -726,6 +726,70 @@ def test_sharded_partials_sum_to_unsharded(G, O, small_submap):
     assert np.abs(res["final_x"] - g.final_state()).max() < 1e-9
 
 
+def test_sharded_min_exchange_unbounded_distance(G, O, small_submap):
+    """The library-default correspondence distance is FLT_MAX (nano_gicp_impl.hpp:59): no halo makes slabs exact, so the
+    ranks exchange nearest neighbours — ngicp_nn1_packed per rank, element-wise minimum (what the min-all-reduce does),
+    ngicp_linearize_won per rank, sum.  Two halves of the target (a plain partition, no overlap) on two handles of ONE
+    GPU, ranks emulated sequentially: the minimum equals the whole target's nearest distances bit for bit, the summed
+    {H, b, err} equal the unsharded linearisation, and the host-stepped LM reproduces the unsharded fused align and the
+    CPU oracle."""
+    from direct_lidar_odometry_b200 import sharded
+    submap, scan, T = small_submap
+    inf = 3.0e38
+    tc = O.Cloud(submap).covariances(20)
+    sc = O.Cloud(scan).covariances(20)
+    guess = synth.perturb_pose(T, (0.2, 0.0, 0.0), 1.0).astype(np.float32)
+    axis = int(np.argmax(submap[:, :3].max(0) - submap[:, :3].min(0)))
+    order = np.argsort(submap[:, axis], kind="stable")
+    halves = [order[:order.size // 2], order[order.size // 2:]]
+    backs = []
+    for r in range(2):
+        be = sharded.CudaShardBackend(0, k=20, max_corr_dist=inf)
+        be.set_target_part(np.ascontiguousarray(submap[halves[r]]), np.ascontiguousarray(tc[halves[r]]))
+        be.set_source(scan, sc)
+        backs.append(be)
+
+    class Both:
+        def nn1_packed(self, T_, rank):
+            return np.minimum(backs[0].nn1_packed(T_, 0), backs[1].nn1_packed(T_, 1))
+
+        def linearize_won(self, T_, rank, won):
+            return sum(np.asarray(b.linearize_won(T_, r, won)) for r, b in enumerate(backs))
+
+        def compute_error_partial(self, T_):
+            return sum(b.compute_error_partial(T_) for b in backs)
+
+    g = G()
+    g.setCorrespondenceRandomness(20); g.setMaxCorrespondenceDistance(inf)
+    g.setMaximumIterations(32); g.setTransformationEpsilon(0.01)
+    g.setInputTarget(submap); g.setTargetCovariances(tc)
+    g.setInputSource(scan); g.setSourceCovariances(sc)
+    Td = np.asarray(guess, dtype=np.float64)
+    won = Both().nn1_packed(Td, 0)
+    whole_nn = g.nn1_packed(Td, 7)
+    assert np.array_equal(won >> np.uint64(32), whole_nn >> np.uint64(32))            # global nearest distances, bit for bit
+    assert set(np.unique(won & np.uint64(0xffffffff)).tolist()) == {0, 1}            # both ranks win some points
+    lin = g.linearize(Td)
+    assert np.array_equal(lin["sqd"].view(np.uint32), (whole_nn >> np.uint64(32)).astype(np.uint32))   # = update_correspondences' distances
+    whole = g.linearize_partial(Td)
+    parts = Both().linearize_won(Td, 0, won)
+    assert np.abs(parts - whole).max() < 1e-9 * np.abs(whole).max()
+    al = sharded.ShardedSubmapAligner(Both(), max_corr_dist=inf, max_iter=32, trans_eps=0.01)
+    assert al.exchange == "min"
+    res = al.align(guess)
+    g.align(guess)
+    assert (res["nr_iterations"], res["n_linearize"], res["n_compute_error"], res["converged"]) == \
+           (g.result.nr_iterations, g.result.n_linearize, g.result.n_compute_error, g.result.converged)
+    assert np.abs(res["final_x"] - g.final_state()).max() < 1e-9
+    o = O.Gicp(k=20, max_corr_dist=inf, max_iter=32, trans_eps=0.01, num_threads=1)
+    o.set_target(O.Cloud(submap)); o.set_target_covs(tc)
+    o.set_source(O.Cloud(scan)); o.set_source_covs(sc)
+    r = o.align(guess)
+    assert (res["nr_iterations"], res["n_linearize"], res["n_compute_error"]) == (r.nr_iterations, r.n_linearize, r.n_compute_error)
+    dt, dr = pose_delta(res["final_x"], r.Tx())
+    assert dt < POSE_T_TOL and dr < POSE_R_TOL
+
+
 def test_sharded_align_fused_exchange_one_gpu():
     """The exchange fused into the persistent LM kernel (ngicp_comm_*): two handles on ONE GPU each hold one slab of
     the target, their kernels run concurrently (grids capped so that both are co-resident) and meet in each other's

@@ -75,6 +75,41 @@ class OracleShardBackend:
     def compute_error_partial(self, T):
         return self.sub.compute_error(T) if self.sub is not None else 0.0
 
+    # -- min-exchange mode: this rank's nearest neighbour of every source point, then the terms of the points it won
+    def set_target_part(self, pts, covs):
+        self.tgt_pts, self.tgt, self.tcovs = pts, self.O.Cloud(pts), covs
+
+    def nn1_packed(self, T, rank):
+        Tf = np.asarray(T, dtype=np.float32)
+        p = self.src[:, :3]
+        q = np.stack([(Tf[r, 0] * p[:, 0] + Tf[r, 1] * p[:, 1]) + (Tf[r, 2] * p[:, 2] + Tf[r, 3]) for r in range(3)], axis=1)
+        t = self.tgt_pts[:, :3]
+        out = np.empty(q.shape[0], dtype=np.uint64)
+        for i0 in range(0, q.shape[0], 512):
+            d = q[i0:i0 + 512, None, :] - t[None, :, :]                       # float32, nanoflann's metric order
+            d2 = (d[..., 0] * d[..., 0] + d[..., 1] * d[..., 1]) + d[..., 2] * d[..., 2]
+            best = d2.min(axis=1).astype(np.float32)
+            out[i0:i0 + 512] = (best.view(np.uint32).astype(np.uint64) << np.uint64(32)) | np.uint64(rank)
+        thr2 = np.float64(self.thr) ** 2
+        none = np.uint64(0x7f800000ffffffff)
+        d2f = (out >> np.uint64(32)).astype(np.uint32).view(np.float32).astype(np.float64)
+        out[~(d2f < thr2)] = none
+        return out
+
+    def linearize_won(self, T, rank, packed_min):
+        m = (packed_min & np.uint64(0xffffffff)) == np.uint64(rank)
+        m &= packed_min != np.uint64(0x7f800000ffffffff)
+        out = np.zeros(43)
+        self.sub = None
+        if m.any():
+            g = self.O.Gicp(k=10, max_corr_dist=self.thr, num_threads=1)
+            g.set_target(self.tgt); g.set_target_covs(self.tcovs)
+            g.set_source(self.O.Cloud(self.src[m], build_index=False)); g.set_source_covs(self.scovs[m])
+            lin = g.linearize(T)
+            out[:36] = lin["H"].T.reshape(36); out[36:42] = lin["b"]; out[42] = lin["err"]
+            self.sub = g
+        return out
+
 
 def _rank_main(rank, world, port, q):
     sys.path.insert(0, ROOT)
@@ -115,6 +150,27 @@ def _rank_main(rank, world, port, q):
         H, b, e = al.linearize(np.asarray(guess, dtype=np.float64))
         lin = g.linearize(np.asarray(guess, dtype=np.float64))
         assert np.abs(H - lin["H"]).max() < 1e-9 * np.abs(lin["H"]).max() and abs(e - lin["err"]) < 1e-9 * abs(lin["err"])
+        # ---- unbounded correspondence distance (the library default): no halo is wide enough, the ranks exchange the
+        #      nearest neighbours (min-all-reduce of packed (distance, rank) words), then the sums ----
+        order = np.argsort(submap[:, axis], kind="stable")
+        half = order[:order.size // 2] if rank == 0 else order[order.size // 2:]       # a plain partition: no overlap, no halo
+        inf = 1e30
+        be2 = OracleShardBackend(inf)
+        be2.set_target_part(np.ascontiguousarray(submap[half]), np.ascontiguousarray(tc[half]))
+        be2.set_source(scan, sc)
+        al2 = sharded.ShardedSubmapAligner(be2, max_corr_dist=inf, max_iter=32, trans_eps=0.01, rank=rank)
+        assert al2.exchange == "min"
+        res2 = al2.align(guess)
+        g2 = O.Gicp(k=10, max_corr_dist=inf, max_iter=32, trans_eps=0.01, num_threads=1)
+        g2.set_target(O.Cloud(submap)); g2.set_target_covs(tc)
+        g2.set_source(O.Cloud(scan)); g2.set_source_covs(sc)
+        ref2 = g2.align(guess)
+        assert (res2["nr_iterations"], res2["converged"], res2["n_linearize"], res2["n_compute_error"]) == \
+               (ref2.nr_iterations, ref2.converged, ref2.n_linearize, ref2.n_compute_error)
+        assert np.abs(res2["final_x"] - ref2.Tx()).max() < 1e-8
+        H2, b2, e2 = al2.linearize(np.asarray(guess, dtype=np.float64))
+        lin2 = g2.linearize(np.asarray(guess, dtype=np.float64))
+        assert np.abs(H2 - lin2["H"]).max() < 1e-9 * np.abs(lin2["H"]).max() and abs(e2 - lin2["err"]) < 1e-9 * abs(lin2["err"])
         q.put((rank, "ok"))
     except Exception as ex:  # noqa: BLE001
         import traceback
