@@ -17,6 +17,8 @@ g.setCorrespondenceRandomness(bench.S2M["k"]); g.setMaxCorrespondenceDistance(be
 g.setMaximumIterations(bench.S2M["max_iter"]); g.setTransformationEpsilon(bench.S2M["trans_eps"])
 if os.environ.get("NGICP_CELL"):
     g.setGridCellSize(float(os.environ["NGICP_CELL"]))   # experiments: fixed cell edge instead of the density-driven one
+if os.environ.get("NGICP_INDEX_PATH"):
+    g.setIndexPath(int(os.environ["NGICP_INDEX_PATH"]))   # experiments: 0 cooperative, 1 multi-kernel, 3 cluster (small clouds)
 wl = bench.make_workload(lambda p, leaf: g.voxel_filter(p, leaf))
 submap = torch.from_numpy(wl["submap"]).cuda()
 scan = torch.from_numpy(wl["scan_0"]).cuda()

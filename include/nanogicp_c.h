@@ -88,7 +88,7 @@ typedef struct {
   int index_path;                      /* setInputSource / setInputTarget: 0 = snapshot + search index in one persistent cooperative
                                           launch (lowest latency for one stream), 1 = the multi-kernel pipeline, 2 = as 0,
                                           3 = one thread-block cluster per cloud (ordinary launch: best when many handles share
-                                          the GPU; clouds above 128k points take 0) */
+                                          the GPU with small voxelised clouds; clouds above 32k points take 0) */
 } ngicp_params;
 
 /* what pcl::Registration / LsqRegistration expose after align() */
