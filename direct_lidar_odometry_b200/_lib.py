@@ -27,7 +27,7 @@ EXPORTS = [
     "ngicp_get_target_covs", "ngicp_align", "ngicp_transform_source", "ngicp_voxel_filter", "ngicp_voxel_assignment",
     "ngicp_knn", "ngicp_linearize", "ngicp_compute_error", "ngicp_linearize_partial", "ngicp_compute_error_partial",
     "ngicp_version", "ngicp_launch_count", "ngicp_grid_info", "ngicp_set_owner_slab", "ngicp_lm_trial",
-    "ngicp_lm_is_converged", "ngicp_comm_export", "ngicp_comm_connect", "ngicp_comm_connect_local", "ngicp_comm_close", "ngicp_preprocess", "ngicp_preprocess_pointcloud2", "ngicp_calc_source_covs_part", "ngicp_covs_device", "ngicp_transform_voxel_filter", "ngicp_kfstore_create", "ngicp_kfstore_destroy", "ngicp_kfstore_size",
+    "ngicp_lm_is_converged", "ngicp_comm_export", "ngicp_comm_connect", "ngicp_comm_connect_local", "ngicp_comm_close", "ngicp_comm_reset", "ngicp_preprocess", "ngicp_preprocess_pointcloud2", "ngicp_calc_source_covs_part", "ngicp_covs_device", "ngicp_transform_voxel_filter", "ngicp_kfstore_create", "ngicp_kfstore_destroy", "ngicp_kfstore_size",
     "ngicp_kfstore_points", "ngicp_kfstore_push", "ngicp_kfstore_set_target", "ngicp_cov_neighbors", "ngicp_align_batch", "ngicp_imu_prior",
     "ngicp_nn1_packed", "ngicp_linearize_won",
     "ngicp_submap_push_indices", "ngicp_submap_convex_hull", "ngicp_submap_concave_hull", "ngicp_submap_selector_create",
@@ -141,5 +141,6 @@ def load() -> C.CDLL:
     proto("ngicp_comm_connect", i32, vp, i32, i32, vp)
     proto("ngicp_comm_connect_local", i32, vp, i32, i32, C.POINTER(vp))
     proto("ngicp_comm_close", i32, vp)
+    proto("ngicp_comm_reset", i32, vp)
     _LIB = L
     return L

@@ -421,6 +421,7 @@ __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
 struct GridSync {
   unsigned* arrive;   // bar[0]
   unsigned* flag;     // bar[1]
+  unsigned* comm_err; // bar[3]: set by the reducing block when the peer exchange failed (sharded mode), read by all blocks
   double* totals;     // [2][NRED] in global memory
   unsigned phase;     // phases completed so far
   unsigned max_blocks;  // stride between the two phase-parity halves of the partials buffer
@@ -492,10 +493,13 @@ __device__ __forceinline__ double peer_exchange_sum(double s, const PeerComm& pc
   return t;
 }
 
+// Returns true when the peer exchange of the sharded mode failed (a rank did not show up in time): the same value in
+// every block of the grid, so that all of them leave the LM loop together instead of iterating on partial sums.
 template <int NV>
-__device__ __forceinline__ void grid_reduce(double* acc, double (*s_red)[NRED], double* s_tot, double* partials, GridSync& gs,
+__device__ __forceinline__ bool grid_reduce(double* acc, double (*s_red)[NRED], double* s_tot, double* partials, GridSync& gs,
                                             const PeerComm& pc) {
   __shared__ int s_last;
+  __shared__ unsigned s_comm_err;
   if (pc.world == 1) {
     // Single GPU: every block waits until all partials of this phase are published, then sums them ITSELF in the same
     // fixed order (identical totals everywhere, bit-deterministic) — no "last block sums, publishes, the others read
@@ -539,7 +543,7 @@ __device__ __forceinline__ void grid_reduce(double* acc, double (*s_red)[NRED], 
     }
     gs.phase++;
     __syncthreads();
-    return;
+    return false;
   }
   block_reduce_store<NV>(acc, s_red, partials + (size_t)blockIdx.x * NRED);
   if (threadIdx.x == 0) {
@@ -579,6 +583,7 @@ __device__ __forceinline__ void grid_reduce(double* acc, double (*s_red)[NRED], 
     }
     if (pc.world > 1) s = peer_exchange_sum<NV>(s, pc);
     if (threadIdx.x < NV) __stcg(tot + threadIdx.x, s);
+    if (threadIdx.x == 0 && pc.world > 1 && *(volatile int*)pc.error) *(volatile unsigned*)gs.comm_err = 1u;
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -592,8 +597,10 @@ __device__ __forceinline__ void grid_reduce(double* acc, double (*s_red)[NRED], 
   }
   __syncthreads();
   if (threadIdx.x < NV) s_tot[threadIdx.x] = __ldcg(tot + threadIdx.x);
+  if (threadIdx.x == 0) s_comm_err = pc.world > 1 ? __ldcg(gs.comm_err) : 0u;
   gs.phase++;
   __syncthreads();
+  return s_comm_err != 0u;
 }
 
 __device__ __forceinline__ void trace_stamp(const LmParams& prm, int& slot) {
@@ -623,7 +630,7 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) align_fused_kernel(AlignArgs
   const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
   const int gstride = gridDim.x * blockDim.x;
   GridSync gs;
-  gs.arrive = bar; gs.flag = bar + 1; gs.totals = totals; gs.phase = 0; gs.max_blocks = (unsigned)a.max_blocks;
+  gs.arrive = bar; gs.flag = bar + 1; gs.comm_err = bar + 3; gs.totals = totals; gs.phase = 0; gs.max_blocks = (unsigned)a.max_blocks;
 
   // scalar LM state, kept by thread 0 of every block (identical everywhere)
   // thread 0's matrices and transforms live in shared memory: in registers they cost the 128-register variants 2 KB of
@@ -639,6 +646,7 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) align_fused_kernel(AlignArgs
   double lambda = -1.0, y0 = 0.0, nu = 2.0;
   int nr_iterations = 0, n_lin = 0, n_err = 0, lm_failed = 0;
   bool converged = false;
+  bool comm_failed = false;
   if (threadIdx.x == 0) {
     double g16[16];
     for (int i = 0; i < 16; i++) g16[i] = (double)guess.g[i];
@@ -660,9 +668,10 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) align_fused_kernel(AlignArgs
       linearize_block<LPP>(a, gp, Tf, T, prm.cap_d2, prm.thr2, blockIdx.x, gridDim.x, s_tq, acc[0]);
       trace_stamp(prm, tslot);
       if (prm.trace && it == 1 && threadIdx.x == 0 && blockIdx.x < 1024) prm.trace[256 + blockIdx.x] = global_timer_ns();
-      grid_reduce<NRED>(acc, s_red, s_tot, a.partials, gs, pc);
+      comm_failed = grid_reduce<NRED>(acc, s_red, s_tot, a.partials, gs, pc);
       trace_stamp(prm, tslot);
     }
+    if (comm_failed) break;          // grid-uniform: every block leaves here (NGICP_E_COMM, see res->reserved)
     int outcome = 0;  // 1: step returned true, 0: LM failed
     if (threadIdx.x == 0) {
       nr_iterations = it;
@@ -713,9 +722,10 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) align_fused_kernel(AlignArgs
           trace_stamp(prm, tslot);
           for (int i = gtid; i < a.ns; i += gstride) acc[0] += error_point(a, T, i);
           trace_stamp(prm, tslot);
-          grid_reduce<1>(acc, s_red, s_tot, a.partials, gs, pc);
+          comm_failed = grid_reduce<1>(acc, s_red, s_tot, a.partials, gs, pc);
           trace_stamp(prm, tslot);
         }
+        if (comm_failed) break;
         if (threadIdx.x == 0) {
           n_err++;
           const double yi = s_tot[0];
@@ -742,6 +752,7 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) align_fused_kernel(AlignArgs
         __syncthreads();
         if (dec != 0) { outcome = 1; break; }
       }
+      if (comm_failed) break;
       if (threadIdx.x == 0) {
         if (outcome == 0) lm_failed = 1;
         else converged = lm_is_converged(delta, prm.rot_eps, prm.trans_eps);
@@ -772,7 +783,7 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) align_fused_kernel(AlignArgs
   // leave the barrier words zeroed for the next launch: the last block to depart does it (nobody polls any more)
   if (threadIdx.x == 0) {
     const unsigned prev = atomicAdd(bar + 2, 1u);
-    if (prev == gridDim.x - 1u) { bar[0] = 0u; bar[1] = 0u; bar[2] = 0u; }
+    if (prev == gridDim.x - 1u) { bar[0] = 0u; bar[1] = 0u; bar[2] = 0u; bar[3] = 0u; }
   }
 }
 

@@ -1158,6 +1158,15 @@ int ngicp_comm_close(ngicp_t* h) {
   return NGICP_OK;
 }
 
+int ngicp_comm_reset(ngicp_t* h) {
+  if (!h) return NGICP_E_INVALID;
+  if (!h->comm_buf) return fail(h, NGICP_E_STATE, "comm_reset: no exchange buffer (ngicp_comm_export / connect first)");
+  DeviceGuard g(h->device);
+  if (h->stream && h->stream_src) sync_both(h);
+  NG_CUDA(h, cudaMemset(h->comm_buf, 0, PEER_BUF_BYTES));      // slots, sequence flags, own sequence number, sticky error
+  return NGICP_OK;
+}
+
 int ngicp_comm_connect(ngicp_t* h, int rank, int world, const void* handles) {
   if (!h || !handles || world < 1 || world > NGICP_MAX_RANKS || rank < 0 || rank >= world) return NGICP_E_INVALID;
   DeviceGuard g(h->device);

@@ -147,7 +147,7 @@ __device__ __forceinline__ float box_face_distance(const GridParams& gp, int x0,
 #else
 #define TQ_CHECK(cond, what, a, b) do { } while (0)
 #endif
-enum { ST_FALLBACK = 0, ST_TIES, ST_TILES, ST_PASSES, ST_LANES, ST_ITEMS, ST_N };
+enum { ST_FALLBACK = 0, ST_TIES, ST_TILES, ST_PASSES, ST_LANES, ST_ITEMS, ST_DEC1, ST_DEC2, ST_DECHI, ST_PASS1, ST_PASS2, ST_PASSHI, ST_CAND, ST_N };
 // control words shared by the plan and tile launches
 enum { CT_ITEMS = 0, CT_NEXT, CT_REST, CT_REST_NEXT, CT_DONE, CT_FIX, CT_N = 8 };
 
@@ -429,6 +429,10 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
   const GridParams gp = load_grid(g.desc);
   const int nitems = ctrl[CT_ITEMS];
   unsigned st_fb = 0, st_ties = 0, st_tiles = 0, st_passes = 0, st_lanes = 0, st_items = 0;
+#ifdef TQ_STATS_DETAIL      // per-radius counters (variants/ build only: they cost 30 registers)
+  unsigned st_dec[3] = {0, 0, 0}, st_pass[3] = {0, 0, 0};
+  unsigned long long st_cand = 0;
+#endif
 
   for (;;) {
     int w = 0;
@@ -558,6 +562,10 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
           const bool active = me && m2 > 0.f && T2 > 0.f;
           st_passes++;
           st_lanes += __popc(__ballot_sync(FULL, active));
+#ifdef TQ_STATS_DETAIL
+          st_pass[s == 1 ? 0 : (s == 2 ? 1 : 2)]++;
+          if (stats != nullptr) st_cand += s <= 2 ? (unsigned)max(S.rowoff[zhi * ny + yhi + 1] - S.rowoff[zlo * ny + ylo], 0) : (unsigned)C;
+#endif
           int c_now = 0;
           const float T2_asked = T2;
           {
@@ -635,6 +643,9 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
           }
           if (decided) prevT = kth;
           const unsigned dmask = __ballot_sync(FULL, decided);
+#ifdef TQ_STATS_DETAIL
+          st_dec[s == 1 ? 0 : (s == 2 ? 1 : 2)] += __popc(dmask);
+#endif
           __syncwarp();
           // ---- coalesced write-out: one query per step, lane j writes the j-th neighbour ----
           for (unsigned mm = dmask; mm; mm &= mm - 1) {
@@ -701,6 +712,13 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
     atomicAdd(stats + ST_PASSES, (unsigned long long)st_passes);
     atomicAdd(stats + ST_LANES, (unsigned long long)st_lanes);
     atomicAdd(stats + ST_ITEMS, (unsigned long long)st_items);
+#ifdef TQ_STATS_DETAIL
+    atomicAdd(stats + ST_DEC1, (unsigned long long)st_dec[0]); atomicAdd(stats + ST_DEC2, (unsigned long long)st_dec[1]);
+    atomicAdd(stats + ST_DECHI, (unsigned long long)st_dec[2]);
+    atomicAdd(stats + ST_PASS1, (unsigned long long)st_pass[0]); atomicAdd(stats + ST_PASS2, (unsigned long long)st_pass[1]);
+    atomicAdd(stats + ST_PASSHI, (unsigned long long)st_pass[2]);
+    atomicAdd(stats + ST_CAND, st_cand);
+#endif
   }
 }
 
@@ -1005,6 +1023,9 @@ cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_sc
       fprintf(stderr, "[ngicp knn] n=%d k=%d warp-search=%llu (%.1f%%, ties %llu) items=%llu tiles=%llu passes=%llu lanes/pass=%.1f\n",
               c.n, k, h[ST_FALLBACK], 100.0 * (double)h[ST_FALLBACK] / (double)c.n, h[ST_TIES], h[ST_ITEMS], h[ST_TILES], h[ST_PASSES],
               h[ST_PASSES] ? (double)h[ST_LANES] / (double)h[ST_PASSES] : 0.0);
+      fprintf(stderr, "[ngicp knn]   decided at radius 1 / 2 / >2: %llu / %llu / %llu, passes %llu / %llu / %llu, candidates per pass %.0f\n",
+              h[ST_DEC1], h[ST_DEC2], h[ST_DECHI], h[ST_PASS1], h[ST_PASS2], h[ST_PASSHI],
+              h[ST_PASSES] ? (double)h[ST_CAND] / (double)h[ST_PASSES] : 0.0);
     }
     launch_cov_kernel(c, k, method, nbr_scratch, covs6, q_lo, q_hi, fb_flags, nullptr, nullptr, st, k == 10 || k == 20);
     if (overlap && (e = cudaStreamWaitEvent(st, side->join, 0)) != cudaSuccess) return e;

@@ -568,6 +568,10 @@ class NanoGICP:
     def comm_close(self) -> None:
         self._check(self._L.ngicp_comm_close(self._h))
 
+    def comm_reset(self) -> None:
+        """After NGICP_E_COMM: every rank resets its exchange buffer (then a host-side barrier), connections stay."""
+        self._check(self._L.ngicp_comm_reset(self._h))
+
     def grid_info(self, which: int) -> dict:
         cell, dims, nc = C.c_float(0), (C.c_int * 3)(), C.c_int(0)
         self._check(self._L.ngicp_grid_info(self._h, which, C.byref(cell), dims, C.byref(nc)))

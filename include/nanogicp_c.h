@@ -269,6 +269,11 @@ int ngicp_comm_export(ngicp_t* h, void* handle64);
 int ngicp_comm_connect(ngicp_t* h, int rank, int world, const void* handles);
 int ngicp_comm_connect_local(ngicp_t* h, int rank, int world, ngicp_t* const* peers);
 int ngicp_comm_close(ngicp_t* h);
+/* After NGICP_E_COMM the ranks' sequence numbers are out of step and the error flag is sticky: EVERY rank calls this
+ * (no align in flight anywhere; put a barrier of the host's process group behind it), which zeroes the rank's own exchange
+ * buffer — slots, flags, sequence number, error — and keeps the connections.  The failed align stopped its LM loop at the
+ * failed exchange (all blocks of the kernel leave together); its result is not meaningful. */
+int ngicp_comm_reset(ngicp_t* h);
 /* host-only: the scalar side of one LM trial (lsq_registration_impl.hpp:172-179): d = solve(H + lambda I, -b),
  * delta = [so3_exp(d[0:3]) | d[3:6]], xi = delta * x0 — the same code the fused kernel runs; lambda = 0 gives the
  * Gauss-Newton step (:147-154).  4x4 matrices column-major. */

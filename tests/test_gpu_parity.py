@@ -806,3 +806,4 @@ def test_sharded_align_fused_exchange_one_gpu():
     r = json.loads(p.stdout.strip().splitlines()[-1])
     assert r["ranks_bit_identical"] and r["counts_equal_unsharded"] and r["max_abs_dT_vs_unsharded"] < 1e-9
     assert r["timeout_reported"]
+    assert r["recovered_after_reset"], r                       # ngicp_comm_reset on every rank, connections kept
