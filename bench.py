@@ -236,6 +236,8 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     g = NanoGICP(local_rank)
     g.setCorrespondenceRandomness(S2M["k"]); g.setMaxCorrespondenceDistance(S2M["thr"])
+    if os.environ.get("NGICP_TILE_MIN"):       # experiments: cloud size from which the tile kNN path is taken
+        g.setKnnPath(0, int(os.environ["NGICP_TILE_MIN"]))
     g.setMaximumIterations(S2M["max_iter"]); g.setTransformationEpsilon(S2M["trans_eps"])
     if args.cell > 0:
         g.setGridCellSize(args.cell)

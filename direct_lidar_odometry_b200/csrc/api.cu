@@ -233,8 +233,17 @@ int calc_covs(ngicp_t* h, int which, int part = 0, int nparts = 1) {
     NG_CUDA(h, cudaEventCreateWithFlags(&sc.cov_side.fork, cudaEventDisableTiming));
     NG_CUDA(h, cudaEventCreateWithFlags(&sc.cov_side.join, cudaEventDisableTiming));
   }
+  // AUTO chooses by cloud size (tiles from knn_tile_min_points on: fewer instructions per point, but a long serial path
+  // per warp — worse LATENCY for a scan).  One exception: the source of a handle whose target is a large submap.  Its
+  // work runs on the second stream BESIDE the submap's, so what counts is the GPU time it takes away from the target
+  // side, not its own latency: tiles (measured on C2: 22k-point scan, step 0.884 -> 0.853 ms).  Both paths give the same
+  // neighbour sets and the same summation order.
+  int knn_path = h->prm.knn_path;
+  if (knn_path == NGICP_KNN_AUTO && which == NGICP_SOURCE && nparts == 1 && c->n >= 8192 && h->tgt &&
+      h->tgt->n >= h->prm.knn_tile_min_points && h->stream_src->s != h->stream->s)
+    knn_path = NGICP_KNN_TILE;
   NG_CUDA(h, launch_covariances(*c, k, h->prm.regularization_method, sc.nbr.as<int>(), cv->c.as<double>(), c->table_cap, st->s,
-                                part, nparts, h->prm.knn_path, h->prm.knn_tile_min_points, &sc.cov_side));
+                                part, nparts, knn_path, h->prm.knn_tile_min_points, &sc.cov_side));
   ph_end(h, ph);
   if (nparts == 1) { h->nbr_cloud = c; h->nbr_k = k; h->nbr_side = which; }
   drop_covs(h, which);
