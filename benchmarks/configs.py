@@ -328,15 +328,34 @@ def run_c3(args):
     if args.pinned:      # raw scans in page-locked host memory (what a driver node that owns its message buffers can do)
         for i in idx:
             raw_in[i] = torch.from_numpy(scans[i][1]).pin_memory()
+    # --pipeline 1: the NEXT scan's upload + preprocess (its own handle and stream) runs on a host thread beside the
+    # registration of the current one — same arithmetic, same poses; a scan then costs max(preprocess, registration)
+    # instead of their sum.  (An odometry node would do this with a two-deep message queue; latency per scan is unchanged.)
+    pipe = bool(getattr(args, "pipeline", 0)) and args.device_store
+    ex = ThreadPoolExecutor(1) if pipe else None
+    nxt = None
+    vox_pre = NanoGICP(0) if pipe else vox      # a handle is single-threaded: the prefetch thread gets its own
+    if pipe:
+        scan_buf.append(torch.empty((1 << 17, 8), dtype=torch.float32, device="cuda"))   # three buffers: i-1 (S2S target), i, i+1
+
+    def pre(j):
+        t = time.perf_counter()
+        r = raw_in.get(j, scans[j][1])
+        s = vox_pre.preprocess(r, 1.0, 0.25, out=scan_buf[j % len(scan_buf)])
+        return s, (time.perf_counter() - t) * 1e3
     for i in idx:
         T_true, raw = scans[i]
         raw = raw_in.get(i, raw)
         t1 = time.perf_counter()
-        if args.device_store:                     # preprocessPoints fused, output stays on the device
+        if pipe:
+            scan, t_pre = nxt.result() if nxt is not None else pre(i)
+            nxt = ex.submit(pre, i + 1) if i + 1 < len(idx) else None
+        elif args.device_store:                   # preprocessPoints fused, output stays on the device
             scan = vox.preprocess(raw, 1.0, 0.25, out=scan_buf[i & 1])
         else:
             scan = vox.voxel_filter(raw, 0.25)    # preprocessPoints: vf_scan (crop box applied by the generator)
-        t_pre = (time.perf_counter() - t1) * 1e3
+        if not pipe:
+            t_pre = (time.perf_counter() - t1) * 1e3
         if i == 0:
             rp.first(scan, T_true)
             continue
@@ -356,7 +375,8 @@ def run_c3(args):
                else f"knn-{rp.knn} submap")
     out = {"config": f"C3: odometry replay, {args.scans} synthetic OS1-64 scans (S2S + S2M + keyframes by OdomNode::updateKeyframes' rule, threshD 5 m / threshR 45 deg; {sel_txt})"
                      + (", device-resident keyframes + fused preprocess (N1/N2)" if args.device_store else ", host keyframes as in OdomNode")
-                     + (", raw scans in pinned host memory" if args.pinned else ", raw scans in pageable host memory"),
+                     + (", raw scans in pinned host memory" if args.pinned else ", raw scans in pageable host memory")
+                     + (", next scan's preprocess pipelined beside the registration" if pipe else ""),
            "gpu": {"ms_per_scan_mean": float(ms.mean()), "ms_per_scan_p50": float(np.percentile(ms, 50)), "ms_per_scan_p99": float(np.percentile(ms, 99)),
                    "keyframes": len(rp.keyframes), "final_translation_error_m": errs[-1][0], "max_translation_error_m": float(max(e[0] for e in errs)),
                    "max_rotation_error_rad": float(max(e[1] for e in errs)), "mean_iterations_s2s": float(np.mean([i[0] for i in iters])),
@@ -737,6 +757,7 @@ if __name__ == "__main__":
     ap.add_argument("--selection", choices=["hull", "knn"], default="hull", help="c3: submap keyframe selection")
     ap.add_argument("--cpu-scans", type=int, default=40)
     ap.add_argument("--pinned", type=int, default=0, help="c3: keep the raw scans in pinned host memory")
+    ap.add_argument("--pipeline", type=int, default=0, help="c3: preprocess scan i+1 on a host thread while scan i is registered")
     ap.add_argument("--pairs", type=int, default=10000)
     ap.add_argument("--wave", type=int, default=64, help="c4: pairs per ngicp_align_batch launch")
     ap.add_argument("--check-pairs", type=int, default=0, help="c4: oracle-check a seeded sample of this many of rank 0's pairs")
