@@ -7,6 +7,7 @@
 // compiled verbatim against include/nano_gicp/nano_gicp.hpp; dlo_stub.hpp supplies the class around them.
 // Same input / output format as odom_sequence.cpp.
 #include "dlo_stub.hpp"
+#include <chrono>
 
 #include "_gen/odom_470_528.inc"
 #include "_gen/odom_790_852.inc"
@@ -42,11 +43,13 @@ int main(int argc, char** argv) {
     node.current_scan = scan;
     node.source_cloud = scan;
     if (s == 0) { node.initializeInputTarget(); node.target_cloud.reset(new pcl::PointCloud<PointType>(*scan)); continue; }
+    const auto t_begin = std::chrono::steady_clock::now();
     node.setInputSources();
     node.getNextPose();
     node.updateKeyframes();
-    std::printf("{\"scan\": %d, \"s2s_iterations\": %d, \"s2m_iterations\": %d, \"keyframes\": %d, \"submap_keyframes\": %zu, \"submap_points\": %zu, \"submap_normals\": %zu, ",
-                s, node.gicp_s2s.getLastResult().nr_iterations, node.gicp.getLastResult().nr_iterations, node.num_keyframes,
+    const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+    std::printf("{\"scan\": %d, \"ms\": %.4f, \"s2s_iterations\": %d, \"s2m_iterations\": %d, \"keyframes\": %d, \"submap_keyframes\": %zu, \"submap_points\": %zu, \"submap_normals\": %zu, ",
+                s, ms, node.gicp_s2s.getLastResult().nr_iterations, node.gicp.getLastResult().nr_iterations, node.num_keyframes,
                 node.submap_kf_idx_curr.size(), node.submap_cloud ? node.submap_cloud->points.size() : (size_t)0, node.submap_normals.size());
     print_T("T", node.T);
     std::printf("}\n");
