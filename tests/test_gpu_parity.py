@@ -178,6 +178,30 @@ def test_index_fused_and_multi_kernel_paths_identical(G, O, scan_pair, vox_pair,
               assert np.array_equal(np.ascontiguousarray(a[key]).view(np.uint64), np.ascontiguousarray(b[key]).view(np.uint64)), key
 
 
+@pytest.mark.parametrize("far", [1.0e13, 1.0e20, 3.0e38])
+def test_index_survives_far_outliers(G, O, scan_pair, far):
+    """DLO only strips NaN / Inf: one stray finite return of 1e20 m is a legal input.  The cell edge must grow until the
+    dense table holds the grid (down to a single cell when the extent overflows float arithmetic) — never a table
+    overrun — and the search must stay exact.  All three index paths."""
+    pts = scan_pair["s0"][:3000].copy()
+    pts[17, :3] = (far, -far * 0.5, far * 0.25)
+    q = np.ascontiguousarray(pts[100:164, :3])                 # (not the outlier itself: its distances overflow float)
+    ref_idx, ref_d2 = O.Cloud(pts).knn(q, 5)
+    for path in (0, 1, 3):
+        g = G()
+        g.setIndexPath(path)
+        g.setInputTarget(pts)
+        info = g.grid_info(1)
+        assert info["ncells"] >= 1 and info["ncells"] <= (1 << 25), info
+        idx, d2 = g.knn(1, q, 5)
+        fin = np.isfinite(ref_d2) & np.isfinite(d2)
+        assert np.array_equal(bits(d2[fin]), bits(ref_d2[fin])), (path, far)
+        assert np.array_equal(np.isfinite(d2), np.isfinite(ref_d2))
+        g.setCorrespondenceRandomness(5)
+        g.calculateTargetCovariances()
+        assert np.isfinite(g.getTargetCovariances()[np.arange(3000) != 17]).all()
+
+
 def test_preprocess_fused_crop_nan_voxel(G, O, scan_pair):
     """ngicp_preprocess = removeNaN + negative CropBox + voxel grid in one pass (odom.cc:443-465), bit-exact against
     the three steps done one after the other by the oracle."""
