@@ -376,6 +376,11 @@ struct IndexFusedArgs {
   int* slice_sum;            // [G]
   unsigned* bar;             // grid barrier words, zero between launches
   float cell_req, target_occ; int table_cap, trial_cap;
+  // {cell edge, point count, builds since the last trial histogram} of the previous cloud indexed through this scratch
+  // (device memory, written by block 0 at the end): a cloud of about the same size re-uses that cell edge and skips the
+  // trial histogram (three barriers and two passes) — consecutive scans / submaps of a stream look alike, and the search
+  // is exact for ANY cell edge (it only costs speed); every 16th build measures again
+  float* hint;
 };
 
 __device__ __forceinline__ void if_grid_barrier(unsigned* bar, unsigned& phase) {
@@ -431,7 +436,7 @@ __device__ __forceinline__ void index_fused_body(const IndexFusedArgs& a, const 
   __shared__ int s_scan[IF_WARPS + 1];
   __shared__ GridShape s_gs;
   __shared__ float s_lo[3], s_hi[3];
-  __shared__ int s_nfinite, s_carry;
+  __shared__ int s_nfinite, s_carry, s_have_cell, s_used_hint;
   __shared__ unsigned long long s_occ[IF_WARPS];
   const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
   const int gtid = blk * IF_THREADS + tid, gstride = G * IF_THREADS;
@@ -505,14 +510,21 @@ __device__ __forceinline__ void index_fused_body(const IndexFusedArgs& a, const 
       // (bb_min / bb_max go through the order-preserving encoding in the multi-kernel path; decode(encode(x)) == x)
       for (int c = 0; c < 3; c++) { s_lo[c] = mn[c]; s_hi[c] = mx[c]; }
       s_nfinite = finite;
+      float cell0 = a.cell_req;
+      s_used_hint = 0;
+      if (!(cell0 > 0.f) && a.hint != nullptr) {
+        const float hc = __ldcg(a.hint), hn = __ldcg(a.hint + 1), cnt = __ldcg(a.hint + 2);
+        if (hc > 0.f && cnt < 15.5f && (float)n >= 0.8f * hn && (float)n <= 1.25f * hn) { cell0 = hc; s_used_hint = 1; }
+      }
       GridShape gs;
-      grid_shape_compute(s_lo, s_hi, finite, a.cell_req > 0.f ? a.cell_req : 1.0f, a.cell_req > 0.f ? a.table_cap : a.trial_cap, gs);
+      grid_shape_compute(s_lo, s_hi, finite, cell0 > 0.f ? cell0 : 1.0f, cell0 > 0.f ? a.table_cap : a.trial_cap, gs);
       s_gs = gs;
+      s_have_cell = cell0 > 0.f ? 1 : 0;
     }
   }
   __syncthreads();
 
-  if (!(a.cell_req > 0.f)) {
+  if (!s_have_cell) {
     // ---- automatic cell edge: histogram of a 1 m trial grid, point-weighted occupancy (count_points / occupancy /
     //      grid_autocell kernels) ----
     {
@@ -574,6 +586,9 @@ __device__ __forceinline__ void index_fused_body(const IndexFusedArgs& a, const 
     d->nfinite = s_nfinite; d->vcount = 0; d->voverflow = 0;
   }
   const int ncells = s_gs.ncells;
+  const bool write_hint = blk == 0 && tid == 0 && a.hint != nullptr && !(a.cell_req > 0.f);
+  const float hint_cnt = write_hint ? (s_used_hint ? __ldcg(a.hint + 2) + 1.f : 0.f) : 0.f;
+  const float hint_cell = s_gs.cell;
 
   // ---- zero the table, histogram of the cell keys (counts of cell c at table[c + 1]) ----
   {
@@ -662,6 +677,8 @@ __device__ __forceinline__ void index_fused_body(const IndexFusedArgs& a, const 
     const float4 v = a.pts[o];
     a.sorted[dst] = make_float4(v.x, v.y, v.z, __uint_as_float(o));
   }
+  // (every block read the hint before the first table pass, i.e. at least one barrier ago: nobody reads it any more)
+  if (write_hint) { a.hint[0] = hint_cell; a.hint[1] = (float)n; a.hint[2] = hint_cnt; }
 }
 
 __global__ void __launch_bounds__(IF_THREADS, 2) index_fused_kernel(IndexFusedArgs a) {
@@ -796,8 +813,8 @@ cudaError_t upload_and_index_fused(DevCloud& c, const void* pts, size_t n, size_
   if ((e = sc.vals_a.reserve(nb, st)) != cudaSuccess) return e;
   if ((e = sc.tile_sums.reserve(sizeof(int) * (size_t)(blocks * 12 + 64), st)) != cudaSuccess) return e;
   if (!sc.index_bar.p) {
-    if ((e = sc.index_bar.reserve(64, st)) != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(sc.index_bar.p, 0, 64, st->s)) != cudaSuccess) return e;
+    if ((e = sc.index_bar.reserve(128, st)) != cudaSuccess) return e;
+    if ((e = cudaMemsetAsync(sc.index_bar.p, 0, 128, st->s)) != cudaSuccess) return e;      // barrier words + cell-edge hint
   }
   IndexFusedArgs a;
   a.raw = raw; a.stride = stride_bytes; a.n = (int)n;
@@ -808,6 +825,8 @@ cudaError_t upload_and_index_fused(DevCloud& c, const void* pts, size_t n, size_
   a.occ = reinterpret_cast<unsigned long long*>(ws + (size_t)blocks * 8);   // [blocks] (8-byte aligned: blocks * 8 ints)
   a.slice_sum = ws + (size_t)blocks * 10;                                   // [blocks]
   a.bar = sc.index_bar.as<unsigned>();
+  static const bool hint_on = !(getenv("NGICP_CELL_HINT") && atoi(getenv("NGICP_CELL_HINT")) == 0);
+  a.hint = hint_on ? reinterpret_cast<float*>(sc.index_bar.as<unsigned>() + 16) : nullptr;
   a.cell_req = cell_req; a.target_occ = auto_target_occupancy(); a.table_cap = table_cap;
   a.trial_cap = table_cap < (1 << 22) ? table_cap : (1 << 22);
   void* kargs[] = {(void*)&a};
