@@ -381,6 +381,7 @@ struct IndexFusedArgs {
   // trial histogram (three barriers and two passes) — consecutive scans / submaps of a stream look alike, and the search
   // is exact for ANY cell edge (it only costs speed); every 16th build measures again
   float* hint;
+  unsigned char* bricks; long long brick_cap;     // brick occupancy flags to fill (nullptr: none), see KNN_BRICK
 };
 
 __device__ __forceinline__ void if_grid_barrier(unsigned* bar, unsigned& phase) {
@@ -598,6 +599,15 @@ __device__ __forceinline__ void index_fused_body(const IndexFusedArgs& a, const 
     for (int i = gtid; i < n4; i += gstride) t4[i] = make_int4(0, 0, 0, 0);
     for (int i = 1 + (n4 << 2) + gtid; i < total; i += gstride) a.table[i] = 0;
     if (gtid == 0) a.table[0] = 0;
+    if (a.bricks != nullptr) {
+      const long long nb = (long long)((s_gs.dim[0] + KNN_BRICK - 1) / KNN_BRICK) * ((s_gs.dim[1] + KNN_BRICK - 1) / KNN_BRICK) *
+                           ((s_gs.dim[2] + KNN_BRICK - 1) / KNN_BRICK);
+      if (nb <= a.brick_cap) {
+        unsigned* f4 = reinterpret_cast<unsigned*>(a.bricks);
+        const long long nw = (nb + 3) / 4;
+        for (long long i = gtid; i < nw; i += gstride) f4[i] = 0u;
+      }
+    }
   }
   bar.sync();
   {
@@ -664,9 +674,17 @@ __device__ __forceinline__ void index_fused_body(const IndexFusedArgs& a, const 
     a.slot_orig[pos] = (unsigned)i;
   }
   bar.sync();
+  const int nbx = (s_gs.dim[0] + KNN_BRICK - 1) / KNN_BRICK, nby = (s_gs.dim[1] + KNN_BRICK - 1) / KNN_BRICK,
+            nbz = (s_gs.dim[2] + KNN_BRICK - 1) / KNN_BRICK;
+  const bool mark = a.bricks != nullptr && (long long)nbx * nby * nbz <= a.brick_cap;
   for (int p = gtid; p < n; p += gstride) {
     const unsigned o = __ldcg(a.slot_orig + p);
     const unsigned key = __ldcg(a.keys + o);
+    if (mark) {       // the point's box: plain stores of the same value, no atomics needed
+      const int cx = (int)(key % (unsigned)s_gs.dim[0]), cyz = (int)(key / (unsigned)s_gs.dim[0]);
+      const int cy = cyz % s_gs.dim[1], cz = cyz / s_gs.dim[1];
+      a.bricks[((long long)(cz / KNN_BRICK) * nby + cy / KNN_BRICK) * nbx + cx / KNN_BRICK] = 1;
+    }
     const int ca = __ldcg(a.table + key), cb = __ldcg(a.table + key + 1);
     int dst = p;
     if (cb - ca <= ORDER_FIX_MAX) {
@@ -827,6 +845,12 @@ cudaError_t upload_and_index_fused(DevCloud& c, const void* pts, size_t n, size_
   a.bar = sc.index_bar.as<unsigned>();
   static const bool hint_on = !(getenv("NGICP_CELL_HINT") && atoi(getenv("NGICP_CELL_HINT")) == 0);
   a.hint = hint_on ? reinterpret_cast<float*>(sc.index_bar.as<unsigned>() + 16) : nullptr;
+  a.bricks = nullptr; a.brick_cap = 0;
+  if (n >= (size_t)KNN_BRICK_MIN_POINTS) {
+    a.brick_cap = brick_flag_bytes(table_cap);
+    if ((e = c.bricks.alloc((size_t)a.brick_cap, st)) != cudaSuccess) return e;
+    a.bricks = c.bricks.as<unsigned char>();
+  }
   a.cell_req = cell_req; a.target_occ = auto_target_occupancy(); a.table_cap = table_cap;
   a.trial_cap = table_cap < (1 << 22) ? table_cap : (1 << 22);
   void* kargs[] = {(void*)&a};

@@ -56,6 +56,13 @@ struct TableBuf {
 };
 
 // ---- device-resident cloud + index ---------------------------------------------------------------
+// Brick occupancy flags of the tile kNN path: one byte per box of KNN_BRICK^3 cells says whether the box holds points
+// (the plan kernel then need not walk the dense cell table).  The fused index kernel fills them as a by-product of its
+// last pass for clouds that may take the tile path; otherwise launch_covariances does (brick_clear / brick_mark).
+constexpr int KNN_BRICK = 4;
+inline long long brick_flag_bytes(int table_cap) { return ((long long)table_cap / 16 + 4096) & ~3ll; }   // 4x the boxes of a cubic grid
+constexpr int KNN_BRICK_MIN_POINTS = 8192;      // smaller clouds never take the tile path by themselves
+
 struct DevCloud {
   int n = 0;
   DevBuf pts;         // float4[n], original order, w = 1
@@ -63,6 +70,7 @@ struct DevCloud {
   DevBuf desc;        // GridDesc
   TableBuf cell_start;  // int[table_cap + 8], recycled
   DevBuf sorted;      // float4[n], cell order, w = original index bits
+  DevBuf bricks;      // brick occupancy flags (see KNN_BRICK) when the index build produced them, else empty
   int table_cap = 0;
   GridView view() const {
     GridView v;

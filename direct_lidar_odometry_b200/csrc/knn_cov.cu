@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(KC_THREADS, KNN_MIN_BLOCKS) knn_lists_kernel(G
 #define TQ_LCAP 40       // per-query collection capacity
 #endif
 #ifndef TQ_CORE
-#define TQ_CORE 4        // box edge in cells
+#define TQ_CORE KNN_BRICK   // box edge in cells
 #endif
 #ifndef TQ_PACKED
 #define TQ_PACKED 1      // 1: packed f32x2 distance arithmetic (two candidates per instruction); 0: scalar
@@ -237,6 +237,12 @@ __global__ void __launch_bounds__(256) brick_clear_kernel(GridView g, unsigned c
   const long long nw = (nb + 3) / 4;
   unsigned* f4 = reinterpret_cast<unsigned*>(flags);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nw; i += (long long)gridDim.x * blockDim.x) f4[i] = 0u;
+}
+// control words and warp-search flags to zero (one launch instead of two memset nodes)
+__global__ void __launch_bounds__(256) knn_zero_kernel(int* __restrict__ ctrl, unsigned* __restrict__ fb_flags4, int nwords) {
+  const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+  if (gtid < CT_N) ctrl[gtid] = 0;
+  for (int i = gtid; i < nwords; i += gridDim.x * blockDim.x) fb_flags4[i] = 0u;
 }
 __global__ void __launch_bounds__(256) brick_mark_kernel(GridView g, int n, unsigned char* __restrict__ flags, long long flag_cap) {
   const GridParams gp = load_grid(g.desc);
@@ -889,6 +895,7 @@ void knn_prime_kernels() {
   cudaFuncGetAttributes(&fa, knn_plan_kernel);
   cudaFuncGetAttributes(&fa, brick_clear_kernel);
   cudaFuncGetAttributes(&fa, brick_mark_kernel);
+  cudaFuncGetAttributes(&fa, knn_zero_kernel);
   cudaFuncGetAttributes(&fa, knn_lists_tile_kernel<0>);
   cudaFuncGetAttributes(&fa, knn_lists_tile_kernel<10>);
   cudaFuncGetAttributes(&fa, knn_lists_tile_kernel<20>);
@@ -917,7 +924,6 @@ cudaError_t launch_knn_queries(const DevCloud& c, const float4* queries, int nq,
 static inline size_t items_offset_ints(int n, int k) { return (((size_t)n * k + CT_N + (size_t)n) + 3) & ~(size_t)3; }
 static inline size_t flags_offset_ints(int n, int k) { return items_offset_ints(n, k) + 4 * (size_t)n + 16; }
 static inline size_t brick_offset_ints(int n, int k) { return flags_offset_ints(n, k) + ((size_t)n + 3) / 4 + 4; }
-static inline long long brick_flag_bytes(int table_cap) { return ((long long)table_cap / 16 + 4096) & ~3ll; }   // 4x the boxes of a cubic grid
 size_t covariance_scratch_ints(int n, int k, int table_cap) { return brick_offset_ints(n, k) + (size_t)(brick_flag_bytes(table_cap) / 4) + 4; }
 
 cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_scratch, double* covs6, int table_cap, cudaStream_t st,
@@ -974,9 +980,9 @@ cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_sc
     int4* items = reinterpret_cast<int4*>(nbr_scratch + items_offset_ints(c.n, k));
     items = reinterpret_cast<int4*>((reinterpret_cast<uintptr_t>(items) + 15) & ~(uintptr_t)15);
     unsigned char* fb_flags = reinterpret_cast<unsigned char*>(nbr_scratch + flags_offset_ints(c.n, k));
-    cudaError_t e = cudaMemsetAsync(ctrl, 0, CT_N * sizeof(int), st);
-    if (e != cudaSuccess) return e;
-    if ((e = cudaMemsetAsync(fb_flags, 0, (size_t)c.n, st)) != cudaSuccess) return e;
+    cudaError_t e = cudaSuccess;
+    knn_zero_kernel<<<148, 256, 0, st>>>(ctrl, reinterpret_cast<unsigned*>(fb_flags), (c.n + 3) / 4);
+    note_launches(1);
     unsigned long long* stats = nullptr;
     if (want_stats) {
       if (cudaMalloc(&stats, ST_N * sizeof(unsigned long long)) != cudaSuccess) return cudaGetLastError();
@@ -988,10 +994,15 @@ cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_sc
     long long plan_warps = max_boxes > 32768 ? (max_boxes + 7) / 8 + 1024 : max_boxes + 1024;
     unsigned char* bricks = reinterpret_cast<unsigned char*>(nbr_scratch + brick_offset_ints(c.n, k));
     const long long brick_cap = brick_flag_bytes(table_cap);
-    brick_clear_kernel<<<148 * 2, 256, 0, st>>>(c.view(), bricks, brick_cap);
-    brick_mark_kernel<<<(c.n + 1023) / 1024, 256, 0, st>>>(c.view(), c.n, bricks, brick_cap);
+    if (c.bricks.p && c.bricks.bytes >= (size_t)brick_cap) {
+      bricks = c.bricks.as<unsigned char>();            // filled by the fused index kernel
+    } else {
+      brick_clear_kernel<<<148 * 2, 256, 0, st>>>(c.view(), bricks, brick_cap);
+      brick_mark_kernel<<<(c.n + 1023) / 1024, 256, 0, st>>>(c.view(), c.n, bricks, brick_cap);
+      note_launches(2);
+    }
     knn_plan_kernel<<<(unsigned)((plan_warps + 7) / 8), 256, 0, st>>>(c.view(), items, ctrl, bricks, brick_cap);
-    note_launches(2);
+    note_launches(1);
     // persistent grid: every resident warp pulls work items until the counter runs out; no block waits for another one,
     // so it does not matter how many of the blocks are resident at a time (other handles may share the GPU)
     int tblocks = sm_count[di] * blocks_per_sm[di];
