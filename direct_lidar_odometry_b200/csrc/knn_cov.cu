@@ -287,17 +287,23 @@ __global__ void __launch_bounds__(256) knn_plan_kernel(GridView g, int4* __restr
       }
       if (!__any_sync(FULL, e != 0)) continue;
     }
-    for (int bi = 0; bi < run; ++bi) {
-      const int bx = rbx + bi;
-      if (bx >= nbx) break;
-      if (!((occ >> bi) & 1u)) continue;
-      const int x0 = bx * TQ_CORE, y0 = rby * TQ_CORE, z0 = rbz * TQ_CORE;
-      const int Q = box_population(g, gp, x0, y0, z0, TQ_CORE, 0, lane, 32);
-      if (Q == 0) continue;
-      if (box_population(g, gp, x0, y0, z0, TQ_CORE, 1, lane, 32) <= TQ_CMAX) {
-        emit_items(lane == 0, x0, y0, z0, TQ_CORE, Q, lane, items, ctrl);
-        continue;
-      }
+    // the run's boxes side by side, 4 lanes each (a dense run used to be 8 x 2 dependent rounds of table lookups by one
+    // warp: the plan kernel's critical path); boxes that fit go out at once, the others are split one after the other
+    const int y0 = rby * TQ_CORE, z0 = rbz * TQ_CORE;
+    unsigned deep_boxes;
+    {
+      const int bi = lane >> 2, sub = lane & 3;
+      const bool valid = bi < run && rbx + bi < nbx && ((occ >> bi) & 1u);
+      const int bx0 = valid ? (rbx + bi) * TQ_CORE : -(1 << 20);       // far outside: box_population touches nothing
+      const int Qb = box_population(g, gp, bx0, y0, z0, TQ_CORE, 0, sub, 4);
+      const int Cb = box_population(g, gp, Qb > 0 ? bx0 : -(1 << 20), y0, z0, TQ_CORE, 1, sub, 4);
+      const bool fits = Qb > 0 && Cb <= TQ_CMAX;
+      emit_items(sub == 0 && fits, bx0, y0, z0, TQ_CORE, Qb, lane, items, ctrl);
+      deep_boxes = __ballot_sync(FULL, sub == 0 && Qb > 0 && !fits);
+    }
+    for (; deep_boxes; deep_boxes &= deep_boxes - 1) {
+      const int bi = (__ffs(deep_boxes) - 1) >> 2;
+      const int x0 = (rbx + bi) * TQ_CORE;
       // 8 children of edge TQ_CORE/2, 4 lanes each
       const int h = TQ_CORE / 2;
       const int ch = lane >> 2, sub = lane & 3;
