@@ -493,13 +493,14 @@ __device__ __forceinline__ double peer_exchange_sum(double s, const PeerComm& pc
   return t;
 }
 
-// Returns true when the peer exchange of the sharded mode failed (a rank did not show up in time): the same value in
-// every block of the grid, so that all of them leave the LM loop together instead of iterating on partial sums.
+// Sharded mode: *s_fail (shared memory) is set when the peer exchange failed (a rank did not show up in time) — the same
+// value in every block of the grid, so that all of them leave the LM loop together instead of iterating on partial sums.
+// (A word in shared memory, read at the two places that need it: a returned flag kept alive in a register cost the
+// 80-register variant 25 % on dense scans.)
 template <int NV>
-__device__ __forceinline__ bool grid_reduce(double* acc, double (*s_red)[NRED], double* s_tot, double* partials, GridSync& gs,
-                                            const PeerComm& pc) {
+__device__ __forceinline__ void grid_reduce(double* acc, double (*s_red)[NRED], double* s_tot, double* partials, GridSync& gs,
+                                            const PeerComm& pc, unsigned* s_fail) {
   __shared__ int s_last;
-  __shared__ unsigned s_comm_err;
   if (pc.world == 1) {
     // Single GPU: every block waits until all partials of this phase are published, then sums them ITSELF in the same
     // fixed order (identical totals everywhere, bit-deterministic) — no "last block sums, publishes, the others read
@@ -543,7 +544,7 @@ __device__ __forceinline__ bool grid_reduce(double* acc, double (*s_red)[NRED], 
     }
     gs.phase++;
     __syncthreads();
-    return false;
+    return;
   }
   block_reduce_store<NV>(acc, s_red, partials + (size_t)blockIdx.x * NRED);
   if (threadIdx.x == 0) {
@@ -597,10 +598,9 @@ __device__ __forceinline__ bool grid_reduce(double* acc, double (*s_red)[NRED], 
   }
   __syncthreads();
   if (threadIdx.x < NV) s_tot[threadIdx.x] = __ldcg(tot + threadIdx.x);
-  if (threadIdx.x == 0) s_comm_err = pc.world > 1 ? __ldcg(gs.comm_err) : 0u;
+  if (threadIdx.x == 0) *s_fail = __ldcg(gs.comm_err);
   gs.phase++;
   __syncthreads();
-  return s_comm_err != 0u;
 }
 
 __device__ __forceinline__ void trace_stamp(const LmParams& prm, int& slot) {
@@ -646,8 +646,9 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) align_fused_kernel(AlignArgs
   double lambda = -1.0, y0 = 0.0, nu = 2.0;
   int nr_iterations = 0, n_lin = 0, n_err = 0, lm_failed = 0;
   bool converged = false;
-  bool comm_failed = false;
+  __shared__ unsigned s_comm_fail;
   if (threadIdx.x == 0) {
+    s_comm_fail = 0u;
     double g16[16];
     for (int i = 0; i < 16; i++) g16[i] = (double)guess.g[i];
     iso_from_colmajor16(g16, x0);
@@ -668,10 +669,9 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) align_fused_kernel(AlignArgs
       linearize_block<LPP>(a, gp, Tf, T, prm.cap_d2, prm.thr2, blockIdx.x, gridDim.x, s_tq, acc[0]);
       trace_stamp(prm, tslot);
       if (prm.trace && it == 1 && threadIdx.x == 0 && blockIdx.x < 1024) prm.trace[256 + blockIdx.x] = global_timer_ns();
-      comm_failed = grid_reduce<NRED>(acc, s_red, s_tot, a.partials, gs, pc);
+      grid_reduce<NRED>(acc, s_red, s_tot, a.partials, gs, pc, &s_comm_fail);
       trace_stamp(prm, tslot);
     }
-    if (comm_failed) break;          // grid-uniform: every block leaves here (NGICP_E_COMM, see res->reserved)
     int outcome = 0;  // 1: step returned true, 0: LM failed
     if (threadIdx.x == 0) {
       nr_iterations = it;
@@ -691,7 +691,7 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) align_fused_kernel(AlignArgs
         for (int i = 0; i < 36; i++) final_H[i] = H36[i];
         converged = lm_is_converged(delta, prm.rot_eps, prm.trans_eps);
         s_x = x0;
-        s_decision = converged ? 2 : 1;
+        s_decision = (pc.world > 1 && s_comm_fail) ? 0 : (converged ? 2 : 1);
       }
       __syncthreads();
       outcome = 1;
@@ -722,10 +722,9 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) align_fused_kernel(AlignArgs
           trace_stamp(prm, tslot);
           for (int i = gtid; i < a.ns; i += gstride) acc[0] += error_point(a, T, i);
           trace_stamp(prm, tslot);
-          comm_failed = grid_reduce<1>(acc, s_red, s_tot, a.partials, gs, pc);
+          grid_reduce<1>(acc, s_red, s_tot, a.partials, gs, pc, &s_comm_fail);
           trace_stamp(prm, tslot);
         }
-        if (comm_failed) break;
         if (threadIdx.x == 0) {
           n_err++;
           const double yi = s_tot[0];
@@ -745,14 +744,16 @@ __global__ void __launch_bounds__(AL_THREADS, MINB) align_fused_kernel(AlignArgs
             for (int i = 0; i < 36; i++) final_H[i] = H36[i];
             dec = 1;
           }
+          // sharded mode, a peer missed an exchange (the same flag in every block): stop through the existing decision
+          // word as a failed LM step — the sums of this iteration are partial, the caller gets NGICP_E_COMM
+          if (pc.world > 1 && s_comm_fail) dec = 4;
           s_decision = dec;
         }
         __syncthreads();
         const int dec = s_decision;
         __syncthreads();
-        if (dec != 0) { outcome = 1; break; }
+        if (dec != 0) { outcome = dec == 4 ? 0 : 1; break; }
       }
-      if (comm_failed) break;
       if (threadIdx.x == 0) {
         if (outcome == 0) lm_failed = 1;
         else converged = lm_is_converged(delta, prm.rot_eps, prm.trans_eps);
