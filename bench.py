@@ -384,7 +384,10 @@ def main():
         import configs as bc
         c4 = c5 = None
         try:
-            c4 = bc.c4_bench(local_rank, rank, world, pairs=args.c4_pairs, wave=64, threads=8, sample_check=24 if world == 1 else 0)
+            # host threads that enqueue the per-pair index + covariance work: what the box's cores allow per rank, at most 8
+            # (8 ranks x 8 threads on 32 cores: 41.7k pairs/s; x 3 threads: 57.2k — the ranks were fighting for cores)
+            c4_threads = max(2, min(8, (os.cpu_count() or 8) // world - 1))
+            c4 = bc.c4_bench(local_rank, rank, world, pairs=args.c4_pairs, wave=64, threads=c4_threads, sample_check=24 if world == 1 else 0)
         except Exception as e:  # keep the headline line even if an extra fails
             c4 = {"error": repr(e)}
         barrier()
