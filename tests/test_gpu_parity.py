@@ -202,6 +202,40 @@ def test_index_survives_far_outliers(G, O, scan_pair, far):
         assert np.isfinite(g.getTargetCovariances()[np.arange(3000) != 17]).all()
 
 
+def test_degenerate_clouds_through_fused_paths(G, O, scan_pair):
+    """Nothing finite, everything cropped away, one point, two identical points: the persistent voxel and index kernels
+    (and their multi-kernel twins) must return the oracle's answer instead of hanging on a barrier or indexing garbage."""
+    s0 = scan_pair["s0"]
+    nan_cloud = s0[:2000].copy(); nan_cloud[:, 0] = np.nan
+    near = s0[:2000].copy(); near[:, :3] = near[:, :3] / np.abs(near[:, :3]).max() * 0.5      # everything inside the +-1 m crop box
+    twin = np.repeat(s0[:1], 2, axis=0)
+    for vpath in (0, 1):
+        g = G()
+        g.setVoxelPath(vpath)
+        assert g.voxel_filter(nan_cloud, 0.25).shape[0] == 0
+        assert g.preprocess(nan_cloud, 1.0, 0.25).shape[0] == 0
+        assert g.preprocess(near, 1.0, 0.25).shape[0] == 0                 # all cropped
+        assert np.array_equal(bits(g.preprocess(near, None, 0.25)), bits(O.preprocess_points(near, None, 0.25)))
+        assert np.array_equal(bits(g.voxel_filter(twin, 0.25)), bits(O.voxel_filter(twin, 0.25)))
+        assert np.array_equal(bits(g.voxel_filter(s0, 0.25)), bits(O.voxel_filter(s0, 0.25)))     # and the handle still works
+    for ipath in (0, 1, 3):
+        g = G()
+        g.setIndexPath(ipath)
+        g.setCorrespondenceRandomness(2)
+        g.setInputTarget(nan_cloud)                                         # nothing finite: a one-cell grid, no neighbours
+        idx, d2 = g.knn(1, np.ascontiguousarray(s0[:4, :3]), 2)
+        assert (idx == -1).all()
+        g.setInputTarget(twin)
+        idx, d2 = g.knn(1, np.ascontiguousarray(twin[:, :3]), 2)
+        assert (d2 == 0).all() and set(idx[0].tolist()) == {0, 1}
+        g.calculateTargetCovariances()
+        assert np.isfinite(g.getTargetCovariances()).all()
+        g.setInputTarget(s0[:3000]); g.setInputSource(s0[:3000])
+        g.setCorrespondenceRandomness(10)
+        g.align()
+        assert np.allclose(g.final_state(), np.eye(4), atol=1e-9)           # a cloud against itself: identity
+
+
 def test_preprocess_fused_crop_nan_voxel(G, O, scan_pair):
     """ngicp_preprocess = removeNaN + negative CropBox + voxel grid in one pass (odom.cc:443-465), bit-exact against
     the three steps done one after the other by the oracle."""
