@@ -15,8 +15,8 @@
 //                 circumsphere radius <= alpha; candidate triangles are the faces of good tetrahedra plus any face whose
 //                 own circumcircle radius <= alpha; a candidate belongs to the shape unless the tetrahedra on BOTH of
 //                 its sides are good.  The result is the set of input points those triangles use.
-// On inputs in general position the vertex sets equal qhull's (tests/test_submap_select.py compares with scipy's qhull
-// on random clouds and on a replay-like loop); on degenerate input (exactly cospherical / coplanar subsets) the
+// On inputs in general position — and on exactly flat or nearly flat ones, a robot on a level floor — the vertex sets
+// equal qhull's (tests/test_submap_select.py compares with scipy's qhull on random clouds, flat sets and a replay-like loop); on degenerate input (exactly cospherical / coplanar subsets) the
 // reference itself is not deterministic (QJ joggles with a random seed).
 #include <algorithm>
 #include <cmath>
@@ -189,9 +189,11 @@ void concave_hull_vertices(const std::vector<P3>& p, const float* xyz_f, double 
   std::vector<Tet> tets;
   std::vector<P3> q(n);
   bool ok = false;
-  for (int attempt = 0; attempt < 6 && !ok; attempt++) {
-    // joggle: +-(1e-9 * 8^attempt) of the extent per coordinate, from a hash of (index, axis, attempt)
-    const R amp = extent * 1e-9L * powl(8.0L, (R)attempt);
+  for (int attempt = 0; attempt < 8 && !ok; attempt++) {
+    // joggle: +-(1e-9 * 10^attempt) of the extent per coordinate, from a hash of (index, axis, attempt) — like qhull's QJ,
+    // which also retries with a ten times larger joggle until the triangulation succeeds (exactly flat or cospherical
+    // input needs a visible perturbation: keyframes of a robot on a perfectly level floor)
+    const R amp = extent * 1e-9L * powl(10.0L, (R)attempt);
     for (int i = 0; i < n; i++) {
       const uint32_t h = (uint32_t)(i * 3 + attempt * 0x9e3779b9u);
       q[i].x = p[i].x + amp * ((R)hash32(h) / 4294967296.0L * 2 - 1);
@@ -227,10 +229,22 @@ void concave_hull_vertices(const std::vector<P3>& p, const float* xyz_f, double 
       if (it == behind.end()) behind[k] = std::make_pair(t, -1);
       else it->second.second = t;
     }
+  // Triangles on the outside of the triangulation are also the real face of a tetrahedron with ONE vertex of the enclosing
+  // tetrahedron.  For (nearly) flat input — keyframes of a robot on a level floor — ALL triangles are of that kind: the
+  // slivers qhull would report have circumspheres so large that they swallow the far vertices and never form.  Such a
+  // sliver is never "good", so the triangle counts as a face with no good tetrahedron behind it.
+  for (const Tet& t : tets) {
+    if (!t.alive) continue;
+    int far = 0, far_at = -1;
+    for (int j = 0; j < 4; j++) if (t.v[j] >= n) { far++; far_at = j; }
+    if (far != 1) continue;
+    const FaceKey k = face_key(t.v[(far_at + 1) & 3], t.v[(far_at + 2) & 3], t.v[(far_at + 3) & 3]);
+    if (behind.find(k) == behind.end()) behind[k] = std::make_pair(-1, -1);
+  }
   std::vector<char> used(n, 0);
   for (const auto& kv : behind) {
     const int t0 = kv.second.first, t1 = kv.second.second;
-    const bool g0 = good[t0] != 0, g1 = t1 >= 0 && good[t1] != 0;
+    const bool g0 = t0 >= 0 && good[t0] != 0, g1 = t1 >= 0 && good[t1] != 0;
     if (g0 && g1) continue;                                // interior of the shape
     bool candidate = g0 || g1;
     if (!candidate) {

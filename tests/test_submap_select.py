@@ -148,3 +148,26 @@ def test_native_keyframe_decision():
     assert ss.native_keyframe_wanted(kf, ident, [1.0, 0, 0], turned, 5.0, 45.0)        # rotated, only one keyframe nearby
     kf2 = np.array([[0, 0, 0], [2, 0, 0]], np.float32)
     assert not ss.native_keyframe_wanted(kf2, np.vstack([ident, ident]), [1.0, 0, 0], turned, 5.0, 45.0)   # two nearby
+
+
+def test_native_hulls_on_flat_and_nearly_flat_keyframes():
+    """Keyframes of a robot on a level floor: exactly flat positions (qhull's 3-D convex hull refuses them: empty; its
+    joggled Delaunay triangulates them as slivers: every triangle with a small circumcircle is on the alpha shape) and
+    positions with a centimetre ripple over tens of metres."""
+    rng = np.random.default_rng(0)
+    for trial in range(6):
+        flat = np.zeros((12 + 5 * trial, 3), np.float32)
+        flat[:, :2] = rng.normal(size=(flat.shape[0], 2)) * 3
+        assert ss.native_convex_hull_vertices(flat) == [] == ss.convex_hull_vertices(flat)
+        for alpha in (2.0, 5.0):
+            assert ss.native_concave_hull_vertices(flat, alpha) == ss.concave_hull_vertices(flat, alpha), (trial, alpha)
+    for trial in range(6):
+        n = 20 + 7 * trial
+        pts = np.zeros((n, 3), np.float32)
+        pts[:, :2] = rng.normal(size=(n, 2)) * 30
+        pts[:, 2] = rng.normal(size=n) * 0.02
+        for alpha in (5.0, 20.0):
+            assert ss.native_concave_hull_vertices(pts, alpha) == ss.concave_hull_vertices(pts, alpha), (trial, alpha)
+    line = np.zeros((10, 3), np.float32)
+    line[:, 0] = np.arange(10)
+    assert ss.native_convex_hull_vertices(line) == [] and ss.native_concave_hull_vertices(line, 5.0) == ss.concave_hull_vertices(line, 5.0)
