@@ -486,12 +486,8 @@ int ngicp_create(int device, ngicp_t** out) {
   h->stream_src.reset(new StreamRef());
   if (cudaStreamCreateWithFlags(&h->stream_src->s, cudaStreamNonBlocking) != cudaSuccess) { h->stream_src.reset(); delete h; return NGICP_E_CUDA; }
   h->stream_src->owned = true;
-  // keep freed blocks in the stream-ordered pool instead of returning them to the driver
-  cudaMemPool_t pool;
-  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
-    uint64_t thr = UINT64_MAX;
-    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &thr);
-  }
+  // (device memory comes from the library's own stream-ordered pool, pool_alloc_async: freed blocks stay there instead of
+  //  going back to the driver, and the application's default pool is left alone)
   // mapped: the fused kernel stores its 496-byte result straight into host memory (no D2H copy node after it)
   bool ok = cudaHostAlloc(&h->res_pinned, sizeof(ngicp_result), cudaHostAllocMapped) == cudaSuccess &&
             cudaHostGetDevicePointer(&h->res_mapped, h->res_pinned, 0) == cudaSuccess &&
@@ -518,7 +514,7 @@ int ngicp_create(int device, ngicp_t** out) {
       const long mb = e1 ? atol(e1) : 512;
       if (mb > 0) {
         void* p = nullptr;
-        if (cudaMallocAsync(&p, (size_t)mb << 20, h->stream->s) == cudaSuccess) cudaFreeAsync(p, h->stream->s);
+        if (pool_alloc_async(&p, (size_t)mb << 20, h->stream->s) == cudaSuccess) cudaFreeAsync(p, h->stream->s);
         cudaGetLastError();
       }
       const char* e2 = getenv("NGICP_TABLE_PRIME");

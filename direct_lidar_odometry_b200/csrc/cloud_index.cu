@@ -21,6 +21,38 @@
 
 namespace ngicp {
 
+// The library's own stream-ordered memory pool (one per device, created on first use, never trimmed): per-scan buffers are
+// pointer bumps, and the embedding application's DEFAULT pool keeps the release threshold it chose (round 1 raised it).
+cudaError_t pool_alloc_async(void** p, size_t nbytes, cudaStream_t s) {
+  static std::mutex mu;
+  static cudaMemPool_t pools[64] = {};
+  static bool tried[64] = {};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  cudaMemPool_t pool = nullptr;
+  if (dev >= 0 && dev < 64) {
+    std::lock_guard<std::mutex> lock(mu);
+    if (!tried[dev]) {
+      tried[dev] = true;
+      cudaMemPoolProps props;
+      memset(&props, 0, sizeof props);
+      props.allocType = cudaMemAllocationTypePinned;
+      props.handleTypes = cudaMemHandleTypeNone;
+      props.location.type = cudaMemLocationTypeDevice;
+      props.location.id = dev;
+      if (cudaMemPoolCreate(&pools[dev], &props) == cudaSuccess) {
+        uint64_t thr = UINT64_MAX;
+        cudaMemPoolSetAttribute(pools[dev], cudaMemPoolAttrReleaseThreshold, &thr);
+      } else {
+        cudaGetLastError();
+        pools[dev] = nullptr;       // (driver without pool support: the default pool, as before)
+      }
+    }
+    pool = pools[dev];
+  }
+  return pool ? cudaMallocFromPoolAsync(p, nbytes, pool, s) : cudaMallocAsync(p, nbytes, s);
+}
+
 cudaError_t DevBuf::alloc(size_t nbytes, const StreamPtr& stream) {
   release();
   if (nbytes == 0) nbytes = 16;
@@ -29,7 +61,7 @@ cudaError_t DevBuf::alloc(size_t nbytes, const StreamPtr& stream) {
   static const bool trace = getenv("NGICP_HOST_TRACE") != nullptr;
   timespec t0, t1;
   if (trace) clock_gettime(CLOCK_MONOTONIC, &t0);
-  if (st && st->owned) e = cudaMallocAsync(&p, nbytes, st->s);
+  if (st && st->owned) e = pool_alloc_async(&p, nbytes, st->s);
   else e = cudaMalloc(&p, nbytes);
   if (trace) {
     clock_gettime(CLOCK_MONOTONIC, &t1);

@@ -22,7 +22,8 @@ struct StreamRef {
 };
 typedef std::shared_ptr<StreamRef> StreamPtr;
 
-// stream-ordered device buffer (cudaMallocAsync on an owned stream, plain cudaMalloc/cudaFree otherwise)
+cudaError_t pool_alloc_async(void** p, size_t nbytes, cudaStream_t s);   // from the library's private memory pool
+// stream-ordered device buffer (the library's own pool on an owned stream, plain cudaMalloc/cudaFree otherwise)
 struct DevBuf {
   void* p = nullptr;
   size_t bytes = 0;
