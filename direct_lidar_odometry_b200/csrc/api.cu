@@ -212,7 +212,7 @@ int calc_covs(ngicp_t* h, int which, int part = 0, int nparts = 1) {
   CloudPtr& c = which == NGICP_SOURCE ? h->src : h->tgt;
   if (!c) return fail(h, NGICP_E_STATE, "calculate covariances: cloud not set");
   const int k = h->prm.k_correspondences;
-  if (k < 1 || k > KNN_MAX_K) return fail(h, NGICP_E_UNSUPPORTED, "k_correspondences must be in [1,32]");
+  if (k < 1 || k > KNN_WIDE_MAX_K) return fail(h, NGICP_E_UNSUPPORTED, "k_correspondences must be in [1,128]");
   if (c->n < k) return fail(h, NGICP_E_TOO_FEW_POINTS, "cloud has fewer points than k_correspondences");
   StreamPtr& st = side_stream(h, which);
   Scratch& sc = side_scratch(h, which);
@@ -604,7 +604,7 @@ int ngicp_get_timings(ngicp_t* h, ngicp_timings* out) {
 
 int ngicp_set_params(ngicp_t* h, const ngicp_params* p) {
   if (!h || !p) return NGICP_E_INVALID;
-  if (p->k_correspondences < 1 || p->k_correspondences > KNN_MAX_K) return fail(h, NGICP_E_UNSUPPORTED, "k_correspondences must be in [1,32]");
+  if (p->k_correspondences < 1 || p->k_correspondences > KNN_WIDE_MAX_K) return fail(h, NGICP_E_UNSUPPORTED, "k_correspondences must be in [1,128]");
   if (p->regularization_method < 0 || p->regularization_method > 4) return fail(h, NGICP_E_INVALID, "unknown regularization method");  // the reference abort()s here (nano_gicp_impl.hpp:336-338)
   if (p->grid_table_cells < 64) return fail(h, NGICP_E_INVALID, "grid_table_cells too small");
   if (p->knn_path < NGICP_KNN_AUTO || p->knn_path > NGICP_KNN_TILE) return fail(h, NGICP_E_INVALID, "unknown knn_path");
@@ -936,7 +936,7 @@ int ngicp_voxel_assignment(ngicp_t* h, int* slot_of_point, size_t n) {
 
 int ngicp_knn(ngicp_t* h, int which, const float* queries, size_t nq, size_t q_stride, int k, int* idx, float* d2) {
   if (!h || (!queries && nq) || !idx || !d2 || q_stride < 12 || (q_stride & 3)) return NGICP_E_INVALID;
-  if (k < 1 || k > KNN_MAX_K) return fail(h, NGICP_E_UNSUPPORTED, "k must be in [1,32]");
+  if (k < 1 || k > KNN_WIDE_MAX_K) return fail(h, NGICP_E_UNSUPPORTED, "k must be in [1,128]");
   DeviceGuard g(h->device);
   CloudPtr& c = which == NGICP_SOURCE ? h->src : h->tgt;
   if (!c) return fail(h, NGICP_E_STATE, "knn: cloud not set");

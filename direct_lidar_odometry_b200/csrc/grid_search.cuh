@@ -95,6 +95,54 @@ struct WarpTopK {
   }
 };
 
+// k > 32: the ascending list lives in the warp's shared memory (KNN_WIDE_MAX_K entries), one insertion at a time —
+// count the entries not larger than the candidate (that is its place: equal distances keep their visiting order, like
+// WarpTopK), move the tail up by one from the top down in warp-wide chunks, store.  Not a tuned path: DLO runs k = 10
+// and 20; this keeps setCorrespondenceRandomness(k) meaningful for the values the reference accepts beyond 32.
+struct WarpTopKWide {
+  float* sd;
+  int* sp;
+  float kth;
+  int k;
+  int lane;
+  __device__ __forceinline__ void init(int k_, int lane_, float* sd_, int* sp_) {
+    k = k_; lane = lane_; sd = sd_; sp = sp_; kth = FLT_MAX;
+    __syncwarp();
+    for (int j = lane; j < k; j += 32) { sd[j] = FLT_MAX; sp[j] = -1; }
+    __syncwarp();
+  }
+  __device__ __forceinline__ float bound() { return kth; }
+  __device__ __forceinline__ void offer(bool valid, float cd, int cp) {
+    unsigned m = __ballot_sync(FULL, valid && cd < kth);
+    while (m) {
+      const int l = __ffs(m) - 1;
+      const float bd = __shfl_sync(FULL, cd, l);
+      const int bp = __shfl_sync(FULL, cp, l);
+      int pos = 0;
+      for (int j0 = 0; j0 < k; j0 += 32) {
+        const int j = j0 + lane;
+        pos += __popc(__ballot_sync(FULL, j < k && sd[j] <= bd));
+      }
+      // bd < kth = sd[k-1], so pos <= k-1; entries [pos, k-2] move to [pos+1, k-1]
+      for (int hi = k - 1; hi > pos; hi -= 32) {
+        const int j = hi - lane;
+        const bool mv = j > pos;
+        float td = 0.f;
+        int tp = 0;
+        if (mv) { td = sd[j - 1]; tp = sp[j - 1]; }
+        __syncwarp();
+        if (mv) { sd[j] = td; sp[j] = tp; }
+        __syncwarp();
+      }
+      if (lane == 0) { sd[pos] = bd; sp[pos] = bp; }
+      __syncwarp();
+      kth = sd[k - 1];
+      const unsigned above = (l == 31) ? 0u : (FULL << (l + 1));
+      m = __ballot_sync(FULL, valid && cd < kth) & above;
+    }
+  }
+};
+
 // 1-NN: every lane keeps the best candidate it has seen; merged at the end
 struct WarpBest1 {
   float d;

@@ -165,7 +165,8 @@ cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_sc
                                const CovSideStream* side = nullptr);
 // test hook: the neighbour lists left in nbr_scratch by launch_covariances, in summation order, as original indices
 cudaError_t launch_export_neighbors(const DevCloud& c, int k, const int* nbr_scratch, int* idx_out, float* d2_out, cudaStream_t st);
-constexpr int KNN_MAX_K = 32;
+constexpr int KNN_MAX_K = 32;        // warp-distributed result set (one entry per lane): every tuned kNN kernel
+constexpr int KNN_WIDE_MAX_K = 128;  // shared-memory result set of the wide warp search: what the library accepts
 
 // ---- align.cu -------------------------------------------------------------------------------------
 struct AlignBuffers {

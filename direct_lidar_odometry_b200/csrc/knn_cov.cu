@@ -63,6 +63,45 @@ __global__ void __launch_bounds__(KC_THREADS, KNN_MIN_BLOCKS) knn_lists_kernel(G
   }
 }
 
+// k in (KNN_MAX_K, KNN_WIDE_MAX_K]: the same growing-cube search with the result set in shared memory (WarpTopKWide)
+__global__ void __launch_bounds__(KC_THREADS) knn_query_wide_kernel(GridView g, const float4* __restrict__ queries, int nq, int k,
+                                                                    int* __restrict__ idx, float* __restrict__ d2) {
+  __shared__ float s_d[KC_WARPS][KNN_WIDE_MAX_K];
+  __shared__ int s_p[KC_WARPS][KNN_WIDE_MAX_K];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const GridParams gp = load_grid(g.desc);
+  for (int q = warp; q < nq; q += nwarps) {
+    const float4 qp = queries[q];
+    WarpTopKWide rs;
+    rs.init(k, lane, s_d[wib], s_p[wib]);
+    if (isfinite(qp.x) && isfinite(qp.y) && isfinite(qp.z)) grid_search_warp(g, gp, qp.x, qp.y, qp.z, FLT_MAX, rs);
+    __syncwarp();
+    for (int j = lane; j < k; j += 32) {
+      const int p = s_p[wib][j];
+      idx[(size_t)q * k + j] = p >= 0 ? __float_as_int(__ldg(g.sorted + p).w) : -1;
+      d2[(size_t)q * k + j] = p >= 0 ? s_d[wib][j] : -1.f;
+    }
+  }
+}
+__global__ void __launch_bounds__(KC_THREADS) knn_lists_wide_kernel(GridView g, int n, int k, int* __restrict__ nbr, int q_lo, int q_hi) {
+  __shared__ float s_d[KC_WARPS][KNN_WIDE_MAX_K];
+  __shared__ int s_p[KC_WARPS][KNN_WIDE_MAX_K];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const GridParams gp = load_grid(g.desc);
+  for (int q = q_lo + warp; q < q_hi; q += nwarps) {
+    const float4 qp = __ldg(g.sorted + q);
+    WarpTopKWide rs;
+    rs.init(k, lane, s_d[wib], s_p[wib]);
+    if (isfinite(qp.x) && isfinite(qp.y) && isfinite(qp.z)) grid_search_warp<WarpTopKWide, false, 4>(g, gp, qp.x, qp.y, qp.z, FLT_MAX, rs, true);
+    __syncwarp();
+    for (int j = lane; j < k; j += 32) nbr[(size_t)q * k + j] = s_p[wib][j];
+  }
+}
+
 // K2, tile variant (the one launch_covariances uses) — cell-major, one THREAD per query.
 // The cell grid is cut into boxes of TQ_CORE^3 cells.  knn_plan_kernel walks the boxes (skipping empty space 8 boxes at
 // a time), splits boxes whose surroundings would not fit a tile (dense cells) into 8 children, down to single cells,
@@ -763,7 +802,7 @@ __global__ void __launch_bounds__(64) knn_lists_rest_kernel(GridView g, int k, i
 template <int KT, bool SORTED>
 __device__ __forceinline__ void cov_point(const GridView& g, int n, int k_rt, int method, const int* __restrict__ nbr, double* __restrict__ covs6,
                                           int q, int* __restrict__ idx_out, float* __restrict__ d2_out) {
-  constexpr int KA = KT > 0 ? KT : KNN_MAX_K;
+  constexpr int KA = KT > 0 ? KT : (KT == 0 ? KNN_MAX_K : KNN_WIDE_MAX_K);   // KT = -1: the wide lists (k up to 128, local-memory keys)
   const int k = KT > 0 ? KT : k_rt;
   const int* my = nbr + (size_t)q * k;
   const float4 qp = __ldg(g.sorted + q);
@@ -877,6 +916,7 @@ static void launch_cov_kernel(const DevCloud& c, int k, int method, const int* n
   else if (k == 20 && sorted) cov_from_lists_kernel<20, true><<<grid, block, 0, st>>>(c.view(), c.n, k, method, nbr, covs6, q_lo, q_hi, skip, idx_out, d2_out);
   else if (k == 10) cov_from_lists_kernel<10, false><<<grid, block, 0, st>>>(c.view(), c.n, k, method, nbr, covs6, q_lo, q_hi, skip, idx_out, d2_out);
   else if (k == 20) cov_from_lists_kernel<20, false><<<grid, block, 0, st>>>(c.view(), c.n, k, method, nbr, covs6, q_lo, q_hi, skip, idx_out, d2_out);
+  else if (k > KNN_MAX_K) cov_from_lists_kernel<-1, false><<<grid, block, 0, st>>>(c.view(), c.n, k, method, nbr, covs6, q_lo, q_hi, skip, idx_out, d2_out);
   else cov_from_lists_kernel<0, false><<<grid, block, 0, st>>>(c.view(), c.n, k, method, nbr, covs6, q_lo, q_hi, skip, idx_out, d2_out);
   note_launches(1);
 }
@@ -906,6 +946,9 @@ void knn_prime_kernels() {
   cudaFuncGetAttributes(&fa, knn_lists_tile_kernel<10>);
   cudaFuncGetAttributes(&fa, knn_lists_tile_kernel<20>);
   cudaFuncGetAttributes(&fa, knn_lists_rest_kernel);
+  cudaFuncGetAttributes(&fa, knn_query_wide_kernel);
+  cudaFuncGetAttributes(&fa, knn_lists_wide_kernel);
+  cudaFuncGetAttributes(&fa, cov_from_lists_kernel<-1, false>);
   cudaFuncGetAttributes(&fa, cov_from_lists_kernel<0, false>);
   cudaFuncGetAttributes(&fa, cov_from_lists_kernel<10, false>);
   cudaFuncGetAttributes(&fa, cov_from_lists_kernel<20, false>);
@@ -921,7 +964,8 @@ cudaError_t launch_knn_queries(const DevCloud& c, const float4* queries, int nq,
   if (nq <= 0) return cudaSuccess;
   int blocks = (nq + KC_WARPS - 1) / KC_WARPS;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  knn_query_kernel<<<blocks, KC_THREADS, 0, st>>>(c.view(), queries, nq, k, idx, d2);
+  if (k > KNN_MAX_K) knn_query_wide_kernel<<<blocks, KC_THREADS, 0, st>>>(c.view(), queries, nq, k, idx, d2);
+  else knn_query_kernel<<<blocks, KC_THREADS, 0, st>>>(c.view(), queries, nq, k, idx, d2);
   note_launches(1);
   return cudaGetLastError();
 }
@@ -950,10 +994,12 @@ cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_sc
   // Cell-major tiles (plan + tile + rest launches): half the instructions per point but a longer serial path per warp,
   // best for submaps — measured on the C2 submap (500k points, k=20) 0.63 ms against 0.82 ms, on a 22k-point scan 0.19 ms
   // against 0.10 ms.  AUTO takes the tiles from knn_tile_min_points (131072) points on.
-  const bool warp_only = knn_path == NGICP_KNN_WARP || (knn_path != NGICP_KNN_TILE && c.n < tile_min_points);
+  // k > 32 has one path, whatever knn_path says: the warp search with the shared-memory result set.
+  const bool warp_only = k > KNN_MAX_K || knn_path == NGICP_KNN_WARP || (knn_path != NGICP_KNN_TILE && c.n < tile_min_points);
   static const bool want_stats = getenv("NGICP_KNN_STATS") != nullptr;
   if (warp_only) {
-    knn_lists_kernel<<<(nq + KC_WARPS - 1) / KC_WARPS, KC_THREADS, 0, st>>>(c.view(), c.n, k, nbr_scratch, q_lo, q_hi);
+    if (k > KNN_MAX_K) knn_lists_wide_kernel<<<(nq + KC_WARPS - 1) / KC_WARPS, KC_THREADS, 0, st>>>(c.view(), c.n, k, nbr_scratch, q_lo, q_hi);
+    else knn_lists_kernel<<<(nq + KC_WARPS - 1) / KC_WARPS, KC_THREADS, 0, st>>>(c.view(), c.n, k, nbr_scratch, q_lo, q_hi);
     note_launches(1);
   } else {
     static std::mutex attr_mutex;

@@ -80,6 +80,8 @@ class NanoGICP:
         self.device = device
         self._p = Params()
         self._L.ngicp_get_params(self._h, C.byref(self._p))
+        self._p_ok = Params()
+        C.memmove(C.byref(self._p_ok), C.byref(self._p), C.sizeof(self._p))
         self._input = None
         self._target = None
         self._res = Result()
@@ -100,7 +102,14 @@ class NanoGICP:
         return rc
 
     def _push_params(self):
-        self._check(self._L.ngicp_set_params(self._h, C.byref(self._p)))
+        # a rejected value must not stay in the struct (every later setter would fail with it): restore the last
+        # accepted parameters before raising
+        rc = self._L.ngicp_set_params(self._h, C.byref(self._p))
+        if rc < 0:
+            C.memmove(C.byref(self._p), C.byref(self._p_ok), C.sizeof(self._p))
+        else:
+            C.memmove(C.byref(self._p_ok), C.byref(self._p), C.sizeof(self._p))
+        self._check(rc)
 
     # ------------------------------------------------------------------ parameters (odom.cc:100-120)
     def setNumThreads(self, n: int):  # OpenMP knob of the reference; the GPU path has no use for it

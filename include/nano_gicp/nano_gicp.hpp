@@ -199,10 +199,11 @@ class NanoGICP {
   void setNumThreads(int) {}   // OpenMP knob; nothing to do on the GPU
   // Every setter changes ONE field and keeps it only if the library accepts it (a rejected value used to stay in prm_
   // and make every later setter fail as well).  A value the GPU path cannot honour is a configuration error and is
-  // reported where it is made: the reference accepts any k, this build k in [1, 32] (warp-wide result set).
+  // reported where it is made: the reference accepts any k, this build k in [1, 128] (k <= 32: warp-wide
+  // result set, the tuned kernels; 33..128: a shared-memory result set on the warp-search path).
   void setCorrespondenceRandomness(int k) {
     if (!set_field(&ngicp_params::k_correspondences, k))
-      throw std::invalid_argument("NanoGICP-B200: setCorrespondenceRandomness(" + std::to_string(k) + "): this build supports 1 <= k <= 32");
+      throw std::invalid_argument("NanoGICP-B200: setCorrespondenceRandomness(" + std::to_string(k) + "): this build supports 1 <= k <= 128");
   }
   void setRegularizationMethod(RegularizationMethod m) { set_field(&ngicp_params::regularization_method, (int)m); }
 

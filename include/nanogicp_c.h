@@ -68,7 +68,8 @@ enum {
 
 typedef struct {
   /* reference parameters and their defaults */
-  int k_correspondences;               /* setCorrespondenceRandomness; nano_gicp_impl.hpp:57 (20) */
+  int k_correspondences;               /* setCorrespondenceRandomness; nano_gicp_impl.hpp:57 (20); 1..128 (above 32: warp search with a
+                                          shared-memory result set, untuned); larger values: NGICP_E_UNSUPPORTED */
   double max_correspondence_distance;  /* setMaxCorrespondenceDistance; nano_gicp_impl.hpp:59 (FLT_MAX) */
   int max_iterations;                  /* setMaximumIterations; lsq_registration_impl.hpp:52 (64) */
   double transformation_epsilon;       /* setTransformationEpsilon; lsq_registration_impl.hpp:54 (5e-4) */

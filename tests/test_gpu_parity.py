@@ -464,6 +464,61 @@ def test_covariances_vs_oracle(G, O, vox_pair, k, method):
         assert rel.max() < COV_RTOL
 
 
+@pytest.mark.parametrize("k", [33, 48, 64, 128])
+def test_wide_k_knn_and_covariances_vs_oracle(G, O, vox_pair, k):
+    """k above the warp-wide result set (the reference takes any k, nano_gicp.hpp:84): shared-memory result set on the
+    warp-search path.  Same bars as k <= 32: distances bit-identical, indices identical off exact ties, covariances <= 1e-5."""
+    v0, v1 = vox_pair
+    g = G()
+    g.setCorrespondenceRandomness(k)
+    g.setKnnPath(2)                      # a forced tile path must not matter for k > 32
+    g.setInputTarget(v0)
+    tree = O.Cloud(v0)
+    rng = np.random.default_rng(9)
+    far = rng.uniform(-120, 120, size=(100, 3)).astype(np.float32)
+    q = np.vstack([v1[:1500, :3], far])
+    idx, d2 = g.knn(1, q, k)
+    ridx, rd2 = tree.knn(q, k)
+    assert np.array_equal(bits(d2), bits(rd2))
+    lo = np.concatenate([np.full((len(q), 1), -1, np.float32), rd2[:, :-1]], axis=1)
+    hi = np.concatenate([rd2[:, 1:], np.full((len(q), 1), np.inf, np.float32)], axis=1)
+    distinct = (rd2 != lo) & (rd2 != hi)
+    distinct[:, -1] = False              # the last place may tie with the (k+1)-th
+    assert distinct.mean() > 0.9
+    assert np.array_equal(idx[distinct], ridx[distinct])
+    assert g.calculateTargetCovariances() is True
+    got = g.getTargetCovariances()
+    ref = tree.covariances(k, method=0)
+    g0 = G()
+    g0.setCorrespondenceRandomness(k); g0.setRegularizationMethod(0); g0.setInputTarget(v0)
+    assert g0.calculateTargetCovariances() is True
+    raw = g0.getTargetCovariances()
+    _, d2p = tree.knn(v0[:, :3].copy(), k + 1)
+    ok = d2p[:, k - 1] != d2p[:, k]
+    assert ok.mean() > 0.99
+    rel = np.linalg.norm((raw - ref)[ok].reshape(-1, 16), axis=1) / np.linalg.norm(ref[ok].reshape(-1, 16), axis=1)
+    assert rel.max() < COV_RTOL
+    ev = np.linalg.eigvalsh(0.5 * (got[:, :3, :3] + got[:, :3, :3].transpose(0, 2, 1)))
+    assert np.allclose(ev, [1e-3, 1, 1], atol=1e-9)
+    # and a registration with it: pose and iteration counts like the oracle's
+    if k in (48, 128):
+        gg, r = _align_both(G, O, v1, v0, dict(k=k, thr=1.0, max_iter=32, trans_eps=0.01), None, 0)
+        res = gg.result
+        assert (res.nr_iterations, res.converged, res.n_linearize, res.n_compute_error) == \
+               (r.nr_iterations, r.converged, r.n_linearize, r.n_compute_error)
+        dt, dr = pose_delta(gg.final_state(), r.Tx())
+        assert dt < POSE_T_TOL and dr < POSE_R_TOL, (dt, dr)
+
+
+def test_k_above_128_is_rejected(G):
+    from direct_lidar_odometry_b200 import NanoGICPError
+    g = G()
+    with pytest.raises(NanoGICPError):
+        g.setCorrespondenceRandomness(129)
+    g.setCorrespondenceRandomness(128)   # and the handle still takes valid values afterwards
+    g.setCorrespondenceRandomness(20)
+
+
 # ---------------------------------------------------------------------------------------------- K4 / K5
 def _setup_pair(G, O, v_src, v_tgt, k, thr, **kw):
     g = G()
