@@ -186,9 +186,9 @@ __device__ __forceinline__ float box_face_distance(const GridParams& gp, int x0,
 #else
 #define TQ_CHECK(cond, what, a, b) do { } while (0)
 #endif
-enum { ST_FALLBACK = 0, ST_TIES, ST_TILES, ST_PASSES, ST_LANES, ST_ITEMS, ST_DEC1, ST_DEC2, ST_DECHI, ST_PASS1, ST_PASS2, ST_PASSHI, ST_CAND, ST_N };
+enum { ST_FALLBACK = 0, ST_TIES, ST_TILES, ST_PASSES, ST_LANES, ST_ITEMS, ST_DEC1, ST_DEC2, ST_DECHI, ST_PASS1, ST_PASS2, ST_PASSHI, ST_CAND, ST_TSUM, ST_TEND, ST_TSTART, ST_TWARPS, ST_N };
 // control words shared by the plan and tile launches
-enum { CT_ITEMS = 0, CT_NEXT, CT_REST, CT_REST_NEXT, CT_DONE, CT_FIX, CT_N = 8 };
+enum { CT_ITEMS = 0, CT_NEXT, CT_REST, CT_REST_NEXT, CT_DONE, CT_FIX, CT_SLOW, CT_N = 8 };
 
 // warp-aggregated append of the lanes in `mask` to the warp-search list
 __device__ __forceinline__ void fb_append(unsigned mask, int slot, int lane, int* __restrict__ fb_list, int* __restrict__ fb_count,
@@ -251,15 +251,35 @@ __device__ __forceinline__ int box_population(const GridView& g, const GridParam
 }
 
 // emit the work items of the boxes held by the lanes with q > 0 (one box per such lane)
-__device__ __forceinline__ void emit_items(bool emit, int x0, int y0, int z0, int sz, int q, int lane, int4* __restrict__ items, int* __restrict__ ctrl) {
+// Two lists in one array of n entries (an item holds at least one point): the LONG items from the front — boxes in
+// sparse surroundings (`slow`: they will need larger tiles, up to 41 rounds of dependent row lookups at radius 16) and
+// items with more than TQ_BIG points (two or more batches per tile) — and the short ones from the back.  The tile kernel
+// takes the front list first: a warp handles only ~6 items per launch, so the launch ends with a tail about one item
+// long (warps were busy 85 % of the kernel's span) — it should be a short item.
+#ifndef TQ_BIG
+#define TQ_BIG 32
+#endif
+__device__ __forceinline__ void emit_items(bool emit, bool slow, int x0, int y0, int z0, int sz, int q, int lane, int n, int4* __restrict__ items,
+                                           int* __restrict__ ctrl) {
   const int nit = emit ? (q + TQ_ITEM - 1) / TQ_ITEM : 0;
-  const int inc = warp_incl_scan(nit, lane);
-  const int total = __shfl_sync(FULL, inc, 31);
-  if (total == 0) return;
-  int base = 0;
-  if (lane == 0) base = atomicAdd(ctrl + CT_ITEMS, total);
-  base = __shfl_sync(FULL, base, 0) + inc - nit;
-  for (int i = 0; i < nit; ++i) items[base + i] = make_int4(x0, y0, z0, sz | (i << 8));
+  // only the last item of a box can be short
+  const int nfront = (slow || nit == 0 || q - (nit - 1) * TQ_ITEM > TQ_BIG) ? nit : nit - 1;
+  const int nback = nit - nfront;
+  if (__any_sync(FULL, nfront > 0)) {
+    const int inc = warp_incl_scan(nfront, lane);
+    const int total = __shfl_sync(FULL, inc, 31);
+    int base = 0;
+    if (lane == 0) base = atomicAdd(ctrl + CT_SLOW, total);
+    base = __shfl_sync(FULL, base, 0) + inc - nfront;
+    for (int i = 0; i < nfront; ++i) items[base + i] = make_int4(x0, y0, z0, sz | (i << 8));
+  }
+  const unsigned bm = __ballot_sync(FULL, nback > 0);
+  if (bm) {
+    int base = 0;
+    if (lane == 0) base = atomicAdd(ctrl + CT_ITEMS, __popc(bm));
+    base = __shfl_sync(FULL, base, 0) + __popc(bm & ((1u << lane) - 1u));
+    if (nback > 0) items[n - 1 - base] = make_int4(x0, y0, z0, sz | ((nit - 1) << 8));
+  }
 }
 
 // one warp per run of x-adjacent boxes (8 on big grids, 1 on small ones): emits the work items of knn_lists_tile_kernel.
@@ -295,7 +315,10 @@ __global__ void __launch_bounds__(256) brick_mark_kernel(GridView g, int n, unsi
   }
 }
 
-__global__ void __launch_bounds__(256) knn_plan_kernel(GridView g, int4* __restrict__ items, int* __restrict__ ctrl,
+#ifndef TQ_SLOW_FACTOR
+#define TQ_SLOW_FACTOR 2      // a box is "slow" when its radius-1 tile holds fewer than this many times k points
+#endif
+__global__ void __launch_bounds__(256) knn_plan_kernel(GridView g, int n, int k, int4* __restrict__ items, int* __restrict__ ctrl,
                                                        const unsigned char* __restrict__ flags, long long flag_cap) {
   const int lane = threadIdx.x & 31;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -337,7 +360,7 @@ __global__ void __launch_bounds__(256) knn_plan_kernel(GridView g, int4* __restr
       const int Qb = box_population(g, gp, bx0, y0, z0, TQ_CORE, 0, sub, 4);
       const int Cb = box_population(g, gp, Qb > 0 ? bx0 : -(1 << 20), y0, z0, TQ_CORE, 1, sub, 4);
       const bool fits = Qb > 0 && Cb <= TQ_CMAX;
-      emit_items(sub == 0 && fits, bx0, y0, z0, TQ_CORE, Qb, lane, items, ctrl);
+      emit_items(sub == 0 && fits, Cb < TQ_SLOW_FACTOR * k, bx0, y0, z0, TQ_CORE, Qb, lane, n, items, ctrl);
       deep_boxes = __ballot_sync(FULL, sub == 0 && Qb > 0 && !fits);
     }
     for (; deep_boxes; deep_boxes &= deep_boxes - 1) {
@@ -350,7 +373,7 @@ __global__ void __launch_bounds__(256) knn_plan_kernel(GridView g, int4* __restr
       const int Qc = box_population(g, gp, cx0, cy0, cz0, h, 0, sub, 4);
       const int Cc = box_population(g, gp, cx0, cy0, cz0, h, 1, sub, 4);
       const bool fits = Cc <= TQ_CMAX;
-      emit_items(sub == 0 && Qc > 0 && fits, cx0, cy0, cz0, h, Qc, lane, items, ctrl);
+      emit_items(sub == 0 && Qc > 0 && fits, false, cx0, cy0, cz0, h, Qc, lane, n, items, ctrl);
       unsigned deep = __ballot_sync(FULL, sub == 0 && Qc > 0 && !fits);
       for (; deep; deep &= deep - 1) {
         const int l = __ffs(deep) - 1;
@@ -358,7 +381,7 @@ __global__ void __launch_bounds__(256) knn_plan_kernel(GridView g, int4* __restr
         // 8 single cells of that child; whether their radius-1 tile fits is left to the tile kernel
         const int gx = px + (ch & 1), gy = py + ((ch >> 1) & 1), gz = pz + (ch >> 2);
         const int Qg = box_population(g, gp, gx, gy, gz, 1, 0, sub, 4);
-        emit_items(sub == 0 && Qg > 0, gx, gy, gz, 1, Qg, lane, items, ctrl);
+        emit_items(sub == 0 && Qg > 0, false, gx, gy, gz, 1, Qg, lane, n, items, ctrl);
       }
     }
   }
@@ -478,11 +501,14 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
   const int lane = threadIdx.x & 31;
   const unsigned lt = (1u << lane) - 1u;
   const GridParams gp = load_grid(g.desc);
-  const int nitems = ctrl[CT_ITEMS];
+  const int nslow = ctrl[CT_SLOW];
+  const int nitems = nslow + ctrl[CT_ITEMS];
   unsigned st_fb = 0, st_ties = 0, st_tiles = 0, st_passes = 0, st_lanes = 0, st_items = 0;
 #ifdef TQ_STATS_DETAIL      // per-radius counters (variants/ build only: they cost 30 registers)
   unsigned st_dec[3] = {0, 0, 0}, st_pass[3] = {0, 0, 0};
   unsigned long long st_cand = 0;
+  unsigned long long st_t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(st_t0));
 #endif
 
   for (;;) {
@@ -491,7 +517,7 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
     w = __shfl_sync(FULL, w, 0);
     if (w >= nitems) break;
     st_items++;
-    const int4 item = __ldg(items + w);
+    const int4 item = __ldg(items + (w < nslow ? w : n - 1 - (w - nslow)));
     TQ_CHECK(nitems <= n, "nitems", nitems, n);
     const int x0 = item.x, y0 = item.y, z0 = item.z, sz = item.w & 255, first = (item.w >> 8) * TQ_ITEM;
     // ---- the item's points: positions [first, first + TQ_ITEM) of the box's sz*sz contiguous slot ranges ----
@@ -769,6 +795,12 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
     atomicAdd(stats + ST_PASS1, (unsigned long long)st_pass[0]); atomicAdd(stats + ST_PASS2, (unsigned long long)st_pass[1]);
     atomicAdd(stats + ST_PASSHI, (unsigned long long)st_pass[2]);
     atomicAdd(stats + ST_CAND, st_cand);
+    unsigned long long st_t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(st_t1));
+    atomicAdd(stats + ST_TSUM, st_t1 - st_t0);
+    atomicMax(stats + ST_TEND, st_t1);
+    atomicMin(stats + ST_TSTART, st_t0);      // the host presets this word to all ones
+    atomicAdd(stats + ST_TWARPS, 1ull);
 #endif
   }
 }
@@ -1039,6 +1071,7 @@ cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_sc
     if (want_stats) {
       if (cudaMalloc(&stats, ST_N * sizeof(unsigned long long)) != cudaSuccess) return cudaGetLastError();
       cudaMemsetAsync(stats, 0, ST_N * sizeof(unsigned long long), st);
+      cudaMemsetAsync(stats + ST_TSTART, 0xff, sizeof(unsigned long long), st);
     }
     // plan: one warp per run of boxes; the grid dimensions live on the device, so cover the table capacity
     // (runs of 8 boxes above 32768 boxes, single boxes below)
@@ -1053,7 +1086,7 @@ cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_sc
       brick_mark_kernel<<<(c.n + 1023) / 1024, 256, 0, st>>>(c.view(), c.n, bricks, brick_cap);
       note_launches(2);
     }
-    knn_plan_kernel<<<(unsigned)((plan_warps + 7) / 8), 256, 0, st>>>(c.view(), items, ctrl, bricks, brick_cap);
+    knn_plan_kernel<<<(unsigned)((plan_warps + 7) / 8), 256, 0, st>>>(c.view(), c.n, k, items, ctrl, bricks, brick_cap);
     note_launches(1);
     // persistent grid: every resident warp pulls work items until the counter runs out; no block waits for another one,
     // so it does not matter how many of the blocks are resident at a time (other handles may share the GPU)
@@ -1089,6 +1122,10 @@ cudaError_t launch_covariances(const DevCloud& c, int k, int method, int* nbr_sc
       fprintf(stderr, "[ngicp knn]   decided at radius 1 / 2 / >2: %llu / %llu / %llu, passes %llu / %llu / %llu, candidates per pass %.0f\n",
               h[ST_DEC1], h[ST_DEC2], h[ST_DECHI], h[ST_PASS1], h[ST_PASS2], h[ST_PASSHI],
               h[ST_PASSES] ? (double)h[ST_CAND] / (double)h[ST_PASSES] : 0.0);
+      if (h[ST_TWARPS])
+        fprintf(stderr, "[ngicp knn]   tile kernel: %llu warps, span %.1f us, mean warp busy %.1f us (%.0f%% of the span)\n", h[ST_TWARPS],
+                1e-3 * (double)(h[ST_TEND] - h[ST_TSTART]), 1e-3 * (double)h[ST_TSUM] / (double)h[ST_TWARPS],
+                100.0 * (double)h[ST_TSUM] / (double)h[ST_TWARPS] / (double)(h[ST_TEND] - h[ST_TSTART]));
     }
     launch_cov_kernel(c, k, method, nbr_scratch, covs6, q_lo, q_hi, fb_flags, nullptr, nullptr, st, k == 10 || k == 20);
     if (overlap && (e = cudaStreamWaitEvent(st, side->join, 0)) != cudaSuccess) return e;
