@@ -700,13 +700,31 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
                 // the k nearest back into the lane's column in ascending lattice order = ascending exact distance, unless
                 // two neighbours share a lattice value (an exact tie or closer than 2^-14 relative): those points are
                 // delivered too but flagged, and the covariance fix-up orders them by exact (distance, slot)
+                // Written out by the lane itself, straight from the registers (KT/4 128-bit stores into its own row of
+                // nbr; the rows of a batch's queries are neighbours in memory most of the time) — the earlier write-out
+                // went back through the shared list and took one dependent round per decided query.
                 bool near = false;
+                constexpr int KW = KT > 0 ? KT : 4;
+                int o[KW];
 #pragma unroll
-                for (int i = 0; i < (KT > 0 ? KT : 1); ++i) {
-                  S.lst[i][lane] = v[i];
+                for (int i = 0; i < KW; ++i) {
+                  o[i] = S.slot[v[i] & TQ_POS_MASK];
                   if (i > 0) near = near || ((v[i - 1] >> TQ_POS_BITS) == (v[i] >> TQ_POS_BITS));
                 }
                 needs_fix = searching && !tie && near;
+                if (searching && !tie) {
+                  int* row = nbr + (size_t)slot * KW;
+                  if (KW % 4 == 0) {
+#pragma unroll
+                    for (int i = 0; i < KW / 4; ++i) reinterpret_cast<int4*>(row)[i] = make_int4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
+                  } else if (KW % 2 == 0) {
+#pragma unroll
+                    for (int i = 0; i < KW / 2; ++i) reinterpret_cast<int2*>(row)[i] = make_int2(o[2 * i], o[2 * i + 1]);
+                  } else {
+#pragma unroll
+                    for (int i = 0; i < KW; ++i) row[i] = o[i];
+                  }
+                }
               } else {
                 const bool compact = searching && !tie;
                 int pos = 0;
@@ -724,8 +742,8 @@ __global__ void __launch_bounds__(TQ_WARPS * 32) knn_lists_tile_kernel(GridView 
           st_dec[s == 1 ? 0 : (s == 2 ? 1 : 2)] += __popc(dmask);
 #endif
           __syncwarp();
-          // ---- coalesced write-out: one query per step, lane j writes the j-th neighbour ----
-          for (unsigned mm = dmask; mm; mm &= mm - 1) {
+          // ---- generic k: coalesced write-out through the shared list, one query per step, lane j writes the j-th neighbour ----
+          for (unsigned mm = KT > 0 ? 0u : dmask; mm; mm &= mm - 1) {
             const int l = __ffs(mm) - 1;
             const int sl = __shfl_sync(FULL, slot, l);
             TQ_CHECK(lane >= k || ((S.lst[lane][l] & TQ_POS_MASK) < (unsigned)C && S.slot[S.lst[lane][l] & TQ_POS_MASK] >= 0), "tilepos", (int)(S.lst[lane][l] & TQ_POS_MASK), C);
