@@ -397,6 +397,42 @@ __global__ void __launch_bounds__(256) knn_plan_kernel(GridView g, int n, int k,
 // thresholds are kept on the lattice of the list entries: 9 low mantissa bits zero (rounded towards zero)
 __device__ __forceinline__ float lattice_floor(float t) { return __uint_as_float(__float_as_uint(t) & ~TQ_POS_MASK); }
 struct Shrunk { float T2; int cnt; };
+#ifndef TQ_COOP_SHRINK
+#define TQ_COOP_SHRINK 1
+#endif
+#if TQ_COOP_SHRINK
+// The lists of the lanes in `om` are about to fill up: each of them LOWERS its threshold (x 3/4 until at most LCAP-4
+// entries survive) and keeps the entries below it.  Done by the whole warp, one list at a time, the list's (at most 40)
+// entries spread over the lanes: two loads, two ballots, two stores per round — the lane-by-lane version (one lane
+// walking its 36 entries while the other 31 wait) was 12 % of the kernel's instructions, two calls per pass.
+// Every lane gets back its own (threshold, count): unchanged unless it was in `om`.
+__device__ __noinline__ Shrunk shrink_lists(TileSmem& S, unsigned om, float T2, int cnt) {
+  const int lane = threadIdx.x & 31;
+  const unsigned lt = (1u << lane) - 1u;
+  Shrunk r;
+  r.T2 = T2; r.cnt = cnt;
+  for (; om; om &= om - 1) {
+    const int L = __ffs(om) - 1;
+    float t = __shfl_sync(FULL, T2, L);
+    int n = __shfl_sync(FULL, cnt, L);
+    do {
+      t = lattice_floor(t * 0.75f);           // counts grow ~linearly in T^2 on surfaces: about 3/4 survive
+      const unsigned tb = __float_as_uint(t);
+      const unsigned e0 = lane < n ? S.lst[lane][L] : 0xffffffffu;
+      const unsigned e1 = lane + 32 < n ? S.lst[lane + 32][L] : 0xffffffffu;
+      const bool k0 = e0 < tb, k1 = e1 < tb;
+      const unsigned m0 = __ballot_sync(FULL, k0), m1 = __ballot_sync(FULL, k1);
+      __syncwarp();
+      if (k0) S.lst[__popc(m0 & lt)][L] = e0;                 // order kept, like the sequential compaction
+      if (k1) S.lst[__popc(m0) + __popc(m1 & lt)][L] = e1;
+      __syncwarp();
+      n = __popc(m0) + __popc(m1);
+    } while (n > TQ_LCAP - 4);
+    if (lane == L) { r.T2 = t; r.cnt = n; }
+  }
+  return r;
+}
+#else
 __device__ __noinline__ Shrunk shrink_list(unsigned* col, float T2, int cnt) {
   do {
     T2 = lattice_floor(T2 * 0.75f);           // counts grow ~linearly in T^2 on surfaces: about 3/4 survive
@@ -412,6 +448,7 @@ __device__ __noinline__ Shrunk shrink_list(unsigned* col, float T2, int cnt) {
   r.T2 = T2; r.cnt = cnt;
   return r;
 }
+#endif
 // packed f32x2 arithmetic (sm_100): one instruction works on two candidates.  Every operation is the IEEE round-to-nearest
 // one of nanoflann's metric, in the same order — d = ((dx*dx) + dy*dy) + dz*dz with every product and sum rounded on its
 // own.  ptxas contracts a packed multiply followed by a packed add into FFMA2 even under -fmad=false, so the sums are
@@ -437,7 +474,7 @@ __device__ __forceinline__ unsigned long long sqdist2_unfused(const Query2& q, u
 // "write, then advance if it passed": the slot after the last accepted entry is simply overwritten by the next
 // candidate, so an offer is one 32-bit shared store plus one predicated pointer bump (row stride 128 B).
 // c and cend are even (rows are padded to even lengths).
-__device__ __forceinline__ int collect_pass(const TileSmem& S, unsigned* const col, int c, int cend, float qx, float qy, float qz, float one, float& T2_io, int cnt) {
+__device__ __forceinline__ int collect_pass(TileSmem& S, unsigned* const col, int c, int cend, float qx, float qy, float qz, float one, float& T2_io, int cnt) {
   float T2 = T2_io;
   Query2 q;
   q.x = f2_pack(qx, qx); q.y = f2_pack(qy, qy); q.z = f2_pack(qz, qz); q.one = f2_pack(one, one);
@@ -450,12 +487,24 @@ __device__ __forceinline__ int collect_pass(const TileSmem& S, unsigned* const c
     asm volatile("st.shared.u32 [%0], %1;" ::"r"(p), "r"((__float_as_uint(D) & ~TQ_POS_MASK) | (unsigned)(CI)) : "memory"); \
     if ((D) < T2) p += 128u;                                                                                 \
   }
+#if TQ_COOP_SHRINK
+#define TQ_MAYBE_SHRINK()                                                       \
+  {                                                                             \
+    const unsigned om_ = __ballot_sync(FULL, p > plim);                         \
+    if (om_) {                                                                  \
+      const Shrunk r = shrink_lists(S, om_, T2, (int)((p - a0) >> 7));          \
+      T2 = r.T2;                                                                \
+      p = a0 + (unsigned)r.cnt * 128u;                                          \
+    }                                                                           \
+  }
+#else
 #define TQ_MAYBE_SHRINK()                                                       \
   if (p > plim) {                                                               \
     const Shrunk r = shrink_list(col, T2, (int)((p - a0) >> 7));                \
     T2 = r.T2;                                                                  \
     p = a0 + (unsigned)r.cnt * 128u;                                            \
   }
+#endif
 #define TQ_PAIR(CI)                                                                                                     \
   {                                                                                                                     \
     const unsigned long long d01 = sqdist2_unfused(q, *reinterpret_cast<const unsigned long long*>(S.xs + (CI)),        \
