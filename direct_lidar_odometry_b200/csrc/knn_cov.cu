@@ -392,11 +392,14 @@ __global__ void __launch_bounds__(256) knn_plan_kernel(GridView g, int n, int k,
 // keeps the entries below it — everything dropped, and everything rejected from then on, is farther than the final T2,
 // so the list still holds every tile point below the threshold the lane ends with.  T2 < 0 switches a lane off.
 #ifndef TQ_TARGET_EXTRA
-#define TQ_TARGET_EXTRA 12     // first guesses aim at k + this many collected points
+#define TQ_TARGET_EXTRA 14     // first guesses aim at k + this many collected points (C2, with the warp-wide shrink: 10 0.572, 12 0.517, 14 0.483, 16 0.481, 18 0.495, 20 0.512 ms)
 #endif
 // thresholds are kept on the lattice of the list entries: 9 low mantissa bits zero (rounded towards zero)
 __device__ __forceinline__ float lattice_floor(float t) { return __uint_as_float(__float_as_uint(t) & ~TQ_POS_MASK); }
 struct Shrunk { float T2; int cnt; };
+#ifndef TQ_SHRINK_F
+#define TQ_SHRINK_F 0.75f
+#endif
 #ifndef TQ_COOP_SHRINK
 #define TQ_COOP_SHRINK 1
 #endif
@@ -416,7 +419,7 @@ __device__ __noinline__ Shrunk shrink_lists(TileSmem& S, unsigned om, float T2, 
     float t = __shfl_sync(FULL, T2, L);
     int n = __shfl_sync(FULL, cnt, L);
     do {
-      t = lattice_floor(t * 0.75f);           // counts grow ~linearly in T^2 on surfaces: about 3/4 survive
+      t = lattice_floor(t * TQ_SHRINK_F);           // counts grow ~linearly in T^2 on surfaces: about 3/4 survive
       const unsigned tb = __float_as_uint(t);
       const unsigned e0 = lane < n ? S.lst[lane][L] : 0xffffffffu;
       const unsigned e1 = lane + 32 < n ? S.lst[lane + 32][L] : 0xffffffffu;
